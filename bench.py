@@ -1,0 +1,384 @@
+#!/usr/bin/env python
+"""bench.py -- YOLOv5s-int8 640x640 images/s on N B200 (BASELINE.json metric).
+
+    python bench.py --gpus N --steps K --warmup W            # this framework (CUDA)
+    python bench.py --impl reference --steps K --warmup W    # the reference's CPU path
+
+A step = one pass of the hot path (all .mars layers, YOLO decode, class-wise NMS) over one
+batch of synthetic images per GPU.  The model is the yolov5s-shaped graph written by
+thingino-accel_b200/marsfile.py (the reference's yolov5s_int8.mars is a missing blob; same layer
+table as the shipped yolov5n_int8.mars at 2x width, SYNTHETIC weights, seed 5).
+
+  value : whole-job images/s with the batch already resident in HBM (device time, CUDA events
+          on the library's stream, max over ranks);
+  e2e   : the same through mars_b200_detect_batch() with HOST (pinned) buffers -- H2D of every
+          image and D2H of the detection lists inside the timed region;
+  roofline / cpu_baseline : see DESIGN.md section 6.
+
+Images shard across ranks (one process per GPU, no data-path collective); rank 0 gathers the
+fixed-size detection records over NCCL at the end of every step.
+"""
+import argparse
+import ctypes as C
+import json
+import multiprocessing as mp
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+from __graft_entry__ import load_package  # noqa: E402
+
+METRIC = "yolov5s_int8_640_images_per_s"
+UNIT = "images/s"
+NMS_THRESH = 0.45
+
+
+def build_model_blob(pkg):
+    mf = pkg.marsfile
+    return mf.build_yolov5(width=0.5, size=640, seed=5).to_bytes(), mf.ARENA_YOLOV5S_INT8
+
+
+def synth_images(first, n):
+    """image b: default_rng(1000+b) int8"""
+    out = np.empty((n, 3 * 640 * 640), dtype=np.int8)
+    for i in range(n):
+        out[i] = np.random.default_rng(1000 + first + i).integers(-128, 128, size=out.shape[1], dtype=np.int8)
+    return out
+
+
+# ---------------------------------------------------------------------------------------
+# clocks
+# ---------------------------------------------------------------------------------------
+class ClockSampler(threading.Thread):
+    """samples SM clock and throttle reasons of one GPU while the timed region runs"""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.stop_flag, self.samples, self.reasons, self.max_mhz = index, False, [], set(), None
+
+    def run(self):
+        try:
+            import pynvml as nv
+            nv.nvmlInit()
+            h = nv.nvmlDeviceGetHandleByIndex(self.index)
+            self.max_mhz = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
+            get_reasons = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or nv.nvmlDeviceGetCurrentClocksThrottleReasons
+            names = {0x2: "applications_clocks_setting", 0x4: "sw_power_cap", 0x8: "hw_slowdown", 0x10: "sync_boost",
+                     0x20: "sw_thermal_slowdown", 0x40: "hw_thermal_slowdown", 0x80: "hw_power_brake_slowdown",
+                     0x100: "display_clock_setting"}
+            while not self.stop_flag:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM))
+                r = get_reasons(h)
+                for bit, nm in names.items():
+                    if r & bit:
+                        self.reasons.add(nm)
+                time.sleep(0.05)
+        except Exception as e:  # nvml missing: record that, do not fail the bench
+            self.reasons.add("nvml_unavailable:%s" % type(e).__name__)
+
+    def result(self):
+        self.stop_flag = True
+        self.join(timeout=2)
+        s = sorted(self.samples)
+        return {"sm_mhz": s[len(s) // 2] if s else None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "samples": len(s)}
+
+
+# ---------------------------------------------------------------------------------------
+# CPU arms (the ONLY place bench.py executes anything under oracle/)
+# ---------------------------------------------------------------------------------------
+def _cpu_worker(args):
+    kind, blob, arena, seed, images = args
+    os.environ["OMP_NUM_THREADS"] = "1"
+    if kind == "reference":
+        from oracle import refbind as rb
+        r = rb.RefRuntime(blob, arena_bytes=arena)
+        t0 = time.perf_counter()
+        for i in range(images):
+            x = np.random.default_rng(seed + i).integers(-128, 128, size=3 * 640 * 640, dtype=np.int8)
+            r.set_input(x)
+            r.run()
+            o = r.output_bytes().view(np.int8)
+            rb.ref_nms(rb.ref_parse_output(o, 25200, r.output().desc.scale))
+        return time.perf_counter() - t0
+    from oracle import oraclebind as ob
+    m = ob.OracleModel(blob, arena_bytes=arena)
+    t0 = time.perf_counter()
+    for i in range(images):
+        x = np.random.default_rng(seed + i).integers(-128, 128, size=3 * 640 * 640, dtype=np.int8)
+        m.set_input(x)
+        m.run()
+        o = m.output_bytes().view(np.int8)
+        ob.nms(ob.parse_output(o, 25200, m.tensor_desc(m.output_index()).scale))
+    return time.perf_counter() - t0
+
+
+def cpu_kind():
+    return "reference" if os.path.exists(os.path.join(ROOT, "oracle", "_ref", "libmars_ref.so")) else "port"
+
+
+def cpu_step(pool, kind, blob, arena, cores, images_per_core=1):
+    """one bounded sample: `cores` processes x images_per_core images; returns images/s"""
+    t0 = time.perf_counter()
+    pool.map(_cpu_worker, [(kind, blob, arena, 1000 + c * images_per_core, images_per_core) for c in range(cores)])
+    dt = time.perf_counter() - t0
+    return cores * images_per_core / dt, dt
+
+
+def host_cores():
+    try:
+        return len(os.sched_getaffinity(0))
+    except Exception:
+        return os.cpu_count() or 1
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    pkg = load_package()  # marsfile only; no CUDA call is made on this arm
+    blob, arena = build_model_blob(pkg)
+    kind = cpu_kind()
+    cores = min(host_cores(), 64)
+    ctx = mp.get_context("spawn")
+    with ctx.Pool(cores) as pool:
+        for _ in range(min(args.warmup, 1)):  # one full warm-up pass is enough on a CPU
+            cpu_step(pool, kind, blob, arena, cores)
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            cpu_step(pool, kind, blob, arena, cores)
+        dt = time.perf_counter() - t0
+    value = args.steps * cores / dt
+    sample = "%d image(s) per step on each of %d processes (one per host core), yolov5s-shaped 640x640 int8, all layers + decode + NMS" % (1, cores)
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "int8", "data": "synthetic",
+            "config": {"workload": "yolov5s_int8.mars-shaped 640x640, %d images per step" % cores, "model_file": "synthetic (marsfile.build_yolov5 width 0.5, seed 5)"},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line))
+    return 0
+
+
+# ---------------------------------------------------------------------------------------
+# roofline bookkeeping
+# ---------------------------------------------------------------------------------------
+KIND_GROUP = {1: "conv", 2: "conv", 3: "conv", 4: "conv"}
+
+
+def roofline_from_profile(prof, batch, peaks, peak_note):
+    """group the per-op CUDA-event times of the timed region; the dominant group is reported"""
+    groups = {}
+    for p in prof:
+        if not p["calls"]:
+            continue
+        if p["kind"] in KIND_GROUP:
+            name = "conv_tcgen05_i8" if p["impl"] == 1 else "conv_direct_i8"
+            work = 2.0 * p["oc"] * p["oh"] * p["ow"] * p["ic"] * p["kh"] * p["kw"] * batch  # int8 ops per launch
+            byts = (p["ic"] * p["ih"] * p["iw"] + p["oc"] * p["oh"] * p["ow"]) * batch + p["oc"] * p["ic"] * p["kh"] * p["kw"]
+        else:
+            name = "memory_bound_layers"
+            n = p["n"] if p["n"] else p["oh"] * p["ow"] * p["ic"]
+            work, byts = 0.0, (3 if p["kind"] in (8, 9) else 2) * n * batch
+        g = groups.setdefault(name, {"ms": 0.0, "calls": 0, "ops": 0.0, "bytes": 0.0, "launches": 0})
+        g["ms"] += p["ms"]
+        g["calls"] += p["calls"]
+        g["ops"] += work * p["calls"]
+        g["bytes"] += byts * p["calls"]
+    if not groups:
+        return None, {}
+    total_ms = sum(g["ms"] for g in groups.values())
+    name, g = max(groups.items(), key=lambda kv: kv[1]["ms"])
+    shares = {k: round(v["ms"] / total_ms, 4) for k, v in groups.items()}
+    if name.startswith("conv"):
+        achieved = g["ops"] / (g["ms"] * 1e-3) / 1e12
+        peak = 2.0 * peaks["bf16_tflops_sustained"]
+        r = {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": None,
+             "kernel": name, "share_of_step": shares[name], "avg_launch_ms": g["ms"] / g["calls"],
+             "peak_source": "2 x bf16_tflops_sustained (int8:bf16 = 2:1 on tcgen05), " + peak_note}
+    else:
+        achieved = g["bytes"] / (g["ms"] * 1e-3) / 1e9
+        peak = peaks["hbm_gbs"]
+        r = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+             "kernel": name, "share_of_step": shares[name], "avg_launch_ms": g["ms"] / g["calls"], "peak_source": peak_note}
+    return r, shares
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return {"hbm_gbs": d["hbm_gbs"], "bf16_tflops_sustained": d.get("bf16_tflops_sustained", d["bf16_tflops"])}, "of measured (MEASURED_PEAKS.json)"
+    return {"hbm_gbs": 6650.0, "bf16_tflops_sustained": 1400.0}, "of fallback (B200_PROFILING.md)"
+
+
+# ---------------------------------------------------------------------------------------
+# the CUDA arm
+# ---------------------------------------------------------------------------------------
+def pinned_array(L, nbytes, dtype=np.uint8):
+    p = L.nna_malloc(nbytes)  # pinned, device-visible host memory (the reference's allocator seam)
+    if not p:
+        raise MemoryError("nna_malloc(%d)" % nbytes)
+    return np.ctypeslib.as_array((C.c_uint8 * nbytes).from_address(p)).view(dtype), p
+
+
+def run_cuda_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    import torch
+    import torch.distributed as dist
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    pkg = load_package()
+    L = pkg.lib()
+    blob, arena = build_model_blob(pkg)
+    B = args.batch
+    gm = pkg.MarsModel(blob, arena_bytes=arena, device=local_rank, batch=B)
+    in_bytes = gm.input_bytes
+    # synthetic inputs in pinned host memory
+    host_in, _ = pinned_array(L, B * in_bytes, np.int8)
+    host_in = host_in.reshape(B, in_bytes)
+    uniq = min(B, 16)  # 16 distinct seeded images tiled over the batch (generation cost, not a cache trick: 19 MB >> per-image reuse)
+    imgs = synth_images(rank * B, uniq)
+    for i in range(B):
+        host_in[i] = imgs[i % uniq]
+    host_dets, _ = pinned_array(L, B * 1000 * 24)
+    host_cnt, _ = pinned_array(L, B * 4, np.int32)
+    gm.upload_inputs(0, B, host_in, in_bytes)
+
+    # device-side gather of detections (the one collective of the path)
+    dptr, cptr, dstride = gm.detections_device()
+
+    class _Dev:
+        def __init__(self, ptr, shape, typestr):
+            self.__cuda_array_interface__ = {"shape": shape, "typestr": typestr, "data": (ptr, False), "version": 3}
+
+    det_t = torch.as_tensor(_Dev(dptr, (B, dstride * 6), "<i4"), device="cuda")
+    cnt_t = torch.as_tensor(_Dev(cptr, (B,), "<i4"), device="cuda")
+    gather_d = [torch.empty_like(det_t) for _ in range(world)] if (world > 1 and rank == 0) else None
+    gather_c = [torch.empty_like(cnt_t) for _ in range(world)] if (world > 1 and rank == 0) else None
+
+    def gather():
+        if world > 1:
+            dist.gather(cnt_t, gather_c, dst=0)
+            dist.gather(det_t, gather_d, dst=0)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def maxr(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # ---- resident: W warm-up + K timed steps --------------------------------------------
+    for _ in range(max(args.warmup, 3)):
+        gm.step_resident(0, B, NMS_THRESH, True)
+        gather()
+    gm.set_profile(True)
+    barrier()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    l0 = gm.launch_count
+    dev_ms = 0.0
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        dev_ms += gm.step_resident(0, B, NMS_THRESH, True)  # CUDA events on the launching stream
+        gather()
+    barrier()
+    wall_ms = (time.perf_counter() - t0) * 1e3
+    clocks = sampler.result()
+    launches = gm.launch_count - l0
+    prof = gm.op_profile()
+    gm.set_profile(False)
+    dev_ms = maxr(dev_ms)
+    wall_ms = maxr(wall_ms)
+    ms_per_step = dev_ms / args.steps
+    value = world * B / (ms_per_step * 1e-3)
+
+    # ---- end to end: host buffers in, detections out ------------------------------------
+    for _ in range(2):
+        gm.detect_batch(B, host_in, in_bytes, host_dets, host_cnt, 1000, NMS_THRESH)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        gm.detect_batch(B, host_in, in_bytes, host_dets, host_cnt, 1000, NMS_THRESH)
+        gather()
+    barrier()
+    e2e_ms = maxr((time.perf_counter() - t0) * 1e3) / args.steps
+    e2e_value = world * B / (e2e_ms * 1e-3)
+    checksum = int(host_cnt.sum())
+
+    peaks, peak_note = load_peaks()
+    roof, shares = roofline_from_profile(prof, B, peaks, peak_note)
+
+    line = None
+    if rank == 0:
+        cpu = None
+        if world == 1 and not args.no_cpu_baseline:
+            kind = cpu_kind()
+            cores = min(host_cores(), 64)
+            ctx = mp.get_context("spawn")
+            with ctx.Pool(cores) as pool:
+                v, dt = cpu_step(pool, kind, blob, arena, cores)
+            cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": kind,
+                   "sample": "1 image on each of %d host processes (%.1f s), same model and input recipe" % (cores, dt)}
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+                "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int8",
+                "data": "synthetic",
+                "config": {"workload": "BASELINE configs[2]: yolov5s_int8.mars-shaped 640x640, %d images per GPU per step "
+                                       "(all layers + decode + NMS)" % B,
+                           "model_file": "synthetic yolov5s-shaped .mars (2x-width copy of the shipped yolov5n_int8 layer table, seed 5); "
+                                         "the reference's yolov5s_int8.mars is a missing blob",
+                           "global_batch": B * world, "per_gpu_batch": B, "image": "3x640x640 int8", "arena_bytes": arena,
+                           "parallelism": "images sharded, dp%d, detections gathered to rank 0 over NCCL" % world,
+                           "l2": "working set %.1f GB per GPU >> 126 MB L2 (no flush needed)" % (B * gm.slot_stride / 1e9)},
+                "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": B * in_bytes * world,
+                        "d2h_bytes_per_step": (B * 1000 * 24 + B * 4) * world, "ms_per_step": e2e_ms},
+                "gpu_launches": int(launches), "wall_ms_per_step": wall_ms / args.steps, "clocks": clocks,
+                "roofline": roof, "kernel_time_shares": shares, "cpu_baseline": cpu, "detections_checksum": checksum}
+        print(json.dumps(line))
+    gm.close()
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="cuda", choices=["cuda", "reference"])
+    ap.add_argument("--batch", type=int, default=int(os.environ.get("MARS_BENCH_BATCH", "128")), help="images per GPU per step")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference_arm(args)
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.gpus > 1 and world == 1:
+        # convenience: re-launch under torchrun (the driver launches torchrun itself)
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(args.gpus),
+               "--master-addr", "127.0.0.1", "--master-port", os.environ.get("MASTER_PORT", "29533"), os.path.abspath(__file__)] + sys.argv[1:]
+        return subprocess.call(cmd)
+    return run_cuda_arm(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -1,0 +1,117 @@
+/*
+ * mars_b200.h -- additive C-ABI entry points of libmars_b200.so (B200 build).
+ *
+ * Nothing here changes a signature of the reference API (include/mars_runtime.h,
+ * include/mars_math.h, include/nna.h); these functions expose what the reference
+ * does not have: an image batch sharded over HBM "slots", device-resident runs,
+ * and the YOLO post-process (reference file-static functions) as library calls.
+ * Plain pointers and sizes only -- no torch / CUDA types cross this boundary.
+ */
+#ifndef MARS_B200_H
+#define MARS_B200_H
+
+#include "mars_runtime.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* det_t of reference src/mars/mars_yolo_test.c:37 (centre box, 24 bytes) */
+typedef struct { float x, y, w, h, conf; int32_t cls; } mars_det_t;
+/* Detection of reference examples/yolo_detect.cpp:39-43 (corner box, 24 bytes) */
+typedef struct { float x0, y0, x1, y1, confidence; int32_t class_id; } mars_box_t;
+
+/* ---- library / device ---------------------------------------------------- */
+const char *mars_b200_version(void);
+/* number of visible CUDA devices, or <0 (MARS_ERR_NNA_INIT_FAILED) without a driver */
+int mars_b200_device_count(void);
+/* select the device used by subsequent mars_load_* calls (default: MARS_DEVICE env or 0) */
+int mars_b200_set_device(int ordinal);
+/* arena bytes for subsequent loads; 0 = the reference's 8 MiB literal
+ * (src/mars/mars_runtime.c:209).  Also settable with MARS_ARENA_BYTES. */
+void mars_b200_set_arena_bytes(size_t bytes);
+/* last diagnostic of the calling thread's most recent failing call */
+const char *mars_b200_last_error(void);
+
+/* ---- whole-arena mirror control (strict drop-in / tests) ---------------- */
+/* copy the host mirror (ddr_base) of image slot `slot` to the device arena / back.
+ * mars_run() itself only moves the work buffers holding model inputs / outputs. */
+mars_error_t mars_b200_arena_upload(mars_model_t *m, int slot);
+mars_error_t mars_b200_arena_download(mars_model_t *m, int slot, void *host_dst, size_t bytes);
+/* zero every work buffer of every slot (the reference never clears them; parity
+ * protocol = zero at load, then compare run k against run k) */
+mars_error_t mars_b200_arena_clear(mars_model_t *m);
+/* run a single layer on slot 0 (per-layer parity tests; mirrors oracle_ref_run_layer) */
+mars_error_t mars_b200_run_layer(mars_model_t *m, uint32_t layer);
+/* per-layer schedule summary as text: kernel kind, hazard class, fusion decision */
+size_t mars_b200_describe(mars_model_t *m, char *dst, size_t cap);
+/* 0 = exact direct kernels only, 1 = + fused epilogues, 2 = + tcgen05 convs (default) */
+void mars_b200_set_opt_level(mars_model_t *m, int level);
+/* 0 = reference semantics (DEPTHWISE_CONV2D is a no-op, src/mars/mars_runtime.c:1168-1170),
+ * 1 = restated depthwise convolution (parity unpinned) */
+void mars_b200_set_depthwise_mode(mars_model_t *m, int mode);
+
+/* ---- image batch ---------------------------------------------------------- */
+/* allocate `capacity` image slots (each = one set of work buffers; weights shared) */
+mars_error_t mars_b200_set_batch(mars_model_t *m, int capacity);
+int mars_b200_get_batch(mars_model_t *m);
+/* bytes of one image's input tensor 0 / output tensor 0 (numel * elem size) */
+size_t mars_b200_input_bytes(mars_model_t *m);
+size_t mars_b200_output_bytes(mars_model_t *m);
+/* host -> slots [first, first+n): n inputs, `stride` bytes apart in host memory */
+mars_error_t mars_b200_upload_inputs(mars_model_t *m, int first, int n, const void *host, size_t stride);
+/* slots -> host: output tensor 0 of n images */
+mars_error_t mars_b200_download_outputs(mars_model_t *m, int first, int n, void *host, size_t stride);
+/* run all layers for slots [first, first+n) with inputs already resident in HBM */
+mars_error_t mars_b200_run_resident(mars_model_t *m, int first, int n);
+/* decode + NMS on the device for slots [first, first+n); results stay resident */
+mars_error_t mars_b200_detect_resident(mars_model_t *m, int first, int n, float nms_thresh);
+/* copy the detections of slots [first, first+n) to the host:
+ * dets[n][maxd] (maxd <= 1000), counts[n] */
+mars_error_t mars_b200_download_detections(mars_model_t *m, int first, int n, mars_det_t *dets, int32_t *counts, int maxd);
+/* end to end from host buffers: H2D, all layers, decode, NMS, D2H (pipelined in chunks) */
+mars_error_t mars_b200_detect_batch(mars_model_t *m, int n, const void *inputs, size_t in_stride,
+                                    mars_det_t *dets, int32_t *counts, int maxd, float nms_thresh);
+/* end to end from host buffers returning raw output tensor 0 per image */
+mars_error_t mars_b200_run_batch(mars_model_t *m, int n, const void *inputs, size_t in_stride,
+                                 void *outputs, size_t out_stride);
+/* run all layers, then (with_detect) decode + NMS, as ONE device-timed region */
+mars_error_t mars_b200_step_resident(mars_model_t *m, int first, int n, float nms_thresh, int with_detect);
+/* device addresses of the resident detection records, for a device-side gather (NCCL):
+ * dets = mars_det_t[capacity][*stride_dets], counts = int32[capacity] */
+void mars_b200_detections_device(mars_model_t *m, void **dets, void **counts, int *stride_dets);
+
+/* ---- introspection (tests, bench) ----------------------------------------- */
+/* record CUDA events around every device op of full passes; read back with mars_b200_op_info */
+void mars_b200_set_profile(mars_model_t *m, int on);
+int mars_b200_num_ops(mars_model_t *m);
+/* info[0..12] = kind, layer, impl, mode, ic, oc, oh, ow, kh, kw, fused_layers, ih, iw */
+int mars_b200_op_info(mars_model_t *m, int op, int32_t *info, double *ms, uint64_t *calls, uint64_t *flat_n);
+/* out5 = weights_size, buffer_size, num_buffers, slot_stride, arena_size */
+void mars_b200_geometry(mars_model_t *m, size_t *out5);
+/* arena offset of tensor table entry `index` (reference planner, src/mars/mars_runtime.c:248-337) */
+size_t mars_b200_tensor_offset(mars_model_t *m, uint32_t index);
+
+/* kernels launched by this model since load (the bench's gpu_launches claim) */
+uint64_t mars_b200_launch_count(mars_model_t *m);
+/* CUDA-event time of the last mars_b200_run_resident / detect_resident, milliseconds */
+float mars_b200_last_gpu_ms(mars_model_t *m);
+
+/* ---- YOLO post-process on host buffers ----------------------------------- */
+/* parse_output of reference src/mars/mars_yolo_test.c:80-104 (conf threshold 0.25) */
+int mars_yolo_parse_output(const int8_t *data, int npred, float scale, mars_det_t *dets, int maxd);
+/* nms of reference src/mars/mars_yolo_test.c:107-130 (exchange sort + greedy, centre boxes) */
+int mars_yolo_nms(mars_det_t *dets, int n, float thresh);
+/* nms of reference examples/yolo_detect.cpp:152-173 (corner boxes; ties keep input order) */
+int mars_yolo_nms_boxes(mars_box_t *dets, int n, float thresh);
+/* scale_detections of reference examples/yolo_detect.cpp:208-227 */
+void mars_yolo_scale_detections(mars_box_t *dets, int n, int orig_w, int orig_h, int net_w, int net_h);
+/* anchor-grid decode (formula: mgk-decompiler/test_yolo_inference.py:136-202, anchors
+ * examples/yolo_detect.cpp:176-181).  head = int8 [3,gh,gw,85]; appends after `cnt`. */
+int mars_yolo_decode_anchor_grid(const int8_t *head, int gh, int gw, float scale, int level,
+                                 float conf_thresh, mars_box_t *dets, int cnt, int maxd);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MARS_B200_H */

@@ -1,0 +1,214 @@
+"""GPU: the CUDA path (through the C-ABI) against the oracle -- bit-exact over the WHOLE arena
+for int8 models (run 1 and run 2, both arena modes), against the committed golden hashes, and
+layer by layer; float32 models bit-exact too on the exact-order kernels."""
+import os
+
+import numpy as np
+import pytest
+
+from conftest import shipped
+from util import GOLDEN, GOLDEN_DIR, first_diff, make_input, numel, sha
+
+pytestmark = pytest.mark.gpu
+
+MODEL_CASES = [k for k, v in GOLDEN.items() if "model" in v]
+
+
+def run_both(pkg, ob, blob, arena, x, runs=2, opt=None, depthwise=False):
+    gm = pkg.MarsModel(blob, arena_bytes=arena)
+    if opt is not None:
+        gm.set_opt_level(opt)
+    if depthwise:
+        gm.set_depthwise_mode(1)
+    om = ob.OracleModel(blob, arena_bytes=arena, depthwise=depthwise)
+    for run in range(runs):
+        gm.set_input(x)
+        gm.run()
+        om.set_input(x)
+        om.run()
+        got = gm.arena_download()
+        want = om.arena()[: got.size]
+        at, cnt = first_diff(got, want)
+        assert cnt == 0, "run %d: %d arena bytes differ, first at %d (weights end %d, buffer %d)" % (
+            run + 1, cnt, at, gm.weights_size, gm.buffer_size)
+        assert np.array_equal(gm.output_bytes(), om.output_bytes())
+    return gm, om
+
+
+@pytest.mark.parametrize("opt", [0, 2])
+@pytest.mark.parametrize("case", MODEL_CASES)
+def test_shipped_models_whole_arena(pkg, ob, case, opt):
+    g = GOLDEN[case]
+    blob = open(shipped(g["model"]), "rb").read()
+    om0 = ob.OracleModel(blob, arena_bytes=g["arena"])
+    x = make_input(g["pattern"], numel(om0.tensor_desc(om0.input_index())))
+    om0.close()
+    gm, om = run_both(pkg, ob, blob, g["arena"], x, opt=opt)
+    # and against the committed golden vectors of the reference itself
+    assert sha(gm.output_bytes()) == g["run2"]["output_sha256"]
+    if "dets" in g:
+        o = gm.output_bytes().view(np.int8)
+        od = gm.output().desc
+        kept = pkg.capi.nms(pkg.capi.parse_output(o, od.shape[1], od.scale))
+        assert kept.tobytes() == np.load(os.path.join(GOLDEN_DIR, g["dets"]["file"])).tobytes()
+    gm.close()
+    om.close()
+
+
+@pytest.mark.parametrize("name,arena", [("yolov5n_int8.mars", 8 << 20), ("yolov5nu.mars", 8 << 20), ("tiny_160_int8.mars", 8 << 20)])
+def test_layer_by_layer(pkg, ob, name, arena):
+    """each GPU layer is fed the oracle's exact bytes (isolates a divergence to one layer)"""
+    blob = open(shipped(name), "rb").read()
+    gm = pkg.MarsModel(blob, arena_bytes=arena)
+    om = ob.OracleModel(blob, arena_bytes=arena)
+    rng = np.random.default_rng(4)
+    x = rng.integers(-128, 128, size=numel(om.tensor_desc(om.input_index())), dtype=np.int8)
+    om.set_input(x)
+    W = om.weights_size
+    nl = om.num_layers
+    step = 1 if nl < 40 else 7  # every layer for small models, a stride for the big ones (plus hazards)
+    hazard = {43, 110, 128, 139, 149, 169, 179, 189, 203, 211, 229}
+    for i in range(nl):
+        before = om.arena().copy()
+        assert om.run_layer(i) == 0
+        if i % step and i not in hazard:
+            continue
+        gm.mirror()[W:om.arena_bytes] = before[W:]
+        gm.arena_upload()
+        assert gm.run_layer(i) == 0, pkg.lib().mars_b200_last_error()
+        got = gm.arena_download()
+        at, cnt = first_diff(got, om.arena()[: got.size])
+        assert cnt == 0, "layer %d: %d bytes differ, first at %d" % (i, cnt, at)
+    gm.close()
+    om.close()
+
+
+def micro(pkg, kind, **kw):
+    return pkg.marsfile.build_single_layer(kind, **kw).to_bytes()
+
+
+MICRO = [
+    ("conv", dict(k=3, s=1)), ("conv", dict(k=3, s=2, c=5, co=7, h=17, w=13)), ("conv", dict(k=1, s=1, c=32, co=24)),
+    ("conv", dict(k=6, s=2, c=3, co=16, h=32, w=32)), ("conv", dict(k=3, s=1, padding=1, act=1)),  # SAME + fused ReLU
+    ("conv", dict(k=3, s=1, no_bias=True)), ("conv", dict(k=3, s=1, nhwc=True)), ("conv", dict(k=1, s=1, nhwc=True, c=16, co=16)),
+    ("conv", dict(k=3, s=2, nhwc=True, padding=1)), ("conv", dict(k=3, s=1, f32=True)), ("conv", dict(k=1, s=1, f32=True, c=16)),
+    ("sigmoid", {}), ("sigmoid", dict(f32=True)), ("relu", {}), ("relu6", {}), ("leaky", {}), ("leaky", dict(f32=True)),
+    ("add", {}), ("mul", {}), ("add", dict(f32=True)), ("mul", dict(f32=True)), ("maxpool", dict(k=2, s=2)),
+    ("maxpool", dict(k=5, s=1, h=20, w=20, c=20)), ("maxpool", dict(k=3, s=2, h=9, w=11)), ("upsample", dict(scale=2)),
+    ("upsample", dict(scale=3, ratio_fallback=True)), ("concat", dict(n=4)), ("concat", dict(n=2)), ("batchnorm", {}),
+    ("batchnorm", dict(f32=True)), ("depthwise", {}),
+]
+
+
+@pytest.mark.parametrize("kind,kw", MICRO)
+def test_micro_models(pkg, ob, kind, kw):
+    blob = micro(pkg, kind, **kw)
+    gm = pkg.MarsModel(blob)
+    om = ob.OracleModel(blob)
+    rng = np.random.default_rng(2)
+    W = om.weights_size
+    if kw.get("f32"):
+        fill = rng.standard_normal((om.arena_bytes - W) // 4).astype(np.float32).view(np.uint8)
+    else:
+        fill = rng.integers(0, 256, size=om.arena_bytes - W, dtype=np.uint8)
+    om.arena()[W:W + fill.size] = fill
+    gm.mirror()[W:W + fill.size] = fill
+    gm.arena_upload()
+    om.run()
+    for i in range(om.num_layers):
+        assert gm.run_layer(i) == 0
+    got = gm.arena_download()
+    want = om.arena()[: got.size]
+    if kind == "sigmoid" and kw.get("f32"):
+        # device expf vs glibc expf: tolerance path (<= 1e-6 absolute on a [0,1] output)
+        n = got.size // 4 * 4
+        assert np.allclose(got[W:n].view(np.float32), want[W:n].view(np.float32), atol=1e-6, rtol=0, equal_nan=True)
+    else:
+        at, cnt = first_diff(got, want)
+        assert cnt == 0, "%s %r: %d bytes differ, first at %d" % (kind, kw, cnt, at)
+    gm.close()
+    om.close()
+
+
+def test_depthwise_modes(pkg, ob):
+    blob = micro(pkg, "depthwise")
+    for mode in (0, 1):
+        gm = pkg.MarsModel(blob)
+        gm.set_depthwise_mode(mode)
+        om = ob.OracleModel(blob, depthwise=bool(mode))
+        x = np.random.default_rng(8).integers(-128, 128, size=8 * 12 * 10, dtype=np.int8)
+        gm.set_input(x)
+        gm.run()
+        om.set_input(x)
+        om.run()
+        assert np.array_equal(gm.arena_download(), om.arena()[: gm.arena_download().size])
+        gm.close()
+        om.close()
+
+
+def test_unknown_layer_fails_like_the_reference(pkg):
+    gm = pkg.MarsModel(micro(pkg, "fc"))
+    with pytest.raises(pkg.capi.MarsError) as e:
+        gm.run()
+    assert e.value.code == -8
+    gm.close()
+
+
+@pytest.mark.parametrize("width,size,arena", [(0.125, 160, 8 << 20), (0.25, 320, 16 << 20)])
+def test_generated_yolov5_batch(pkg, ob, width, size, arena):
+    """batch sharded over image slots == oracle per image (run + decode + NMS)"""
+    blob = pkg.marsfile.build_yolov5(width=width, size=size, seed=9).to_bytes()
+    n = 5
+    gm = pkg.MarsModel(blob, arena_bytes=arena, batch=n)
+    rng = np.random.default_rng(11)
+    xs = rng.integers(-128, 128, size=(n, 3 * size * size), dtype=np.int8)
+    gm.upload_inputs(0, n, xs, xs.shape[1])
+    gm.step_resident(0, n, 0.45, True)
+    outs = gm.download_outputs(0, n)
+    dets, counts = gm.download_detections(0, n)
+    # the same through the host-buffer pipeline (chunks of capacity/2)
+    dets2 = np.zeros((n, 1000), dtype=pkg.capi.DET_DTYPE)
+    counts2 = np.zeros(n, dtype=np.int32)
+    for i in range(n):
+        om = ob.OracleModel(blob, arena_bytes=arena)
+        om.set_input(xs[i])
+        om.run()
+        assert np.array_equal(outs[i], om.output_bytes()), "image %d" % i
+        got = gm.arena_download(i)
+        at, cnt = first_diff(got, om.arena()[: got.size])
+        assert cnt == 0, "image %d: %d arena bytes differ, first at %d" % (i, cnt, at)
+        o = om.output_bytes().view(np.int8)
+        d = ob.nms(ob.parse_output(o, o.size // 85, om.tensor_desc(om.output_index()).scale))
+        assert counts[i] == len(d)
+        assert dets[i, : len(d)].tobytes() == d.tobytes()
+        om.close()
+    gm.arena_clear()
+    gm.detect_batch(n, xs, xs.shape[1], dets2, counts2)
+    assert np.array_equal(counts, counts2)
+    for i in range(n):
+        assert dets[i, : counts[i]].tobytes() == dets2[i, : counts[i]].tobytes()
+    gm.close()
+
+
+def test_yolov5s_full_size(pkg, ob):
+    """BASELINE config 3 shape: yolov5s-shaped 640x640 int8, a few images, bit-exact vs the oracle"""
+    mf = pkg.marsfile
+    blob = mf.build_yolov5(width=0.5, size=640, seed=5).to_bytes()
+    n = 3
+    gm = pkg.MarsModel(blob, arena_bytes=mf.ARENA_YOLOV5S_INT8, batch=n)
+    xs = np.stack([np.random.default_rng(1000 + b).integers(-128, 128, size=3 * 640 * 640, dtype=np.int8) for b in range(n)])
+    gm.upload_inputs(0, n, xs, xs.shape[1])
+    gm.step_resident(0, n, 0.45, True)
+    dets, counts = gm.download_detections(0, n)
+    for i in range(n):
+        om = ob.OracleModel(blob, arena_bytes=mf.ARENA_YOLOV5S_INT8)
+        om.set_input(xs[i])
+        om.run()
+        got = gm.arena_download(i)
+        at, cnt = first_diff(got, om.arena()[: got.size])
+        assert cnt == 0, "image %d: %d arena bytes differ, first at %d" % (i, cnt, at)
+        o = om.output_bytes().view(np.int8)
+        d = ob.nms(ob.parse_output(o, 25200, om.tensor_desc(om.output_index()).scale))
+        assert counts[i] == len(d) and dets[i, : len(d)].tobytes() == d.tobytes()
+        om.close()
+    gm.close()

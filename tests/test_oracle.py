@@ -1,0 +1,109 @@
+"""CPU: pin the oracle (oracle/mars_oracle.c) against the committed golden vectors (outputs of
+the reference's own C path, tests/golden/make_golden.py) and, where oracle/_ref/libmars_ref.so
+is present, against the reference library directly (whole arena, run 1 and run 2)."""
+import os
+
+import numpy as np
+import pytest
+
+from conftest import shipped
+from util import GOLDEN, GOLDEN_DIR, make_input, numel, sha
+
+MODEL_CASES = [k for k, v in GOLDEN.items() if "model" in v]
+FAST = [k for k in MODEL_CASES if not k.startswith("yolov5n/f32")]
+
+
+@pytest.mark.parametrize("case", MODEL_CASES)
+def test_oracle_matches_golden(ob, case):
+    g = GOLDEN[case]
+    m = ob.OracleModel(shipped(g["model"]), arena_bytes=g["arena"])
+    d = m.tensor_desc(m.input_index())
+    x = make_input(g["pattern"], numel(d))
+    for run in (1, 2):
+        m.set_input(x)
+        m.run()
+        r = g["run%d" % run]
+        assert sha(m.output_bytes()) == r["output_sha256"], "%s run %d output" % (case, run)
+        assert sha(m.arena()[: r["arena_bytes_hashed"]]) == r["arena_sha256"], "%s run %d arena" % (case, run)
+    if "dets" in g:
+        o = m.output_bytes().view(np.int8)
+        od = m.tensor_desc(m.output_index())
+        raw = ob.parse_output(o, od.shape[1], od.scale)
+        kept = ob.nms(raw)
+        gold = np.load(os.path.join(GOLDEN_DIR, g["dets"]["file"]))
+        assert len(raw) == g["dets"]["raw"] and len(kept) == g["dets"]["kept"]
+        assert kept.tobytes() == gold.tobytes()
+    m.close()
+
+
+@pytest.mark.parametrize("case", ["tiny_160_int8/rng", "yolov5nu/p0", "test_simple/f32"])
+def test_oracle_matches_reference_library(ob, rb, case):
+    g = GOLDEN[case]
+    path = shipped(g["model"])
+    r = rb.RefRuntime(path, arena_bytes=g["arena"])
+    m = ob.OracleModel(path, arena_bytes=g["arena"])
+    x = make_input(g["pattern"], numel(m.tensor_desc(m.input_index())))
+    for _ in range(2):
+        r.set_input(x)
+        r.run()
+        m.set_input(x)
+        m.run()
+        assert np.array_equal(r.arena()[: m.arena_bytes], m.arena())
+    # per-layer stepping agrees too
+    r.close()
+    m.close()
+
+
+@pytest.mark.parametrize("tag", [k for k in GOLDEN if k.startswith("post_")])
+def test_oracle_postprocess_matches_golden(ob, tag):
+    g = GOLDEN[tag]
+    rng = np.random.default_rng(g["seed"])
+    heads = {"post_random": rng.integers(-128, 128, size=(4000, 85), dtype=np.int8)}
+    heads["post_ties"] = rng.choice(np.array([-128, 0, 60, 127], dtype=np.int8), size=(3000, 85))
+    h = heads[tag.rsplit("_s", 1)[0]]
+    assert sha(h) == g["head_sha256"]
+    raw = ob.parse_output(h, h.shape[0], g["scale"])
+    kept = ob.nms(raw)
+    assert (len(raw), len(kept)) == (g["raw"], g["kept"])
+    assert kept.tobytes() == np.load(os.path.join(GOLDEN_DIR, g["file"])).tobytes()
+
+
+def test_oracle_postprocess_matches_reference_statics(ob, rb):
+    rng = np.random.default_rng(5)
+    for trial in range(6):
+        n = int(rng.integers(1, 1200))
+        h = rng.integers(-128, 128, size=(n, 85), dtype=np.int8)
+        if trial % 2:
+            h = (h // 40 * 40).astype(np.int8)  # tie-heavy
+        scale = float(rng.choice([0.02, 0.1, 1.0]))
+        a, b = rb.ref_parse_output(h, n, scale), ob.parse_output(h, n, scale)
+        assert a.tobytes() == b.tobytes()
+        assert rb.ref_nms(a).tobytes() == ob.nms(b).tobytes()
+    # corner-box NMS vs the reference C++ (tie-free input: std::sort's tie order is unspecified)
+    boxes = np.zeros(300, dtype=ob.BOX_DTYPE)
+    xy = rng.uniform(0, 600, size=(300, 2)).astype(np.float32)
+    wh = rng.uniform(5, 120, size=(300, 2)).astype(np.float32)
+    boxes["x0"], boxes["y0"] = xy[:, 0], xy[:, 1]
+    boxes["x1"], boxes["y1"] = xy[:, 0] + wh[:, 0], xy[:, 1] + wh[:, 1]
+    boxes["confidence"] = rng.permutation(300).astype(np.float32) / 300
+    boxes["class_id"] = rng.integers(0, 3, size=300)
+    lib = rb.RefRuntime.lib()
+    d = boxes.copy()
+    n = lib.oracle_ref_cpp_nms(d.ctypes.data, len(d), 0.45)
+    assert d[:n].tobytes() == ob.nms_corner(boxes, 0.45).tobytes()
+
+
+def test_mars_math_known_answers(ob):
+    """reference examples/mars_math_test.c:38-82 -- the only known-answer test on this path"""
+    L = ob.lib()
+    a = np.array([1, 2, 3, 4], dtype=np.float32)
+    b = np.array([5, 6, 7, 8], dtype=np.float32)
+    out = np.zeros(4, dtype=np.float32)
+    L.mo_vec_add_f32(out.ctypes.data, a.ctypes.data, b.ctypes.data, 4)
+    assert out.tolist() == [6, 8, 10, 12]
+    assert L.mo_vec_dot_f32(a.ctypes.data, b.ctypes.data, 4) == 70.0
+    A = np.arange(1, 7, dtype=np.float32)
+    B = np.arange(7, 13, dtype=np.float32)
+    Cm = np.zeros(4, dtype=np.float32)
+    L.mo_matmul_f32(Cm.ctypes.data, A.ctypes.data, B.ctypes.data, 2, 3, 2)
+    assert Cm.tolist() == [58, 64, 139, 154]

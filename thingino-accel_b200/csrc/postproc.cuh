@@ -1,0 +1,335 @@
+/*
+ * postproc.cuh -- YOLO decode + class-wise NMS kernels.
+ *
+ *  k_parse_output : parse_output() of reference src/mars/mars_yolo_test.c:80-104 --
+ *                   per-row objectness/class decode through host-built libm tables,
+ *                   ORDER-PRESERVING compaction with the reference's hard cap;
+ *  k_nms_center   : nms() of reference src/mars/mars_yolo_test.c:107-130 -- the exchange
+ *                   sort is emulated pass by pass (its permutation under ties is NOT a
+ *                   stable sort), then greedy same-class suppression;
+ *  k_nms_corner   : nms() of reference examples/yolo_detect.cpp:152-173 (corner boxes);
+ *  k_anchor_decode: anchor-grid decode (mgk-decompiler/test_yolo_inference.py:136-202).
+ * One thread block per image; blocks are independent (images shard with no exchange).
+ */
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "kernels_exact.cuh"
+
+namespace marsb200 {
+
+#define MARS_MAX_DETS 1024
+
+/* tables built on the host with the host libm (bit-exact w.r.t. the reference's expf) */
+struct DecodeTables {
+    float obj[256];  /* 1/(1+expf(-(v*scale)))                      mars_yolo_test.c:84 */
+    float den[257];  /* 1+expf(-(v*scale)); [256] = the "no class beat -1e9f" case  :92 */
+};
+
+/* block-wide exclusive scan of one int per thread (blockDim.x <= 1024, multiple of 32) */
+__device__ __forceinline__ int block_excl_scan(int v, int *total, int *warp_sums /* [32] shared */) {
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    int x = v;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        int y = __shfl_up_sync(0xffffffffu, x, d);
+        if (lane >= d) x += y;
+    }
+    if (lane == 31) warp_sums[wid] = x;
+    __syncthreads();
+    if (wid == 0) {
+        int s = lane < nw ? warp_sums[lane] : 0;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            int y = __shfl_up_sync(0xffffffffu, s, d);
+            if (lane >= d) s += y;
+        }
+        warp_sums[lane] = s; /* inclusive over warps */
+    }
+    __syncthreads();
+    int base = wid ? warp_sums[wid - 1] : 0;
+    *total = warp_sums[nw - 1];
+    __syncthreads();
+    return base + x - v;
+}
+
+/* data: int8 [npred][85] per image at data + img*img_stride; dets: [maxd] per image */
+__global__ void __launch_bounds__(256) k_parse_output(const int8_t *data, size_t img_stride, int npred, float scale,
+                                                      const DecodeTables *tab, mars_det_t *dets, int32_t *counts,
+                                                      int maxd, int det_stride) {
+    __shared__ int warp_sums[32];
+    const int8_t *rows = data + (size_t)blockIdx.x * img_stride;
+    mars_det_t *out = dets + (size_t)blockIdx.x * det_stride;
+    int cnt = 0;
+    for (int base = 0; base < npred && cnt < maxd; base += blockDim.x) {
+        int i = base + threadIdx.x;
+        int pass = 0, best_c = 0;
+        float conf = 0.0f;
+        const int8_t *p = rows + (size_t)i * 85;
+        if (i < npred) {
+            float obj = tab->obj[(int)p[4] + 128];
+            if (!(obj < 0.25f)) {
+                float best_s = -1e9f;
+                int best_v = 256 - 128; /* -> den[256] */
+                for (int c = 0; c < 80; c++) {
+                    int v = p[5 + c];
+                    float s = __fmul_rn((float)v, scale);
+                    if (s > best_s) { best_s = s; best_c = c; best_v = v; }
+                }
+                conf = __fdiv_rn(obj, tab->den[best_v + 128]);
+                pass = !(conf < 0.25f);
+            }
+        }
+        int total;
+        int rank = cnt + block_excl_scan(pass, &total, warp_sums);
+        if (pass && rank < maxd) {
+            mars_det_t d;
+            d.x = __fmul_rn((float)p[0], scale); d.y = __fmul_rn((float)p[1], scale);
+            d.w = __fmul_rn((float)p[2], scale); d.h = __fmul_rn((float)p[3], scale);
+            d.conf = conf; d.cls = best_c;
+            out[rank] = d;
+        }
+        cnt += total;
+    }
+    if (threadIdx.x == 0) counts[blockIdx.x] = cnt < maxd ? cnt : maxd;
+}
+
+/* reference src/mars/mars_yolo_test.c:115-121, every operation rounded separately */
+__device__ __forceinline__ float iou_center(const mars_det_t &a, const mars_det_t &b) {
+    float ahw = __fdiv_rn(a.w, 2.0f), ahh = __fdiv_rn(a.h, 2.0f), bhw = __fdiv_rn(b.w, 2.0f), bhh = __fdiv_rn(b.h, 2.0f);
+    float x1 = fmaxf(__fsub_rn(a.x, ahw), __fsub_rn(b.x, bhw));
+    float y1 = fmaxf(__fsub_rn(a.y, ahh), __fsub_rn(b.y, bhh));
+    float x2 = fminf(__fadd_rn(a.x, ahw), __fadd_rn(b.x, bhw));
+    float y2 = fminf(__fadd_rn(a.y, ahh), __fadd_rn(b.y, bhh));
+    float inter = __fmul_rn(fmaxf(0.0f, __fsub_rn(x2, x1)), fmaxf(0.0f, __fsub_rn(y2, y1)));
+    float u = __fadd_rn(__fsub_rn(__fadd_rn(__fmul_rn(a.w, a.h), __fmul_rn(b.w, b.h)), inter), 1e-6f);
+    return __fdiv_rn(inter, u);
+}
+
+/* reference examples/yolo_detect.cpp:138-149 */
+__device__ __forceinline__ float iou_corner(const mars_box_t &a, const mars_box_t &b) {
+    float x0 = fmaxf(a.x0, b.x0), y0 = fmaxf(a.y0, b.y0), x1 = fminf(a.x1, b.x1), y1 = fminf(a.y1, b.y1);
+    float inter = __fmul_rn(fmaxf(0.0f, __fsub_rn(x1, x0)), fmaxf(0.0f, __fsub_rn(y1, y0)));
+    float aa = __fmul_rn(__fsub_rn(a.x1, a.x0), __fsub_rn(a.y1, a.y0));
+    float ab = __fmul_rn(__fsub_rn(b.x1, b.x0), __fsub_rn(b.y1, b.y0));
+    return __fdiv_rn(inter, __fadd_rn(__fsub_rn(__fadd_rn(aa, ab), inter), 1e-6f));
+}
+
+/*
+ * Exchange-sort emulation, executed by warp 0 of the block over keys in shared memory.
+ * Pass i of `for i: for j>i: if d[j].conf > d[i].conf swap` walks the strict prefix-maximum
+ * records r0=i < r1 < ... < rk of key[i..n): afterwards key[i]=old key[rk] and every record
+ * position holds the previous record's element.  Finding "first j > p with key[j] > x" uses
+ * a two-level structure: bmax[b] = max of the 32 keys of block b (one ballot over bmax finds
+ * the block, one ballot inside finds the element).  NaN keys never compare greater, exactly
+ * as in the C loop.
+ */
+__device__ __forceinline__ void exchange_sort_warp(float *key, uint16_t *idx, float *bmax, int n) {
+    const int lane = threadIdx.x & 31;
+    const int nb = (n + 31) >> 5;
+    for (int b = lane; b < 32; b += 32) bmax[b] = -__int_as_float(0x7f800000); /* -inf */
+    __syncwarp();
+    for (int b = 0; b < nb; b++) { /* block maxima (NaN-free max: NaN never wins a '>' test) */
+        int j = b * 32 + lane;
+        float v = j < n ? key[j] : -__int_as_float(0x7f800000);
+        if (v != v) v = -__int_as_float(0x7f800000);
+#pragma unroll
+        for (int d = 16; d; d >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, d));
+        if (lane == 0) bmax[b] = v;
+    }
+    __syncwarp();
+    for (int i = 0; i + 1 < n; i++) {
+        float carry_k = key[i];
+        uint16_t carry_i = idx[i];
+        int pos = i; /* position whose element is currently "in hand" (the last record) */
+        int start = i + 1;
+        bool changed = false;
+        while (start < n) {
+            /* first j >= start with key[j] > carry_k */
+            int b0 = start >> 5;
+            int j = -1;
+            { /* inside the first (partial) block */
+                int jj = b0 * 32 + lane;
+                bool hit = jj >= start && jj < n && key[jj] > carry_k;
+                unsigned m = __ballot_sync(0xffffffffu, hit);
+                if (m) j = b0 * 32 + __ffs(m) - 1;
+            }
+            if (j < 0) {
+                bool hitb = lane > b0 && lane < nb && bmax[lane] > carry_k;
+                unsigned mb = __ballot_sync(0xffffffffu, hitb);
+                if (!mb) break;
+                int b = __ffs(mb) - 1;
+                int jj = b * 32 + lane;
+                bool hit = jj < n && key[jj] > carry_k;
+                unsigned m = __ballot_sync(0xffffffffu, hit);
+                j = b * 32 + __ffs(m) - 1; /* m != 0 because bmax[b] > carry */
+            }
+            /* record at j: it receives the element in hand, its own element becomes the carry */
+            float nk = key[j];
+            uint16_t ni = idx[j];
+            __syncwarp();
+            if (lane == 0) { key[j] = carry_k; idx[j] = carry_i; }
+            __syncwarp();
+            { /* recompute bmax of j's block (its maximum element left) */
+                int b = j >> 5, jj = b * 32 + lane;
+                float v = jj < n ? key[jj] : -__int_as_float(0x7f800000);
+                if (v != v) v = -__int_as_float(0x7f800000);
+#pragma unroll
+                for (int d = 16; d; d >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, d));
+                if (lane == 0) bmax[b] = v;
+            }
+            __syncwarp();
+            carry_k = nk; carry_i = ni; pos = j; start = j + 1; changed = true;
+        }
+        (void)pos;
+        if (changed) {
+            if (lane == 0) { key[i] = carry_k; idx[i] = carry_i; }
+            __syncwarp();
+            /* bmax of i's block: its new key is the global max of the suffix, so max() suffices */
+            if (lane == 0 && carry_k == carry_k) bmax[i >> 5] = fmaxf(bmax[i >> 5], carry_k);
+            __syncwarp();
+        }
+        /* position i is final: it must no longer be found by later passes (start = i+2 handles
+         * in-block search; bmax may over-estimate a block, which only costs one extra ballot
+         * that finds nothing -- handled below by the m==0 check) */
+    }
+}
+
+/* dets_in/dets_out: [det_stride] per image; counts in/out per image.  blockDim.x = 128. */
+__global__ void __launch_bounds__(128) k_nms_center(const mars_det_t *dets_in, const int32_t *counts_in,
+                                                    mars_det_t *dets_out, int32_t *counts_out, int det_stride,
+                                                    float thresh) {
+    __shared__ float key[MARS_MAX_DETS];
+    __shared__ uint16_t idx[MARS_MAX_DETS];
+    __shared__ float bmax[32];
+    __shared__ unsigned char sup[MARS_MAX_DETS];
+    __shared__ int warp_sums[32];
+    const mars_det_t *in = dets_in + (size_t)blockIdx.x * det_stride;
+    mars_det_t *out = dets_out + (size_t)blockIdx.x * det_stride;
+    int n = counts_in[blockIdx.x];
+    if (n > MARS_MAX_DETS) n = MARS_MAX_DETS;
+    for (int j = threadIdx.x; j < n; j += blockDim.x) { key[j] = in[j].conf; idx[j] = (uint16_t)j; sup[j] = 0; }
+    __syncthreads();
+    if (threadIdx.x < 32) exchange_sort_warp(key, idx, bmax, n);
+    __syncthreads();
+    /* greedy suppression, i ascending (mars_yolo_test.c:113-123) */
+    for (int i = 0; i < n; i++) {
+        if (sup[i]) continue; /* uniform: sup[i] was settled before the previous barrier */
+        mars_det_t a = in[idx[i]];
+        for (int j = i + 1 + threadIdx.x; j < n; j += blockDim.x) {
+            if (sup[j]) continue;
+            mars_det_t b = in[idx[j]];
+            if (a.cls != b.cls) continue;
+            if (iou_center(a, b) > thresh) sup[j] = 1;
+        }
+        __syncthreads();
+    }
+    /* ordered compaction */
+    int cnt = 0;
+    for (int base = 0; base < n; base += blockDim.x) {
+        int j = base + threadIdx.x;
+        int keep = j < n && !sup[j];
+        int total;
+        int r = cnt + block_excl_scan(keep, &total, warp_sums);
+        if (keep) out[r] = in[idx[j]];
+        cnt += total;
+    }
+    if (threadIdx.x == 0) counts_out[blockIdx.x] = cnt;
+}
+
+/* corner-box variant: descending by confidence, equal confidences keep input order */
+__global__ void __launch_bounds__(128) k_nms_corner(const mars_box_t *in, int n, mars_box_t *out, int32_t *count_out,
+                                                    float thresh) {
+    __shared__ uint16_t idx[MARS_MAX_DETS];
+    __shared__ unsigned char sup[MARS_MAX_DETS];
+    __shared__ int warp_sums[32];
+    for (int j = threadIdx.x; j < n; j += blockDim.x) {
+        float c = in[j].confidence;
+        int r = 0;
+        for (int k = 0; k < n; k++) {
+            float ck = in[k].confidence;
+            r += (ck > c) || (ck == c && k < j) || (c != c && ck == ck) || (c != c && ck != ck && k < j);
+        }
+        idx[r] = (uint16_t)j;
+        sup[j] = 0;
+    }
+    __syncthreads();
+    for (int i = 0; i < n; i++) {
+        if (sup[i]) continue;
+        mars_box_t a = in[idx[i]];
+        for (int j = i + 1 + threadIdx.x; j < n; j += blockDim.x) {
+            if (sup[j]) continue;
+            mars_box_t b = in[idx[j]];
+            if (a.class_id == b.class_id && iou_corner(a, b) > thresh) sup[j] = 1;
+        }
+        __syncthreads();
+    }
+    int cnt = 0;
+    for (int base = 0; base < n; base += blockDim.x) {
+        int j = base + threadIdx.x;
+        int keep = j < n && !sup[j];
+        int total;
+        int r = cnt + block_excl_scan(keep, &total, warp_sums);
+        if (keep) out[r] = in[idx[j]];
+        cnt += total;
+    }
+    if (threadIdx.x == 0) *count_out = cnt;
+}
+
+/* reference examples/yolo_detect.cpp:208-227; sc/px/py computed on the host */
+__global__ void k_scale_detections(mars_box_t *d, int n, float sc, float px, float py, float wmax, float hmax) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    mars_box_t b = d[i];
+    b.x0 = fmaxf(0.0f, fminf(__fdiv_rn(__fsub_rn(b.x0, px), sc), wmax));
+    b.y0 = fmaxf(0.0f, fminf(__fdiv_rn(__fsub_rn(b.y0, py), sc), hmax));
+    b.x1 = fmaxf(0.0f, fminf(__fdiv_rn(__fsub_rn(b.x1, px), sc), wmax));
+    b.y1 = fmaxf(0.0f, fminf(__fdiv_rn(__fsub_rn(b.y1, py), sc), hmax));
+    d[i] = b;
+}
+
+/* anchor-grid decode of one head [3,gh,gw,85]; sig[v+128] = 1/(1+expf(-(v*scale))) from the host.
+ * Ordered compaction in (anchor, y, x) order appended after cnt0, capped at maxd. */
+__global__ void __launch_bounds__(256) k_anchor_decode(const int8_t *head, int gh, int gw, const float *sig,
+                                                       float stride, float aw0, float ah0, float aw1, float ah1,
+                                                       float aw2, float ah2, float conf_thresh, mars_box_t *dets,
+                                                       int cnt0, int maxd, int32_t *count_out) {
+    __shared__ int warp_sums[32];
+    const int ncell = 3 * gh * gw;
+    int cnt = cnt0;
+    for (int base = 0; base < ncell && cnt < maxd; base += blockDim.x) {
+        int i = base + threadIdx.x;
+        int pass = 0, best = 0;
+        float conf = 0.0f;
+        const int8_t *p = head + (size_t)i * 85;
+        if (i < ncell) {
+            float obj = sig[(int)p[4] + 128];
+            if (!(obj < conf_thresh)) {
+                int bv = p[5];
+                for (int c = 1; c < 80; c++) if (p[5 + c] > bv) { bv = p[5 + c]; best = c; }
+                conf = __fmul_rn(obj, sig[bv + 128]);
+                pass = !(conf < conf_thresh);
+            }
+        }
+        int total;
+        int rank = cnt + block_excl_scan(pass, &total, warp_sums);
+        if (pass && rank < maxd) {
+            int a = i / (gh * gw), rem = i % (gh * gw), y = rem / gw, x = rem % gw;
+            float aw = a == 0 ? aw0 : (a == 1 ? aw1 : aw2), ah = a == 0 ? ah0 : (a == 1 ? ah1 : ah2);
+            float cx = __fmul_rn(__fadd_rn(__fsub_rn(__fmul_rn(sig[(int)p[0] + 128], 2.0f), 0.5f), (float)x), stride);
+            float cy = __fmul_rn(__fadd_rn(__fsub_rn(__fmul_rn(sig[(int)p[1] + 128], 2.0f), 0.5f), (float)y), stride);
+            float tw = __fmul_rn(sig[(int)p[2] + 128], 2.0f), th = __fmul_rn(sig[(int)p[3] + 128], 2.0f);
+            float w = __fmul_rn(__fmul_rn(tw, tw), aw), h = __fmul_rn(__fmul_rn(th, th), ah);
+            float hw = __fdiv_rn(w, 2.0f), hh = __fdiv_rn(h, 2.0f);
+            mars_box_t d;
+            d.x0 = __fsub_rn(cx, hw); d.y0 = __fsub_rn(cy, hh); d.x1 = __fadd_rn(cx, hw); d.y1 = __fadd_rn(cy, hh);
+            d.confidence = conf; d.class_id = best;
+            dets[rank] = d;
+        }
+        cnt += total;
+    }
+    if (threadIdx.x == 0) *count_out = cnt < maxd ? cnt : maxd;
+}
+
+} // namespace marsb200

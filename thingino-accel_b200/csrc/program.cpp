@@ -1,0 +1,547 @@
+/*
+ * program.cpp -- compiles a .mars layer table into a list of device ops.
+ *
+ * This is the host-side replacement of the reference's execute_layer() switch
+ * (src/mars/mars_runtime.c:1161-1224): what the reference decides per layer at run
+ * time (tensor lookup, dimension extraction, SAME-only padding, kernel choice) is
+ * decided once here, together with the two analyses the reference does not need
+ * because it runs on one thread:
+ *   - hazard analysis: which layers alias their own inputs through the planner's
+ *     round-robin work buffers and must keep the reference's loop order to stay
+ *     byte-exact;
+ *   - observability analysis + fusion (opt_level >= 1): which writes are dead and
+ *     which following int8 unary layers fold into a producer's epilogue.
+ */
+#include <math.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <algorithm>
+
+#include "mars_internal.h"
+
+namespace marsb200 {
+
+/* ---- arithmetic contracts evaluated on the host (tables) ------------------ */
+/* (int32_t)float as x86-64 cvttss2si does it: NaN / out of range -> INT_MIN */
+static inline int32_t f2i_x86(float v) {
+    if (!(v > -2147483904.0f && v < 2147483648.0f)) return INT32_MIN;
+    return (int32_t)v;
+}
+static inline int8_t clamp_i8(int32_t r) { return (int8_t)(r > 127 ? 127 : (r < -128 ? -128 : r)); }
+
+static int pool_add(Program *p, const int8_t lut[256]) {
+    /* de-duplicate identical tables */
+    for (size_t o = 0; o + 256 <= p->const_pool.size(); o += 256)
+        if (memcmp(&p->const_pool[o], lut, 256) == 0) return (int)o;
+    size_t o = p->const_pool.size();
+    p->const_pool.resize(o + 256);
+    memcpy(&p->const_pool[o], lut, 256);
+    return (int)o;
+}
+
+/* reference src/mars/mars_runtime.c:752-768 tabulated over the 256 possible inputs;
+ * expf is the host libm's, the same one the reference would call */
+static void build_sigmoid_lut(float in_scale, float out_scale_raw, int8_t lut[256]) {
+    float os = out_scale_raw > 0 ? out_scale_raw : 1.0f;
+    for (int v = -128; v < 128; v++) {
+        volatile float x = (float)v * in_scale;
+        volatile float e = expf(-x);
+        volatile float den = 1.0f + e;
+        volatile float y = 1.0f / den;
+        volatile float t = y / os;
+        volatile float u = t + 0.5f;
+        lut[v + 128] = clamp_i8(f2i_x86(u));
+    }
+}
+
+/* reference src/mars/mars_runtime.c:1072-1085 */
+static void build_relu_lut(int leaky, int8_t lut[256]) {
+    for (int v = -128; v < 128; v++) {
+        if (v > 0) lut[v + 128] = (int8_t)v;
+        else if (leaky) {
+            volatile float t = (float)v * 0.01f;
+            int32_t q = f2i_x86(t);
+            lut[v + 128] = (int8_t)(q < -128 ? -128 : q);
+        } else lut[v + 128] = 0;
+    }
+}
+
+static bool overlap(int64_t a0, int64_t a1, int64_t b0, int64_t b1) { return a0 < a1 && b0 < b1 && a0 < b1 && b0 < a1; }
+
+static uint64_t numel_of(const mars_tensor_t &t) {
+    uint64_t n = 1;
+    for (uint32_t i = 0; i < t.ndims && i < MARS_MAX_DIMS; i++) n *= (uint64_t)(t.shape[i] < 0 ? 0 : t.shape[i]);
+    return n;
+}
+
+struct Ctx {
+    const mars_header_t &h;
+    const mars_runtime_tensor_t *tensors;
+    const std::vector<size_t> &toff;
+    int64_t W, A;
+    Program *prog;
+    int find(uint32_t id) const { return find_tensor(h, tensors, id); }
+    int64_t off(int idx) const { return (int64_t)toff[idx]; }
+    const mars_tensor_t &desc(int idx) const { return tensors[idx].desc; }
+};
+
+static Op fail_op(int layer, mars_error_t err, const char *why) {
+    Op o;
+    o.kind = OP_NOP;
+    o.layer = layer;
+    o.mode = -(int)err + 1000; /* >= 1000: run stops here and returns -(mode-1000) */
+    o.note = why;
+    return o;
+}
+
+/* true when [lo,hi) crosses the weights/slot boundary */
+static bool straddles(const Ctx &c, int64_t lo, int64_t hi) { return lo < hi && lo < c.W && hi > c.W; }
+
+static mars_error_t check_write(const Ctx &c, int layer, int64_t lo, int64_t hi) {
+    if (lo >= hi) return MARS_OK;
+    if (lo < c.W) {
+        set_last_error("layer %d writes into the weight blob (arena offset %lld < %lld): unsupported, weights are shared by all images",
+                       layer, (long long)lo, (long long)c.W);
+        return MARS_ERR_INVALID_LAYER;
+    }
+    if (hi > c.A) {
+        set_last_error("layer %d writes past the arena end (%lld > %lld); the reference would corrupt its heap here",
+                       layer, (long long)hi, (long long)c.A);
+        return MARS_ERR_INVALID_LAYER;
+    }
+    return MARS_OK;
+}
+static mars_error_t check_read(const Ctx &c, int layer, int64_t lo, int64_t hi) {
+    if (lo >= hi) return MARS_OK;
+    if (lo < 0 || hi > c.A) {
+        set_last_error("layer %d reads outside the arena [%lld,%lld) (arena %lld bytes)", layer, (long long)lo,
+                       (long long)hi, (long long)c.A);
+        return MARS_ERR_INVALID_LAYER;
+    }
+    return MARS_OK;
+}
+
+/* Conv in place (output range overlaps input range), NCHW: decide whether one launch per
+ * output channel reproduces the reference's oc-outermost loop (src/mars/mxu_conv.c:642-669)
+ * exactly.  cross: some pixel's write is read by a different pixel of the same pass;
+ * later_reads_earlier: ... by a LATER pixel (then even a staged pass differs). */
+static void conv_pass_analysis(const Op &o, int es, bool *cross, bool *later_reads_earlier, bool *misaligned) {
+    *cross = *later_reads_earlier = *misaligned = false;
+    const int64_t Po = (int64_t)o.oh * o.ow, Pi = (int64_t)o.ih * o.iw;
+    for (int oc = 0; oc < o.oc; oc++) {
+        int64_t wlo = o.out + (int64_t)oc * Po * es, whi = wlo + Po * es;
+        for (int ic = 0; ic < o.ic; ic++) {
+            int64_t rlo = o.in0 + (int64_t)ic * Pi * es, rhi = rlo + Pi * es;
+            if (!overlap(wlo, whi, rlo, rhi)) continue;
+            for (int oh = 0; oh < o.oh; oh++)
+                for (int ow = 0; ow < o.ow; ow++) {
+                    int64_t pp = (int64_t)oh * o.ow + ow;
+                    for (int y = 0; y < o.kh; y++) {
+                        int ih = oh * o.sh - o.pt + y;
+                        if (ih < 0 || ih >= o.ih) continue;
+                        for (int x = 0; x < o.kw; x++) {
+                            int iw = ow * o.sw - o.pl + x;
+                            if (iw < 0 || iw >= o.iw) continue;
+                            int64_t r = rlo + ((int64_t)ih * o.iw + iw) * es;
+                            if (r + es <= wlo || r >= whi) continue;
+                            if ((r - wlo) % es) { *misaligned = true; return; }
+                            int64_t p = (r - wlo) / es;
+                            if (p != pp) *cross = true;
+                            if (p < pp) *later_reads_earlier = true;
+                        }
+                    }
+                }
+        }
+    }
+}
+
+/* NHWC conv in place: loop order oh, ow, oc (src/mars/mxu_conv.c:726-756).  Thread-per-pixel
+ * with the oc loop kept sequential inside the thread is exact iff no pixel reads a byte that a
+ * different pixel writes. */
+static bool nhwc_pixel_private(const Op &o) {
+    for (int oh = 0; oh < o.oh; oh++)
+        for (int ow = 0; ow < o.ow; ow++) {
+            int64_t wlo = o.out + ((int64_t)oh * o.ow + ow) * o.oc, whi = wlo + o.oc;
+            (void)whi;
+            for (int y = 0; y < o.kh; y++) {
+                int ih = oh * o.sh - o.pt + y;
+                if (ih < 0 || ih >= o.ih) continue;
+                for (int x = 0; x < o.kw; x++) {
+                    int iw = ow * o.sw - o.pl + x;
+                    if (iw < 0 || iw >= o.iw) continue;
+                    int64_t rlo = o.in0 + ((int64_t)ih * o.iw + iw) * o.ic, rhi = rlo + o.ic;
+                    /* which output pixels' byte ranges does [rlo,rhi) touch? */
+                    int64_t olo = o.out, ohi = o.out + (int64_t)o.oh * o.ow * o.oc;
+                    if (!overlap(rlo, rhi, olo, ohi)) continue;
+                    int64_t first = (std::max(rlo, olo) - o.out) / o.oc, last = (std::min(rhi, ohi) - 1 - o.out) / o.oc;
+                    int64_t me = (int64_t)oh * o.ow + ow;
+                    if (first != me || last != me) return false;
+                }
+            }
+        }
+    return true;
+}
+
+static mars_error_t compile_conv(Ctx &c, int li, const mars_layer_t &L, int depthwise) {
+    const mars_conv_params_t &p = L.params.conv;
+    int ii = c.find(L.input_tensor_ids[0]), oi = c.find(L.output_tensor_ids[0]);
+    int wi = c.find(p.weight_tensor_id), bi = c.find(p.bias_tensor_id);
+    if (ii < 0 || oi < 0 || wi < 0) { /* reference src/mars/mars_runtime.c:524,535,546 */
+        c.prog->ops.push_back(fail_op(li, MARS_ERR_INVALID_TENSOR, "conv: tensor id not found"));
+        return MARS_OK;
+    }
+    const mars_tensor_t &it = c.desc(ii), &ot = c.desc(oi), &wt = c.desc(wi);
+    Op o;
+    o.layer = li;
+    bool in_nhwc = it.format == MARS_FORMAT_NHWC, out_nhwc = ot.format == MARS_FORMAT_NHWC;
+    if (in_nhwc) { o.ih = it.shape[1]; o.iw = it.shape[2]; o.ic = it.shape[3]; }
+    else { o.ic = it.shape[1]; o.ih = it.shape[2]; o.iw = it.shape[3]; }
+    if (out_nhwc) { o.oh = ot.shape[1]; o.ow = ot.shape[2]; o.oc = ot.shape[3]; }
+    else { o.oc = ot.shape[1]; o.oh = ot.shape[2]; o.ow = ot.shape[3]; }
+    o.kh = (int)p.kernel_h; o.kw = (int)p.kernel_w; o.sh = (int)p.stride_h; o.sw = (int)p.stride_w;
+    if (p.padding == MARS_PAD_SAME) { /* :591-598; EXPLICIT pads are ignored by the reference */
+        o.pt = ((o.oh - 1) * o.sh + o.kh - o.ih) / 2;
+        o.pl = ((o.ow - 1) * o.sw + o.kw - o.iw) / 2;
+    }
+    if (depthwise && p.padding == MARS_PAD_EXPLICIT) { o.pt = (int)p.pad_top; o.pl = (int)p.pad_left; }
+    bool is_float = it.dtype == MARS_DTYPE_FLOAT32;
+    int es = is_float ? 4 : 1;
+    o.in0 = c.off(ii); o.out = c.off(oi); o.w = c.off(wi); o.bias = bi >= 0 ? c.off(bi) : -1;
+    if (o.kh < 0 || o.kw < 0 || o.sh < 0 || o.sw < 0) {
+        set_last_error("layer %d: conv kernel/stride out of range", li);
+        return MARS_ERR_INVALID_LAYER;
+    }
+    bool empty = o.oc <= 0 || o.oh <= 0 || o.ow <= 0;
+    int64_t nout = empty ? 0 : (int64_t)o.oc * o.oh * o.ow;
+    int64_t nin = (o.ic > 0 && o.ih > 0 && o.iw > 0) ? (int64_t)o.ic * o.ih * o.iw : 0;
+    int64_t icp = o.ic > 0 ? o.ic : 0;
+    int64_t wbytes = depthwise ? (int64_t)(o.oc > 0 ? o.oc : 0) * o.kh * o.kw * es
+                               : (int64_t)(o.oc > 0 ? o.oc : 0) * icp * o.kh * o.kw * es;
+    if (!empty) {
+        if (depthwise) {
+            if (is_float) { c.prog->ops.push_back(fail_op(li, MARS_ERR_INVALID_LAYER, "restated depthwise: int8 only")); return MARS_OK; }
+            o.kind = OP_DW_I8;
+            o.coff = in_nhwc ? 1 : 0; /* layout flag for the depthwise kernels */
+        } else o.kind = is_float ? OP_CONV_F32_NCHW : (in_nhwc ? OP_CONV_I8_NHWC : OP_CONV_I8_NCHW);
+        if (!is_float) {
+            volatile float prod = it.scale * wt.scale; /* reference src/mars/mxu_conv.c:639 */
+            o.f0 = prod / ot.scale;
+        }
+        o.wlo = o.out; o.whi = o.out + nout * es;
+        mars_error_t e;
+        if ((e = check_write(c, li, o.wlo, o.whi))) return e;
+        /* the kernels only touch taps inside the input plane, so the read extent is the tensor */
+        if (nin && (o.kh > 0 && o.kw > 0) && (e = check_read(c, li, o.in0, o.in0 + nin * es))) return e;
+        if (nin && (e = check_read(c, li, o.w, o.w + wbytes))) return e;
+        if (o.bias >= 0 && (e = check_read(c, li, o.bias, o.bias + 4 * (int64_t)o.oc))) return e;
+        o.xlat = straddles(c, o.in0, o.in0 + nin * es) || straddles(c, o.w, o.w + wbytes) ||
+                 (o.bias >= 0 && straddles(c, o.bias, o.bias + 4 * (int64_t)o.oc));
+        bool haz_in = nin && overlap(o.wlo, o.whi, o.in0, o.in0 + nin * es);
+        bool haz_w = overlap(o.wlo, o.whi, o.w, o.w + wbytes) ||
+                     (o.bias >= 0 && overlap(o.wlo, o.whi, o.bias, o.bias + 4 * (int64_t)o.oc));
+        if (haz_w || (haz_in && depthwise)) {
+            o.mode = EXEC_SERIAL;
+            o.note = "output aliases weights/bias: literal order";
+        } else if (haz_in) {
+            if (o.kind == OP_CONV_I8_NHWC) {
+                o.mode = nhwc_pixel_private(o) ? EXEC_PIXEL_SERIAL : EXEC_SERIAL;
+                o.note = "in-place NHWC conv";
+            } else {
+                bool cross, lre, mis;
+                conv_pass_analysis(o, es, &cross, &lre, &mis);
+                if (mis || lre) o.mode = EXEC_SERIAL;
+                else if (cross) {
+                    o.mode = EXEC_OC_PASSES_SCRATCH;
+                    c.prog->scratch_bytes = std::max(c.prog->scratch_bytes, (size_t)((int64_t)o.oh * o.ow * es));
+                } else o.mode = EXEC_OC_PASSES;
+                o.note = "in-place NCHW conv: sequential over output channels";
+            }
+        }
+        c.prog->ops.push_back(o);
+    }
+    if (p.activation == MARS_ACT_RELU) { /* :700-707: signed-byte clamp of the first oh*ow*oc BYTES */
+        int64_t total = (int64_t)o.oh * o.ow * o.oc;
+        if (total > 0 && o.oh > 0 && o.ow > 0) {
+            Op r;
+            r.kind = OP_BYTE_RELU; r.layer = li; r.out = o.out; r.in0 = o.out; r.n = (uint64_t)total;
+            r.wlo = r.out; r.whi = r.out + total;
+            mars_error_t e;
+            if ((e = check_write(c, li, r.wlo, r.whi))) return e;
+            c.prog->ops.push_back(r);
+        }
+    }
+    return MARS_OK;
+}
+
+/* flat unary / binary layers */
+static mars_error_t compile_eltwise(Ctx &c, int li, const mars_layer_t &L) {
+    int type = (int)L.type;
+    bool binary = type == MARS_LAYER_ADD || type == MARS_LAYER_MUL;
+    int ai = c.find(L.input_tensor_ids[0]), bi = binary ? c.find(L.input_tensor_ids[1]) : -1;
+    int oi = c.find(L.output_tensor_ids[0]);
+    if (ai < 0 || oi < 0 || (binary && bi < 0)) {
+        c.prog->ops.push_back(fail_op(li, MARS_ERR_INVALID_TENSOR, "eltwise: tensor id not found"));
+        return MARS_OK;
+    }
+    const mars_tensor_t &at = c.desc(ai), &ot = c.desc(oi);
+    Op o;
+    o.layer = li;
+    o.n = numel_of(at); /* numel always from input A (reference :788-791 etc.) */
+    if (o.n == 0) return MARS_OK;
+    bool is_float = at.dtype == MARS_DTYPE_FLOAT32;
+    int es = is_float ? 4 : 1;
+    o.in0 = c.off(ai); o.in1 = binary ? c.off(bi) : -1; o.out = c.off(oi);
+    switch (type) {
+        case MARS_LAYER_SIGMOID:
+            if (is_float) o.kind = OP_SIGMOID_F32;
+            else {
+                int8_t lut[256];
+                build_sigmoid_lut(at.scale, ot.scale, lut);
+                o.kind = OP_SIGMOID_I8; o.lut = pool_add(c.prog, lut);
+            }
+            break;
+        case MARS_LAYER_RELU: case MARS_LAYER_RELU6: case MARS_LAYER_LEAKY_RELU:
+            if (is_float) { o.kind = OP_RELU_F32; o.f0 = type == MARS_LAYER_LEAKY_RELU ? 0.01f : 0.0f; }
+            else {
+                int8_t lut[256];
+                build_relu_lut(type == MARS_LAYER_LEAKY_RELU, lut);
+                o.kind = OP_RELU_I8; o.lut = pool_add(c.prog, lut);
+            }
+            break;
+        case MARS_LAYER_ADD: case MARS_LAYER_MUL: {
+            const mars_tensor_t &bt = c.desc(bi);
+            if (is_float) o.kind = type == MARS_LAYER_ADD ? OP_ADD_F32 : OP_MUL_F32;
+            else {
+                o.kind = type == MARS_LAYER_ADD ? OP_ADD_I8 : OP_MUL_I8;
+                float so = ot.scale > 0 ? ot.scale : 1.0f;
+                o.f0 = at.scale; o.f1 = bt.scale;
+                volatile float inv = 1.0f / so; /* reference :825, :892 */
+                o.f2 = inv;
+            }
+            break;
+        }
+    }
+    int64_t bytes = (int64_t)o.n * es;
+    o.wlo = o.out; o.whi = o.out + bytes;
+    mars_error_t e;
+    if ((e = check_write(c, li, o.wlo, o.whi))) return e;
+    if ((e = check_read(c, li, o.in0, o.in0 + bytes))) return e;
+    if (binary && (e = check_read(c, li, o.in1, o.in1 + bytes))) return e;
+    o.xlat = straddles(c, o.in0, o.in0 + bytes) || (binary && straddles(c, o.in1, o.in1 + bytes));
+    /* same base = each element reads then writes its own position: order-free.  A shifted
+     * overlap makes the reference's ascending loop observable -> literal order. */
+    if ((o.in0 != o.out && overlap(o.wlo, o.whi, o.in0, o.in0 + bytes)) ||
+        (binary && o.in1 != o.out && overlap(o.wlo, o.whi, o.in1, o.in1 + bytes))) {
+        o.mode = EXEC_SERIAL;
+        o.note = "shifted in/out overlap: literal order";
+    }
+    c.prog->ops.push_back(o);
+    return MARS_OK;
+}
+
+static mars_error_t compile_batchnorm(Ctx &c, int li, const mars_layer_t &L) {
+    int ii = c.find(L.input_tensor_ids[0]), si = c.find(L.input_tensor_ids[1]);
+    int bi = c.find(L.input_tensor_ids[2]), oi = c.find(L.output_tensor_ids[0]);
+    if (ii < 0 || oi < 0) {
+        c.prog->ops.push_back(fail_op(li, MARS_ERR_INVALID_TENSOR, "batchnorm: tensor id not found"));
+        return MARS_OK;
+    }
+    const mars_tensor_t &it = c.desc(ii), &ot = c.desc(oi);
+    Op o;
+    o.layer = li;
+    int n = it.shape[0] > 0 ? it.shape[0] : 1, ch = it.shape[1] > 0 ? it.shape[1] : 1;
+    int h = it.shape[2] > 0 ? it.shape[2] : 1, w = it.shape[3] > 0 ? it.shape[3] : 1;
+    bool is_float = it.dtype == MARS_DTYPE_FLOAT32;
+    int es = is_float ? 4 : 1;
+    o.kind = is_float ? OP_BN_F32 : OP_BN_I8;
+    o.ic = ch; o.ih = h; o.iw = w; o.oc = n;
+    o.n = (uint64_t)n * ch * h * w;
+    o.in0 = c.off(ii); o.out = c.off(oi); o.in1 = si >= 0 ? c.off(si) : -1; o.in2 = bi >= 0 ? c.off(bi) : -1;
+    o.f0 = it.scale > 0 ? it.scale : 1.0f; /* :1135 */
+    o.f1 = ot.scale > 0 ? ot.scale : 1.0f; /* :1136 */
+    int64_t bytes = (int64_t)o.n * es;
+    o.wlo = o.out; o.whi = o.out + bytes;
+    mars_error_t e;
+    if ((e = check_write(c, li, o.wlo, o.whi))) return e;
+    if ((e = check_read(c, li, o.in0, o.in0 + bytes))) return e;
+    if (o.in1 >= 0 && (e = check_read(c, li, o.in1, o.in1 + 4 * (int64_t)ch))) return e;
+    if (o.in2 >= 0 && (e = check_read(c, li, o.in2, o.in2 + 4 * (int64_t)ch))) return e;
+    o.xlat = straddles(c, o.in0, o.in0 + bytes) || (o.in1 >= 0 && straddles(c, o.in1, o.in1 + 4 * (int64_t)ch)) ||
+             (o.in2 >= 0 && straddles(c, o.in2, o.in2 + 4 * (int64_t)ch));
+    if ((o.in0 != o.out && overlap(o.wlo, o.whi, o.in0, o.in0 + bytes)) ||
+        (o.in1 >= 0 && overlap(o.wlo, o.whi, o.in1, o.in1 + 4 * (int64_t)ch)) ||
+        (o.in2 >= 0 && overlap(o.wlo, o.whi, o.in2, o.in2 + 4 * (int64_t)ch))) {
+        o.mode = EXEC_SERIAL;
+        o.note = "batchnorm output aliases an operand: literal order";
+    }
+    c.prog->ops.push_back(o);
+    return MARS_OK;
+}
+
+/* maxpool / upsample: NHWC indexing of shape[1..3] whatever the tag */
+static mars_error_t compile_spatial(Ctx &c, int li, const mars_layer_t &L) {
+    int ii = c.find(L.input_tensor_ids[0]), oi = c.find(L.output_tensor_ids[0]);
+    if (ii < 0 || oi < 0) {
+        c.prog->ops.push_back(fail_op(li, MARS_ERR_INVALID_TENSOR, "pool/upsample: tensor id not found"));
+        return MARS_OK;
+    }
+    const mars_tensor_t &it = c.desc(ii), &ot = c.desc(oi);
+    Op o;
+    o.layer = li;
+    o.ih = it.shape[1]; o.iw = it.shape[2]; o.ic = it.shape[3]; o.oh = ot.shape[1]; o.ow = ot.shape[2];
+    o.oc = o.ic;
+    o.in0 = c.off(ii); o.out = c.off(oi);
+    if (o.oh <= 0 || o.ow <= 0 || o.ic <= 0) return MARS_OK;
+    if ((int)L.type == MARS_LAYER_MAXPOOL) {
+        const mars_pool_params_t &p = L.params.pool;
+        o.kind = OP_MAXPOOL;
+        o.kh = (int)p.kernel_h; o.kw = (int)p.kernel_w; o.sh = (int)p.stride_h; o.sw = (int)p.stride_w;
+        if (o.kh < 0 || o.kw < 0 || o.sh < 0 || o.sw < 0) { set_last_error("layer %d: pool params out of range", li); return MARS_ERR_INVALID_LAYER; }
+    } else {
+        const mars_upsample_params_t &p = L.params.upsample;
+        o.kind = OP_UPSAMPLE;
+        if ((p.scale_h == 0 && o.ih == 0) || (p.scale_w == 0 && o.iw == 0)) {
+            c.prog->ops.push_back(fail_op(li, MARS_ERR_INVALID_LAYER, "upsample: the reference divides by zero here"));
+            return MARS_OK;
+        }
+        o.sh = p.scale_h > 0 ? (int)p.scale_h : o.oh / o.ih; /* :1020-1021 */
+        o.sw = p.scale_w > 0 ? (int)p.scale_w : o.ow / o.iw;
+        if (o.sh == 0 || o.sw == 0) {
+            c.prog->ops.push_back(fail_op(li, MARS_ERR_INVALID_LAYER, "upsample: zero scale (division by zero in the reference)"));
+            return MARS_OK;
+        }
+    }
+    int64_t nin = (o.ih > 0 && o.iw > 0) ? (int64_t)o.ih * o.iw * o.ic : 0, nout = (int64_t)o.oh * o.ow * o.ic;
+    o.wlo = o.out; o.whi = o.out + nout;
+    mars_error_t e;
+    if ((e = check_write(c, li, o.wlo, o.whi))) return e;
+    if ((e = check_read(c, li, o.in0, o.in0 + nin))) return e;
+    if (o.kind == OP_UPSAMPLE && nin == 0) { /* ih clamps to in_h-1 < 0: the reference reads before the tensor */
+        c.prog->ops.push_back(fail_op(li, MARS_ERR_INVALID_LAYER, "upsample of an empty input"));
+        return MARS_OK;
+    }
+    o.xlat = straddles(c, o.in0, o.in0 + nin);
+    if (overlap(o.wlo, o.whi, o.in0, o.in0 + nin)) {
+        o.mode = EXEC_SERIAL;
+        o.note = "in-place pool/upsample: literal order";
+    }
+    c.prog->ops.push_back(o);
+    return MARS_OK;
+}
+
+static mars_error_t compile_concat(Ctx &c, int li, const mars_layer_t &L) {
+    int oi = c.find(L.output_tensor_ids[0]);
+    if (oi < 0) {
+        c.prog->ops.push_back(fail_op(li, MARS_ERR_INVALID_TENSOR, "concat: output id not found"));
+        return MARS_OK;
+    }
+    const mars_tensor_t &ot = c.desc(oi);
+    int OH = ot.shape[1], OW = ot.shape[2], OC = ot.shape[3];
+    int coff = 0;
+    uint32_t nin = L.num_inputs > 4 ? 4 : L.num_inputs;
+    for (uint32_t n = 0; n < nin; n++) {
+        int ii = c.find(L.input_tensor_ids[n]);
+        if (ii < 0) continue; /* :980: skipped inputs do not advance the channel offset */
+        int IC = c.desc(ii).shape[3];
+        if (OH > 0 && OW > 0 && IC > 0) {
+            Op o;
+            o.layer = li; o.kind = OP_CONCAT;
+            o.oh = OH; o.ow = OW; o.oc = OC; o.ic = IC; o.coff = coff;
+            o.in0 = c.off(ii); o.out = c.off(oi);
+            int64_t npix = (int64_t)OH * OW, len = npix * IC;
+            int64_t wlo = o.out + coff, whi = o.out + (npix - 1) * OC + coff + IC;
+            if (OC < 0) { set_last_error("layer %d: concat with negative channel count", li); return MARS_ERR_INVALID_LAYER; }
+            o.wlo = wlo; o.whi = whi; o.n = (uint64_t)len;
+            mars_error_t e;
+            if ((e = check_write(c, li, wlo, whi))) return e;
+            if ((e = check_read(c, li, o.in0, o.in0 + len))) return e;
+            o.xlat = straddles(c, o.in0, o.in0 + len);
+            if (overlap(wlo, whi, o.in0, o.in0 + len)) {
+                if (o.in0 == o.out && IC == OC) {
+                    /* out_idx - in_idx == coff for every element */
+                    if (coff == 0) o.kind = OP_NOP; /* self copy */
+                    else { o.kind = OP_CONCAT_PERIODIC; o.note = "in-place concat: periodic replication"; }
+                } else {
+                    o.mode = EXEC_SERIAL;
+                    o.note = "overlapping concat with varying shift: literal order";
+                }
+            }
+            if (o.kind != OP_NOP) c.prog->ops.push_back(o);
+        }
+        coff += IC;
+    }
+    return MARS_OK;
+}
+
+mars_error_t compile_program(const mars_header_t &h, const mars_runtime_tensor_t *tensors,
+                             const mars_runtime_layer_t *layers, const std::vector<size_t> &toff,
+                             size_t weights_size, size_t arena_size, int opt_level, int depthwise_mode,
+                             Program *out) {
+    (void)opt_level;
+    out->ops.clear();
+    out->const_pool.clear();
+    out->scratch_bytes = 0;
+    Ctx c{h, tensors, toff, (int64_t)weights_size, (int64_t)arena_size, out};
+    for (uint32_t i = 0; i < h.num_layers; i++) {
+        const mars_layer_t &L = layers[i].desc;
+        mars_error_t e = MARS_OK;
+        switch ((int)L.type) {
+            case MARS_LAYER_CONV2D: e = compile_conv(c, (int)i, L, 0); break;
+            case MARS_LAYER_DEPTHWISE_CONV2D:
+                if (depthwise_mode) e = compile_conv(c, (int)i, L, 1); /* else no-op, reference :1168-1170 */
+                break;
+            case MARS_LAYER_MAXPOOL: case MARS_LAYER_UPSAMPLE: e = compile_spatial(c, (int)i, L); break;
+            case MARS_LAYER_RELU: case MARS_LAYER_RELU6: case MARS_LAYER_LEAKY_RELU:
+            case MARS_LAYER_SIGMOID: case MARS_LAYER_ADD: case MARS_LAYER_MUL:
+                e = compile_eltwise(c, (int)i, L); break;
+            case MARS_LAYER_CONCAT: e = compile_concat(c, (int)i, L); break;
+            case MARS_LAYER_BATCHNORM: e = compile_batchnorm(c, (int)i, L); break;
+            case MARS_LAYER_AVGPOOL: case MARS_LAYER_SILU: case MARS_LAYER_RESHAPE:
+            case MARS_LAYER_TRANSPOSE: case MARS_LAYER_SOFTMAX:
+                break; /* no-ops in the reference (:1175-1213) */
+            default: /* GLOBAL_AVGPOOL(4), FC(16), unknown: reference :1218-1220 */
+                out->ops.push_back(fail_op((int)i, MARS_ERR_INVALID_LAYER, "unknown layer type"));
+                break;
+        }
+        if (e != MARS_OK) return e;
+    }
+    /* tables are addressed in 256-byte units; keep the pool non-empty so the upload is uniform */
+    if (out->const_pool.empty()) out->const_pool.resize(256, 0);
+    return MARS_OK;
+}
+
+static const char *kind_name(int k) {
+    static const char *n[] = {"nop", "conv_i8_nchw", "conv_i8_nhwc", "conv_f32_nchw", "dw_i8", "byte_relu",
+                              "sigmoid_i8", "sigmoid_f32", "mul_i8", "add_i8", "mul_f32", "add_f32", "relu_i8",
+                              "relu_f32", "bn_i8", "bn_f32", "maxpool", "concat", "concat_periodic", "upsample", "lut_i8"};
+    return (k >= 0 && k < OP_KIND_COUNT) ? n[k] : "?";
+}
+static const char *mode_name(int m) {
+    switch (m) {
+        case EXEC_PARALLEL: return "parallel";
+        case EXEC_OC_PASSES: return "oc-passes";
+        case EXEC_OC_PASSES_SCRATCH: return "oc-passes+scratch";
+        case EXEC_PIXEL_SERIAL: return "pixel-serial";
+        case EXEC_SERIAL: return "serial";
+        default: return m >= 1000 ? "FAIL" : "?";
+    }
+}
+
+std::string describe_program(const Program &p) {
+    std::string s;
+    char line[512];
+    for (size_t i = 0; i < p.ops.size(); i++) {
+        const Op &o = p.ops[i];
+        snprintf(line, sizeof line,
+                 "op %3zu layer %3d %-16s %-18s impl=%d in=%lld out=%lld ic=%d ih=%d iw=%d oc=%d oh=%d ow=%d k=%dx%d s=%d,%d p=%d,%d n=%llu fused=%d%s %s\n",
+                 i, o.layer, kind_name(o.kind), mode_name(o.mode), o.impl, (long long)o.in0, (long long)o.out, o.ic,
+                 o.ih, o.iw, o.oc, o.oh, o.ow, o.kh, o.kw, o.sh, o.sw, o.pt, o.pl, (unsigned long long)o.n,
+                 o.fused_layers, o.xlat ? " xlat" : "", o.note.c_str());
+        s += line;
+    }
+    return s;
+}
+
+} // namespace marsb200
