@@ -45,7 +45,8 @@ mars_error_t mars_b200_arena_clear(mars_model_t *m);
 mars_error_t mars_b200_run_layer(mars_model_t *m, uint32_t layer);
 /* per-layer schedule summary as text: kernel kind, hazard class, fusion decision */
 size_t mars_b200_describe(mars_model_t *m, char *dst, size_t cap);
-/* 0 = exact direct kernels only, 1 = + fused epilogues, 2 = + tcgen05 convs (default) */
+/* 0 = exact direct kernels only; 1 = + tcgen05 convolutions and vectorised memory-bound kernels,
+ * one device op per layer (per-layer semantics kept); 2 = + cross-layer fusion (default) */
 void mars_b200_set_opt_level(mars_model_t *m, int level);
 /* 0 = reference semantics (DEPTHWISE_CONV2D is a no-op, src/mars/mars_runtime.c:1168-1170),
  * 1 = restated depthwise convolution (parity unpinned) */

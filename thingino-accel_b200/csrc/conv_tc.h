@@ -26,9 +26,18 @@ struct TcPlan {
     void *impl = nullptr; /* TcPlanImpl*, owned */
 };
 
-/* true when the op can run on the tensor-core kernel; fills `plan` */
-bool tc_plan(const Op &o, const ArenaGeom &g, const uint8_t *d_cpool, TcPlan *plan);
-bool tc_launch(const TcPlan &plan, int first, int n, cudaStream_t s);
+/* can this op run on the tensor-core kernel at all (shape / hazard rules)? */
+bool tc_supported(const Op &o);
+/* how many N tiles the kernel would use for `oc` output channels */
+int tc_n_tiles(int oc);
+/* does the kernel read its activations from a private copy (pre-pass) rather than the arena? */
+bool tc_uses_copy(const Op &o);
+/* per-image bytes of the padded / phase-split input copy the op needs (0 = reads the arena) */
+size_t tc_scratch_need(const Op &o);
+/* build the plan: tensor maps, repacked weights, epilogue description */
+bool tc_plan(const Op &o, const ArenaGeom &g, const uint8_t *d_cpool, uint8_t *scratch, size_t scratch_stride, TcPlan *plan);
+/* pre-pass (if any) + conv kernel for image slots [first, first+n) */
+bool tc_launch(const TcPlan &plan, uint8_t *slots_base, int first, int n, cudaStream_t s, uint64_t *launches);
 void tc_release(std::vector<TcPlan> &plans);
 
 } // namespace marsb200

@@ -81,6 +81,12 @@ struct Op {
     int lut = -1;          /* const-pool offset of a 256-byte table (sigmoid/relu/fused) */
     int post_relu = 0;     /* conv: byte-ReLU folded into the epilogue */
     int post_lut = -1;     /* conv: fused following unary chain */
+    /* conv with the following SIGMOID and MUL layers folded into its epilogue: y = conv output
+     * byte, S = lut_s[y] stored at out_s, Z = lut_z[y] stored at out_z; store_y=false when a
+     * later stage of the same chain overwrites Y's bytes anyway */
+    bool store_y = true;
+    int64_t out_s = -1, out_z = -1;
+    int lut_s = -1, lut_z = -1;
     /* write/read extents for hazard analysis and bounds checks */
     int64_t wlo = 0, whi = 0;
     std::string note;

@@ -19,6 +19,7 @@
 
 #include <algorithm>
 
+#include "conv_tc.h"
 #include "mars_internal.h"
 
 namespace marsb200 {
@@ -475,11 +476,77 @@ static mars_error_t compile_concat(Ctx &c, int li, const mars_layer_t &L) {
     return MARS_OK;
 }
 
+
+/* ---- opt_level >= 1: route hazard-free GEMM-shaped convs to the tcgen05 kernel ---------- */
+static void select_tensor_core_convs(Program *p) {
+    for (auto &o : p->ops)
+        if (o.kind == OP_CONV_I8_NCHW && o.mode == EXEC_PARALLEL && !o.xlat && tc_supported(o)) o.impl = CONV_TC_NCHW;
+}
+
+/* reference src/mars/mars_runtime.c:818-835 for one (a, b) byte pair */
+static int8_t mul_point(int a, int b, float sa, float sb, float inv) {
+    volatile float va = (float)a * sa;
+    volatile float vb = (float)b * sb;
+    volatile float y = va * vb;
+    volatile float t = y * inv;
+    volatile float u = t + 0.5f;
+    return clamp_i8(f2i_x86(u));
+}
+
+/* ---- opt_level >= 2: fold SIGMOID + MUL (the compiler's SiLU) into the conv epilogue ------
+ * Y = conv output byte, S = sigmoid_table[Y], Z = mul(Y, S): both followers are pure functions
+ * of the one byte Y, so the epilogue needs two 256-entry tables.  Legal only when the fused
+ * write order cannot be observed through the planner's buffer aliasing:
+ *   - S must not live in Y's buffer (the MUL would then read S where it expects Y);
+ *   - S / Z may overwrite the conv's own INPUT buffer (they usually do, round-robin) only if
+ *     the kernel reads its input from a private copy (3x3, stride 2) or every CTA reads exactly
+ *     the pixels it later writes (1x1 with a single N tile). */
+static void fuse_silu(Program *p, int64_t W) {
+    std::vector<Op> &ops = p->ops;
+    for (size_t i = 0; i + 2 < ops.size(); i++) {
+        Op &c = ops[i];
+        if (c.impl != CONV_TC_NCHW || c.kind != OP_CONV_I8_NCHW || c.post_relu) continue;
+        Op &s = ops[i + 1], &m = ops[i + 2];
+        if (s.kind != OP_SIGMOID_I8 || s.mode != EXEC_PARALLEL || s.xlat) continue;
+        if (m.kind != OP_MUL_I8 || m.mode != EXEC_PARALLEL || m.xlat) continue;
+        const int64_t numel = (int64_t)c.oc * c.oh * c.ow;
+        if (s.in0 != c.out || (int64_t)s.n != numel || (int64_t)m.n != numel) continue;
+        const bool y_first = m.in0 == c.out && m.in1 == s.out, s_first = m.in0 == s.out && m.in1 == c.out;
+        if (!y_first && !s_first) continue;
+        if (s.out == c.out) continue;
+        if (s.out < W || m.out < W) continue;
+        const int64_t x0 = c.in0, x1 = c.in0 + (int64_t)c.ic * c.ih * c.iw;
+        const bool touches_input = overlap(s.out, s.out + numel, x0, x1) || overlap(m.out, m.out + numel, x0, x1);
+        if (touches_input) {
+            const bool same_tile = c.kh == 1 && c.kw == 1 && tc_n_tiles(c.oc) == 1 && c.oh == c.ih && c.ow == c.iw &&
+                                   (s.out == c.in0 || !overlap(s.out, s.out + numel, x0, x1)) &&
+                                   (m.out == c.in0 || !overlap(m.out, m.out + numel, x0, x1));
+            if (!tc_uses_copy(c) && !same_tile) continue;
+        }
+        /* neither follower may clobber the weights or the bias the kernel is still reading: both live below W */
+        int8_t lut[256];
+        const int8_t *sig = reinterpret_cast<const int8_t *>(&p->const_pool[s.lut]);
+        for (int y = -128; y < 128; y++) {
+            int sv = sig[y + 128];
+            lut[y + 128] = y_first ? mul_point(y, sv, m.f0, m.f1, m.f2) : mul_point(sv, y, m.f0, m.f1, m.f2);
+        }
+        c.lut_s = s.lut;
+        c.lut_z = pool_add(p, lut);
+        c.out_s = s.out == m.out ? -1 : s.out; /* an in-place MUL replaces S */
+        c.out_z = m.out;
+        c.store_y = c.out != m.out;
+        c.fused_layers = 2;
+        c.whi = std::max(c.whi, std::max(s.whi, m.whi));
+        c.note = "conv+sigmoid+mul fused";
+        s.kind = OP_NOP; s.note = "folded into the conv epilogue";
+        m.kind = OP_NOP; m.note = "folded into the conv epilogue";
+    }
+}
+
 mars_error_t compile_program(const mars_header_t &h, const mars_runtime_tensor_t *tensors,
                              const mars_runtime_layer_t *layers, const std::vector<size_t> &toff,
                              size_t weights_size, size_t arena_size, int opt_level, int depthwise_mode,
                              Program *out) {
-    (void)opt_level;
     out->ops.clear();
     out->const_pool.clear();
     out->scratch_bytes = 0;
@@ -507,6 +574,8 @@ mars_error_t compile_program(const mars_header_t &h, const mars_runtime_tensor_t
         }
         if (e != MARS_OK) return e;
     }
+    if (opt_level >= 1) select_tensor_core_convs(out);
+    if (opt_level >= 2) fuse_silu(out, (int64_t)weights_size);
     /* tables are addressed in 256-byte units; keep the pool non-empty so the upload is uniform */
     if (out->const_pool.empty()) out->const_pool.resize(256, 0);
     return MARS_OK;

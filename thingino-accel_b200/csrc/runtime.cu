@@ -145,6 +145,8 @@ struct Model {
     uint8_t *d_scratch = nullptr;
     size_t scratch_stride = 0;
     uint8_t *d_cpool = nullptr;
+    uint8_t *d_tc_scratch = nullptr; /* padded / phase-split conv inputs, one region per image slot */
+    size_t tc_scratch_stride = 0;
     Program prog;
     int opt_level = 2, depthwise_mode = 0;
     cudaStream_t stream = nullptr, h2d_stream = nullptr, d2h_stream = nullptr;
@@ -185,7 +187,7 @@ static void model_release(Model *m) {
     if (m->stream) cudaStreamSynchronize(m->stream);
     tc_release(m->tc);
     for (auto e : m->prof_ev) cudaEventDestroy(e);
-    cudaFree(m->d_weights); cudaFree(m->d_slots); cudaFree(m->d_scratch); cudaFree(m->d_cpool);
+    cudaFree(m->d_weights); cudaFree(m->d_slots); cudaFree(m->d_scratch); cudaFree(m->d_cpool); cudaFree(m->d_tc_scratch);
     cudaFree(m->d_raw); cudaFree(m->d_det); cudaFree(m->d_raw_cnt); cudaFree(m->d_det_cnt); cudaFree(m->d_tab);
     if (m->h_arena) cudaFreeHost(m->h_arena);
     if (m->ev0) cudaEventDestroy(m->ev0);
@@ -236,8 +238,11 @@ static mars_error_t set_capacity(Model *m, int capacity) {
     m->capacity = capacity;
     m->pub.ddr_paddr = m->d_slots;
     for (uint32_t i = 0; i < m->pub.header.num_tensors; i++) m->pub.tensors[i].paddr = dev_addr(m, m->toff[i], 0);
-    /* tensor maps embed slot addresses */
+    /* tensor maps embed slot addresses and the slot count */
     tc_release(m->tc);
+    cudaFree(m->d_tc_scratch);
+    m->d_tc_scratch = nullptr;
+    m->tc_scratch_stride = 0;
     m->compiled = false;
     return MARS_OK;
 }
@@ -262,14 +267,27 @@ static mars_error_t compile_model(Model *m) {
     }
     tc_release(m->tc);
     m->tc.assign(m->prog.ops.size(), TcPlan());
-    if (m->opt_level >= 2) {
-        ArenaGeom g{m->d_weights, m->d_slots, m->weights_size, m->slot_stride, m->capacity};
-        for (size_t i = 0; i < m->prog.ops.size(); i++) {
-            Op &o = m->prog.ops[i];
-            if (o.impl == CONV_TC_NCHW && !tc_plan(o, g, m->d_cpool, &m->tc[i])) o.impl = CONV_DIRECT;
+    size_t need = 0;
+    for (const Op &o : m->prog.ops)
+        if (o.impl == CONV_TC_NCHW) need = std::max(need, tc_scratch_need(o));
+    need = (need + 1023) & ~(size_t)1023;
+    if (need > m->tc_scratch_stride || (need && !m->d_tc_scratch)) {
+        cudaFree(m->d_tc_scratch);
+        m->d_tc_scratch = nullptr;
+        m->tc_scratch_stride = need;
+        CU_OK(cudaMalloc(&m->d_tc_scratch, (size_t)m->capacity * need), MARS_ERR_ALLOC_FAILED);
+    }
+    ArenaGeom g{m->d_weights, m->d_slots, m->weights_size, m->slot_stride, m->capacity};
+    for (size_t i = 0; i < m->prog.ops.size(); i++) {
+        Op &o = m->prog.ops[i];
+        if (o.impl != CONV_TC_NCHW) continue;
+        if (!tc_plan(o, g, m->d_cpool, m->d_tc_scratch, m->tc_scratch_stride, &m->tc[i])) {
+            /* a fused op cannot simply fall back (its followers were folded): recompile exact */
+            fprintf(stderr, "mars_b200: tensor-core plan failed for layer %d (%s); using the direct CUDA kernels\n", o.layer, g_err);
+            tc_release(m->tc);
+            m->opt_level = 0;
+            return compile_model(m);
         }
-    } else {
-        for (auto &o : m->prog.ops) o.impl = CONV_DIRECT;
     }
     m->prof_ms.assign(m->prog.ops.size(), 0.0);
     m->prof_calls.assign(m->prog.ops.size(), 0);
@@ -320,8 +338,7 @@ static mars_error_t launch_op(Model *m, size_t op_index, int first, int n) {
         const uint64_t P = (uint64_t)o.oh * o.ow;
         const int es = o.kind == OP_CONV_F32_NCHW ? 4 : 1;
         if (o.impl == CONV_TC_NCHW && m->tc[op_index].valid) {
-            if (!tc_launch(m->tc[op_index], first, n, s)) return MARS_ERR_LAYER_FAILED;
-            m->launches++;
+            if (!tc_launch(m->tc[op_index], m->d_slots, first, n, s, &m->launches)) return MARS_ERR_LAYER_FAILED;
         } else if (o.mode == EXEC_PARALLEL) {
             if (o.kind == OP_CONV_I8_NCHW && !xl && fast_conv_nchw_ok(k)) {
                 launch_fast_conv_nchw(v, k, n, s);
