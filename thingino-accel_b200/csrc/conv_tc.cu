@@ -266,6 +266,45 @@ __global__ void __launch_bounds__(256) k_to_nhwc(const uint8_t *src_base, unsign
         if (pix < npix && c < C) dst[(long long)pix * C + c] = tile[tx][ty + 8 * k];
     }
 }
+/* ---- pre-pass for small-Ci convs (the 6x6 stride-2 stem, Ci = 3): explicit im2col ------
+ * dst[q][k], q = oh*Wo + ow, k = (ci*KH + y)*KW + x (the OIHW row order, so the weights need no
+ * permutation), zero for k >= Kt and for taps outside the input.  One thread writes 4 k's. */
+__global__ void __launch_bounds__(256) k_im2col(const uint8_t *src_base, unsigned long long src_stride, uint8_t *dst_base,
+                                                unsigned long long dst_stride, int C, int H, int W, int Ho, int Wo, int KH, int KW,
+                                                int S, int pt, int pl, int Kt, int Kp) {
+    __shared__ int s_off[256]; /* per k: packed (ci, y, x) */
+    for (int k = threadIdx.x; k < Kp; k += blockDim.x) {
+        int ci = k / (KH * KW), r = k - ci * KH * KW, y = r / KW, x = r - y * KW;
+        s_off[k] = k < Kt ? (ci << 16) | (y << 8) | x : -1;
+    }
+    __syncthreads();
+    const uint8_t *src = src_base + (unsigned long long)blockIdx.z * src_stride;
+    uint8_t *dst = dst_base + (unsigned long long)blockIdx.z * dst_stride;
+    const int words = Kp >> 2;
+    const long long total = (long long)Ho * Wo * words;
+    for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
+        const int q = (int)(t / words), wk = (int)(t - (long long)q * words);
+        const int oh = q / Wo, ow = q - oh * Wo;
+        uint32_t word = 0;
+#pragma unroll
+        for (int b = 0; b < 4; b++) {
+            const int code = s_off[wk * 4 + b];
+            if (code >= 0) {
+                const int ci = code >> 16, ih = oh * S - pt + ((code >> 8) & 0xFF), iw = ow * S - pl + (code & 0xFF);
+                if (ih >= 0 && ih < H && iw >= 0 && iw < W) word |= (uint32_t)src[((long long)ci * H + ih) * W + iw] << (8 * b);
+            }
+        }
+        reinterpret_cast<uint32_t *>(dst)[t] = word;
+    }
+}
+/* OIHW rows (Kt bytes) -> [Co_pad][Kp], zero padded */
+__global__ void k_repack_rows(const int8_t *w, int8_t *dst, int Co, int Co_pad, int Kt, int Kp) {
+    long long total = (long long)Co_pad * Kp;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        int k = (int)(i % Kp), co = (int)(i / Kp);
+        dst[i] = (co < Co && k < Kt) ? w[(long long)co * Kt + k] : (int8_t)0;
+    }
+}
 /* OIHW -> [tap][Co_pad][Ci], rows beyond Co zero */
 __global__ void k_repack_weights(const int8_t *w, int8_t *dst, int Co, int Co_pad, int Ci, int ntaps) {
     long long total = (long long)ntaps * Co_pad * Ci;
@@ -282,7 +321,7 @@ struct TcPlanImpl {
     CUtensorMap mapA, mapB;
     TcParams p;
     int prepass = 0;
-    int C = 0, H = 0, W = 0, pt = 0, pl = 0, plane = 0, npix = 0;
+    int C = 0, H = 0, W = 0, pt = 0, pl = 0, plane = 0, npix = 0, Kp = 0, KH = 0, KW = 0, S = 1, Ho = 0, Wo = 0;
     const uint8_t *src_slot0 = nullptr; /* input tensor in slot 0 */
     uint8_t *scratch = nullptr;
     size_t scratch_stride = 0, slot_stride = 0;
@@ -327,20 +366,31 @@ static bool make_map3(CUtensorMap *m, void *base, uint64_t d0, uint64_t d1, uint
     return true;
 }
 
+
 static int round_up(int x, int a) { return (x + a - 1) / a * a; }
 
 /* geometry shared by tc_scratch_need and tc_plan */
 struct TcGeom {
     bool ok = false;
-    int prepass = 0; /* 0: A from the arena (1x1); 1: NHWC copy, rows padded (stride 1); 2: NHWC 2x2 phase split (stride 2) */
-    int Wp = 0, plane = 0, npix = 0, ntaps = 0;
+    int prepass = 0; /* 0: A from the arena (1x1); 1: NHWC copy, rows padded (stride 1); 2: NHWC 2x2 phase split (stride 2);
+                        3: explicit im2col rows of Kp bytes (small Ci) */
+    int Wp = 0, plane = 0, npix = 0, ntaps = 0, Kp = 0;
     size_t scratch_bytes = 0;
 };
 static TcGeom tc_geometry(const Op &o) {
     TcGeom g;
     if (o.kind != OP_CONV_I8_NCHW || o.mode != EXEC_PARALLEL || o.xlat) return g;
-    if (o.ic < 32 || o.ic % 32 || o.oc < 16 || o.kh != o.kw || o.sh != o.sw) return g;
-    if (o.oh <= 0 || o.ow <= 0 || o.ih <= 0 || o.iw <= 0) return g;
+    if (o.oc < 16 || o.sh != o.sw || o.sh < 1 || o.kh < 1 || o.kw < 1) return g;
+    if (o.oh <= 0 || o.ow <= 0 || o.ih <= 0 || o.iw <= 0 || o.ic <= 0) return g;
+    if (o.ic < 32 || o.ic % 32 || o.kh != o.kw) {
+        /* small / odd channel counts: im2col rows, if one row stays small */
+        const int Kt = o.ic * o.kh * o.kw;
+        if (Kt > 256 || o.kh > 255 || o.kw > 255 || (long long)o.oh * o.ow < 4096) return g;
+        g.prepass = 3; g.Kp = round_up(Kt, 32); g.ntaps = 1; g.Wp = o.ow; g.npix = o.oh * o.ow;
+        g.scratch_bytes = (size_t)g.npix * g.Kp;
+        g.ok = true;
+        return g;
+    }
     g.ntaps = o.kh * o.kw;
     if (g.ntaps > TC_MAX_TAPS) return g;
     if (o.kh == 1 && o.sh == 1 && o.pt == 0 && o.pl == 0 && o.oh <= o.ih && o.ow == o.iw && ((long long)o.ih * o.iw) % 16 == 0) {
@@ -386,13 +436,14 @@ bool tc_plan(const Op &o, const ArenaGeom &ag, const uint8_t *d_cpool, uint8_t *
     TcPlanImpl *t = new TcPlanImpl();
     TcParams &p = t->p;
     memset(&p, 0, sizeof p);
-    p.Ci = o.ic; p.Co = o.oc; p.Ho = o.oh; p.Wo = o.ow; p.Wp = g.Wp; p.mflat = o.oh * g.Wp;
+    const int ci_eff = g.prepass == 3 ? g.Kp : o.ic; /* K extent of one tap */
+    p.Ci = ci_eff; p.Co = o.oc; p.Ho = o.oh; p.Wo = o.ow; p.Wp = g.Wp; p.mflat = o.oh * g.Wp;
     const int co_pad = round_up(o.oc, 16);
     p.n_tile = co_pad <= 256 ? co_pad : (co_pad % 256 == 0 ? 256 : 128);
     if (co_pad > 256 && co_pad % 128) { delete t; return false; }
     p.n_tiles = (co_pad + p.n_tile - 1) / p.n_tile;
-    p.bk = o.ic % 64 == 0 ? 64 : 32;
-    p.ksteps_per_tap = o.ic / p.bk;
+    p.bk = ci_eff % 64 == 0 ? 64 : 32;
+    p.ksteps_per_tap = ci_eff / p.bk;
     p.ntaps = g.ntaps;
     p.a_stage_bytes = (uint32_t)(TC_BM * p.bk);
     p.b_stage_bytes = (uint32_t)round_up(p.n_tile * p.bk, 1024);
@@ -406,13 +457,13 @@ bool tc_plan(const Op &o, const ArenaGeom &ag, const uint8_t *d_cpool, uint8_t *
     p.b_layout = p.bk == 64 ? 4u : 6u;
     p.a_kmajor = g.prepass != 0;
     if (!p.a_kmajor) p.idesc |= 1u << 15; /* A MN-major */
-    for (int kh = 0; kh < o.kh; kh++)
-        for (int kw = 0; kw < o.kw; kw++) {
+    for (int kh = 0; kh < (g.prepass == 3 ? 1 : o.kh); kh++)
+        for (int kw = 0; kw < (g.prepass == 3 ? 1 : o.kw); kw++) {
             const int tap = kh * o.kw + kw;
-            if (g.prepass == 0) p.a_shift[tap] = 0;
+            if (g.prepass == 0 || g.prepass == 3) { if (tap < TC_MAX_TAPS) p.a_shift[tap] = 0; }
             else if (g.prepass == 1) p.a_shift[tap] = (kh - o.pt) * g.Wp + kw;
             else p.a_shift[tap] = ((kh & 1) * 2 + (kw & 1)) * g.plane + (kh / 2) * g.Wp + kw / 2;
-            p.a_cbase[tap] = 0;
+            if (tap < TC_MAX_TAPS) p.a_cbase[tap] = 0;
         }
     p.bias = o.bias >= 0 ? reinterpret_cast<const int32_t *>(ag.d_weights + o.bias) : nullptr;
     if (o.bias >= 0 && (o.bias % 4 || o.bias + 4 * (int64_t)o.oc > (int64_t)ag.W)) { delete t; return false; }
@@ -425,16 +476,19 @@ bool tc_plan(const Op &o, const ArenaGeom &ag, const uint8_t *d_cpool, uint8_t *
     p.lut_s = o.lut_s >= 0 ? d_cpool + o.lut_s : nullptr;
     p.lut_z = o.lut_z >= 0 ? d_cpool + o.lut_z : nullptr;
     t->prepass = g.prepass; t->C = o.ic; t->H = o.ih; t->W = o.iw; t->pt = o.pt; t->pl = o.pl;
-    t->plane = g.plane; t->npix = g.npix;
+    t->plane = g.plane; t->npix = g.npix; t->Kp = g.Kp; t->KH = o.kh; t->KW = o.kw; t->S = o.sh; t->Ho = o.oh; t->Wo = o.ow;
     t->src_slot0 = ag.d_slots + (o.in0 - (int64_t)ag.W);
     t->scratch = scratch; t->scratch_stride = scratch_stride; t->slot_stride = ag.slot_stride;
     t->m_tiles = (p.mflat + TC_BM - 1) / TC_BM;
     t->smem = 1024 + (size_t)p.stages * stage_bytes;
 
     /* weights: [tap][co_pad][Ci] K-major */
-    const size_t wr_bytes = (size_t)g.ntaps * co_pad * o.ic;
+    const size_t wr_bytes = (size_t)g.ntaps * co_pad * ci_eff;
     if (cudaMalloc(&t->d_wr, wr_bytes) != cudaSuccess) { delete t; return false; }
-    k_repack_weights<<<256, 256>>>(reinterpret_cast<const int8_t *>(ag.d_weights + o.w), t->d_wr, o.oc, co_pad, o.ic, g.ntaps);
+    if (g.prepass == 3)
+        k_repack_rows<<<256, 256>>>(reinterpret_cast<const int8_t *>(ag.d_weights + o.w), t->d_wr, o.oc, co_pad, o.ic * o.kh * o.kw, g.Kp);
+    else
+        k_repack_weights<<<256, 256>>>(reinterpret_cast<const int8_t *>(ag.d_weights + o.w), t->d_wr, o.oc, co_pad, o.ic, g.ntaps);
     if (cudaDeviceSynchronize() != cudaSuccess) { cudaFree(t->d_wr); delete t; return false; }
 
     bool ok;
@@ -442,10 +496,10 @@ bool tc_plan(const Op &o, const ArenaGeom &ag, const uint8_t *d_cpool, uint8_t *
         ok = make_map3(&t->mapA, (void *)t->src_slot0, (uint64_t)o.ih * o.iw, (uint64_t)o.ic, (uint64_t)ag.capacity,
                        (uint64_t)o.ih * o.iw, ag.slot_stride, TC_BM, (uint32_t)p.bk, CU_TENSOR_MAP_SWIZZLE_128B);
     else /* NHWC copy: dims (C, pixels, images), K-major box {bk, 128} */
-        ok = make_map3(&t->mapA, scratch, (uint64_t)o.ic, (uint64_t)g.npix, (uint64_t)ag.capacity, (uint64_t)o.ic,
+        ok = make_map3(&t->mapA, scratch, (uint64_t)ci_eff, (uint64_t)g.npix, (uint64_t)ag.capacity, (uint64_t)ci_eff,
                        scratch_stride, (uint32_t)p.bk, TC_BM, p.bk == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
-    ok = ok && make_map3(&t->mapB, t->d_wr, (uint64_t)o.ic, (uint64_t)co_pad, (uint64_t)g.ntaps, (uint64_t)o.ic,
-                         (uint64_t)co_pad * o.ic, (uint32_t)p.bk, (uint32_t)p.n_tile,
+    ok = ok && make_map3(&t->mapB, t->d_wr, (uint64_t)ci_eff, (uint64_t)co_pad, (uint64_t)g.ntaps, (uint64_t)ci_eff,
+                         (uint64_t)co_pad * ci_eff, (uint32_t)p.bk, (uint32_t)p.n_tile,
                          p.bk == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
     if (ok) ok = cudaFuncSetAttribute(k_conv_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) == cudaSuccess;
     if (!ok) { cudaFree(t->d_wr); delete t; return false; }
@@ -459,7 +513,13 @@ bool tc_launch(const TcPlan &plan, uint8_t *slots_base, int first, int n, cudaSt
     if (!t) return false;
     const uint8_t *src = t->src_slot0 + (size_t)first * t->slot_stride;
     uint8_t *scr = t->scratch + (size_t)first * t->scratch_stride;
-    if (t->prepass) {
+    if (t->prepass == 3) {
+        const long long total = (long long)t->npix * (t->Kp / 4);
+        dim3 g((unsigned)std::min<long long>((total + 255) / 256, 148 * 32), 1, n);
+        k_im2col<<<g, 256, 0, s>>>(src, t->slot_stride, scr, t->scratch_stride, t->C, t->H, t->W, t->Ho, t->Wo, t->KH, t->KW, t->S,
+                                   t->pt, t->pl, t->C * t->KH * t->KW, t->Kp);
+        (*launches)++;
+    } else if (t->prepass) {
         dim3 g((t->npix + 31) / 32, (t->C + 31) / 32, n);
         k_to_nhwc<<<g, 256, 0, s>>>(src, t->slot_stride, scr, t->scratch_stride, t->C, t->H, t->W, t->p.Wp, t->plane, t->npix,
                                     t->prepass == 2, t->pt, t->pl);

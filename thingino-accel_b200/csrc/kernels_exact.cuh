@@ -338,6 +338,49 @@ __global__ void __launch_bounds__(128) k_conv_nhwc_pixel_serial(ArenaView v, KOp
     }
 }
 
+
+/* NCHW 1x1 conv whose output planes ARE its input planes (out == in, same plane size): the
+ * reference's oc-outermost loop (src/mars/mxu_conv.c:642-669) makes pass oc read planes ic < oc in
+ * their OUTPUT form.  A 1x1 conv couples no two pixels, so one thread per pixel walking oc in
+ * order -- and feeding each result back into its private copy of the pixel's channel vector --
+ * reproduces that exactly.  Channel vector and weights live in shared memory as 4-byte words
+ * (dp4a); blockDim.x = 128 pixels.  smem = (Ci/4)*128*4 + Co*(Ci/4)*4 bytes. */
+__global__ void __launch_bounds__(128) k_conv1x1_nchw_inplace(ArenaView v, KOp o) {
+    extern __shared__ uint32_t smem_w[];
+    const Img im = make_img(v, blockIdx.y);
+    const int ci4 = o.ic >> 2;
+    uint32_t *xs = smem_w;                  /* [ci4][128] */
+    uint32_t *ws = smem_w + ci4 * 128;      /* [oc][ci4]  */
+    const int64_t P = (int64_t)o.oh * o.ow;
+    const int64_t p = (int64_t)blockIdx.x * 128 + threadIdx.x;
+    const uint8_t *in = im.s_minus_W + o.in0;
+    const uint8_t *w = (o.w < im.W ? im.w : (const uint8_t *)im.s_minus_W) + o.w;
+    for (int i = threadIdx.x; i < o.oc * ci4; i += 128) {
+        const uint8_t *q = w + (int64_t)i * 4;
+        ws[i] = (uint32_t)q[0] | ((uint32_t)q[1] << 8) | ((uint32_t)q[2] << 16) | ((uint32_t)q[3] << 24);
+    }
+    if (p < P)
+        for (int k = 0; k < ci4; k++) {
+            const uint8_t *q = in + (int64_t)(4 * k) * P + p;
+            xs[k * 128 + threadIdx.x] = (uint32_t)q[0] | ((uint32_t)q[P] << 8) | ((uint32_t)q[2 * P] << 16) | ((uint32_t)q[3 * P] << 24);
+        }
+    __syncthreads();
+    if (p >= P) return;
+    uint8_t *out = wr_ptr(im, o.out);
+    for (int oc = 0; oc < o.oc; oc++) {
+        int acc = bias_i32<false>(im, o, oc);
+        const uint32_t *wr = ws + oc * ci4;
+        for (int k = 0; k < ci4; k++) acc = __dp4a((int)xs[k * 128 + threadIdx.x], (int)wr[k], acc);
+        const int8_t r = requant_conv(acc, o.f0);
+        out[(int64_t)oc * P + p] = (uint8_t)r;
+        if (oc < o.ic) { /* feed the result back: later passes read it as input plane oc */
+            const int sh = (oc & 3) * 8;
+            uint32_t &word = xs[(oc >> 2) * 128 + threadIdx.x];
+            word = (word & ~(0xFFu << sh)) | ((uint32_t)(uint8_t)r << sh);
+        }
+    }
+}
+
 template <bool XL>
 __global__ void __launch_bounds__(256) k_flat(ArenaView v, KOp o) {
     const Img im = make_img(v, blockIdx.y);

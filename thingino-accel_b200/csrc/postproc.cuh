@@ -117,125 +117,117 @@ __device__ __forceinline__ float iou_corner(const mars_box_t &a, const mars_box_
 }
 
 /*
- * Exchange-sort emulation, executed by warp 0 of the block over keys in shared memory.
- * Pass i of `for i: for j>i: if d[j].conf > d[i].conf swap` walks the strict prefix-maximum
- * records r0=i < r1 < ... < rk of key[i..n): afterwards key[i]=old key[rk] and every record
- * position holds the previous record's element.  Finding "first j > p with key[j] > x" uses
- * a two-level structure: bmax[b] = max of the 32 keys of block b (one ballot over bmax finds
- * the block, one ballot inside finds the element).  NaN keys never compare greater, exactly
- * as in the C loop.
+ * Exchange-sort emulation, one PASS at a time, the whole block working on each pass.
+ * Pass i of `for i: for j>i: if d[j].conf > d[i].conf swap` (reference
+ * src/mars/mars_yolo_test.c:108-110) walks the strict prefix-maximum records
+ * r0 = i < r1 < ... < rk of key[i..n): afterwards position r0 holds the element of rk and every
+ * other record position holds the previous record's element.  The records are found
+ * with a block-wide prefix-max scan, ranked with a prefix sum, and rotated in parallel, so a pass
+ * costs a few barriers whatever the data looks like (a warp-serial walk degenerates to O(n^2)
+ * on ascending runs).  NaN keys never compare greater, exactly as in the C loop.
+ * blockDim.x = NMS_THREADS >= n.
  */
-__device__ __forceinline__ void exchange_sort_warp(float *key, uint16_t *idx, float *bmax, int n) {
-    const int lane = threadIdx.x & 31;
-    const int nb = (n + 31) >> 5;
-    for (int b = lane; b < 32; b += 32) bmax[b] = -__int_as_float(0x7f800000); /* -inf */
-    __syncwarp();
-    for (int b = 0; b < nb; b++) { /* block maxima (NaN-free max: NaN never wins a '>' test) */
-        int j = b * 32 + lane;
-        float v = j < n ? key[j] : -__int_as_float(0x7f800000);
-        if (v != v) v = -__int_as_float(0x7f800000);
-#pragma unroll
-        for (int d = 16; d; d >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, d));
-        if (lane == 0) bmax[b] = v;
-    }
-    __syncwarp();
+#define NMS_THREADS 1024
+
+__device__ __forceinline__ void exchange_sort_block(float *key, uint16_t *idx, int n, float *wmax, int *wsum, uint16_t *pos) {
+    const int j = threadIdx.x, lane = j & 31, wid = j >> 5;
+    const float NEG_INF = -__int_as_float(0x7f800000);
     for (int i = 0; i + 1 < n; i++) {
-        float carry_k = key[i];
-        uint16_t carry_i = idx[i];
-        int pos = i; /* position whose element is currently "in hand" (the last record) */
-        int start = i + 1;
-        bool changed = false;
-        while (start < n) {
-            /* first j >= start with key[j] > carry_k */
-            int b0 = start >> 5;
-            int j = -1;
-            { /* inside the first (partial) block */
-                int jj = b0 * 32 + lane;
-                bool hit = jj >= start && jj < n && key[jj] > carry_k;
-                unsigned m = __ballot_sync(0xffffffffu, hit);
-                if (m) j = b0 * 32 + __ffs(m) - 1;
-            }
-            if (j < 0) {
-                bool hitb = lane > b0 && lane < nb && bmax[lane] > carry_k;
-                unsigned mb = __ballot_sync(0xffffffffu, hitb);
-                if (!mb) break;
-                int b = __ffs(mb) - 1;
-                int jj = b * 32 + lane;
-                bool hit = jj < n && key[jj] > carry_k;
-                unsigned m = __ballot_sync(0xffffffffu, hit);
-                j = b * 32 + __ffs(m) - 1; /* m != 0 because bmax[b] > carry */
-            }
-            /* record at j: it receives the element in hand, its own element becomes the carry */
-            float nk = key[j];
-            uint16_t ni = idx[j];
-            __syncwarp();
-            if (lane == 0) { key[j] = carry_k; idx[j] = carry_i; }
-            __syncwarp();
-            { /* recompute bmax of j's block (its maximum element left) */
-                int b = j >> 5, jj = b * 32 + lane;
-                float v = jj < n ? key[jj] : -__int_as_float(0x7f800000);
-                if (v != v) v = -__int_as_float(0x7f800000);
+        const float ki = key[i];
+        if (ki != ki) continue; /* NaN in hand: no comparison succeeds (uniform branch) */
+        const bool act = j >= i && j < n;
+        const float kj = act ? key[j] : NEG_INF;
+        float v = (kj == kj) ? kj : NEG_INF;
+        /* inclusive prefix max inside the warp */
+        float inc = v;
 #pragma unroll
-                for (int d = 16; d; d >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, d));
-                if (lane == 0) bmax[b] = v;
+        for (int d = 1; d < 32; d <<= 1) {
+            float y = __shfl_up_sync(0xffffffffu, inc, d);
+            if (lane >= d) inc = fmaxf(inc, y);
+        }
+        if (lane == 31) wmax[wid] = inc;
+        __syncthreads();
+        float before = NEG_INF; /* max over all earlier warps */
+        {
+            float t = lane < wid ? wmax[lane] : NEG_INF;
+#pragma unroll
+            for (int d = 16; d; d >>= 1) t = fmaxf(t, __shfl_xor_sync(0xffffffffu, t, d));
+            before = t;
+        }
+        float excl = __shfl_up_sync(0xffffffffu, inc, 1);
+        excl = lane ? fmaxf(excl, before) : before;
+        const bool rec = act && (j == i || kj > excl);
+        const unsigned m = __ballot_sync(0xffffffffu, rec);
+        if (lane == 0) wsum[wid] = __popc(m);
+        __syncthreads();
+        int base = 0, total = 0;
+        {
+            int t = wsum[lane];
+            int inc_s = t;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                int y = __shfl_up_sync(0xffffffffu, inc_s, d);
+                if (lane >= d) inc_s += y;
             }
-            __syncwarp();
-            carry_k = nk; carry_i = ni; pos = j; start = j + 1; changed = true;
+            total = __shfl_sync(0xffffffffu, inc_s, 31);
+            base = __shfl_sync(0xffffffffu, inc_s - t, wid);
         }
-        (void)pos;
-        if (changed) {
-            if (lane == 0) { key[i] = carry_k; idx[i] = carry_i; }
-            __syncwarp();
-            /* bmax of i's block: its new key is the global max of the suffix, so max() suffices */
-            if (lane == 0 && carry_k == carry_k) bmax[i >> 5] = fmaxf(bmax[i >> 5], carry_k);
-            __syncwarp();
+        if (total <= 1) continue; /* d[i] already dominates the suffix: nothing moves (uniform) */
+        const int rank = base + __popc(m & ((1u << lane) - 1u));
+        if (rec) pos[rank] = (uint16_t)j;
+        __syncthreads();
+        float nk = 0.0f;
+        uint16_t ni = 0;
+        if (rec) {
+            const int src = pos[rank == 0 ? total - 1 : rank - 1];
+            nk = key[src];
+            ni = idx[src];
         }
-        /* position i is final: it must no longer be found by later passes (start = i+2 handles
-         * in-block search; bmax may over-estimate a block, which only costs one extra ballot
-         * that finds nothing -- handled below by the m==0 check) */
+        __syncthreads();
+        if (rec) { key[j] = nk; idx[j] = ni; }
+        __syncthreads();
     }
 }
 
-/* dets_in/dets_out: [det_stride] per image; counts in/out per image.  blockDim.x = 128. */
-__global__ void __launch_bounds__(128) k_nms_center(const mars_det_t *dets_in, const int32_t *counts_in,
-                                                    mars_det_t *dets_out, int32_t *counts_out, int det_stride,
-                                                    float thresh) {
+/* dets_in/dets_out: [det_stride] per image; counts in/out per image.  blockDim.x = NMS_THREADS. */
+__global__ void __launch_bounds__(NMS_THREADS) k_nms_center(const mars_det_t *dets_in, const int32_t *counts_in,
+                                                            mars_det_t *dets_out, int32_t *counts_out, int det_stride,
+                                                            float thresh) {
     __shared__ float key[MARS_MAX_DETS];
     __shared__ uint16_t idx[MARS_MAX_DETS];
-    __shared__ float bmax[32];
+    __shared__ uint16_t pos[MARS_MAX_DETS];
+    __shared__ float wmax[32];
+    __shared__ int wsum[32];
     __shared__ unsigned char sup[MARS_MAX_DETS];
     __shared__ int warp_sums[32];
     const mars_det_t *in = dets_in + (size_t)blockIdx.x * det_stride;
     mars_det_t *out = dets_out + (size_t)blockIdx.x * det_stride;
     int n = counts_in[blockIdx.x];
     if (n > MARS_MAX_DETS) n = MARS_MAX_DETS;
-    for (int j = threadIdx.x; j < n; j += blockDim.x) { key[j] = in[j].conf; idx[j] = (uint16_t)j; sup[j] = 0; }
+    const int j = threadIdx.x;
+    if (j < n) { key[j] = in[j].conf; idx[j] = (uint16_t)j; }
+    if (j < MARS_MAX_DETS) sup[j] = 0;
+    if (j < 32) wsum[j] = 0;
     __syncthreads();
-    if (threadIdx.x < 32) exchange_sort_warp(key, idx, bmax, n);
+    exchange_sort_block(key, idx, n, wmax, wsum, pos);
     __syncthreads();
-    /* greedy suppression, i ascending (mars_yolo_test.c:113-123) */
+    /* greedy suppression, i ascending (mars_yolo_test.c:113-123): thread j owns sorted element j */
+    mars_det_t me;
+    if (j < n) me = in[idx[j]];
+    __shared__ mars_det_t cur;
     for (int i = 0; i < n; i++) {
         if (sup[i]) continue; /* uniform: sup[i] was settled before the previous barrier */
-        mars_det_t a = in[idx[i]];
-        for (int j = i + 1 + threadIdx.x; j < n; j += blockDim.x) {
-            if (sup[j]) continue;
-            mars_det_t b = in[idx[j]];
-            if (a.cls != b.cls) continue;
-            if (iou_center(a, b) > thresh) sup[j] = 1;
-        }
+        if (j == i) cur = me;
+        __syncthreads();
+        if (j > i && j < n && !sup[j] && me.cls == cur.cls && iou_center(cur, me) > thresh) sup[j] = 1;
         __syncthreads();
     }
     /* ordered compaction */
-    int cnt = 0;
-    for (int base = 0; base < n; base += blockDim.x) {
-        int j = base + threadIdx.x;
-        int keep = j < n && !sup[j];
-        int total;
-        int r = cnt + block_excl_scan(keep, &total, warp_sums);
-        if (keep) out[r] = in[idx[j]];
-        cnt += total;
-    }
-    if (threadIdx.x == 0) counts_out[blockIdx.x] = cnt;
+    const int keep = j < n && !sup[j];
+    int total;
+    const int r = block_excl_scan(keep, &total, warp_sums);
+    if (keep) out[r] = me;
+    if (j == 0) counts_out[blockIdx.x] = total;
 }
 
 /* corner-box variant: descending by confidence, equal confidences keep input order */

@@ -250,6 +250,17 @@ static mars_error_t compile_conv(Ctx &c, int li, const mars_layer_t &L, int dept
                 o.mode = nhwc_pixel_private(o) ? EXEC_PIXEL_SERIAL : EXEC_SERIAL;
                 o.note = "in-place NHWC conv";
             } else {
+                /* 1x1 in place on its own planes, channel vector + weights fit shared memory: per-pixel serial */
+                const bool pix_serial = !is_float && !depthwise && o.kh == 1 && o.kw == 1 && o.sh == 1 && o.sw == 1 && o.pt == 0 &&
+                                        o.pl == 0 && o.out == o.in0 && o.oh == o.ih && o.ow == o.iw && o.ic % 4 == 0 && !o.xlat &&
+                                        o.w < c.W && (o.bias < 0 || o.bias + 4 * (int64_t)o.oc <= c.W) &&
+                                        (size_t)o.ic * 128 + (size_t)o.oc * o.ic <= 160 * 1024;
+                if (pix_serial) {
+                    o.mode = EXEC_PIXEL_SERIAL;
+                    o.note = "in-place NCHW 1x1 conv: per-pixel serial over output channels";
+                    c.prog->ops.push_back(o);
+                    goto conv_done;
+                }
                 bool cross, lre, mis;
                 conv_pass_analysis(o, es, &cross, &lre, &mis);
                 if (mis || lre) o.mode = EXEC_SERIAL;
@@ -262,6 +273,7 @@ static mars_error_t compile_conv(Ctx &c, int li, const mars_layer_t &L, int dept
         }
         c.prog->ops.push_back(o);
     }
+conv_done:
     if (p.activation == MARS_ACT_RELU) { /* :700-707: signed-byte clamp of the first oh*ow*oc BYTES */
         int64_t total = (int64_t)o.oh * o.ow * o.oc;
         if (total > 0 && o.oh > 0 && o.ow > 0) {

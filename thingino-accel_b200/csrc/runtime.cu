@@ -360,6 +360,13 @@ static mars_error_t launch_op(Model *m, size_t op_index, int first, int n) {
                     m->launches++;
                 }
             }
+        } else if (o.mode == EXEC_PIXEL_SERIAL && o.kind == OP_CONV_I8_NCHW) {
+            dim3 g(blocks_for(P, 128), n);
+            const size_t smem = (size_t)o.ic * 128 + (size_t)o.oc * o.ic;
+            static bool attr_set = false;
+            if (!attr_set) { cudaFuncSetAttribute(k_conv1x1_nchw_inplace, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); attr_set = true; }
+            k_conv1x1_nchw_inplace<<<g, 128, smem, s>>>(v, k);
+            m->launches++;
         } else if (o.mode == EXEC_PIXEL_SERIAL) {
             dim3 g(blocks_for(P, 128), n);
             if (xl) k_conv_nhwc_pixel_serial<true><<<g, 128, 0, s>>>(v, k); else k_conv_nhwc_pixel_serial<false><<<g, 128, 0, s>>>(v, k);
@@ -489,7 +496,7 @@ static mars_error_t enqueue_detect(Model *m, int first, int n, float thresh) {
     k_parse_output<<<n, 256, 0, m->stream>>>(data, m->slot_stride, d.shape[1], d.scale, m->d_tab,
                                             m->d_raw + (size_t)first * MARS_MAX_DETS, m->d_raw_cnt + first, 1000,
                                             MARS_MAX_DETS);
-    k_nms_center<<<n, 128, 0, m->stream>>>(m->d_raw + (size_t)first * MARS_MAX_DETS, m->d_raw_cnt + first,
+    k_nms_center<<<n, NMS_THREADS, 0, m->stream>>>(m->d_raw + (size_t)first * MARS_MAX_DETS, m->d_raw_cnt + first,
                                           m->d_det + (size_t)first * MARS_MAX_DETS, m->d_det_cnt + first, MARS_MAX_DETS,
                                           thresh);
     m->launches += 2;
