@@ -46,7 +46,9 @@ mars_error_t mars_b200_run_layer(mars_model_t *m, uint32_t layer);
 /* per-layer schedule summary as text: kernel kind, hazard class, fusion decision */
 size_t mars_b200_describe(mars_model_t *m, char *dst, size_t cap);
 /* 0 = exact direct kernels only; 1 = + tcgen05 convolutions and vectorised memory-bound kernels,
- * one device op per layer (per-layer semantics kept); 2 = + cross-layer fusion (default) */
+ * one device op per layer (per-layer semantics kept); 2 = + SIGMOID/MUL folded into conv epilogues (whole arena
+ * still byte-identical to the reference's); 3 = + stores that no later layer, no later run and no output
+ * buffer can observe are dropped from fused epilogues (default; every model OUTPUT stays bit-exact) */
 void mars_b200_set_opt_level(mars_model_t *m, int level);
 /* 0 = reference semantics (DEPTHWISE_CONV2D is a no-op, src/mars/mars_runtime.c:1168-1170),
  * 1 = restated depthwise convolution (parity unpinned) */

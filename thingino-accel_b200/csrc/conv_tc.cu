@@ -61,6 +61,7 @@ struct TcParams {
     long long out_y, out_s, out_z; /* slot-relative byte offsets, -1 = not stored */
     const uint8_t *lut_s, *lut_z;  /* 256-byte tables or null */
     int img0;                /* first image (TMA coordinate of the slot dimension) */
+    int vec_store;           /* tile rows are consecutive, 16-byte aligned output pixels */
 };
 
 /* ---- PTX wrappers ------------------------------------------------------------- */
@@ -133,6 +134,7 @@ k_conv_tc(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUte
     __shared__ __align__(8) uint64_t bar_full[8], bar_empty[8], bar_tmem;
     __shared__ uint32_t tmem_base_slot;
     __shared__ int32_t s_bias[256];
+    __shared__ uint8_t s_lut[512];
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int m_tile = blockIdx.x, n_blk = blockIdx.y, img = blockIdx.z;
@@ -191,30 +193,65 @@ k_conv_tc(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUte
             }
             umma_commit(smem_u32(&bar_tmem));
         }
-    } else { /* ===== epilogue: TMEM -> registers -> requant -> NCHW stores ===== */
+    } else { /* ===== epilogue: TMEM -> registers -> requant (+ SiLU tables) -> NCHW stores ===== */
         const int quad = warp & 3; /* TMEM lane quadrant this warp may touch */
-        const int q = q0 + quad * 32 + lane;
+        const int r = quad * 32 + lane; /* accumulator row = pixel of the tile */
+        const int q = q0 + r;
         const int oh = q / p.Wp, ow = q - oh * p.Wp;
         const bool valid = q < p.mflat && ow < p.Wo;
         const long long plane = (long long)p.Ho * p.Wo;
         uint8_t *img_base = p.out_base + (unsigned long long)img * p.slot_stride;
         const long long pix = (long long)oh * p.Wo + ow;
+        const int et = threadIdx.x - 64; /* 0..127 */
+        if (p.lut_s) for (int i = et; i < 256; i += 128) s_lut[i] = p.lut_s[i];
+        if (p.lut_z) for (int i = et; i < 256; i += 128) s_lut[256 + i] = p.lut_z[i];
+        asm volatile("bar.sync 1, 128;" ::: "memory");
         mbar_wait(smem_u32(&bar_tmem), 0);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        /* all MMAs have retired: the operand stages are free and serve as the store staging area */
+        uint8_t *stage = smem_raw + (smem_base - smem_u32(smem_raw));
+        const long long outs[3] = {p.out_y, p.out_s, p.out_z};
         for (int c0 = 0; c0 < p.n_tile; c0 += 32) {
             uint32_t v[32];
             tmem_ld32(tmem_d + ((uint32_t)(quad * 32) << 16) + (uint32_t)c0, v);
-            if (!valid) continue;
+            if (p.vec_store) {
+                /* tile pixels are 128 consecutive output pixels: transpose through shared memory and
+                 * store 16 bytes per thread along the pixel axis */
 #pragma unroll
-            for (int j = 0; j < 32; j++) {
-                const int co = n0 + c0 + j;
-                if (c0 + j < p.n_tile && co < p.Co) {
+                for (int j = 0; j < 32; j++) {
                     int y = requant_i8((int32_t)(v[j] + (uint32_t)s_bias[c0 + j]), p.cs);
                     if (p.post_relu && y < 0) y = 0;
-                    const long long e = (long long)co * plane + pix;
-                    if (p.out_y >= 0) img_base[p.out_y + e] = (uint8_t)y;
-                    if (p.out_s >= 0) img_base[p.out_s + e] = p.lut_s[y + 128];
-                    if (p.out_z >= 0) img_base[p.out_z + e] = p.lut_z[y + 128];
+                    stage[j * 128 + r] = (uint8_t)y;
+                    if (p.out_s >= 0) stage[4096 + j * 128 + r] = s_lut[y + 128];
+                    if (p.out_z >= 0) stage[8192 + j * 128 + r] = s_lut[256 + y + 128];
+                }
+                asm volatile("bar.sync 1, 128;" ::: "memory");
+#pragma unroll
+                for (int t = 0; t < 3; t++) {
+                    if (outs[t] < 0) continue;
+#pragma unroll
+                    for (int h = 0; h < 2; h++) {
+                        const int vi = et + h * 128, jl = vi >> 3, ch = vi & 7;
+                        const int co = n0 + c0 + jl;
+                        if (c0 + jl < p.n_tile && co < p.Co && q0 + ch * 16 < p.mflat) {
+                            const uint4 val = *reinterpret_cast<const uint4 *>(stage + t * 4096 + jl * 128 + ch * 16);
+                            *reinterpret_cast<uint4 *>(img_base + outs[t] + (long long)co * plane + q0 + ch * 16) = val;
+                        }
+                    }
+                }
+                asm volatile("bar.sync 1, 128;" ::: "memory");
+            } else if (valid) {
+#pragma unroll
+                for (int j = 0; j < 32; j++) {
+                    const int co = n0 + c0 + j;
+                    if (c0 + j < p.n_tile && co < p.Co) {
+                        int y = requant_i8((int32_t)(v[j] + (uint32_t)s_bias[c0 + j]), p.cs);
+                        if (p.post_relu && y < 0) y = 0;
+                        const long long e = (long long)co * plane + pix;
+                        if (p.out_y >= 0) img_base[p.out_y + e] = (uint8_t)y;
+                        if (p.out_s >= 0) img_base[p.out_s + e] = s_lut[y + 128];
+                        if (p.out_z >= 0) img_base[p.out_z + e] = s_lut[256 + y + 128];
+                    }
                 }
             }
         }
@@ -469,6 +506,7 @@ bool tc_plan(const Op &o, const ArenaGeom &ag, const uint8_t *d_cpool, uint8_t *
     if (o.bias >= 0 && (o.bias % 4 || o.bias + 4 * (int64_t)o.oc > (int64_t)ag.W)) { delete t; return false; }
     p.cs = o.f0;
     p.post_relu = o.post_relu;
+    p.vec_store = (g.Wp == o.ow && ((long long)o.oh * o.ow) % 16 == 0 && (ag.slot_stride % 16) == 0) ? 1 : 0;
     p.slot_stride = ag.slot_stride;
     p.out_y = o.store_y ? o.out - (int64_t)ag.W : -1;
     p.out_s = o.out_s >= 0 ? o.out_s - (int64_t)ag.W : -1;

@@ -555,6 +555,109 @@ static void fuse_silu(Program *p, int64_t W) {
     }
 }
 
+/* ---- opt_level >= 3: dead-store elision in fused epilogues ------------------
+ * Backward liveness over byte intervals of the image slot.  A byte is live after op i when some
+ * later op -- or op 0.. of the NEXT run on the same slot (work buffers are never cleared), or the
+ * host through a model output's work buffer -- may read it before it is unconditionally
+ * overwritten.  Reads are over-approximated, kills are exact.  Only the extra stores of a fused
+ * conv (its pre-activation Y and the sigmoid S) are ever dropped; every layer's arithmetic runs. */
+struct IvSet {
+    std::vector<std::pair<int64_t, int64_t>> v; /* sorted, disjoint, non-empty [lo,hi) */
+    void add(int64_t a, int64_t b) {
+        if (a >= b) return;
+        std::vector<std::pair<int64_t, int64_t>> r;
+        size_t i = 0;
+        while (i < v.size() && v[i].second < a) r.push_back(v[i++]);
+        while (i < v.size() && v[i].first <= b) { a = std::min(a, v[i].first); b = std::max(b, v[i].second); i++; }
+        r.emplace_back(a, b);
+        while (i < v.size()) r.push_back(v[i++]);
+        v.swap(r);
+    }
+    void sub(int64_t a, int64_t b) {
+        if (a >= b) return;
+        std::vector<std::pair<int64_t, int64_t>> r;
+        for (auto &iv : v) {
+            if (iv.second <= a || iv.first >= b) { r.push_back(iv); continue; }
+            if (iv.first < a) r.emplace_back(iv.first, a);
+            if (iv.second > b) r.emplace_back(b, iv.second);
+        }
+        v.swap(r);
+    }
+    bool hits(int64_t a, int64_t b) const {
+        for (auto &iv : v) if (a < iv.second && iv.first < b && a < b) return true;
+        return false;
+    }
+    bool operator==(const IvSet &o) const { return v == o.v; }
+};
+
+struct Access { std::vector<std::pair<int64_t, int64_t>> reads, kills; };
+
+static int elem_size(int kind) {
+    switch (kind) {
+        case OP_CONV_F32_NCHW: case OP_SIGMOID_F32: case OP_MUL_F32: case OP_ADD_F32: case OP_RELU_F32: case OP_BN_F32: return 4;
+        default: return 1;
+    }
+}
+
+static void op_access(const Op &o, Access *a) {
+    a->reads.clear(); a->kills.clear();
+    if (o.mode >= 1000) return;
+    const int64_t es = elem_size(o.kind);
+    auto R = [&](int64_t lo, int64_t n) { if (lo >= 0 && n > 0) a->reads.emplace_back(lo, lo + n); };
+    auto K = [&](int64_t lo, int64_t n) { if (lo >= 0 && n > 0) a->kills.emplace_back(lo, lo + n); };
+    switch (o.kind) {
+        case OP_CONV_I8_NCHW: case OP_CONV_I8_NHWC: case OP_CONV_F32_NCHW: case OP_DW_I8: {
+            const int64_t numel = (int64_t)o.oc * o.oh * o.ow;
+            R(o.in0, (int64_t)o.ic * o.ih * o.iw * es);
+            R(o.w, (int64_t)o.oc * (o.kind == OP_DW_I8 ? 1 : o.ic) * o.kh * o.kw * es);
+            if (o.bias >= 0) R(o.bias, 4 * (int64_t)o.oc);
+            if (o.store_y) K(o.out, numel * es);
+            if (o.out_s >= 0) K(o.out_s, numel);
+            if (o.out_z >= 0) K(o.out_z, numel);
+            break;
+        }
+        case OP_BYTE_RELU: R(o.out, (int64_t)o.n); break;
+        case OP_SIGMOID_I8: case OP_SIGMOID_F32: case OP_RELU_I8: case OP_RELU_F32: case OP_LUT_I8:
+            R(o.in0, (int64_t)o.n * es); K(o.out, (int64_t)o.n * es); break;
+        case OP_MUL_I8: case OP_ADD_I8: case OP_MUL_F32: case OP_ADD_F32:
+            R(o.in0, (int64_t)o.n * es); R(o.in1, (int64_t)o.n * es); K(o.out, (int64_t)o.n * es); break;
+        case OP_BN_I8: case OP_BN_F32:
+            R(o.in0, (int64_t)o.n * es); R(o.in1, 4 * (int64_t)o.ic); R(o.in2, 4 * (int64_t)o.ic); K(o.out, (int64_t)o.n * es); break;
+        case OP_MAXPOOL: case OP_UPSAMPLE:
+            R(o.in0, (int64_t)o.ih * o.iw * o.ic); K(o.out, (int64_t)o.oh * o.ow * o.ic); break;
+        case OP_CONCAT:
+            R(o.in0, (int64_t)o.n);
+            if (o.ic == o.oc) K(o.out + o.coff, (int64_t)o.n); /* strided writes kill nothing (conservative) */
+            break;
+        case OP_CONCAT_PERIODIC: R(o.out, o.coff); K(o.out + o.coff, (int64_t)o.n); break;
+        default: break;
+    }
+}
+
+static void elide_dead_stores(Program *p, const IvSet &observed, const IvSet &host_written) {
+    IvSet live_in; /* live at the start of a run */
+    Access a;
+    for (int iter = 0; iter < 8; iter++) {
+        IvSet live = observed;
+        for (auto &iv : live_in.v) live.add(iv.first, iv.second);
+        for (size_t k = p->ops.size(); k-- > 0;) {
+            Op &o = p->ops[k];
+            if (o.fused_layers > 0 && o.kind == OP_CONV_I8_NCHW) {
+                const int64_t numel = (int64_t)o.oc * o.oh * o.ow;
+                /* later stages of the chain overwrite equal ranges, so test each against what is live AFTER the op */
+                if (o.store_y && !live.hits(o.out, o.out + numel)) { o.store_y = false; o.note += " -Y"; }
+                if (o.out_s >= 0 && !live.hits(o.out_s, o.out_s + numel)) { o.out_s = -1; o.note += " -S"; }
+            }
+            op_access(o, &a);
+            for (auto &iv : a.kills) live.sub(iv.first, iv.second);
+            for (auto &iv : a.reads) live.add(iv.first, iv.second);
+        }
+        for (auto &iv : host_written.v) live.sub(iv.first, iv.second); /* the host rewrites the inputs before every run */
+        if (live == live_in) break;
+        live_in = live;
+    }
+}
+
 mars_error_t compile_program(const mars_header_t &h, const mars_runtime_tensor_t *tensors,
                              const mars_runtime_layer_t *layers, const std::vector<size_t> &toff,
                              size_t weights_size, size_t arena_size, int opt_level, int depthwise_mode,
@@ -588,6 +691,21 @@ mars_error_t compile_program(const mars_header_t &h, const mars_runtime_tensor_t
     }
     if (opt_level >= 1) select_tensor_core_convs(out);
     if (opt_level >= 2) fuse_silu(out, (int64_t)weights_size);
+    if (opt_level >= 3) {
+        IvSet observed, host_written;
+        for (uint32_t i = 0; i < h.num_outputs && i < 4; i++) { /* callers may read a whole output work buffer (alloc_size) */
+            uint32_t ti = h.output_tensor_ids[i];
+            if (ti < h.num_tensors) observed.add((int64_t)toff[ti], (int64_t)toff[ti] + (int64_t)tensors[ti].alloc_size);
+        }
+        for (uint32_t i = 0; i < h.num_inputs && i < 4; i++) {
+            uint32_t ti = h.input_tensor_ids[i];
+            if (ti >= h.num_tensors) continue;
+            const mars_tensor_t &d = tensors[ti].desc;
+            int64_t es = (d.dtype == MARS_DTYPE_FLOAT32 || d.dtype == MARS_DTYPE_INT32) ? 4 : (d.dtype == MARS_DTYPE_INT16 ? 2 : 1);
+            host_written.add((int64_t)toff[ti], (int64_t)toff[ti] + (int64_t)numel_of(d) * es);
+        }
+        elide_dead_stores(out, observed, host_written);
+    }
     /* tables are addressed in 256-byte units; keep the pool non-empty so the upload is uniform */
     if (out->const_pool.empty()) out->const_pool.resize(256, 0);
     return MARS_OK;

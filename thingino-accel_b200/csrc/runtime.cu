@@ -148,7 +148,7 @@ struct Model {
     uint8_t *d_tc_scratch = nullptr; /* padded / phase-split conv inputs, one region per image slot */
     size_t tc_scratch_stride = 0;
     Program prog;
-    int opt_level = 2, depthwise_mode = 0;
+    int opt_level = 3, depthwise_mode = 0;
     cudaStream_t stream = nullptr, h2d_stream = nullptr, d2h_stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     cudaEvent_t ev_in[2] = {nullptr, nullptr}, ev_done[2] = {nullptr, nullptr}, ev_out[2] = {nullptr, nullptr};
@@ -378,7 +378,7 @@ static mars_error_t launch_op(Model *m, size_t op_index, int first, int n) {
             /* chunks of `coff` bytes depend on the previous chunk only through position j mod coff,
              * whose source bytes [0, coff) are never written: order-free */
         }
-        if (!xl && fast_spatial_ok(k)) {
+        if (!xl && m->opt_level >= 1 && fast_spatial_ok(v, k)) {
             launch_fast_spatial(v, k, n, s);
         } else {
             dim3 g(blocks_for(total, 256), n);
@@ -386,7 +386,7 @@ static mars_error_t launch_op(Model *m, size_t op_index, int first, int n) {
         }
         m->launches++;
     } else {
-        if (!xl && fast_flat_ok(k)) {
+        if (!xl && m->opt_level >= 1 && fast_flat_ok(v, k)) {
             launch_fast_flat(v, k, n, s);
         } else {
             dim3 g(blocks_for(o.n, 256), n);
