@@ -39,7 +39,7 @@
 namespace marsb200 {
 
 #define TC_MAX_TAPS 36
-#define TC_THREADS 192
+#define TC_THREADS 320 /* warp 0 TMA, warp 1 MMA, warps 2..9 epilogue (two per TMEM lane quadrant) */
 #define TC_BM 128
 
 struct TcParams {
@@ -62,6 +62,7 @@ struct TcParams {
     const uint8_t *lut_s, *lut_z;  /* 256-byte tables or null */
     int img0;                /* first image (TMA coordinate of the slot dimension) */
     int vec_store;           /* tile rows are consecutive, 16-byte aligned output pixels */
+    int m_tiles, tiles_per_cta;
 };
 
 /* ---- PTX wrappers ------------------------------------------------------------- */
@@ -110,6 +111,15 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];\n"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+          "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
 /* UMMA shared-memory matrix descriptor (cute/arch/mma_sm100_desc.hpp layout):
  * [0,14) start>>4, [16,30) LBO>>4, [32,46) SBO>>4, [46,48) version=1, [61,64) layout type */
 __device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes, uint32_t layout) {
@@ -120,39 +130,51 @@ __device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo_bytes
 /* reference src/mars/mxu_conv.c:663-666 with the x86 cvttss2si rule: NaN and |v| >= 2^31 become
  * INT_MIN, which then clamps to -128 (cvt.rzi.sat alone would give +127 / 0) */
 __device__ __forceinline__ int requant_i8(int32_t acc, float cs) {
-    float scaled = __fmul_rn(__int2float_rn(acc), cs);
-    float biased = __fadd_rn(scaled, scaled >= 0.0f ? 0.5f : -0.5f);
-    int r = __float2int_rz(biased);
-    r = max(-128, min(127, r));
+    const float scaled = __fmul_rn(__int2float_rn(acc), cs);
+    const float biased = __fadd_rn(scaled, copysignf(0.5f, scaled)); /* scaled >= 0 ? +0.5 : -0.5; -0.0f cannot occur (int * positive or any cs: sign of zero only matters when scaled == 0, where +-0.5 both truncate to 0) */
+    int r;
+    asm("cvt.rzi.sat.s8.f32 %0, %1;" : "=r"(r) : "f"(biased)); /* truncate + clamp to [-128,127]; NaN -> 0 */
     return (biased < 2147483648.0f) ? r : -128;
 }
 
 /* ---- the kernel -------------------------------------------------------------- */
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+
+/* Each CTA walks `tiles_per_cta` consecutive 128-pixel tiles of one (image, N tile): the TMA ring,
+ * the barriers and the TMEM allocation are set up once, and the accumulator is double buffered in
+ * TMEM so the epilogue of tile t overlaps the MMAs of tile t+1. */
 __global__ void __launch_bounds__(TC_THREADS, 2)
 k_conv_tc(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, const TcParams p) {
     extern __shared__ uint8_t smem_raw[];
-    __shared__ __align__(8) uint64_t bar_full[8], bar_empty[8], bar_tmem;
+    __shared__ __align__(8) uint64_t bar_full[8], bar_empty[8], bar_tmem_full[2], bar_tmem_empty[2];
     __shared__ uint32_t tmem_base_slot;
-    __shared__ int32_t s_bias[256];
+    __shared__ __align__(16) int32_t s_bias[256];
     __shared__ uint8_t s_lut[512];
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int m_tile = blockIdx.x, n_blk = blockIdx.y, img = blockIdx.z;
-    const int q0 = m_tile * TC_BM, n0 = n_blk * p.n_tile;
+    const int n_blk = blockIdx.y, img = blockIdx.z;
+    const int tile0 = blockIdx.x * p.tiles_per_cta;
+    const int ntiles = min(p.tiles_per_cta, p.m_tiles - tile0);
+    const int n0 = n_blk * p.n_tile;
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     const uint32_t a_base = smem_base, b_base = smem_base + p.stages * p.a_stage_bytes;
+    uint8_t *stage_out = smem_raw + (smem_base - smem_u32(smem_raw)) + p.stages * (p.a_stage_bytes + p.b_stage_bytes);
     const int nsteps = p.ntaps * p.ksteps_per_tap;
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < p.stages; s++) { mbar_init(smem_u32(&bar_full[s]), 1); mbar_init(smem_u32(&bar_empty[s]), 1); }
-        mbar_init(smem_u32(&bar_tmem), 1);
+        for (int b = 0; b < 2; b++) { mbar_init(smem_u32(&bar_tmem_full[b]), 1); mbar_init(smem_u32(&bar_tmem_empty[b]), 8); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) { /* TMEM allocation is a warp-wide operation; this warp also frees it */
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_slot)), "r"((uint32_t)p.tmem_cols) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
-    for (int i = threadIdx.x; i < p.n_tile; i += blockDim.x) s_bias[i] = (p.bias && n0 + i < p.Co) ? p.bias[n0 + i] : 0;
+    for (int i = threadIdx.x; i < 256; i += blockDim.x) s_bias[i] = (p.bias && i < p.n_tile && n0 + i < p.Co) ? p.bias[n0 + i] : 0;
+    if (p.lut_s) for (int i = threadIdx.x; i < 256; i += blockDim.x) s_lut[i] = p.lut_s[i];
+    if (p.lut_z) for (int i = threadIdx.x; i < 256; i += blockDim.x) s_lut[256 + i] = p.lut_z[i];
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -161,98 +183,125 @@ k_conv_tc(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUte
     if (warp == 0) {
         if (lane == 0) { /* ===== TMA producer ===== */
             const uint32_t tx = p.tx_bytes;
-            for (int i = 0; i < nsteps; i++) {
-                const int s = i % p.stages, ph = (i / p.stages) & 1;
-                const int tap = i / p.ksteps_per_tap, kb = i - tap * p.ksteps_per_tap;
-                mbar_wait(smem_u32(&bar_empty[s]), ph ^ 1);
-                const uint32_t full = smem_u32(&bar_full[s]);
-                mbar_expect_tx(full, tx);
-                if (p.a_kmajor) tma_load_3d(a_base + s * p.a_stage_bytes, &mapA, full, kb * p.bk, q0 + p.a_shift[tap], p.img0 + img);
-                else tma_load_3d(a_base + s * p.a_stage_bytes, &mapA, full, q0, kb * p.bk, p.img0 + img);
-                tma_load_3d(b_base + s * p.b_stage_bytes, &mapB, full, kb * p.bk, n0, tap);
+            int it = 0;
+            for (int tl = 0; tl < ntiles; tl++) {
+                const int q0 = (tile0 + tl) * TC_BM;
+                for (int i = 0; i < nsteps; i++, it++) {
+                    const int s = it % p.stages, ph = (it / p.stages) & 1;
+                    const int tap = i / p.ksteps_per_tap, kb = i - tap * p.ksteps_per_tap;
+                    mbar_wait(smem_u32(&bar_empty[s]), ph ^ 1);
+                    const uint32_t full = smem_u32(&bar_full[s]);
+                    mbar_expect_tx(full, tx);
+                    if (p.a_kmajor) tma_load_3d(a_base + s * p.a_stage_bytes, &mapA, full, kb * p.bk, q0 + p.a_shift[tap], p.img0 + img);
+                    else tma_load_3d(a_base + s * p.a_stage_bytes, &mapA, full, q0, kb * p.bk, p.img0 + img);
+                    tma_load_3d(b_base + s * p.b_stage_bytes, &mapB, full, kb * p.bk, n0, tap);
+                }
             }
         }
     } else if (warp == 1) {
         if (lane == 0) { /* ===== MMA issuer ===== */
             const uint32_t b_sbo = 8u * (uint32_t)p.bk;
-            for (int i = 0; i < nsteps; i++) {
-                const int s = i % p.stages, ph = (i / p.stages) & 1;
-                mbar_wait(smem_u32(&bar_full[s]), ph);
+            int it = 0;
+            for (int tl = 0; tl < ntiles; tl++) {
+                const int buf = tl & 1;
+                mbar_wait(smem_u32(&bar_tmem_empty[buf]), ((tl >> 1) & 1) ^ 1); /* epilogue drained this accumulator */
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                const uint32_t a_addr = a_base + s * p.a_stage_bytes, b_addr = b_base + s * p.b_stage_bytes;
-                for (int j = 0; j < p.bk / 32; j++) {
-                    /* A MN-major, 128B swizzle: 32 K-rows of 128 bytes = 4 atoms of 8 rows, 1024 B apart;
-                     * A K-major: same layout rules as B */
-                    const uint64_t da = p.a_kmajor ? umma_desc(a_addr + j * 32u, 16u, b_sbo, p.b_layout)
-                                                   : umma_desc(a_addr + j * 4096u, 0, 1024u, 2u);
-                    /* B: K-major, swizzle = bk bytes: rows of bk bytes, 8-row groups 8*bk apart; advance 32 B per MMA */
-                    const uint64_t db = umma_desc(b_addr + j * 32u, 16u, b_sbo, p.b_layout);
-                    umma_i8(tmem_d, da, db, p.idesc, (uint32_t)((i | j) != 0));
+                const uint32_t acc = tmem_d + (uint32_t)(buf * p.n_tile);
+                for (int i = 0; i < nsteps; i++, it++) {
+                    const int s = it % p.stages, ph = (it / p.stages) & 1;
+                    mbar_wait(smem_u32(&bar_full[s]), ph);
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    const uint32_t a_addr = a_base + s * p.a_stage_bytes, b_addr = b_base + s * p.b_stage_bytes;
+                    for (int j = 0; j < p.bk / 32; j++) {
+                        /* A MN-major, 128B swizzle: 32 K-rows of 128 bytes = 4 atoms of 8 rows, 1024 B apart;
+                         * A K-major: same layout rules as B */
+                        const uint64_t da = p.a_kmajor ? umma_desc(a_addr + j * 32u, 16u, b_sbo, p.b_layout)
+                                                       : umma_desc(a_addr + j * 4096u, 0, 1024u, 2u);
+                        /* B: K-major, swizzle = bk bytes: rows of bk bytes, 8-row groups 8*bk apart; advance 32 B per MMA */
+                        const uint64_t db = umma_desc(b_addr + j * 32u, 16u, b_sbo, p.b_layout);
+                        umma_i8(acc, da, db, p.idesc, (uint32_t)((i | j) != 0));
+                    }
+                    umma_commit(smem_u32(&bar_empty[s])); /* frees the stage when these MMAs retire */
                 }
-                umma_commit(smem_u32(&bar_empty[s])); /* frees the stage when these MMAs retire */
+                umma_commit(smem_u32(&bar_tmem_full[buf]));
             }
-            umma_commit(smem_u32(&bar_tmem));
         }
     } else { /* ===== epilogue: TMEM -> registers -> requant (+ SiLU tables) -> NCHW stores ===== */
-        const int quad = warp & 3; /* TMEM lane quadrant this warp may touch */
-        const int r = quad * 32 + lane; /* accumulator row = pixel of the tile */
-        const int q = q0 + r;
-        const int oh = q / p.Wp, ow = q - oh * p.Wp;
-        const bool valid = q < p.mflat && ow < p.Wo;
-        const long long plane = (long long)p.Ho * p.Wo;
+        /* Two warps share each TMEM lane quadrant and split the accumulator columns in units of 16.
+         * Valid tile rows (pad columns of the flat pixel index skipped) are CONSECUTIVE output pixels,
+         * so each unit is transposed through shared memory -- staged at its final 16-byte phase --
+         * and stored as 16-byte vectors along the pixel axis, bytes only at the ragged ends. */
+        const int ew = warp - 2, grp = ew >> 2, quad = warp & 3;
+        const int r = quad * 32 + lane;       /* accumulator row = pixel of the tile */
+        const int et = (ew & 3) * 32 + lane;  /* 0..127 inside the group */
+        const int plane = p.Ho * p.Wo;
         uint8_t *img_base = p.out_base + (unsigned long long)img * p.slot_stride;
-        const long long pix = (long long)oh * p.Wo + ow;
-        const int et = threadIdx.x - 64; /* 0..127 */
-        if (p.lut_s) for (int i = et; i < 256; i += 128) s_lut[i] = p.lut_s[i];
-        if (p.lut_z) for (int i = et; i < 256; i += 128) s_lut[256 + i] = p.lut_z[i];
-        asm volatile("bar.sync 1, 128;" ::: "memory");
-        mbar_wait(smem_u32(&bar_tmem), 0);
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        /* all MMAs have retired: the operand stages are free and serve as the store staging area */
-        uint8_t *stage = smem_raw + (smem_base - smem_u32(smem_raw));
+        uint8_t *stg = stage_out + grp * (3 * 16 * 144);
         const long long outs[3] = {p.out_y, p.out_s, p.out_z};
-        for (int c0 = 0; c0 < p.n_tile; c0 += 32) {
-            uint32_t v[32];
-            tmem_ld32(tmem_d + ((uint32_t)(quad * 32) << 16) + (uint32_t)c0, v);
-            if (p.vec_store) {
-                /* tile pixels are 128 consecutive output pixels: transpose through shared memory and
-                 * store 16 bytes per thread along the pixel axis */
-#pragma unroll
-                for (int j = 0; j < 32; j++) {
-                    int y = requant_i8((int32_t)(v[j] + (uint32_t)s_bias[c0 + j]), p.cs);
-                    if (p.post_relu && y < 0) y = 0;
-                    stage[j * 128 + r] = (uint8_t)y;
-                    if (p.out_s >= 0) stage[4096 + j * 128 + r] = s_lut[y + 128];
-                    if (p.out_z >= 0) stage[8192 + j * 128 + r] = s_lut[256 + y + 128];
+        const int n_units = p.n_tile >> 4;
+        const uint32_t bar_id = 1 + grp;
+        for (int tl = 0; tl < ntiles; tl++) {
+            const int buf = tl & 1;
+            const int q0 = (tile0 + tl) * TC_BM;
+            const int q = q0 + r;
+            const int oh = q / p.Wp, ow = q - oh * p.Wp;
+            const bool valid = q < p.mflat && ow < p.Wo;
+            /* output pixel index of flat q = number of valid flat indices before it */
+            const int oh0 = q0 / p.Wp, ow0 = q0 - oh0 * p.Wp;
+            const int pix_first = oh0 * p.Wo + min(ow0, p.Wo);
+            const int qe = min(q0 + TC_BM, p.mflat), ohe = qe / p.Wp, owe = qe - ohe * p.Wp;
+            const int pix_end = ohe * p.Wo + min(owe, p.Wo);
+            const int mis = p.vec_store ? (pix_first & 15) : 0;
+            const int sidx = oh * p.Wo + ow - pix_first + mis; /* staging column of this row */
+            const int len = pix_end - pix_first;
+            mbar_wait(smem_u32(&bar_tmem_full[buf]), (tl >> 1) & 1);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const uint32_t acc = tmem_d + ((uint32_t)(quad * 32) << 16) + (uint32_t)(buf * p.n_tile);
+            if (grp >= n_units) { /* nothing to read for this group: release the accumulator at once */
+                __syncwarp();
+                if (lane == 0) mbar_arrive(smem_u32(&bar_tmem_empty[buf]));
+            }
+            for (int u = grp; u < n_units; u += 2) {
+                uint32_t v[16];
+                tmem_ld16(acc + (uint32_t)(u * 16), v);
+                if (u + 2 >= n_units) { /* last read of this accumulator by this warp: hand it back */
+                    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(smem_u32(&bar_tmem_empty[buf]));
                 }
-                asm volatile("bar.sync 1, 128;" ::: "memory");
+                if (valid) {
+                    const int4 *bv = reinterpret_cast<const int4 *>(s_bias + u * 16);
 #pragma unroll
-                for (int t = 0; t < 3; t++) {
-                    if (outs[t] < 0) continue;
+                    for (int j4 = 0; j4 < 4; j4++) {
+                        const int4 b4 = bv[j4];
+                        const int bb[4] = {b4.x, b4.y, b4.z, b4.w};
 #pragma unroll
-                    for (int h = 0; h < 2; h++) {
-                        const int vi = et + h * 128, jl = vi >> 3, ch = vi & 7;
-                        const int co = n0 + c0 + jl;
-                        if (c0 + jl < p.n_tile && co < p.Co && q0 + ch * 16 < p.mflat) {
-                            const uint4 val = *reinterpret_cast<const uint4 *>(stage + t * 4096 + jl * 128 + ch * 16);
-                            *reinterpret_cast<uint4 *>(img_base + outs[t] + (long long)co * plane + q0 + ch * 16) = val;
+                        for (int k = 0; k < 4; k++) {
+                            const int j = j4 * 4 + k;
+                            int y = requant_i8((int32_t)(v[j] + (uint32_t)bb[k]), p.cs);
+                            if (p.post_relu) y = max(y, 0);
+                            if (p.out_y >= 0) stg[j * 144 + sidx] = (uint8_t)y;
+                            if (p.out_s >= 0) stg[16 * 144 + j * 144 + sidx] = s_lut[y + 128];
+                            if (p.out_z >= 0) stg[32 * 144 + j * 144 + sidx] = s_lut[256 + y + 128];
                         }
                     }
                 }
-                asm volatile("bar.sync 1, 128;" ::: "memory");
-            } else if (valid) {
+                asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
 #pragma unroll
-                for (int j = 0; j < 32; j++) {
-                    const int co = n0 + c0 + j;
-                    if (c0 + j < p.n_tile && co < p.Co) {
-                        int y = requant_i8((int32_t)(v[j] + (uint32_t)s_bias[c0 + j]), p.cs);
-                        if (p.post_relu && y < 0) y = 0;
-                        const long long e = (long long)co * plane + pix;
-                        if (p.out_y >= 0) img_base[p.out_y + e] = (uint8_t)y;
-                        if (p.out_s >= 0) img_base[p.out_s + e] = s_lut[y + 128];
-                        if (p.out_z >= 0) img_base[p.out_z + e] = s_lut[256 + y + 128];
+                for (int t = 0; t < 3; t++) {
+                    if (outs[t] < 0) continue;
+                    for (int slot = et; slot < 16 * 9; slot += 128) {
+                        const int jl = slot / 9, ch = slot - jl * 9;
+                        const int co = n0 + u * 16 + jl;
+                        const int lo = max(ch * 16, mis), hi = min(ch * 16 + 16, mis + len);
+                        if (co >= p.Co || lo >= hi) continue;
+                        const uint8_t *src = stg + t * (16 * 144) + jl * 144;
+                        uint8_t *dst = img_base + outs[t] + (long long)co * plane + (pix_first - mis);
+                        if (p.vec_store && hi - lo == 16) *reinterpret_cast<uint4 *>(dst + ch * 16) = *reinterpret_cast<const uint4 *>(src + ch * 16);
+                        else for (int b2 = lo; b2 < hi; b2++) dst[b2] = src[b2];
                     }
                 }
+                asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
             }
         }
     }
@@ -486,9 +535,9 @@ bool tc_plan(const Op &o, const ArenaGeom &ag, const uint8_t *d_cpool, uint8_t *
     p.b_stage_bytes = (uint32_t)round_up(p.n_tile * p.bk, 1024);
     p.tx_bytes = p.a_stage_bytes + (uint32_t)(p.n_tile * p.bk);
     const int stage_bytes = (int)(p.a_stage_bytes + p.b_stage_bytes);
-    p.stages = std::max(2, std::min(8, (100 * 1024) / stage_bytes));
+    p.stages = std::max(2, std::min(8, (94 * 1024) / stage_bytes));
     p.tmem_cols = 32;
-    while (p.tmem_cols < p.n_tile) p.tmem_cols <<= 1;
+    while (p.tmem_cols < 2 * p.n_tile) p.tmem_cols <<= 1; /* two accumulators */
     /* cute/arch/mma_sm100_desc.hpp InstrDescriptor: c=S32, a=b=signed 8 bit, A MN-major, B K-major, N>>3, M>>4 */
     p.idesc = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.n_tile >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
     p.b_layout = p.bk == 64 ? 4u : 6u;
@@ -506,7 +555,7 @@ bool tc_plan(const Op &o, const ArenaGeom &ag, const uint8_t *d_cpool, uint8_t *
     if (o.bias >= 0 && (o.bias % 4 || o.bias + 4 * (int64_t)o.oc > (int64_t)ag.W)) { delete t; return false; }
     p.cs = o.f0;
     p.post_relu = o.post_relu;
-    p.vec_store = (g.Wp == o.ow && ((long long)o.oh * o.ow) % 16 == 0 && (ag.slot_stride % 16) == 0) ? 1 : 0;
+    p.vec_store = (((long long)o.oh * o.ow) % 16 == 0 && (ag.slot_stride % 16) == 0) ? 1 : 0;
     p.slot_stride = ag.slot_stride;
     p.out_y = o.store_y ? o.out - (int64_t)ag.W : -1;
     p.out_s = o.out_s >= 0 ? o.out_s - (int64_t)ag.W : -1;
@@ -518,7 +567,9 @@ bool tc_plan(const Op &o, const ArenaGeom &ag, const uint8_t *d_cpool, uint8_t *
     t->src_slot0 = ag.d_slots + (o.in0 - (int64_t)ag.W);
     t->scratch = scratch; t->scratch_stride = scratch_stride; t->slot_stride = ag.slot_stride;
     t->m_tiles = (p.mflat + TC_BM - 1) / TC_BM;
-    t->smem = 1024 + (size_t)p.stages * stage_bytes;
+    p.m_tiles = t->m_tiles;
+    t->smem = 1024 + (size_t)p.stages * stage_bytes + 2 * 3 * 16 * 144;
+    if (p.tmem_cols > 256) t->smem = std::max<size_t>(t->smem, 120 * 1024); /* one CTA per SM: it owns all of TMEM */
 
     /* weights: [tap][co_pad][Ci] K-major */
     const size_t wr_bytes = (size_t)g.ntaps * co_pad * ci_eff;
@@ -566,7 +617,12 @@ bool tc_launch(const TcPlan &plan, uint8_t *slots_base, int first, int n, cudaSt
     TcParams p = t->p;
     p.out_base = slots_base + (size_t)first * t->slot_stride;
     p.img0 = first;
-    dim3 grid(t->m_tiles, p.n_tiles, n);
+    /* enough CTAs for a few waves of 2 per SM, each amortising its setup over several tiles */
+    const long long total_tiles = (long long)t->m_tiles * p.n_tiles * n;
+    int tpc = (int)std::min<long long>(16, std::max<long long>(1, total_tiles / (148 * 2 * 4)));
+    tpc = std::min(tpc, t->m_tiles);
+    p.tiles_per_cta = tpc;
+    dim3 grid((t->m_tiles + tpc - 1) / tpc, p.n_tiles, n);
     k_conv_tc<<<grid, TC_THREADS, t->smem, s>>>(t->mapA, t->mapB, p);
     (*launches)++;
     return cudaGetLastError() == cudaSuccess;
