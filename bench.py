@@ -35,6 +35,9 @@ sys.path.insert(0, ROOT)
 from __graft_entry__ import load_package  # noqa: E402
 
 METRIC = "yolov5s_int8_640_images_per_s"
+WORKLOAD = "BASELINE configs[2]: yolov5s_int8.mars-shaped 640x640 int8, all layers + decode + NMS"
+MODEL_FILE = ("synthetic yolov5s-shaped .mars (2x-width copy of the shipped yolov5n_int8 layer table, writer seed 5); "
+              "the reference's yolov5s_int8.mars is a missing blob")
 UNIT = "images/s"
 NMS_THRESH = 0.45
 
@@ -159,7 +162,8 @@ def run_reference_arm(args):
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "int8", "data": "synthetic",
-            "config": {"workload": "yolov5s_int8.mars-shaped 640x640, %d images per step" % cores, "model_file": "synthetic (marsfile.build_yolov5 width 0.5, seed 5)"},
+            "config": {"workload": WORKLOAD, "model_file": MODEL_FILE, "images_per_step": cores, "image": "3x640x640 int8",
+                       "arena_bytes": arena, "parallelism": "%d independent host processes, one image each per step" % cores},
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
@@ -266,13 +270,8 @@ def run_cuda_arm(args):
 
     det_t = torch.as_tensor(_Dev(dptr, (B, dstride * 6), "<i4"), device="cuda")
     cnt_t = torch.as_tensor(_Dev(cptr, (B,), "<i4"), device="cuda")
-    gather_d = [torch.empty_like(det_t) for _ in range(world)] if (world > 1 and rank == 0) else None
-    gather_c = [torch.empty_like(cnt_t) for _ in range(world)] if (world > 1 and rank == 0) else None
-
-    def gather():
-        if world > 1:
-            dist.gather(cnt_t, gather_c, dst=0)
-            dist.gather(det_t, gather_d, dst=0)
+    gatherer = pkg.shard.DetectionGather(det_t, cnt_t, dist if world > 1 else None)
+    gather = gatherer.run
 
     def barrier():
         torch.cuda.synchronize()
@@ -342,10 +341,7 @@ def run_cuda_arm(args):
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
                 "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int8",
                 "data": "synthetic",
-                "config": {"workload": "BASELINE configs[2]: yolov5s_int8.mars-shaped 640x640, %d images per GPU per step "
-                                       "(all layers + decode + NMS)" % B,
-                           "model_file": "synthetic yolov5s-shaped .mars (2x-width copy of the shipped yolov5n_int8 layer table, seed 5); "
-                                         "the reference's yolov5s_int8.mars is a missing blob",
+                "config": {"workload": WORKLOAD, "model_file": MODEL_FILE, "images_per_step": B * world,
                            "global_batch": B * world, "per_gpu_batch": B, "image": "3x640x640 int8", "arena_bytes": arena,
                            "parallelism": "images sharded, dp%d, detections gathered to rank 0 over NCCL" % world,
                            "l2": "working set %.1f GB per GPU >> 126 MB L2 (no flush needed)" % (B * gm.slot_stride / 1e9)},

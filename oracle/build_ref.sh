@@ -46,3 +46,23 @@ g++ $CFLAGS $QUIET $INC -DSTB_IMAGE_STATIC -DSTB_IMAGE_RESIZE_STATIC \
 g++ -shared -Wl,-Bsymbolic -o "$OUT/libmars_ref.so" "$TMP"/*.o -lm
 cp -f "$REF_DIR"/models/*.mars "$OUT/models/"
 echo "build_ref: wrote $OUT/libmars_ref.so and $(ls "$OUT/models" | wc -l) model blobs"
+
+# --- drop-in proof: the reference's own CALLER programs, unmodified ---------------------
+# *.b200 : compiled against THIS repository's include/ and linked with libmars_b200.so only
+#          (the link line INTEGRATION.md section 2 gives a maintainer);
+# *.ref  : the same sources against the reference's headers and its own runtime (libmars_ref.so).
+# tests/test_gpu_dropin.py runs both on the GPU box and compares what they print.
+REPO="$(cd "$HERE/.." && pwd)"
+B200_LIB="$REPO/thingino-accel_b200/lib"
+mkdir -p "$OUT/bin"
+if [ -f "$B200_LIB/libmars_b200.so" ]; then
+    for app in mars_test mars_yolo_test; do
+        gcc -O2 -w -I"$REPO/include" -I"$REF_DIR/include" "$REF_DIR/src/mars/$app.c" -o "$OUT/bin/$app.b200" \
+            -L"$B200_LIB" -lmars_b200 -Wl,-rpath,'$ORIGIN/../../../thingino-accel_b200/lib' -lm
+        gcc -O2 -w $INC "$REF_DIR/src/mars/$app.c" -o "$OUT/bin/$app.ref" \
+            -L"$OUT" -lmars_ref -Wl,-rpath,'$ORIGIN/..' -lm
+    done
+    echo "build_ref: wrote drop-in caller binaries to $OUT/bin"
+else
+    echo "build_ref: libmars_b200.so not built yet; skipping the drop-in caller binaries" >&2
+fi

@@ -8,11 +8,11 @@
  *
  * Parity pin: every function below is validated byte-for-byte (whole arena)
  * against oracle/_ref/libmars_ref.so -- the reference's own sources compiled by
- * oracle/build_ref.sh -- on all shipped models by tests/test_oracle_vs_ref.py,
+ * oracle/build_ref.sh -- on all shipped models by tests/test_oracle.py,
  * and against the committed fixtures in tests/golden/ (generated from that
  * binary by tests/golden/make_golden.py).  The reference's only known-answer test
  * on this path (examples/mars_math_test.c:38-82) is restated in
- * tests/test_mars_math.py.  Two functions have NO reference implementation and
+ * tests/test_oracle.py::test_mars_math_known_answers.  Two functions have NO reference implementation and
  * are labelled "restatement, parity unpinned": mo_depthwise_* (the reference's
  * depthwise layer is a no-op, src/mars/mars_runtime.c:1168-1170) and
  * mo_decode_anchor_grid (C stub at examples/yolo_detect.cpp:184-205; formula from

@@ -6,5 +6,5 @@ the bench: `capi` binds the library with ctypes (same names and argument meaning
 reference's include/mars_runtime.h), `marsfile` reads/writes `.mars` files.  Nothing here
 computes: without the built CUDA library every call fails loudly.
 """
-from . import capi, marsfile  # noqa: F401
+from . import capi, marsfile, shard  # noqa: F401
 from .capi import MarsLibraryMissing, MarsModel, lib  # noqa: F401
