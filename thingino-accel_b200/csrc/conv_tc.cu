@@ -39,30 +39,43 @@
 namespace marsb200 {
 
 #define TC_MAX_TAPS 36
-#define TC_THREADS 320 /* warp 0 TMA, warp 1 MMA, warps 2..9 epilogue (two per TMEM lane quadrant) */
 #define TC_BM 128
+#define TC_EPI_WARPS 8   /* warps 0..7: epilogue, two per TMEM lane quadrant (quadrant = warp & 3) */
+#define TC_WARP_MMA 8    /* TMEM allocator + MMA issuer (one elected lane) */
+#define TC_WARP_PROD 9   /* TMA producer (lane 0); gather mode: warps 9..12 build the A tile in shared memory */
+#define TC_THREADS_TMA 320
+#define TC_THREADS_GATHER 416
+#define TC_MAX_CO 1024
 
 struct TcParams {
-    int Ci, Co, Ho, Wo, Wp;  /* Wp = row pitch of the flat pixel index */
-    int mflat;               /* Ho * Wp */
-    int n_tile, n_tiles, bk, ksteps_per_tap, ntaps, stages;
+    int Co, Ho, Wo, Wp;      /* Wp = row pitch of the flat pixel index */
+    int mflat, plane;        /* Ho * Wp, Ho * Wo */
+    int n_tile, n_tiles, m_tiles, bk, ksteps_per_tap, ntaps, stages;
     int tmem_cols;
     uint32_t idesc;
-    uint32_t b_layout;       /* UMMA LayoutType of B: 2 = SW128, 4 = SW64, 6 = SW32 */
-    int a_kmajor;            /* 0: A = NCHW planes (MN-major, SW128); 1: A = NHWC copy (K-major, swizzle = bk) */
+    uint32_t b_layout;       /* UMMA LayoutType of the K-major operands: 2 = SW128, 4 = SW64, 6 = SW32 */
+    int a_kmajor;            /* 0: A = NCHW planes (MN-major, SW128); 1: A = channel-innermost rows (K-major, swizzle = bk) */
     uint32_t a_stage_bytes, b_stage_bytes, tx_bytes;
     int a_shift[TC_MAX_TAPS];
-    int a_cbase[TC_MAX_TAPS];
     const int32_t *bias;     /* device pointer or null */
     float cs;
-    int post_relu;
+    const uint32_t *lutw;    /* 512-entry word table: index = sign << 8 | magnitude, byte k = value of output stream k */
     uint8_t *out_base;       /* slot 0 of the launch */
     unsigned long long slot_stride;
-    long long out_y, out_s, out_z; /* slot-relative byte offsets, -1 = not stored */
-    const uint8_t *lut_s, *lut_z;  /* 256-byte tables or null */
-    int img0;                /* first image (TMA coordinate of the slot dimension) */
-    int vec_store;           /* tile rows are consecutive, 16-byte aligned output pixels */
-    int m_tiles, tiles_per_cta;
+    long long out_off[3];    /* slot-relative byte offset of output stream k (NCHW), -1 = not stored */
+    /* optional channel-innermost side output: the padded / phase-split copy the consuming kxk conv reads */
+    int nhwc_sel;            /* -1 = none, else the table byte to write */
+    int nhwc_mode, nhwc_Wp, nhwc_plane, nhwc_pt, nhwc_pl, nhwc_C;
+    uint8_t *nhwc_base;
+    unsigned long long nhwc_stride;
+    int img0, n_img;         /* first image (TMA coordinate of the slot dimension), images of this launch */
+    /* gather mode: A rows are built from a private NCHW copy of the input (small Ci, e.g. the 6x6 stride-2 stem) */
+    const uint8_t *g_src;
+    unsigned long long g_stride;
+    int gC, gH, gW, gS, gpt, gpl, gKH, gKW, gKt;
+    int tw_shift, tiles_x;   /* M tile = (1 << tw_shift) x (128 >> tw_shift) output pixels */
+    int gPH, gPWW, gdx;      /* patch rows per channel, 4-byte words per patch row, byte column of tap x = 0 */
+    int g_align2;
 };
 
 /* ---- PTX wrappers ------------------------------------------------------------- */
@@ -72,6 +85,9 @@ __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
 }
 __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     asm volatile(
@@ -99,18 +115,6 @@ __device__ __forceinline__ void umma_i8(uint32_t tmem_d, uint64_t desc_a, uint64
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n"
-        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
-          "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
-          "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
-          "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
-        : "r"(taddr));
-    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-}
-
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
     asm volatile(
         "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];\n"
@@ -127,65 +131,228 @@ __device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo_bytes
            ((uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32) | ((uint64_t)1 << 46) | ((uint64_t)layout << 61);
 }
 
-/* reference src/mars/mxu_conv.c:663-666 with the x86 cvttss2si rule: NaN and |v| >= 2^31 become
- * INT_MIN, which then clamps to -128 (cvt.rzi.sat alone would give +127 / 0) */
-__device__ __forceinline__ int requant_i8(int32_t acc, float cs) {
-    const float scaled = __fmul_rn(__int2float_rn(acc), cs);
-    const float biased = __fadd_rn(scaled, copysignf(0.5f, scaled)); /* scaled >= 0 ? +0.5 : -0.5; -0.0f cannot occur (int * positive or any cs: sign of zero only matters when scaled == 0, where +-0.5 both truncate to 0) */
-    int r;
-    asm("cvt.rzi.sat.s8.f32 %0, %1;" : "=r"(r) : "f"(biased)); /* truncate + clamp to [-128,127]; NaN -> 0 */
-    return (biased < 2147483648.0f) ? r : -128;
+/* ---- requantisation ------------------------------------------------------------
+ * reference src/mars/mxu_conv.c:663-666: r = (int32)(sc + (sc >= 0 ? 0.5f : -0.5f)), sc = (float)acc * cs, clamped to
+ * int8, with the x86 cvttss2si rule (NaN and |v| >= 2^31 become INT_MIN, hence -128).  Both variants return the index
+ * sign << 8 | min(|r|, 128) into the per-op word table, which holds the clamped int8 and its fused followers.
+ *
+ * FAST (chosen per layer on the host when max|acc| < 2^22 and |cs| < 512, so |sc| < 2^31 and nothing overflows):
+ * no int<->float conversion instructions (they issue at a quarter of the FP32 rate):
+ *   (float)acc = as_float(acc + 0x4B400000) - 1.5*2^23          exact for |acc| < 2^22
+ *   |r| = floor(|sc| + 0.5f) = low bits of RZ(min(|sc| + 0.5f, 128) + 2^23)   (|sc| + 0.5f rounds exactly like sc +- 0.5f)
+ * `t` arrives with the magic constant already folded into the bias. */
+template <bool FAST>
+__device__ __forceinline__ uint32_t requant_index(int32_t t, float cs) {
+    if (FAST) {
+        const float f = __fsub_rn(__int_as_float(t), 12582912.0f);
+        const float sc = __fmul_rn(f, cs);
+        const float m = fminf(__fadd_rn(fabsf(sc), 0.5f), 128.0f);
+        const float u = __fadd_rz(m, 8388608.0f);
+        return (__float_as_uint(u) - 0x4B000000u) | ((__float_as_uint(sc) >> 23) & 0x100u);
+    } else {
+        const float scaled = __fmul_rn(__int2float_rn(t), cs);
+        const float biased = __fadd_rn(scaled, copysignf(0.5f, scaled)); /* scaled == +-0: both signs truncate to 0 */
+        int r;
+        asm("cvt.rzi.sat.s8.f32 %0, %1;" : "=r"(r) : "f"(biased)); /* truncate + clamp to [-128,127]; NaN -> 0 */
+        if (!(biased < 2147483648.0f)) r = -128;                    /* x86: +overflow and NaN -> INT_MIN -> -128 */
+        return r >= 0 ? (uint32_t)r : (0x100u | (uint32_t)(-r));
+    }
 }
 
-/* ---- the kernel -------------------------------------------------------------- */
-__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+/* ---- epilogue of one unit: 16 accumulator columns (output channels) of this thread's pixel -----------------
+ * NST = number of NCHW output streams stored (table bytes 0..NST-1), NHWC = also pack the `sel8/8`-th table byte of
+ * the 16 channels into one 16-byte store of the consumer's channel-innermost copy.  o0..o2 point at channel c0 of
+ * this pixel; nch = how many of the 16 channels exist (16 = all, <= 0 = none / pixel outside the image). */
+template <bool FAST, int NST, bool NHWC>
+__device__ __forceinline__ void epilogue_unit(const uint32_t (&v)[16], const int32_t *cm, const uint32_t *lutw, float cs,
+                                              uint8_t *o0, uint8_t *o1, uint8_t *o2, long long plane, int nch, uint8_t *nh,
+                                              int sel8) {
+    if (nch <= 0) return;
+    uint32_t pk[4] = {0u, 0u, 0u, 0u};
+    const int4 *cmv = reinterpret_cast<const int4 *>(cm);
+    if (nch >= 16) {
+#pragma unroll
+        for (int j4 = 0; j4 < 4; j4++) {
+            const int4 c4 = cmv[j4];
+            const int cc[4] = {c4.x, c4.y, c4.z, c4.w};
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                const uint32_t w = lutw[requant_index<FAST>((int32_t)(v[j4 * 4 + k] + (uint32_t)cc[k]), cs)];
+                if (NST > 0) { *o0 = (uint8_t)w; o0 += plane; }
+                if (NST > 1) { *o1 = (uint8_t)(w >> 8); o1 += plane; }
+                if (NST > 2) { *o2 = (uint8_t)(w >> 16); o2 += plane; }
+                if (NHWC) pk[j4] |= ((w >> sel8) & 0xFFu) << (8 * k);
+            }
+        }
+    } else { /* ragged last unit (e.g. 255 head channels) */
+#pragma unroll
+        for (int j = 0; j < 16; j++) {
+            const uint32_t w = lutw[requant_index<FAST>((int32_t)(v[j] + (uint32_t)cm[j]), cs)];
+            if (j < nch) {
+                if (NST > 0) o0[(long long)j * plane] = (uint8_t)w;
+                if (NST > 1) o1[(long long)j * plane] = (uint8_t)(w >> 8);
+                if (NST > 2) o2[(long long)j * plane] = (uint8_t)(w >> 16);
+            }
+            if (NHWC) pk[j >> 2] |= ((w >> sel8) & 0xFFu) << (8 * (j & 3));
+        }
+    }
+    if (NHWC) *reinterpret_cast<uint4 *>(nh) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
 }
 
-/* Each CTA walks `tiles_per_cta` consecutive 128-pixel tiles of one (image, N tile): the TMA ring,
- * the barriers and the TMEM allocation are set up once, and the accumulator is double buffered in
- * TMEM so the epilogue of tile t overlaps the MMAs of tile t+1. */
-__global__ void __launch_bounds__(TC_THREADS, 2)
+/* ---- the kernel ----------------------------------------------------------------
+ * Persistent: CTA b walks tiles b, b + gridDim.x, ... of the launch's (image, M tile, N tile) space; barriers, TMEM
+ * and tables are set up once.  The accumulator is double buffered in TMEM, so the epilogue of tile t overlaps the
+ * loads and MMAs of tile t+1.  Epilogue warps never synchronise with each other: thread = output pixel (TMEM lane),
+ * registers = 16 output channels; per channel the 32 lanes of a warp store 32 consecutive pixels of one NCHW plane.
+ * GATHER (small Ci, e.g. the 6x6 stride-2 stem): M tiles are tw x th output pixels; four producer warps stage the
+ * input patch of the tile in shared memory (next tile's patch is in flight in registers meanwhile) and build the
+ * 128-byte K rows of the A operand from it, in the 128B-swizzled K-major layout TMA would have produced. */
+template <bool FAST, bool GATHER, int NST, bool NHWC>
+__global__ void __launch_bounds__(GATHER ? TC_THREADS_GATHER : TC_THREADS_TMA, 2)
 k_conv_tc(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, const TcParams p) {
     extern __shared__ uint8_t smem_raw[];
-    __shared__ __align__(8) uint64_t bar_full[8], bar_empty[8], bar_tmem_full[2], bar_tmem_empty[2];
+    __shared__ __align__(8) uint64_t bar_full[8], bar_empty[8], bar_tmem_full[2], bar_tmem_empty[2], bar_b;
     __shared__ uint32_t tmem_base_slot;
-    __shared__ __align__(16) int32_t s_bias[256];
-    __shared__ uint8_t s_lut[512];
+    __shared__ __align__(16) int32_t s_cm[TC_MAX_CO];   /* bias (+ the int->float magic when FAST) */
+    __shared__ __align__(16) uint32_t s_lutw[512];
+    __shared__ __align__(16) int s_koff[GATHER ? 128 : 4]; /* gather: patch-relative byte offset of tap k */
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int n_blk = blockIdx.y, img = blockIdx.z;
-    const int tile0 = blockIdx.x * p.tiles_per_cta;
-    const int ntiles = min(p.tiles_per_cta, p.m_tiles - tile0);
-    const int n0 = n_blk * p.n_tile;
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    uint8_t *smem_al = smem_raw + (smem_base - smem_u32(smem_raw));
     const uint32_t a_base = smem_base, b_base = smem_base + p.stages * p.a_stage_bytes;
-    uint8_t *stage_out = smem_raw + (smem_base - smem_u32(smem_raw)) + p.stages * (p.a_stage_bytes + p.b_stage_bytes);
     const int nsteps = p.ntaps * p.ksteps_per_tap;
+    const long long tiles_per_img = (long long)p.m_tiles * p.n_tiles;
+    const long long total = tiles_per_img * p.n_img;
+    /* gather-mode shared regions behind the weight tile */
+    uint8_t *g_patch = smem_al + (size_t)p.stages * p.a_stage_bytes + p.b_stage_bytes;
+    int *g_poff = reinterpret_cast<int *>(g_patch + 4096); /* per patch word: offset inside the input copy */
+    int *g_pyx = g_poff + 1024;                            /* per patch word: patch row << 16 | byte column */
 
     if (threadIdx.x == 0) {
-        for (int s = 0; s < p.stages; s++) { mbar_init(smem_u32(&bar_full[s]), 1); mbar_init(smem_u32(&bar_empty[s]), 1); }
-        for (int b = 0; b < 2; b++) { mbar_init(smem_u32(&bar_tmem_full[b]), 1); mbar_init(smem_u32(&bar_tmem_empty[b]), 8); }
+        for (int s = 0; s < p.stages; s++) { mbar_init(smem_u32(&bar_full[s]), GATHER ? 4 : 1); mbar_init(smem_u32(&bar_empty[s]), 1); }
+        for (int b = 0; b < 2; b++) { mbar_init(smem_u32(&bar_tmem_full[b]), 1); mbar_init(smem_u32(&bar_tmem_empty[b]), TC_EPI_WARPS); }
+        mbar_init(smem_u32(&bar_b), 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (warp == 1) { /* TMEM allocation is a warp-wide operation; this warp also frees it */
+    if (warp == TC_WARP_MMA) { /* TMEM allocation is a warp-wide operation; this warp also frees it */
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_slot)), "r"((uint32_t)p.tmem_cols) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
-    for (int i = threadIdx.x; i < 256; i += blockDim.x) s_bias[i] = (p.bias && i < p.n_tile && n0 + i < p.Co) ? p.bias[n0 + i] : 0;
-    if (p.lut_s) for (int i = threadIdx.x; i < 256; i += blockDim.x) s_lut[i] = p.lut_s[i];
-    if (p.lut_z) for (int i = threadIdx.x; i < 256; i += blockDim.x) s_lut[256 + i] = p.lut_z[i];
+    for (int i = threadIdx.x; i < TC_MAX_CO; i += blockDim.x)
+        s_cm[i] = (int32_t)((uint32_t)((p.bias && i < p.Co) ? p.bias[i] : 0) + (FAST ? 0x4B400000u : 0u));
+    for (int i = threadIdx.x; i < 512; i += blockDim.x) s_lutw[i] = p.lutw[i];
+    if (GATHER) {
+        const int PP = p.gPWW * 4;
+        for (int k = threadIdx.x; k < 128; k += blockDim.x) {
+            const int ci = k / (p.gKH * p.gKW), r = k - ci * p.gKH * p.gKW, y = r / p.gKW, x = r - y * p.gKW;
+            s_koff[k] = k < p.gKt ? (ci * p.gPH + y) * PP + x + p.gdx : 0;
+        }
+        for (int i = threadIdx.x; i < p.gC * p.gPH * p.gPWW; i += blockDim.x) {
+            const int ci = i / (p.gPH * p.gPWW), r = i - ci * p.gPH * p.gPWW, py = r / p.gPWW, wi = r - py * p.gPWW;
+            g_poff[i] = (ci * p.gH + py) * p.gW + 4 * wi;
+            g_pyx[i] = (py << 16) | (4 * wi);
+        }
+    }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem_d = tmem_base_slot;
 
-    if (warp == 0) {
-        if (lane == 0) { /* ===== TMA producer ===== */
+    if (warp < TC_EPI_WARPS) {
+        /* ===== epilogue: TMEM -> registers -> requant index -> word table -> stores ===== */
+        const int quad = warp & 3, half = warp >> 2;
+        const int r = quad * 32 + lane; /* accumulator row = pixel of the tile */
+        const int n_units = p.n_tile >> 4;
+        const long long plane = p.plane;
+        const float cs = p.cs;
+        const int sel8 = p.nhwc_sel * 8;
+        int tl = 0;
+        for (long long tile = blockIdx.x; tile < total; tile += gridDim.x, tl++) {
+            const int img = (int)(tile / tiles_per_img);
+            const int rem = (int)(tile - (long long)img * tiles_per_img);
+            const int mt = rem / p.n_tiles, n_blk = rem - mt * p.n_tiles;
+            const int buf = tl & 1, n0 = n_blk * p.n_tile;
+            int oh, ow;
+            bool valid;
+            if (GATHER) {
+                const int ty = mt / p.tiles_x, tx = mt - ty * p.tiles_x;
+                oh = ty * (TC_BM >> p.tw_shift) + (r >> p.tw_shift);
+                ow = (tx << p.tw_shift) + (r & ((1 << p.tw_shift) - 1));
+                valid = oh < p.Ho && ow < p.Wo;
+            } else {
+                const int q = mt * TC_BM + r;
+                oh = q / p.Wp; ow = q - oh * p.Wp;
+                valid = q < p.mflat && ow < p.Wo;
+            }
+            uint8_t *pix_base = p.out_base + (unsigned long long)img * p.slot_stride + (oh * p.Wo + ow);
+            uint8_t *nh = nullptr;
+            if (NHWC) {
+                long long dp;
+                if (p.nhwc_mode == 2) {
+                    const int yy = oh + p.nhwc_pt, xx = ow + p.nhwc_pl;
+                    dp = (long long)(((yy & 1) << 1) | (xx & 1)) * p.nhwc_plane + (long long)(yy >> 1) * p.nhwc_Wp + (xx >> 1);
+                } else dp = (long long)oh * p.nhwc_Wp + ow + p.nhwc_pl;
+                nh = p.nhwc_base + (unsigned long long)img * p.nhwc_stride + dp * p.nhwc_C;
+            }
+            mbar_wait(smem_u32(&bar_tmem_full[buf]), (tl >> 1) & 1);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const uint32_t acc = tmem_d + ((uint32_t)(quad * 32) << 16) + (uint32_t)(buf * p.n_tile);
+            if (half >= n_units) { /* nothing to read for this warp: release the accumulator at once */
+                __syncwarp();
+                if (lane == 0) mbar_arrive(smem_u32(&bar_tmem_empty[buf]));
+            }
+            for (int u = half; u < n_units; u += 2) {
+                uint32_t v[16];
+                tmem_ld16(acc + (uint32_t)(u * 16), v);
+                if (u + 2 >= n_units) { /* last read of this accumulator by this warp: hand it back */
+                    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(smem_u32(&bar_tmem_empty[buf]));
+                }
+                const int c0 = n0 + u * 16;
+                const long long coff = (long long)c0 * plane;
+                epilogue_unit<FAST, NST, NHWC>(v, s_cm + c0, s_lutw, cs, pix_base + p.out_off[0] + coff, pix_base + p.out_off[1] + coff,
+                                               pix_base + p.out_off[2] + coff, plane, valid ? p.Co - c0 : 0, nh + c0, sel8);
+            }
+        }
+    } else if (warp == TC_WARP_MMA) {
+        if (lane == 0) { /* ===== MMA issuer ===== */
+            const uint32_t k_sbo = 8u * (uint32_t)p.bk;
+            if (GATHER) mbar_wait(smem_u32(&bar_b), 0);
+            int it = 0, tl = 0;
+            for (long long tile = blockIdx.x; tile < total; tile += gridDim.x, tl++) {
+                const int buf = tl & 1;
+                mbar_wait(smem_u32(&bar_tmem_empty[buf]), ((tl >> 1) & 1) ^ 1); /* epilogue drained this accumulator */
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const uint32_t acc = tmem_d + (uint32_t)(buf * p.n_tile);
+                for (int i = 0; i < nsteps; i++, it++) {
+                    const int s = it % p.stages, ph = (it / p.stages) & 1;
+                    mbar_wait(smem_u32(&bar_full[s]), ph);
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    const uint32_t a_addr = a_base + s * p.a_stage_bytes, b_addr = GATHER ? b_base : b_base + s * p.b_stage_bytes;
+                    for (int j = 0; j < p.bk / 32; j++) {
+                        /* A MN-major, 128B swizzle: 32 K-rows of 128 bytes = 4 atoms of 8 rows, 1024 B apart;
+                         * K-major operands: rows of bk bytes, 8-row groups 8*bk apart, advance 32 B per MMA */
+                        const uint64_t da = p.a_kmajor ? umma_desc(a_addr + j * 32u, 16u, k_sbo, p.b_layout)
+                                                       : umma_desc(a_addr + j * 4096u, 0, 1024u, 2u);
+                        const uint64_t db = umma_desc(b_addr + j * 32u, 16u, k_sbo, p.b_layout);
+                        umma_i8(acc, da, db, p.idesc, (uint32_t)((i | j) != 0));
+                    }
+                    umma_commit(smem_u32(&bar_empty[s])); /* frees the stage when these MMAs retire */
+                }
+                umma_commit(smem_u32(&bar_tmem_full[buf]));
+            }
+        }
+    } else if (!GATHER) {
+        if (warp == TC_WARP_PROD && lane == 0) { /* ===== TMA producer ===== */
             const uint32_t tx = p.tx_bytes;
             int it = 0;
-            for (int tl = 0; tl < ntiles; tl++) {
-                const int q0 = (tile0 + tl) * TC_BM;
+            for (long long tile = blockIdx.x; tile < total; tile += gridDim.x) {
+                const int img = (int)(tile / tiles_per_img);
+                const int rem = (int)(tile - (long long)img * tiles_per_img);
+                const int mt = rem / p.n_tiles, n0 = (rem - mt * p.n_tiles) * p.n_tile;
+                const int q0 = mt * TC_BM;
                 for (int i = 0; i < nsteps; i++, it++) {
                     const int s = it % p.stages, ph = (it / p.stages) & 1;
                     const int tap = i / p.ksteps_per_tap, kb = i - tap * p.ksteps_per_tap;
@@ -198,116 +365,81 @@ k_conv_tc(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUte
                 }
             }
         }
-    } else if (warp == 1) {
-        if (lane == 0) { /* ===== MMA issuer ===== */
-            const uint32_t b_sbo = 8u * (uint32_t)p.bk;
-            int it = 0;
-            for (int tl = 0; tl < ntiles; tl++) {
-                const int buf = tl & 1;
-                mbar_wait(smem_u32(&bar_tmem_empty[buf]), ((tl >> 1) & 1) ^ 1); /* epilogue drained this accumulator */
-                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                const uint32_t acc = tmem_d + (uint32_t)(buf * p.n_tile);
-                for (int i = 0; i < nsteps; i++, it++) {
-                    const int s = it % p.stages, ph = (it / p.stages) & 1;
-                    mbar_wait(smem_u32(&bar_full[s]), ph);
-                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                    const uint32_t a_addr = a_base + s * p.a_stage_bytes, b_addr = b_base + s * p.b_stage_bytes;
-                    for (int j = 0; j < p.bk / 32; j++) {
-                        /* A MN-major, 128B swizzle: 32 K-rows of 128 bytes = 4 atoms of 8 rows, 1024 B apart;
-                         * A K-major: same layout rules as B */
-                        const uint64_t da = p.a_kmajor ? umma_desc(a_addr + j * 32u, 16u, b_sbo, p.b_layout)
-                                                       : umma_desc(a_addr + j * 4096u, 0, 1024u, 2u);
-                        /* B: K-major, swizzle = bk bytes: rows of bk bytes, 8-row groups 8*bk apart; advance 32 B per MMA */
-                        const uint64_t db = umma_desc(b_addr + j * 32u, 16u, b_sbo, p.b_layout);
-                        umma_i8(acc, da, db, p.idesc, (uint32_t)((i | j) != 0));
-                    }
-                    umma_commit(smem_u32(&bar_empty[s])); /* frees the stage when these MMAs retire */
-                }
-                umma_commit(smem_u32(&bar_tmem_full[buf]));
-            }
+    } else {
+        /* ===== gather producer: 128 threads, one A row (output pixel) each ===== */
+        if (warp == TC_WARP_PROD && lane == 0) { /* the whole weight matrix once */
+            mbar_expect_tx(smem_u32(&bar_b), (uint32_t)(p.n_tile * 128));
+            tma_load_3d(b_base, &mapB, smem_u32(&bar_b), 0, 0, 0);
         }
-    } else { /* ===== epilogue: TMEM -> registers -> requant (+ SiLU tables) -> NCHW stores ===== */
-        /* Two warps share each TMEM lane quadrant and split the accumulator columns in units of 16.
-         * Valid tile rows (pad columns of the flat pixel index skipped) are CONSECUTIVE output pixels,
-         * so each unit is transposed through shared memory -- staged at its final 16-byte phase --
-         * and stored as 16-byte vectors along the pixel axis, bytes only at the ragged ends. */
-        const int ew = warp - 2, grp = ew >> 2, quad = warp & 3;
-        const int r = quad * 32 + lane;       /* accumulator row = pixel of the tile */
-        const int et = (ew & 3) * 32 + lane;  /* 0..127 inside the group */
-        const int plane = p.Ho * p.Wo;
-        uint8_t *img_base = p.out_base + (unsigned long long)img * p.slot_stride;
-        uint8_t *stg = stage_out + grp * (3 * 16 * 144);
-        const long long outs[3] = {p.out_y, p.out_s, p.out_z};
-        const int n_units = p.n_tile >> 4;
-        const uint32_t bar_id = 1 + grp;
-        for (int tl = 0; tl < ntiles; tl++) {
-            const int buf = tl & 1;
-            const int q0 = (tile0 + tl) * TC_BM;
-            const int q = q0 + r;
-            const int oh = q / p.Wp, ow = q - oh * p.Wp;
-            const bool valid = q < p.mflat && ow < p.Wo;
-            /* output pixel index of flat q = number of valid flat indices before it */
-            const int oh0 = q0 / p.Wp, ow0 = q0 - oh0 * p.Wp;
-            const int pix_first = oh0 * p.Wo + min(ow0, p.Wo);
-            const int qe = min(q0 + TC_BM, p.mflat), ohe = qe / p.Wp, owe = qe - ohe * p.Wp;
-            const int pix_end = ohe * p.Wo + min(owe, p.Wo);
-            const int mis = p.vec_store ? (pix_first & 15) : 0;
-            const int sidx = oh * p.Wo + ow - pix_first + mis; /* staging column of this row */
-            const int len = pix_end - pix_first;
-            mbar_wait(smem_u32(&bar_tmem_full[buf]), (tl >> 1) & 1);
-            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            const uint32_t acc = tmem_d + ((uint32_t)(quad * 32) << 16) + (uint32_t)(buf * p.n_tile);
-            if (grp >= n_units) { /* nothing to read for this group: release the accumulator at once */
-                __syncwarp();
-                if (lane == 0) mbar_arrive(smem_u32(&bar_tmem_empty[buf]));
-            }
-            for (int u = grp; u < n_units; u += 2) {
-                uint32_t v[16];
-                tmem_ld16(acc + (uint32_t)(u * 16), v);
-                if (u + 2 >= n_units) { /* last read of this accumulator by this warp: hand it back */
-                    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(smem_u32(&bar_tmem_empty[buf]));
+        const int pr = (warp - TC_WARP_PROD) * 32 + lane;
+        const int PP = p.gPWW * 4, nwords = p.gC * p.gPH * p.gPWW;
+        const int th = TC_BM >> p.tw_shift;
+        const int tb = ((pr >> p.tw_shift) * p.gS) * PP + (pr & ((1 << p.tw_shift) - 1)) * p.gS; /* this pixel's origin in the patch */
+        const int kwords = (p.gKt + 3) >> 2;
+        uint32_t pre[8];
+        auto prefetch = [&](long long tile) {
+            const int img = (int)(tile / tiles_per_img);
+            const int mt = (int)(tile - (long long)img * tiles_per_img); /* n_tiles == 1 in gather mode */
+            const int ty = mt / p.tiles_x, tx = mt - ty * p.tiles_x;
+            const int y0 = ty * th * p.gS - p.gpt, xs = (tx << p.tw_shift) * p.gS - p.gpl - p.gdx;
+            const uint8_t *src = p.g_src + (unsigned long long)img * p.g_stride + ((long long)y0 * p.gW + xs);
+#pragma unroll
+            for (int i = 0; i < 8; i++) {
+                const int wi = pr + 128 * i;
+                pre[i] = 0u;
+                if (wi < nwords) {
+                    const int yx = g_pyx[wi], y = y0 + (yx >> 16), x = xs + (yx & 0xFFFF);
+                    if ((unsigned)y < (unsigned)p.gH && (unsigned)x < (unsigned)p.gW) pre[i] = *reinterpret_cast<const uint32_t *>(src + g_poff[wi]);
                 }
-                if (valid) {
-                    const int4 *bv = reinterpret_cast<const int4 *>(s_bias + u * 16);
+            }
+        };
+        int it = 0;
+        if ((long long)blockIdx.x < total) prefetch(blockIdx.x);
+        for (long long tile = blockIdx.x; tile < total; tile += gridDim.x, it++) {
+            const int s = it % p.stages, ph = (it / p.stages) & 1;
+            asm volatile("bar.sync 2, 128;" ::: "memory"); /* the previous tile's rows have been built: the patch may be replaced */
 #pragma unroll
-                    for (int j4 = 0; j4 < 4; j4++) {
-                        const int4 b4 = bv[j4];
-                        const int bb[4] = {b4.x, b4.y, b4.z, b4.w};
+            for (int i = 0; i < 8; i++)
+                if (pr + 128 * i < nwords) reinterpret_cast<uint32_t *>(g_patch)[pr + 128 * i] = pre[i];
+            asm volatile("bar.sync 2, 128;" ::: "memory");
+            if (tile + gridDim.x < total) prefetch(tile + gridDim.x); /* in flight while this tile's rows are built */
+            mbar_wait(smem_u32(&bar_empty[s]), ph ^ 1);
+            uint8_t *row = smem_al + (size_t)s * p.a_stage_bytes + pr * 128;
+            const uint8_t *pb = g_patch + tb;
+            for (int c = 0; c < 8; c++) {
+                uint32_t wds[4] = {0u, 0u, 0u, 0u};
+                if (c * 4 < kwords) {
+                    if (p.g_align2) { /* taps come in aligned byte pairs (even stride, even kernel width): 2-byte loads */
 #pragma unroll
-                        for (int k = 0; k < 4; k++) {
-                            const int j = j4 * 4 + k;
-                            int y = requant_i8((int32_t)(v[j] + (uint32_t)bb[k]), p.cs);
-                            if (p.post_relu) y = max(y, 0);
-                            if (p.out_y >= 0) stg[j * 144 + sidx] = (uint8_t)y;
-                            if (p.out_s >= 0) stg[16 * 144 + j * 144 + sidx] = s_lut[y + 128];
-                            if (p.out_z >= 0) stg[32 * 144 + j * 144 + sidx] = s_lut[256 + y + 128];
+                        for (int g = 0; g < 4; g++) {
+                            const int4 o4 = reinterpret_cast<const int4 *>(s_koff)[c * 4 + g];
+                            if (c * 4 + g < kwords) {
+                                const uint32_t lo = *reinterpret_cast<const uint16_t *>(pb + o4.x);
+                                const uint32_t hi = (c * 16 + g * 4 + 2 < p.gKt) ? *reinterpret_cast<const uint16_t *>(pb + o4.z) : 0u;
+                                wds[g] = lo | (hi << 16);
+                            }
+                        }
+                    } else {
+#pragma unroll
+                        for (int g = 0; g < 4; g++) {
+                            const int4 o4 = reinterpret_cast<const int4 *>(s_koff)[c * 4 + g];
+                            const int off[4] = {o4.x, o4.y, o4.z, o4.w};
+#pragma unroll
+                            for (int b = 0; b < 4; b++)
+                                if (c * 16 + g * 4 + b < p.gKt) wds[g] |= (uint32_t)pb[off[b]] << (8 * b);
                         }
                     }
                 }
-                asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
-#pragma unroll
-                for (int t = 0; t < 3; t++) {
-                    if (outs[t] < 0) continue;
-                    for (int slot = et; slot < 16 * 9; slot += 128) {
-                        const int jl = slot / 9, ch = slot - jl * 9;
-                        const int co = n0 + u * 16 + jl;
-                        const int lo = max(ch * 16, mis), hi = min(ch * 16 + 16, mis + len);
-                        if (co >= p.Co || lo >= hi) continue;
-                        const uint8_t *src = stg + t * (16 * 144) + jl * 144;
-                        uint8_t *dst = img_base + outs[t] + (long long)co * plane + (pix_first - mis);
-                        if (p.vec_store && hi - lo == 16) *reinterpret_cast<uint4 *>(dst + ch * 16) = *reinterpret_cast<const uint4 *>(src + ch * 16);
-                        else for (int b2 = lo; b2 < hi; b2++) dst[b2] = src[b2];
-                    }
-                }
-                asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
+                *reinterpret_cast<uint4 *>(row + ((c ^ (pr & 7)) << 4)) = make_uint4(wds[0], wds[1], wds[2], wds[3]);
             }
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); /* generic-proxy writes -> visible to the MMA's async proxy */
+            __syncwarp();
+            if (lane == 0) mbar_arrive(smem_u32(&bar_full[s]));
         }
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
-    if (warp == 1) {
+    if (warp == TC_WARP_MMA) {
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "r"((uint32_t)p.tmem_cols) : "memory");
     }
@@ -352,37 +484,6 @@ __global__ void __launch_bounds__(256) k_to_nhwc(const uint8_t *src_base, unsign
         if (pix < npix && c < C) dst[(long long)pix * C + c] = tile[tx][ty + 8 * k];
     }
 }
-/* ---- pre-pass for small-Ci convs (the 6x6 stride-2 stem, Ci = 3): explicit im2col ------
- * dst[q][k], q = oh*Wo + ow, k = (ci*KH + y)*KW + x (the OIHW row order, so the weights need no
- * permutation), zero for k >= Kt and for taps outside the input.  One thread writes 4 k's. */
-__global__ void __launch_bounds__(256) k_im2col(const uint8_t *src_base, unsigned long long src_stride, uint8_t *dst_base,
-                                                unsigned long long dst_stride, int C, int H, int W, int Ho, int Wo, int KH, int KW,
-                                                int S, int pt, int pl, int Kt, int Kp) {
-    __shared__ int s_off[256]; /* per k: packed (ci, y, x) */
-    for (int k = threadIdx.x; k < Kp; k += blockDim.x) {
-        int ci = k / (KH * KW), r = k - ci * KH * KW, y = r / KW, x = r - y * KW;
-        s_off[k] = k < Kt ? (ci << 16) | (y << 8) | x : -1;
-    }
-    __syncthreads();
-    const uint8_t *src = src_base + (unsigned long long)blockIdx.z * src_stride;
-    uint8_t *dst = dst_base + (unsigned long long)blockIdx.z * dst_stride;
-    const int words = Kp >> 2;
-    const long long total = (long long)Ho * Wo * words;
-    for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
-        const int q = (int)(t / words), wk = (int)(t - (long long)q * words);
-        const int oh = q / Wo, ow = q - oh * Wo;
-        uint32_t word = 0;
-#pragma unroll
-        for (int b = 0; b < 4; b++) {
-            const int code = s_off[wk * 4 + b];
-            if (code >= 0) {
-                const int ci = code >> 16, ih = oh * S - pt + ((code >> 8) & 0xFF), iw = ow * S - pl + (code & 0xFF);
-                if (ih >= 0 && ih < H && iw >= 0 && iw < W) word |= (uint32_t)src[((long long)ci * H + ih) * W + iw] << (8 * b);
-            }
-        }
-        reinterpret_cast<uint32_t *>(dst)[t] = word;
-    }
-}
 /* OIHW rows (Kt bytes) -> [Co_pad][Kp], zero padded */
 __global__ void k_repack_rows(const int8_t *w, int8_t *dst, int Co, int Co_pad, int Kt, int Kp) {
     long long total = (long long)Co_pad * Kp;
@@ -403,17 +504,23 @@ __global__ void k_repack_weights(const int8_t *w, int8_t *dst, int Co, int Co_pa
 }
 
 /* ---- host side ------------------------------------------------------------------ */
+typedef void (*TcKernel)(const CUtensorMap, const CUtensorMap, const TcParams);
 struct TcPlanImpl {
     CUtensorMap mapA, mapB;
     TcParams p;
     int prepass = 0;
-    int C = 0, H = 0, W = 0, pt = 0, pl = 0, plane = 0, npix = 0, Kp = 0, KH = 0, KW = 0, S = 1, Ho = 0, Wo = 0;
+    bool fast = false;
+    int C = 0, H = 0, W = 0, pt = 0, pl = 0, plane = 0, npix = 0;
     const uint8_t *src_slot0 = nullptr; /* input tensor in slot 0 */
     uint8_t *scratch = nullptr;
     size_t scratch_stride = 0, slot_stride = 0;
-    int8_t *d_wr = nullptr;
-    int m_tiles = 0;
+    int8_t *d_wr = nullptr;     /* repacked weights */
+    uint32_t *d_lutw = nullptr; /* epilogue word table */
+    int nst = 0;                /* NCHW streams stored */
+    int stream_byte[3] = {-1, -1, -1}; /* table byte of stream Z / S / Y (plain conv: Y is stream 0), -1 = not in the table */
+    TcKernel kernel = nullptr;
     size_t smem = 0;
+    int ctas_per_sm = 2;
 };
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
@@ -452,15 +559,15 @@ static bool make_map3(CUtensorMap *m, void *base, uint64_t d0, uint64_t d1, uint
     return true;
 }
 
-
 static int round_up(int x, int a) { return (x + a - 1) / a * a; }
 
 /* geometry shared by tc_scratch_need and tc_plan */
 struct TcGeom {
     bool ok = false;
     int prepass = 0; /* 0: A from the arena (1x1); 1: NHWC copy, rows padded (stride 1); 2: NHWC 2x2 phase split (stride 2);
-                        3: explicit im2col rows of Kp bytes (small Ci) */
+                        3: gather -- A rows built in shared memory from a private NCHW copy of the input (small Ci) */
     int Wp = 0, plane = 0, npix = 0, ntaps = 0, Kp = 0;
+    int tw_shift = 0, PH = 0, PWW = 0, dx = 0; /* gather: M tile shape and input patch geometry */
     size_t scratch_bytes = 0;
 };
 static TcGeom tc_geometry(const Op &o) {
@@ -468,12 +575,26 @@ static TcGeom tc_geometry(const Op &o) {
     if (o.kind != OP_CONV_I8_NCHW || o.mode != EXEC_PARALLEL || o.xlat) return g;
     if (o.oc < 16 || o.sh != o.sw || o.sh < 1 || o.kh < 1 || o.kw < 1) return g;
     if (o.oh <= 0 || o.ow <= 0 || o.ih <= 0 || o.iw <= 0 || o.ic <= 0) return g;
+    if (round_up(o.oc, 16) > TC_MAX_CO) return g;
     if (o.ic < 32 || o.ic % 32 || o.kh != o.kw) {
-        /* small / odd channel counts: im2col rows, if one row stays small */
+        /* small / odd channel counts: one 128-byte K row per pixel, built in shared memory from a staged input patch */
         const int Kt = o.ic * o.kh * o.kw;
-        if (Kt > 256 || o.kh > 255 || o.kw > 255 || (long long)o.oh * o.ow < 4096) return g;
-        g.prepass = 3; g.Kp = round_up(Kt, 32); g.ntaps = 1; g.Wp = o.ow; g.npix = o.oh * o.ow;
-        g.scratch_bytes = (size_t)g.npix * g.Kp;
+        if (Kt > 128 || o.kh > 255 || o.kw > 255 || (long long)o.oh * o.ow < 4096 || round_up(o.oc, 16) > 256) return g;
+        if (o.iw % 4 || o.pl < 0 || o.pt < 0) return g;
+        /* M tile = tw x (128/tw) output pixels: least padding, then the widest */
+        long long best = -1;
+        for (int sh = 7; sh >= 4; sh--) {
+            const int tw = 1 << sh, th = 128 >> sh;
+            if ((tw * o.sh) % 4) continue;
+            const int dx = ((-o.pl) % 4 + 4) % 4;
+            const int PH = (th - 1) * o.sh + o.kh, PWW = (dx + (tw - 1) * o.sw + o.kw + 3) / 4;
+            if ((long long)o.ic * PH * PWW > 1024) continue;
+            const long long padded = (long long)((o.ow + tw - 1) / tw) * tw * ((o.oh + th - 1) / th) * th;
+            if (best < 0 || padded < best) { best = padded; g.tw_shift = sh; g.PH = PH; g.PWW = PWW; g.dx = dx; }
+        }
+        if (best < 0) return g;
+        g.prepass = 3; g.Kp = 128; g.ntaps = 1; g.Wp = o.ow; g.npix = o.oh * o.ow;
+        g.scratch_bytes = (size_t)o.ic * o.ih * o.iw;
         g.ok = true;
         return g;
     }
@@ -514,7 +635,61 @@ int tc_n_tiles(int oc) {
 }
 bool tc_uses_copy(const Op &o) { return tc_geometry(o).prepass != 0; }
 
-bool tc_plan(const Op &o, const ArenaGeom &ag, const uint8_t *d_cpool, uint8_t *scratch, size_t scratch_stride, TcPlan *plan) {
+/* the word table of the epilogue: index = sign << 8 | magnitude (0..128); byte k = value of output stream k.
+ * Stream order: a fused conv stores [Z, S, Y] (Z = SiLU product, the stream almost every consumer reads, sits in the
+ * low byte), a plain conv stores [Y]. */
+static void build_lutw(const Op &o, const uint8_t *h_cpool, const int stream_byte[3], uint32_t *t) {
+    const int8_t *ls = o.lut_s >= 0 ? reinterpret_cast<const int8_t *>(h_cpool + o.lut_s) : nullptr;
+    const int8_t *lz = o.lut_z >= 0 ? reinterpret_cast<const int8_t *>(h_cpool + o.lut_z) : nullptr;
+    for (int idx = 0; idx < 512; idx++) {
+        const int mag = idx & 0xFF;
+        int y = (idx & 0x100) ? -std::min(mag, 128) : std::min(mag, 127);
+        if (o.post_relu && y < 0) y = 0;
+        /* stream values: fused conv = {Z, S, Y}, plain conv = {Y} */
+        uint8_t val[3] = {(uint8_t)y, 0, 0};
+        if (o.fused_layers > 0) { val[0] = (uint8_t)(lz ? lz[y + 128] : 0); val[1] = (uint8_t)(ls ? ls[y + 128] : 0); val[2] = (uint8_t)y; }
+        uint32_t w = 0;
+        for (int k = 0; k < 3; k++)
+            if (stream_byte[k] >= 0) w |= (uint32_t)val[k] << (8 * stream_byte[k]);
+        t[idx] = w;
+    }
+}
+
+/* may the layer use the conversion-free requantisation?  max |acc| over all output channels, from the real weights */
+static bool fast_requant_ok(const Op &o, const ArenaGeom &ag) {
+    if (!(fabsf(o.f0) < 512.0f)) return false; /* also rejects NaN */
+    const int8_t *w = reinterpret_cast<const int8_t *>(ag.h_weights + o.w);
+    const long long K = (long long)o.ic * o.kh * o.kw;
+    for (int co = 0; co < o.oc; co++) {
+        long long sum = 0;
+        for (long long k = 0; k < K; k++) sum += std::abs((int)w[co * K + k]);
+        long long b = 0;
+        if (o.bias >= 0) { int32_t bv; memcpy(&bv, ag.h_weights + o.bias + 4 * (size_t)co, 4); b = std::llabs((long long)bv); }
+        if (sum * 128 + b >= (1ll << 22)) return false;
+    }
+    return true;
+}
+
+/* kernel variants: FAST requant x GATHER producer x number of stored NCHW streams x NHWC side output */
+template <bool FAST, bool GATHER>
+static TcKernel pick_kernel2(int nst, bool nhwc) {
+    switch (nst * 2 + (nhwc ? 1 : 0)) {
+        case 0: return k_conv_tc<FAST, GATHER, 0, false>;
+        case 1: return k_conv_tc<FAST, GATHER, 0, true>;
+        case 2: return k_conv_tc<FAST, GATHER, 1, false>;
+        case 3: return k_conv_tc<FAST, GATHER, 1, true>;
+        case 4: return k_conv_tc<FAST, GATHER, 2, false>;
+        case 5: return k_conv_tc<FAST, GATHER, 2, true>;
+        case 6: return k_conv_tc<FAST, GATHER, 3, false>;
+        default: return k_conv_tc<FAST, GATHER, 3, true>;
+    }
+}
+static TcKernel pick_kernel(bool fast, bool gather, int nst, bool nhwc) {
+    if (fast) return gather ? pick_kernel2<true, true>(nst, nhwc) : pick_kernel2<true, false>(nst, nhwc);
+    return gather ? pick_kernel2<false, true>(nst, nhwc) : pick_kernel2<false, false>(nst, nhwc);
+}
+
+bool tc_plan(const Op &o, const ArenaGeom &ag, uint8_t *scratch, size_t scratch_stride, TcPlan *plan) {
     TcGeom g = tc_geometry(o);
     if (!g.ok || !encode_tiled()) return false;
     if (o.in0 < (int64_t)ag.W || o.out < (int64_t)ag.W || o.w >= (int64_t)ag.W) return false;
@@ -522,76 +697,111 @@ bool tc_plan(const Op &o, const ArenaGeom &ag, const uint8_t *d_cpool, uint8_t *
     TcPlanImpl *t = new TcPlanImpl();
     TcParams &p = t->p;
     memset(&p, 0, sizeof p);
-    const int ci_eff = g.prepass == 3 ? g.Kp : o.ic; /* K extent of one tap */
-    p.Ci = ci_eff; p.Co = o.oc; p.Ho = o.oh; p.Wo = o.ow; p.Wp = g.Wp; p.mflat = o.oh * g.Wp;
+    const bool gather = g.prepass == 3;
+    const int ci_eff = gather ? g.Kp : o.ic; /* K extent of one tap */
+    p.Co = o.oc; p.Ho = o.oh; p.Wo = o.ow; p.Wp = g.Wp; p.mflat = o.oh * g.Wp; p.plane = o.oh * o.ow;
     const int co_pad = round_up(o.oc, 16);
     p.n_tile = co_pad <= 256 ? co_pad : (co_pad % 256 == 0 ? 256 : 128);
     if (co_pad > 256 && co_pad % 128) { delete t; return false; }
     p.n_tiles = (co_pad + p.n_tile - 1) / p.n_tile;
-    p.bk = ci_eff % 64 == 0 ? 64 : 32;
+    p.bk = ci_eff % 128 == 0 ? 128 : (ci_eff % 64 == 0 ? 64 : 32);
     p.ksteps_per_tap = ci_eff / p.bk;
     p.ntaps = g.ntaps;
     p.a_stage_bytes = (uint32_t)(TC_BM * p.bk);
     p.b_stage_bytes = (uint32_t)round_up(p.n_tile * p.bk, 1024);
     p.tx_bytes = p.a_stage_bytes + (uint32_t)(p.n_tile * p.bk);
-    const int stage_bytes = (int)(p.a_stage_bytes + p.b_stage_bytes);
-    p.stages = std::max(2, std::min(8, (94 * 1024) / stage_bytes));
     p.tmem_cols = 32;
     while (p.tmem_cols < 2 * p.n_tile) p.tmem_cols <<= 1; /* two accumulators */
+    t->ctas_per_sm = p.tmem_cols > 256 ? 1 : 2;
+    const int budget = t->ctas_per_sm == 1 ? 200 * 1024 : 100 * 1024;
+    if (gather) { /* + 4 KiB patch + 8 KiB patch-word tables */
+        p.stages = std::max(2, std::min(8, (budget - (int)p.b_stage_bytes - 12288 - 1024) / (int)p.a_stage_bytes));
+        t->smem = 1024 + (size_t)p.stages * p.a_stage_bytes + p.b_stage_bytes + 12288;
+    } else {
+        const int stage_bytes = (int)(p.a_stage_bytes + p.b_stage_bytes);
+        p.stages = std::max(2, std::min(8, budget / stage_bytes));
+        t->smem = 1024 + (size_t)p.stages * stage_bytes;
+    }
+    /* keep residency at ctas_per_sm: a further CTA would fit the registers but stall in tcgen05.alloc */
+    t->smem = std::max<size_t>(t->smem, t->ctas_per_sm == 1 ? 120 * 1024 : 80 * 1024);
     /* cute/arch/mma_sm100_desc.hpp InstrDescriptor: c=S32, a=b=signed 8 bit, A MN-major, B K-major, N>>3, M>>4 */
     p.idesc = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.n_tile >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
-    p.b_layout = p.bk == 64 ? 4u : 6u;
+    p.b_layout = p.bk == 128 ? 2u : (p.bk == 64 ? 4u : 6u);
     p.a_kmajor = g.prepass != 0;
     if (!p.a_kmajor) p.idesc |= 1u << 15; /* A MN-major */
-    for (int kh = 0; kh < (g.prepass == 3 ? 1 : o.kh); kh++)
-        for (int kw = 0; kw < (g.prepass == 3 ? 1 : o.kw); kw++) {
+    for (int kh = 0; kh < (gather ? 1 : o.kh); kh++)
+        for (int kw = 0; kw < (gather ? 1 : o.kw); kw++) {
             const int tap = kh * o.kw + kw;
-            if (g.prepass == 0 || g.prepass == 3) { if (tap < TC_MAX_TAPS) p.a_shift[tap] = 0; }
+            if (g.prepass == 0 || gather) p.a_shift[tap] = 0;
             else if (g.prepass == 1) p.a_shift[tap] = (kh - o.pt) * g.Wp + kw;
             else p.a_shift[tap] = ((kh & 1) * 2 + (kw & 1)) * g.plane + (kh / 2) * g.Wp + kw / 2;
-            if (tap < TC_MAX_TAPS) p.a_cbase[tap] = 0;
         }
     p.bias = o.bias >= 0 ? reinterpret_cast<const int32_t *>(ag.d_weights + o.bias) : nullptr;
     if (o.bias >= 0 && (o.bias % 4 || o.bias + 4 * (int64_t)o.oc > (int64_t)ag.W)) { delete t; return false; }
     p.cs = o.f0;
-    p.post_relu = o.post_relu;
-    p.vec_store = (((long long)o.oh * o.ow) % 16 == 0 && (ag.slot_stride % 16) == 0) ? 1 : 0;
     p.slot_stride = ag.slot_stride;
-    p.out_y = o.store_y ? o.out - (int64_t)ag.W : -1;
-    p.out_s = o.out_s >= 0 ? o.out_s - (int64_t)ag.W : -1;
-    p.out_z = o.out_z >= 0 ? o.out_z - (int64_t)ag.W : -1;
-    p.lut_s = o.lut_s >= 0 ? d_cpool + o.lut_s : nullptr;
-    p.lut_z = o.lut_z >= 0 ? d_cpool + o.lut_z : nullptr;
+    p.m_tiles = (p.mflat + TC_BM - 1) / TC_BM;
+    if (gather) {
+        const int tw = 1 << g.tw_shift, th = TC_BM >> g.tw_shift;
+        p.tw_shift = g.tw_shift;
+        p.tiles_x = (o.ow + tw - 1) / tw;
+        p.m_tiles = p.tiles_x * ((o.oh + th - 1) / th);
+        p.gPH = g.PH; p.gPWW = g.PWW; p.gdx = g.dx;
+        p.g_align2 = (o.sh % 2 == 0 && o.kw % 2 == 0 && g.dx % 2 == 0) ? 1 : 0;
+    }
+    /* output streams: the values the op produces per element, in table-byte order (see build_lutw); the ones the
+     * planner keeps are compacted to table bytes 0..nst-1 */
+    int64_t stream_off[3] = {-1, -1, -1};
+    if (o.fused_layers > 0) {
+        stream_off[0] = o.out_z; stream_off[1] = o.out_s; stream_off[2] = o.store_y ? o.out : -1;
+    } else stream_off[0] = o.store_y ? o.out : -1;
+    t->nst = 0;
+    for (int k = 0; k < 3; k++) {
+        t->stream_byte[k] = -1;
+        p.out_off[k] = 0;
+    }
+    for (int k = 0; k < 3; k++)
+        if (stream_off[k] >= 0) { t->stream_byte[k] = t->nst; p.out_off[t->nst++] = stream_off[k] - (int64_t)ag.W; }
+    p.nhwc_sel = -1;
+    t->fast = fast_requant_ok(o, ag);
     t->prepass = g.prepass; t->C = o.ic; t->H = o.ih; t->W = o.iw; t->pt = o.pt; t->pl = o.pl;
-    t->plane = g.plane; t->npix = g.npix; t->Kp = g.Kp; t->KH = o.kh; t->KW = o.kw; t->S = o.sh; t->Ho = o.oh; t->Wo = o.ow;
+    t->plane = g.plane; t->npix = g.npix;
     t->src_slot0 = ag.d_slots + (o.in0 - (int64_t)ag.W);
     t->scratch = scratch; t->scratch_stride = scratch_stride; t->slot_stride = ag.slot_stride;
-    t->m_tiles = (p.mflat + TC_BM - 1) / TC_BM;
-    p.m_tiles = t->m_tiles;
-    t->smem = 1024 + (size_t)p.stages * stage_bytes + 2 * 3 * 16 * 144;
-    if (p.tmem_cols > 256) t->smem = std::max<size_t>(t->smem, 120 * 1024); /* one CTA per SM: it owns all of TMEM */
+    if (gather) {
+        p.g_src = scratch; p.g_stride = scratch_stride;
+        p.gC = o.ic; p.gH = o.ih; p.gW = o.iw; p.gS = o.sh; p.gpt = o.pt; p.gpl = o.pl; p.gKH = o.kh; p.gKW = o.kw;
+        p.gKt = o.ic * o.kh * o.kw;
+    }
 
-    /* weights: [tap][co_pad][Ci] K-major */
+    /* weights: [tap][co_pad][Ci] K-major, and the epilogue table */
     const size_t wr_bytes = (size_t)g.ntaps * co_pad * ci_eff;
-    if (cudaMalloc(&t->d_wr, wr_bytes) != cudaSuccess) { delete t; return false; }
-    if (g.prepass == 3)
+    uint32_t lutw[512];
+    build_lutw(o, ag.h_cpool, t->stream_byte, lutw);
+    if (cudaMalloc(&t->d_wr, wr_bytes) != cudaSuccess || cudaMalloc(&t->d_lutw, sizeof lutw) != cudaSuccess) {
+        cudaFree(t->d_wr); delete t; return false;
+    }
+    cudaMemcpy(t->d_lutw, lutw, sizeof lutw, cudaMemcpyHostToDevice);
+    p.lutw = t->d_lutw;
+    if (gather)
         k_repack_rows<<<256, 256>>>(reinterpret_cast<const int8_t *>(ag.d_weights + o.w), t->d_wr, o.oc, co_pad, o.ic * o.kh * o.kw, g.Kp);
     else
         k_repack_weights<<<256, 256>>>(reinterpret_cast<const int8_t *>(ag.d_weights + o.w), t->d_wr, o.oc, co_pad, o.ic, g.ntaps);
-    if (cudaDeviceSynchronize() != cudaSuccess) { cudaFree(t->d_wr); delete t; return false; }
+    bool ok = cudaDeviceSynchronize() == cudaSuccess;
 
-    bool ok;
-    if (g.prepass == 0)
+    const CUtensorMapSwizzle ksw = p.bk == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : (p.bk == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
+    if (ok && g.prepass == 0)
         ok = make_map3(&t->mapA, (void *)t->src_slot0, (uint64_t)o.ih * o.iw, (uint64_t)o.ic, (uint64_t)ag.capacity,
                        (uint64_t)o.ih * o.iw, ag.slot_stride, TC_BM, (uint32_t)p.bk, CU_TENSOR_MAP_SWIZZLE_128B);
-    else /* NHWC copy: dims (C, pixels, images), K-major box {bk, 128} */
+    else if (ok && !gather) /* NHWC copy: dims (C, pixels, images), K-major box {bk, 128} */
         ok = make_map3(&t->mapA, scratch, (uint64_t)ci_eff, (uint64_t)g.npix, (uint64_t)ag.capacity, (uint64_t)ci_eff,
-                       scratch_stride, (uint32_t)p.bk, TC_BM, p.bk == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
+                       scratch_stride, (uint32_t)p.bk, TC_BM, ksw);
+    else if (ok) t->mapA = CUtensorMap(); /* unused in gather mode */
     ok = ok && make_map3(&t->mapB, t->d_wr, (uint64_t)ci_eff, (uint64_t)co_pad, (uint64_t)g.ntaps, (uint64_t)ci_eff,
-                         (uint64_t)co_pad * ci_eff, (uint32_t)p.bk, (uint32_t)p.n_tile,
-                         p.bk == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
-    if (ok) ok = cudaFuncSetAttribute(k_conv_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) == cudaSuccess;
-    if (!ok) { cudaFree(t->d_wr); delete t; return false; }
+                         (uint64_t)co_pad * ci_eff, (uint32_t)p.bk, (uint32_t)p.n_tile, ksw);
+    t->kernel = pick_kernel(t->fast, gather, t->nst, false);
+    ok = ok && cudaFuncSetAttribute((const void *)t->kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 210 * 1024) == cudaSuccess;
+    if (!ok) { cudaFree(t->d_wr); cudaFree(t->d_lutw); delete t; return false; }
     plan->impl = t;
     plan->valid = true;
     return true;
@@ -603,11 +813,9 @@ bool tc_launch(const TcPlan &plan, uint8_t *slots_base, int first, int n, cudaSt
     const uint8_t *src = t->src_slot0 + (size_t)first * t->slot_stride;
     uint8_t *scr = t->scratch + (size_t)first * t->scratch_stride;
     if (t->prepass == 3) {
-        const long long total = (long long)t->npix * (t->Kp / 4);
-        dim3 g((unsigned)std::min<long long>((total + 255) / 256, 148 * 32), 1, n);
-        k_im2col<<<g, 256, 0, s>>>(src, t->slot_stride, scr, t->scratch_stride, t->C, t->H, t->W, t->Ho, t->Wo, t->KH, t->KW, t->S,
-                                   t->pt, t->pl, t->C * t->KH * t->KW, t->Kp);
-        (*launches)++;
+        /* private copy of the input tensor: the fused outputs may overwrite the input's work buffer */
+        if (cudaMemcpy2DAsync(scr, t->scratch_stride, src, t->slot_stride, (size_t)t->C * t->H * t->W, (size_t)n,
+                              cudaMemcpyDeviceToDevice, s) != cudaSuccess) return false;
     } else if (t->prepass) {
         dim3 g((t->npix + 31) / 32, (t->C + 31) / 32, n);
         k_to_nhwc<<<g, 256, 0, s>>>(src, t->slot_stride, scr, t->scratch_stride, t->C, t->H, t->W, t->p.Wp, t->plane, t->npix,
@@ -617,13 +825,13 @@ bool tc_launch(const TcPlan &plan, uint8_t *slots_base, int first, int n, cudaSt
     TcParams p = t->p;
     p.out_base = slots_base + (size_t)first * t->slot_stride;
     p.img0 = first;
-    /* enough CTAs for a few waves of 2 per SM, each amortising its setup over several tiles */
-    const long long total_tiles = (long long)t->m_tiles * p.n_tiles * n;
-    int tpc = (int)std::min<long long>(16, std::max<long long>(1, total_tiles / (148 * 2 * 4)));
-    tpc = std::min(tpc, t->m_tiles);
-    p.tiles_per_cta = tpc;
-    dim3 grid((t->m_tiles + tpc - 1) / tpc, p.n_tiles, n);
-    k_conv_tc<<<grid, TC_THREADS, t->smem, s>>>(t->mapA, t->mapB, p);
+    p.n_img = n;
+    if (t->prepass == 3) p.g_src = scr;
+    const long long total_tiles = (long long)p.m_tiles * p.n_tiles * n;
+    static int sms = 0;
+    if (!sms) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); if (sms <= 0) sms = 148; }
+    const unsigned grid = (unsigned)std::min<long long>(total_tiles, (long long)sms * t->ctas_per_sm);
+    t->kernel<<<grid, t->prepass == 3 ? TC_THREADS_GATHER : TC_THREADS_TMA, t->smem, s>>>(t->mapA, t->mapB, p);
     (*launches)++;
     return cudaGetLastError() == cudaSuccess;
 }
@@ -631,7 +839,7 @@ bool tc_launch(const TcPlan &plan, uint8_t *slots_base, int first, int n, cudaSt
 void tc_release(std::vector<TcPlan> &plans) {
     for (auto &pl : plans) {
         TcPlanImpl *t = static_cast<TcPlanImpl *>(pl.impl);
-        if (t) { cudaFree(t->d_wr); delete t; }
+        if (t) { cudaFree(t->d_wr); cudaFree(t->d_lutw); delete t; }
         pl.impl = nullptr;
         pl.valid = false;
     }

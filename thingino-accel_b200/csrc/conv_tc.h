@@ -19,6 +19,8 @@ struct ArenaGeom {
     uint8_t *d_slots;
     size_t W, slot_stride;
     int capacity;
+    const uint8_t *h_weights; /* host copy of the weight blob (requantisation bounds are computed from the real weights) */
+    const uint8_t *h_cpool;   /* host copy of the const pool (256-byte tables) */
 };
 
 struct TcPlan {
@@ -35,7 +37,7 @@ bool tc_uses_copy(const Op &o);
 /* per-image bytes of the padded / phase-split input copy the op needs (0 = reads the arena) */
 size_t tc_scratch_need(const Op &o);
 /* build the plan: tensor maps, repacked weights, epilogue description */
-bool tc_plan(const Op &o, const ArenaGeom &g, const uint8_t *d_cpool, uint8_t *scratch, size_t scratch_stride, TcPlan *plan);
+bool tc_plan(const Op &o, const ArenaGeom &g, uint8_t *scratch, size_t scratch_stride, TcPlan *plan);
 /* pre-pass (if any) + conv kernel for image slots [first, first+n) */
 bool tc_launch(const TcPlan &plan, uint8_t *slots_base, int first, int n, cudaStream_t s, uint64_t *launches);
 void tc_release(std::vector<TcPlan> &plans);

@@ -277,11 +277,11 @@ static mars_error_t compile_model(Model *m) {
         m->tc_scratch_stride = need;
         CU_OK(cudaMalloc(&m->d_tc_scratch, (size_t)m->capacity * need), MARS_ERR_ALLOC_FAILED);
     }
-    ArenaGeom g{m->d_weights, m->d_slots, m->weights_size, m->slot_stride, m->capacity};
+    ArenaGeom g{m->d_weights, m->d_slots, m->weights_size, m->slot_stride, m->capacity, m->h_arena, m->prog.const_pool.data()};
     for (size_t i = 0; i < m->prog.ops.size(); i++) {
         Op &o = m->prog.ops[i];
         if (o.impl != CONV_TC_NCHW) continue;
-        if (!tc_plan(o, g, m->d_cpool, m->d_tc_scratch, m->tc_scratch_stride, &m->tc[i])) {
+        if (!tc_plan(o, g, m->d_tc_scratch, m->tc_scratch_stride, &m->tc[i])) {
             /* a fused op cannot simply fall back (its followers were folded): recompile exact */
             fprintf(stderr, "mars_b200: tensor-core plan failed for layer %d (%s); using the direct CUDA kernels\n", o.layer, g_err);
             tc_release(m->tc);
