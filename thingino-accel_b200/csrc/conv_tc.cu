@@ -506,7 +506,8 @@ __global__ void k_repack_weights(const int8_t *w, int8_t *dst, int Co, int Co_pa
 /* ---- host side ------------------------------------------------------------------ */
 typedef void (*TcKernel)(const CUtensorMap, const CUtensorMap, const TcParams);
 struct TcPlanImpl {
-    CUtensorMap mapA, mapB;
+    CUtensorMap mapA, mapB, mapA_linked;
+    bool has_linked = false;
     TcParams p;
     int prepass = 0;
     bool fast = false;
@@ -634,6 +635,7 @@ int tc_n_tiles(int oc) {
     return (co_pad + nt - 1) / nt;
 }
 bool tc_uses_copy(const Op &o) { return tc_geometry(o).prepass != 0; }
+bool tc_linkable(const Op &o) { const TcGeom g = tc_geometry(o); return g.ok && (g.prepass == 1 || g.prepass == 2); }
 
 /* the word table of the epilogue: index = sign << 8 | magnitude (0..128); byte k = value of output stream k.
  * Stream order: a fused conv stores [Z, S, Y] (Z = SiLU product, the stream almost every consumer reads, sits in the
@@ -689,7 +691,8 @@ static TcKernel pick_kernel(bool fast, bool gather, int nst, bool nhwc) {
     return gather ? pick_kernel2<false, true>(nst, nhwc) : pick_kernel2<false, false>(nst, nhwc);
 }
 
-bool tc_plan(const Op &o, const ArenaGeom &ag, uint8_t *scratch, size_t scratch_stride, TcPlan *plan) {
+bool tc_plan(const Op &o, const ArenaGeom &ag, uint8_t *scratch, size_t scratch_stride, uint8_t *linked, size_t linked_stride,
+             const Op *consumer, TcPlan *plan) {
     TcGeom g = tc_geometry(o);
     if (!g.ok || !encode_tiled()) return false;
     if (o.in0 < (int64_t)ag.W || o.out < (int64_t)ag.W || o.w >= (int64_t)ag.W) return false;
@@ -753,7 +756,7 @@ bool tc_plan(const Op &o, const ArenaGeom &ag, uint8_t *scratch, size_t scratch_
      * planner keeps are compacted to table bytes 0..nst-1 */
     int64_t stream_off[3] = {-1, -1, -1};
     if (o.fused_layers > 0) {
-        stream_off[0] = o.out_z; stream_off[1] = o.out_s; stream_off[2] = o.store_y ? o.out : -1;
+        stream_off[0] = o.store_z ? o.out_z : -1; stream_off[1] = o.out_s; stream_off[2] = o.store_y ? o.out : -1;
     } else stream_off[0] = o.store_y ? o.out : -1;
     t->nst = 0;
     for (int k = 0; k < 3; k++) {
@@ -763,6 +766,17 @@ bool tc_plan(const Op &o, const ArenaGeom &ag, uint8_t *scratch, size_t scratch_
     for (int k = 0; k < 3; k++)
         if (stream_off[k] >= 0) { t->stream_byte[k] = t->nst; p.out_off[t->nst++] = stream_off[k] - (int64_t)ag.W; }
     p.nhwc_sel = -1;
+    if (consumer && linked) { /* this op's epilogue also writes the consumer's channel-innermost input copy */
+        const TcGeom cg = tc_geometry(*consumer);
+        const int sidx = o.fused_layers > 0 ? o.nhwc_stream : 0; /* stream index in {Z,S,Y} order; a plain conv only has Y = 0 */
+        if (!cg.ok || (cg.prepass != 1 && cg.prepass != 2) || sidx < 0 || sidx > 2 || consumer->ic != o.oc) { delete t; return false; }
+        if (t->stream_byte[sidx] < 0) t->stream_byte[sidx] = t->nst; /* not stored in the arena: next free table byte (nst <= 2 then) */
+        p.nhwc_sel = t->stream_byte[sidx];
+        p.nhwc_mode = cg.prepass; p.nhwc_Wp = cg.Wp; p.nhwc_plane = cg.plane; p.nhwc_pt = consumer->pt; p.nhwc_pl = consumer->pl;
+        p.nhwc_C = consumer->ic;
+        p.nhwc_base = linked + consumer->copy_off;
+        p.nhwc_stride = linked_stride;
+    }
     t->fast = fast_requant_ok(o, ag);
     t->prepass = g.prepass; t->C = o.ic; t->H = o.ih; t->W = o.iw; t->pt = o.pt; t->pl = o.pl;
     t->plane = g.plane; t->npix = g.npix;
@@ -797,9 +811,14 @@ bool tc_plan(const Op &o, const ArenaGeom &ag, uint8_t *scratch, size_t scratch_
         ok = make_map3(&t->mapA, scratch, (uint64_t)ci_eff, (uint64_t)g.npix, (uint64_t)ag.capacity, (uint64_t)ci_eff,
                        scratch_stride, (uint32_t)p.bk, TC_BM, ksw);
     else if (ok) t->mapA = CUtensorMap(); /* unused in gather mode */
+    if (ok && o.copy_from >= 0 && linked && !gather && g.prepass != 0) {
+        ok = make_map3(&t->mapA_linked, linked + o.copy_off, (uint64_t)ci_eff, (uint64_t)g.npix, (uint64_t)ag.capacity, (uint64_t)ci_eff,
+                       linked_stride, (uint32_t)p.bk, TC_BM, ksw);
+        t->has_linked = ok;
+    }
     ok = ok && make_map3(&t->mapB, t->d_wr, (uint64_t)ci_eff, (uint64_t)co_pad, (uint64_t)g.ntaps, (uint64_t)ci_eff,
                          (uint64_t)co_pad * ci_eff, (uint32_t)p.bk, (uint32_t)p.n_tile, ksw);
-    t->kernel = pick_kernel(t->fast, gather, t->nst, false);
+    t->kernel = pick_kernel(t->fast, gather, t->nst, p.nhwc_sel >= 0);
     ok = ok && cudaFuncSetAttribute((const void *)t->kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 210 * 1024) == cudaSuccess;
     if (!ok) { cudaFree(t->d_wr); cudaFree(t->d_lutw); delete t; return false; }
     plan->impl = t;
@@ -807,7 +826,7 @@ bool tc_plan(const Op &o, const ArenaGeom &ag, uint8_t *scratch, size_t scratch_
     return true;
 }
 
-bool tc_launch(const TcPlan &plan, uint8_t *slots_base, int first, int n, cudaStream_t s, uint64_t *launches) {
+bool tc_launch(const TcPlan &plan, uint8_t *slots_base, int first, int n, bool use_linked, cudaStream_t s, uint64_t *launches) {
     TcPlanImpl *t = static_cast<TcPlanImpl *>(plan.impl);
     if (!t) return false;
     const uint8_t *src = t->src_slot0 + (size_t)first * t->slot_stride;
@@ -816,7 +835,7 @@ bool tc_launch(const TcPlan &plan, uint8_t *slots_base, int first, int n, cudaSt
         /* private copy of the input tensor: the fused outputs may overwrite the input's work buffer */
         if (cudaMemcpy2DAsync(scr, t->scratch_stride, src, t->slot_stride, (size_t)t->C * t->H * t->W, (size_t)n,
                               cudaMemcpyDeviceToDevice, s) != cudaSuccess) return false;
-    } else if (t->prepass) {
+    } else if (t->prepass && !(use_linked && t->has_linked)) {
         dim3 g((t->npix + 31) / 32, (t->C + 31) / 32, n);
         k_to_nhwc<<<g, 256, 0, s>>>(src, t->slot_stride, scr, t->scratch_stride, t->C, t->H, t->W, t->p.Wp, t->plane, t->npix,
                                     t->prepass == 2, t->pt, t->pl);
@@ -827,11 +846,12 @@ bool tc_launch(const TcPlan &plan, uint8_t *slots_base, int first, int n, cudaSt
     p.img0 = first;
     p.n_img = n;
     if (t->prepass == 3) p.g_src = scr;
+    if (p.nhwc_sel >= 0) p.nhwc_base += (size_t)first * p.nhwc_stride;
     const long long total_tiles = (long long)p.m_tiles * p.n_tiles * n;
     static int sms = 0;
     if (!sms) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); if (sms <= 0) sms = 148; }
     const unsigned grid = (unsigned)std::min<long long>(total_tiles, (long long)sms * t->ctas_per_sm);
-    t->kernel<<<grid, t->prepass == 3 ? TC_THREADS_GATHER : TC_THREADS_TMA, t->smem, s>>>(t->mapA, t->mapB, p);
+    t->kernel<<<grid, t->prepass == 3 ? TC_THREADS_GATHER : TC_THREADS_TMA, t->smem, s>>>((use_linked && t->has_linked) ? t->mapA_linked : t->mapA, t->mapB, p);
     (*launches)++;
     return cudaGetLastError() == cudaSuccess;
 }

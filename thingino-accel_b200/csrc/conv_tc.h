@@ -34,12 +34,18 @@ bool tc_supported(const Op &o);
 int tc_n_tiles(int oc);
 /* does the kernel read its activations from a private copy (pre-pass) rather than the arena? */
 bool tc_uses_copy(const Op &o);
+/* is that copy the padded / phase-split channel-innermost layout a producing conv's epilogue can write directly? */
+bool tc_linkable(const Op &o);
 /* per-image bytes of the padded / phase-split input copy the op needs (0 = reads the arena) */
 size_t tc_scratch_need(const Op &o);
 /* build the plan: tensor maps, repacked weights, epilogue description */
-bool tc_plan(const Op &o, const ArenaGeom &g, uint8_t *scratch, size_t scratch_stride, TcPlan *plan);
+/* linked / linked_stride: the per-image area of producer-written copies (Op::copy_off, Program::linked_bytes);
+ * consumer: the op whose input copy this op's epilogue writes (Op::nhwc_consumer), or null */
+bool tc_plan(const Op &o, const ArenaGeom &g, uint8_t *scratch, size_t scratch_stride, uint8_t *linked, size_t linked_stride,
+             const Op *consumer, TcPlan *plan);
 /* pre-pass (if any) + conv kernel for image slots [first, first+n) */
-bool tc_launch(const TcPlan &plan, uint8_t *slots_base, int first, int n, cudaStream_t s, uint64_t *launches);
+/* use_linked: read the producer-written copy (full passes) instead of running the layout pre-pass on the arena tensor */
+bool tc_launch(const TcPlan &plan, uint8_t *slots_base, int first, int n, bool use_linked, cudaStream_t s, uint64_t *launches);
 void tc_release(std::vector<TcPlan> &plans);
 
 } // namespace marsb200

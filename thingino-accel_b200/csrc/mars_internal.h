@@ -84,9 +84,15 @@ struct Op {
     /* conv with the following SIGMOID and MUL layers folded into its epilogue: y = conv output
      * byte, S = lut_s[y] stored at out_s, Z = lut_z[y] stored at out_z; store_y=false when a
      * later stage of the same chain overwrites Y's bytes anyway */
-    bool store_y = true;
+    bool store_y = true, store_z = true;
     int64_t out_s = -1, out_z = -1;
     int lut_s = -1, lut_z = -1;
+    /* producer -> consumer link: a kxk tensor-core conv reads a channel-innermost, zero-padded copy of
+     * its input; when that input is exactly one output stream of an earlier tensor-core conv, the producer's
+     * epilogue writes the copy itself (nhwc_consumer / nhwc_stream: 0 = Z, 1 = S, 2 = Y) and the consumer skips its
+     * own layout pre-pass (copy_from = producer op, copy_off = byte offset of its region in the per-image link area) */
+    int copy_from = -1, nhwc_consumer = -1, nhwc_stream = -1;
+    int64_t copy_off = 0;
     /* write/read extents for hazard analysis and bounds checks */
     int64_t wlo = 0, whi = 0;
     std::string note;
@@ -96,6 +102,7 @@ struct Program {
     std::vector<Op> ops;
     std::vector<uint8_t> const_pool; /* 256-byte tables, uploaded once */
     size_t scratch_bytes = 0;        /* per-image scratch for EXEC_OC_PASSES_SCRATCH */
+    size_t linked_bytes = 0;         /* per-image bytes of producer-written conv input copies */
 };
 
 /* device-side view of the arena; passed by value to kernels */

@@ -555,6 +555,50 @@ static void fuse_silu(Program *p, int64_t W) {
     }
 }
 
+
+/* ---- opt_level >= 2: producer-written channel-innermost copies for kxk tensor-core convs ------------------- */
+static bool op_writes(const Op &o, int64_t lo, int64_t hi) {
+    if (o.kind == OP_NOP || o.mode >= 1000) return false;
+    if (o.kind == OP_CONV_I8_NCHW || o.kind == OP_CONV_I8_NHWC || o.kind == OP_CONV_F32_NCHW || o.kind == OP_DW_I8) {
+        const int64_t numel = (int64_t)o.oc * o.oh * o.ow, es = o.kind == OP_CONV_F32_NCHW ? 4 : 1;
+        return overlap(o.out, o.out + numel * es, lo, hi) || (o.out_s >= 0 && overlap(o.out_s, o.out_s + numel, lo, hi)) ||
+               (o.out_z >= 0 && overlap(o.out_z, o.out_z + numel, lo, hi));
+    }
+    return overlap(o.wlo, o.whi, lo, hi);
+}
+
+static void link_nhwc_copies(Program *p) {
+    std::vector<Op> &ops = p->ops;
+    size_t total = 0;
+    for (size_t j = 0; j < ops.size(); j++) {
+        Op &c = ops[j];
+        if (c.impl != CONV_TC_NCHW || !tc_linkable(c)) continue;
+        const int64_t numel = (int64_t)c.ic * c.ih * c.iw, lo = c.in0, hi = c.in0 + numel;
+        for (size_t i = j; i-- > 0;) {
+            Op &o = ops[i];
+            if (!op_writes(o, lo, hi)) continue;
+            /* o is the last op that touches the consumer's input: link iff it is a tensor-core conv whose final value
+             * over exactly that range is one of its output streams */
+            if (o.impl != CONV_TC_NCHW || o.kind != OP_CONV_I8_NCHW || o.mode != EXEC_PARALLEL || o.nhwc_consumer >= 0) break;
+            if (o.oc != c.ic || o.oh != c.ih || o.ow != c.iw) break;
+            int stream = -1;
+            if (o.fused_layers > 0) {
+                if (o.out_z == lo) stream = 0;
+                else if (o.out_s == lo && !overlap(o.out_z, o.out_z + numel, lo, hi)) stream = 1;
+                else if (o.out == lo && o.store_y && !overlap(o.out_z, o.out_z + numel, lo, hi) &&
+                         !(o.out_s >= 0 && overlap(o.out_s, o.out_s + numel, lo, hi))) stream = 2;
+            } else if (o.out == lo) stream = 2;
+            if (stream < 0) break;
+            o.nhwc_consumer = (int)j; o.nhwc_stream = stream;
+            c.copy_from = (int)i; c.copy_off = (int64_t)total;
+            total += (tc_scratch_need(c) + 1023) & ~(size_t)1023;
+            o.note += " +copy"; c.note += " <copy";
+            break;
+        }
+    }
+    p->linked_bytes = total;
+}
+
 /* ---- opt_level >= 3: dead-store elision in fused epilogues ------------------
  * Backward liveness over byte intervals of the image slot.  A byte is live after op i when some
  * later op -- or op 0.. of the NEXT run on the same slot (work buffers are never cleared), or the
@@ -608,12 +652,12 @@ static void op_access(const Op &o, Access *a) {
     switch (o.kind) {
         case OP_CONV_I8_NCHW: case OP_CONV_I8_NHWC: case OP_CONV_F32_NCHW: case OP_DW_I8: {
             const int64_t numel = (int64_t)o.oc * o.oh * o.ow;
-            R(o.in0, (int64_t)o.ic * o.ih * o.iw * es);
+            if (o.copy_from < 0) R(o.in0, (int64_t)o.ic * o.ih * o.iw * es); /* else: reads the producer-written copy */
             R(o.w, (int64_t)o.oc * (o.kind == OP_DW_I8 ? 1 : o.ic) * o.kh * o.kw * es);
             if (o.bias >= 0) R(o.bias, 4 * (int64_t)o.oc);
             if (o.store_y) K(o.out, numel * es);
             if (o.out_s >= 0) K(o.out_s, numel);
-            if (o.out_z >= 0) K(o.out_z, numel);
+            if (o.out_z >= 0 && o.store_z) K(o.out_z, numel);
             break;
         }
         case OP_BYTE_RELU: R(o.out, (int64_t)o.n); break;
@@ -647,6 +691,7 @@ static void elide_dead_stores(Program *p, const IvSet &observed, const IvSet &ho
                 /* later stages of the chain overwrite equal ranges, so test each against what is live AFTER the op */
                 if (o.store_y && !live.hits(o.out, o.out + numel)) { o.store_y = false; o.note += " -Y"; }
                 if (o.out_s >= 0 && !live.hits(o.out_s, o.out_s + numel)) { o.out_s = -1; o.note += " -S"; }
+                if (o.out_z >= 0 && o.store_z && o.nhwc_consumer >= 0 && !live.hits(o.out_z, o.out_z + numel)) { o.store_z = false; o.note += " -Z"; }
             }
             op_access(o, &a);
             for (auto &iv : a.kills) live.sub(iv.first, iv.second);
@@ -665,6 +710,7 @@ mars_error_t compile_program(const mars_header_t &h, const mars_runtime_tensor_t
     out->ops.clear();
     out->const_pool.clear();
     out->scratch_bytes = 0;
+    out->linked_bytes = 0;
     Ctx c{h, tensors, toff, (int64_t)weights_size, (int64_t)arena_size, out};
     for (uint32_t i = 0; i < h.num_layers; i++) {
         const mars_layer_t &L = layers[i].desc;
@@ -691,6 +737,7 @@ mars_error_t compile_program(const mars_header_t &h, const mars_runtime_tensor_t
     }
     if (opt_level >= 1) select_tensor_core_convs(out);
     if (opt_level >= 2) fuse_silu(out, (int64_t)weights_size);
+    if (opt_level >= 2) link_nhwc_copies(out);
     if (opt_level >= 3) {
         IvSet observed, host_written;
         for (uint32_t i = 0; i < h.num_outputs && i < 4; i++) { /* callers may read a whole output work buffer (alloc_size) */

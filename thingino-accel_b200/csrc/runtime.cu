@@ -147,6 +147,8 @@ struct Model {
     uint8_t *d_cpool = nullptr;
     uint8_t *d_tc_scratch = nullptr; /* padded / phase-split conv inputs, one region per image slot */
     size_t tc_scratch_stride = 0;
+    uint8_t *d_linked = nullptr;     /* producer-written conv input copies (Program::linked_bytes per image), pads stay zero */
+    size_t linked_stride = 0;
     Program prog;
     int opt_level = 3, depthwise_mode = 0;
     cudaStream_t stream = nullptr, h2d_stream = nullptr, d2h_stream = nullptr;
@@ -187,7 +189,7 @@ static void model_release(Model *m) {
     if (m->stream) cudaStreamSynchronize(m->stream);
     tc_release(m->tc);
     for (auto e : m->prof_ev) cudaEventDestroy(e);
-    cudaFree(m->d_weights); cudaFree(m->d_slots); cudaFree(m->d_scratch); cudaFree(m->d_cpool); cudaFree(m->d_tc_scratch);
+    cudaFree(m->d_weights); cudaFree(m->d_slots); cudaFree(m->d_scratch); cudaFree(m->d_cpool); cudaFree(m->d_tc_scratch); cudaFree(m->d_linked);
     cudaFree(m->d_raw); cudaFree(m->d_det); cudaFree(m->d_raw_cnt); cudaFree(m->d_det_cnt); cudaFree(m->d_tab);
     if (m->h_arena) cudaFreeHost(m->h_arena);
     if (m->ev0) cudaEventDestroy(m->ev0);
@@ -243,6 +245,9 @@ static mars_error_t set_capacity(Model *m, int capacity) {
     cudaFree(m->d_tc_scratch);
     m->d_tc_scratch = nullptr;
     m->tc_scratch_stride = 0;
+    cudaFree(m->d_linked);
+    m->d_linked = nullptr;
+    m->linked_stride = 0;
     m->compiled = false;
     return MARS_OK;
 }
@@ -277,11 +282,20 @@ static mars_error_t compile_model(Model *m) {
         m->tc_scratch_stride = need;
         CU_OK(cudaMalloc(&m->d_tc_scratch, (size_t)m->capacity * need), MARS_ERR_ALLOC_FAILED);
     }
+    /* the link area is private to one compiled program: pads must be zero, so (re)allocate it zeroed every time */
+    cudaFree(m->d_linked);
+    m->d_linked = nullptr;
+    m->linked_stride = (m->prog.linked_bytes + 1023) & ~(size_t)1023;
+    if (m->linked_stride) {
+        CU_OK(cudaMalloc(&m->d_linked, (size_t)m->capacity * m->linked_stride), MARS_ERR_ALLOC_FAILED);
+        CU_OK(cudaMemset(m->d_linked, 0, (size_t)m->capacity * m->linked_stride), MARS_ERR_ALLOC_FAILED);
+    }
     ArenaGeom g{m->d_weights, m->d_slots, m->weights_size, m->slot_stride, m->capacity, m->h_arena, m->prog.const_pool.data()};
     for (size_t i = 0; i < m->prog.ops.size(); i++) {
         Op &o = m->prog.ops[i];
         if (o.impl != CONV_TC_NCHW) continue;
-        if (!tc_plan(o, g, m->d_tc_scratch, m->tc_scratch_stride, &m->tc[i])) {
+        const Op *consumer = o.nhwc_consumer >= 0 ? &m->prog.ops[o.nhwc_consumer] : nullptr;
+        if (!tc_plan(o, g, m->d_tc_scratch, m->tc_scratch_stride, m->d_linked, m->linked_stride, consumer, &m->tc[i])) {
             /* a fused op cannot simply fall back (its followers were folded): recompile exact */
             fprintf(stderr, "mars_b200: tensor-core plan failed for layer %d (%s); using the direct CUDA kernels\n", o.layer, g_err);
             tc_release(m->tc);
@@ -312,7 +326,7 @@ static KOp to_kop(const Op &o) {
 
 static inline unsigned blocks_for(uint64_t n, unsigned per) { return (unsigned)((n + per - 1) / per); }
 
-static mars_error_t launch_op(Model *m, size_t op_index, int first, int n) {
+static mars_error_t launch_op(Model *m, size_t op_index, int first, int n, bool full_pass) {
     const Op &o = m->prog.ops[op_index];
     if (o.mode >= 1000) {
         set_last_error("layer %d: %s", o.layer, o.note.c_str());
@@ -338,7 +352,7 @@ static mars_error_t launch_op(Model *m, size_t op_index, int first, int n) {
         const uint64_t P = (uint64_t)o.oh * o.ow;
         const int es = o.kind == OP_CONV_F32_NCHW ? 4 : 1;
         if (o.impl == CONV_TC_NCHW && m->tc[op_index].valid) {
-            if (!tc_launch(m->tc[op_index], m->d_slots, first, n, s, &m->launches)) return MARS_ERR_LAYER_FAILED;
+            if (!tc_launch(m->tc[op_index], m->d_slots, first, n, full_pass, s, &m->launches)) return MARS_ERR_LAYER_FAILED;
         } else if (o.mode == EXEC_PARALLEL) {
             if (o.kind == OP_CONV_I8_NCHW && !xl && fast_conv_nchw_ok(k)) {
                 launch_fast_conv_nchw(v, k, n, s);
@@ -418,7 +432,7 @@ static mars_error_t enqueue_ops(Model *m, int first, int n, int only_layer) {
     for (size_t i = 0; i < nops; i++) {
         if (only_layer >= 0 && m->prog.ops[i].layer != only_layer) continue;
         if (prof) cudaEventRecord(m->prof_ev[i], m->stream);
-        e = launch_op(m, i, first, n);
+        e = launch_op(m, i, first, n, only_layer < 0);
         if (e != MARS_OK) return e;
     }
     if (prof) {
