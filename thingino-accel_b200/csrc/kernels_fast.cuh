@@ -115,13 +115,52 @@ static inline void launch_fast_flat(const ArenaView &v, const KOp &o, int n_img,
     else k_lut16<<<g, 256, 0, s>>>(v, o);
 }
 
+/* maxpool / upsample over 4 channels per thread (reference src/mars/mars_runtime.c:934-956, :1027-1040; NHWC indexing of
+ * shape[1..3] whatever the tag): signed per-byte max with __vmaxs4, window clipped at the bottom/right edge,
+ * pads ignored, exactly like the point functions. */
+__global__ void __launch_bounds__(256) k_spatial_vec4(ArenaView v, KOp o) {
+    const Img im = make_img(v, blockIdx.y);
+    const uint32_t *in = reinterpret_cast<const uint32_t *>(im.s_minus_W + o.in0);
+    uint32_t *out = reinterpret_cast<uint32_t *>(im.s_minus_W + o.out);
+    const int c4 = o.ic >> 2;
+    const int64_t total = (int64_t)o.oh * o.ow * c4;
+    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
+        const int c = (int)(t % c4);
+        const int64_t p = t / c4;
+        const int oh = (int)(p / o.ow), ow = (int)(p - (int64_t)oh * o.ow);
+        uint32_t r;
+        if (o.kind == OP_MAXPOOL) {
+            r = 0x80808080u; /* four times -128 */
+            const int ih0 = oh * o.sh, iw0 = ow * o.sw;
+            const int ky = min(o.kh, o.ih - ih0), kx = min(o.kw, o.iw - iw0);
+            for (int y = 0; y < ky; y++) {
+                const uint32_t *row = in + ((int64_t)(ih0 + y) * o.iw + iw0) * c4 + c;
+                for (int x = 0; x < kx; x++) r = __vmaxs4(r, row[(int64_t)x * c4]);
+            }
+        } else {
+            int ih = oh / o.sh; if (ih >= o.ih) ih = o.ih - 1;
+            int iw = ow / o.sw; if (iw >= o.iw) iw = o.iw - 1;
+            r = in[((int64_t)ih * o.iw + iw) * c4 + c];
+        }
+        out[t] = r;
+    }
+}
+
 static inline bool fast_spatial_ok(const ArenaView &v, const KOp &o) {
-    if (o.mode != EXEC_PARALLEL || o.out < (int64_t)v.W || (o.kind == OP_CONCAT && o.in0 < (int64_t)v.W)) return false;
-    if (o.kind == OP_CONCAT) return o.ic == o.oc && o.n >= 64;
+    if (o.mode != EXEC_PARALLEL || o.out < (int64_t)v.W) return false;
+    if (o.kind == OP_CONCAT) return o.in0 >= (int64_t)v.W && o.ic == o.oc && o.n >= 64;
     if (o.kind == OP_CONCAT_PERIODIC) return o.coff > 0 && o.n >= 64;
+    if (o.kind == OP_MAXPOOL || o.kind == OP_UPSAMPLE)
+        return o.in0 >= (int64_t)v.W && o.ic > 0 && o.ic % 4 == 0 && ((o.in0 - (int64_t)v.W) & 3) == 0 && ((o.out - (int64_t)v.W) & 3) == 0 &&
+               o.ih > 0 && o.iw > 0 && o.sh > 0 && o.sw > 0;
     return false;
 }
 static inline void launch_fast_spatial(const ArenaView &v, const KOp &o, int n_img, cudaStream_t s) {
+    if (o.kind == OP_MAXPOOL || o.kind == OP_UPSAMPLE) {
+        dim3 g(fast_grid((uint64_t)o.oh * o.ow * (o.ic >> 2)), n_img);
+        k_spatial_vec4<<<g, 256, 0, s>>>(v, o);
+        return;
+    }
     const int periodic = o.kind == OP_CONCAT_PERIODIC;
     const int64_t dst = o.out + o.coff, src = periodic ? o.out : o.in0;
     /* slot bases are 1 KiB aligned and W-relative offsets keep their low bits: alignment of the

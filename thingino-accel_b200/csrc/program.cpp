@@ -454,6 +454,7 @@ static mars_error_t compile_concat(Ctx &c, int li, const mars_layer_t &L) {
     int OH = ot.shape[1], OW = ot.shape[2], OC = ot.shape[3];
     int coff = 0;
     uint32_t nin = L.num_inputs > 4 ? 4 : L.num_inputs;
+    const size_t first_op = c.prog->ops.size();
     for (uint32_t n = 0; n < nin; n++) {
         int ii = c.find(L.input_tensor_ids[n]);
         if (ii < 0) continue; /* :980: skipped inputs do not advance the channel offset */
@@ -484,6 +485,23 @@ static mars_error_t compile_concat(Ctx &c, int li, const mars_layer_t &L) {
             if (o.kind != OP_NOP) c.prog->ops.push_back(o);
         }
         coff += IC;
+    }
+    /* With NCHW-shaped descriptors every input is a flat copy shifted by its channel offset, and each
+     * later input overwrites all but the first bytes of the earlier ones.  Those overwritten bytes are dead inside the
+     * layer (no later input of a hazard-free copy reads the output), so the earlier copies shrink to the slivers that
+     * survive; the arena after the layer is unchanged. */
+    int64_t later_lo = -1, later_hi = -1;
+    for (size_t k = c.prog->ops.size(); k-- > first_op;) {
+        Op &o = c.prog->ops[k];
+        if (o.kind != OP_CONCAT || o.mode != EXEC_PARALLEL || o.ic != o.oc || o.xlat) break;
+        const int64_t lo = o.wlo, hi = o.wlo + (int64_t)o.n;
+        if (later_lo >= 0 && later_lo > lo && later_lo < hi && later_hi >= hi) {
+            o.n = (uint64_t)(later_lo - lo);
+            o.whi = later_lo;
+            o.note = "concat input trimmed to the bytes later inputs do not overwrite";
+        }
+        later_lo = later_lo < 0 ? lo : std::min(later_lo, lo);
+        later_hi = std::max(later_hi, hi);
     }
     return MARS_OK;
 }
