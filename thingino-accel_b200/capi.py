@@ -321,9 +321,11 @@ class MarsModel:
 
     def run_resident(self, first, n):
         self._check(lib().mars_b200_run_resident(self.m, first, n), "run_resident")
+        return float(lib().mars_b200_last_gpu_ms(self.m))
 
     def detect_resident(self, first, n, thresh=0.45):
         self._check(lib().mars_b200_detect_resident(self.m, first, n, thresh), "detect_resident")
+        return float(lib().mars_b200_last_gpu_ms(self.m))
 
     def step_resident(self, first, n, thresh=0.45, with_detect=True):
         self._check(lib().mars_b200_step_resident(self.m, first, n, thresh, 1 if with_detect else 0), "step_resident")

@@ -121,113 +121,156 @@ __device__ __forceinline__ float iou_corner(const mars_box_t &a, const mars_box_
  * Pass i of `for i: for j>i: if d[j].conf > d[i].conf swap` (reference
  * src/mars/mars_yolo_test.c:108-110) walks the strict prefix-maximum records
  * r0 = i < r1 < ... < rk of key[i..n): afterwards position r0 holds the element of rk and every
- * other record position holds the previous record's element.  The records are found
- * with a block-wide prefix-max scan, ranked with a prefix sum, and rotated in parallel, so a pass
- * costs a few barriers whatever the data looks like (a warp-serial walk degenerates to O(n^2)
- * on ascending runs).  NaN keys never compare greater, exactly as in the C loop.
- * blockDim.x = NMS_THREADS >= n.
+ * other record position holds the previous record's element (NOT a stable sort).
+ * Thread j owns position j and keeps its element in registers.  Per pass: a warp-level prefix
+ * max + one barrier gives every thread the maximum of all earlier positions, hence the records;
+ * the last record of every warp + a second barrier gives every record its predecessor, whose
+ * element it then reads from the shared copy of the array as it stood before the pass.  The shared
+ * copy is double buffered (written after the reads of a pass, read again only behind the next
+ * pass's barriers), so a pass costs two barriers whatever the data looks like.  NaN keys never
+ * compare greater, exactly as in the C loop.  blockDim.x = NMS_THREADS >= n.
  */
 #define NMS_THREADS 1024
 
-__device__ __forceinline__ void exchange_sort_block(float *key, uint16_t *idx, int n, float *wmax, int *wsum, uint16_t *pos) {
+struct NmsSortShared {
+    float key[2][MARS_MAX_DETS];
+    uint16_t idx[2][MARS_MAX_DETS];
+    float wmax[32];
+    int wlast[32];
+    int skip[2];
+};
+
+/* on return thread j < n holds the index (into the unsorted input) of sorted element j */
+__device__ __forceinline__ int exchange_sort_block(NmsSortShared &sh, float myk, int n) {
     const int j = threadIdx.x, lane = j & 31, wid = j >> 5;
     const float NEG_INF = -__int_as_float(0x7f800000);
+    int myi = j, cur = 0;
+    sh.key[0][j] = myk;
+    sh.idx[0][j] = (uint16_t)j;
+    __syncthreads();
     for (int i = 0; i + 1 < n; i++) {
-        const float ki = key[i];
-        if (ki != ki) continue; /* NaN in hand: no comparison succeeds (uniform branch) */
         const bool act = j >= i && j < n;
-        const float kj = act ? key[j] : NEG_INF;
-        float v = (kj == kj) ? kj : NEG_INF;
-        /* inclusive prefix max inside the warp */
-        float inc = v;
+        const float v = (act && myk == myk) ? myk : NEG_INF;
+        float inc = v; /* inclusive prefix max inside the warp */
 #pragma unroll
         for (int d = 1; d < 32; d <<= 1) {
-            float y = __shfl_up_sync(0xffffffffu, inc, d);
+            const float y = __shfl_up_sync(0xffffffffu, inc, d);
             if (lane >= d) inc = fmaxf(inc, y);
         }
-        if (lane == 31) wmax[wid] = inc;
+        if (lane == 31) sh.wmax[wid] = inc;
+        if (j == i) sh.skip[i & 1] = (myk != myk); /* NaN in hand: no comparison succeeds, the pass moves nothing */
         __syncthreads();
-        float before = NEG_INF; /* max over all earlier warps */
-        {
-            float t = lane < wid ? wmax[lane] : NEG_INF;
+        if (sh.skip[i & 1]) continue; /* uniform; slot i & 1 is rewritten two passes later, behind the next pass's barrier */
+        float before = (lane < wid) ? sh.wmax[lane] : NEG_INF; /* max over all earlier warps */
 #pragma unroll
-            for (int d = 16; d; d >>= 1) t = fmaxf(t, __shfl_xor_sync(0xffffffffu, t, d));
-            before = t;
-        }
+        for (int d = 16; d; d >>= 1) before = fmaxf(before, __shfl_xor_sync(0xffffffffu, before, d));
         float excl = __shfl_up_sync(0xffffffffu, inc, 1);
         excl = lane ? fmaxf(excl, before) : before;
-        const bool rec = act && (j == i || kj > excl);
+        const bool rec = act && (j == i || myk > excl);
         const unsigned m = __ballot_sync(0xffffffffu, rec);
-        if (lane == 0) wsum[wid] = __popc(m);
+        if (lane == 0) sh.wlast[wid] = m ? (wid * 32 + 31 - __clz(m)) : -1;
         __syncthreads();
-        int base = 0, total = 0;
+        /* predecessor record of each record; the first record (position i) takes the LAST record's element */
+        const int wl = sh.wlast[lane];
+        const unsigned has = __ballot_sync(0xffffffffu, wl >= 0);
+        float nk = myk;
+        int ni = myi;
+        /* every lane computes the warp-level predecessor (convergent shuffle), record lanes then select */
         {
-            int t = wsum[lane];
-            int inc_s = t;
-#pragma unroll
-            for (int d = 1; d < 32; d <<= 1) {
-                int y = __shfl_up_sync(0xffffffffu, inc_s, d);
-                if (lane >= d) inc_s += y;
+            const unsigned prevw = has & ((1u << wid) - 1u);
+            const int w = prevw ? 31 - __clz(prevw) : 31 - __clz(has | 1u);
+            const int from_prev = __shfl_sync(0xffffffffu, wl, w);
+            if (rec) {
+                const unsigned lower = m & ((1u << lane) - 1u);
+                const int src = lower ? wid * 32 + 31 - __clz(lower) : from_prev;
+                if (src != j) { nk = sh.key[cur][src]; ni = sh.idx[cur][src]; }
             }
-            total = __shfl_sync(0xffffffffu, inc_s, 31);
-            base = __shfl_sync(0xffffffffu, inc_s - t, wid);
         }
-        if (total <= 1) continue; /* d[i] already dominates the suffix: nothing moves (uniform) */
-        const int rank = base + __popc(m & ((1u << lane) - 1u));
-        if (rec) pos[rank] = (uint16_t)j;
-        __syncthreads();
-        float nk = 0.0f;
-        uint16_t ni = 0;
-        if (rec) {
-            const int src = pos[rank == 0 ? total - 1 : rank - 1];
-            nk = key[src];
-            ni = idx[src];
-        }
-        __syncthreads();
-        if (rec) { key[j] = nk; idx[j] = ni; }
-        __syncthreads();
+        myk = nk; myi = ni;
+        cur ^= 1;
+        sh.key[cur][j] = myk;
+        sh.idx[cur][j] = (uint16_t)myi;
     }
+    return myi;
 }
 
-/* dets_in/dets_out: [det_stride] per image; counts in/out per image.  blockDim.x = NMS_THREADS. */
+/* dynamic shared memory of k_nms_center */
+struct NmsShared {
+    NmsSortShared sort;
+    float x[MARS_MAX_DETS], y[MARS_MAX_DETS], w[MARS_MAX_DETS], h[MARS_MAX_DETS];
+    int cls[MARS_MAX_DETS];
+    unsigned mask[MARS_MAX_DETS][32]; /* row i, bit j: sorted element j > i has i's class and IoU(i, j) > thresh */
+    unsigned removed[32];
+    int warp_sums[32];
+};
+
+/* dets_in/dets_out: [det_stride] per image; counts in/out per image.  blockDim.x = NMS_THREADS, dynamic smem = sizeof(NmsShared).
+ * Greedy suppression (mars_yolo_test.c:113-123) as a bit matrix: all pair tests in parallel (class test first, the IoU
+ * with its two divisions only for same-class pairs), then one warp walks i ascending and ORs row i into the removed
+ * set iff i is still alive -- the same result as the sequential double loop. */
 __global__ void __launch_bounds__(NMS_THREADS) k_nms_center(const mars_det_t *dets_in, const int32_t *counts_in,
                                                             mars_det_t *dets_out, int32_t *counts_out, int det_stride,
                                                             float thresh) {
-    __shared__ float key[MARS_MAX_DETS];
-    __shared__ uint16_t idx[MARS_MAX_DETS];
-    __shared__ uint16_t pos[MARS_MAX_DETS];
-    __shared__ float wmax[32];
-    __shared__ int wsum[32];
-    __shared__ unsigned char sup[MARS_MAX_DETS];
-    __shared__ int warp_sums[32];
+    extern __shared__ __align__(16) uint8_t nms_smem[];
+    NmsShared &sh = *reinterpret_cast<NmsShared *>(nms_smem);
     const mars_det_t *in = dets_in + (size_t)blockIdx.x * det_stride;
     mars_det_t *out = dets_out + (size_t)blockIdx.x * det_stride;
     int n = counts_in[blockIdx.x];
     if (n > MARS_MAX_DETS) n = MARS_MAX_DETS;
-    const int j = threadIdx.x;
-    if (j < n) { key[j] = in[j].conf; idx[j] = (uint16_t)j; }
-    if (j < MARS_MAX_DETS) sup[j] = 0;
-    if (j < 32) wsum[j] = 0;
-    __syncthreads();
-    exchange_sort_block(key, idx, n, wmax, wsum, pos);
-    __syncthreads();
-    /* greedy suppression, i ascending (mars_yolo_test.c:113-123): thread j owns sorted element j */
+    const int j = threadIdx.x, lane = j & 31, wid = j >> 5;
+    const float NEG_INF = -__int_as_float(0x7f800000);
+    const int src = exchange_sort_block(sh.sort, j < n ? in[j].conf : NEG_INF, n);
     mars_det_t me;
-    if (j < n) me = in[idx[j]];
-    __shared__ mars_det_t cur;
-    for (int i = 0; i < n; i++) {
-        if (sup[i]) continue; /* uniform: sup[i] was settled before the previous barrier */
-        if (j == i) cur = me;
-        __syncthreads();
-        if (j > i && j < n && !sup[j] && me.cls == cur.cls && iou_center(cur, me) > thresh) sup[j] = 1;
-        __syncthreads();
+    if (j < n) {
+        me = in[src];
+        sh.x[j] = me.x; sh.y[j] = me.y; sh.w[j] = me.w; sh.h[j] = me.h; sh.cls[j] = me.cls;
     }
+    __syncthreads();
+    const int nwords = (n + 31) >> 5;
+    for (int i = wid; i < n; i += NMS_THREADS / 32) { /* one warp per row, lane = bit */
+        mars_det_t a;
+        a.x = sh.x[i]; a.y = sh.y[i]; a.w = sh.w[i]; a.h = sh.h[i]; a.conf = 0.0f; a.cls = sh.cls[i];
+        for (int w = i >> 5; w < nwords; w++) {
+            const int jj = w * 32 + lane;
+            bool s = false;
+            if (jj > i && jj < n && sh.cls[jj] == a.cls) {
+                mars_det_t b;
+                b.x = sh.x[jj]; b.y = sh.y[jj]; b.w = sh.w[jj]; b.h = sh.h[jj]; b.conf = 0.0f; b.cls = a.cls;
+                s = iou_center(a, b) > thresh;
+            }
+            const unsigned bits = __ballot_sync(0xffffffffu, s);
+            if (lane == 0) sh.mask[i][w] = bits;
+        }
+    }
+    __syncthreads();
+    if (wid == 0) {
+        unsigned removed = 0u; /* lane w: bits of elements [32w, 32w+32) */
+        for (int i = 0; i < n; i++) {
+            const unsigned row = (lane >= (i >> 5) && lane < nwords) ? sh.mask[i][lane] : 0u;
+            const unsigned word = __shfl_sync(0xffffffffu, removed, i >> 5);
+            if (!((word >> (i & 31)) & 1u)) removed |= row;
+        }
+        sh.removed[lane] = removed;
+    }
+    __syncthreads();
     /* ordered compaction */
-    const int keep = j < n && !sup[j];
+    const int keep = j < n && !((sh.removed[wid] >> lane) & 1u);
     int total;
-    const int r = block_excl_scan(keep, &total, warp_sums);
+    const int r = block_excl_scan(keep, &total, sh.warp_sums);
     if (keep) out[r] = me;
     if (j == 0) counts_out[blockIdx.x] = total;
+}
+
+static inline cudaError_t launch_nms_center(const mars_det_t *dets_in, const int32_t *counts_in, mars_det_t *dets_out,
+                                            int32_t *counts_out, int det_stride, float thresh, int n_img, cudaStream_t s) {
+    static bool attr = false;
+    if (!attr) {
+        cudaError_t e = cudaFuncSetAttribute(k_nms_center, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(NmsShared));
+        if (e != cudaSuccess) return e;
+        attr = true;
+    }
+    k_nms_center<<<n_img, NMS_THREADS, sizeof(NmsShared), s>>>(dets_in, counts_in, dets_out, counts_out, det_stride, thresh);
+    return cudaGetLastError();
 }
 
 /* corner-box variant: descending by confidence, equal confidences keep input order */

@@ -510,9 +510,8 @@ static mars_error_t enqueue_detect(Model *m, int first, int n, float thresh) {
     k_parse_output<<<n, 256, 0, m->stream>>>(data, m->slot_stride, d.shape[1], d.scale, m->d_tab,
                                             m->d_raw + (size_t)first * MARS_MAX_DETS, m->d_raw_cnt + first, 1000,
                                             MARS_MAX_DETS);
-    k_nms_center<<<n, NMS_THREADS, 0, m->stream>>>(m->d_raw + (size_t)first * MARS_MAX_DETS, m->d_raw_cnt + first,
-                                          m->d_det + (size_t)first * MARS_MAX_DETS, m->d_det_cnt + first, MARS_MAX_DETS,
-                                          thresh);
+    CU_OK(launch_nms_center(m->d_raw + (size_t)first * MARS_MAX_DETS, m->d_raw_cnt + first, m->d_det + (size_t)first * MARS_MAX_DETS,
+                            m->d_det_cnt + first, MARS_MAX_DETS, thresh, n, m->stream), MARS_ERR_LAYER_FAILED);
     m->launches += 2;
     CU_OK(cudaGetLastError(), MARS_ERR_LAYER_FAILED);
     return MARS_OK;
