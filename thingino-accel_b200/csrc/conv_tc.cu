@@ -68,6 +68,8 @@ struct TcParams {
     int nhwc_mode, nhwc_Wp, nhwc_plane, nhwc_pt, nhwc_pl, nhwc_C;
     uint8_t *nhwc_base;
     unsigned long long nhwc_stride;
+    unsigned wp_magic;       /* floor(2^32 / Wp) + 1 */
+    int b_resident;          /* all weight blocks of the (single) N tile stay in shared memory for the whole launch */
     int img0, n_img;         /* first image (TMA coordinate of the slot dimension), images of this launch */
     /* gather mode: A rows are built from a private NCHW copy of the input (small Ci, e.g. the 6x6 stride-2 stem) */
     const uint8_t *g_src;
@@ -159,6 +161,19 @@ __device__ __forceinline__ uint32_t requant_index(int32_t t, float cs) {
     }
 }
 
+/* walks the tiles b, b + G, b + 2G, ... of a launch as (image, tile inside the image) without divisions in the loop */
+struct TileIter {
+    int img, rem, tpi, step_img, step_rem;
+    __device__ __forceinline__ TileIter(int first, int G, int tiles_per_img) : tpi(tiles_per_img) {
+        img = first / tpi; rem = first - img * tpi;
+        step_img = G / tpi; step_rem = G - step_img * tpi;
+    }
+    __device__ __forceinline__ void next() {
+        img += step_img; rem += step_rem;
+        if (rem >= tpi) { rem -= tpi; img++; }
+    }
+};
+
 /* ---- epilogue of one unit: 16 accumulator columns (output channels) of this thread's pixel -----------------
  * NST = number of NCHW output streams stored (table bytes 0..NST-1), NHWC = also pack the `sel8/8`-th table byte of
  * the 16 channels into one 16-byte store of the consumer's channel-innermost copy.  o0..o2 point at channel c0 of
@@ -216,16 +231,16 @@ k_conv_tc(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUte
     __shared__ __align__(16) int32_t s_cm[TC_MAX_CO];   /* bias (+ the int->float magic when FAST) */
     __shared__ __align__(16) uint32_t s_lutw[512];
     __shared__ __align__(16) int s_koff[GATHER ? 128 : 4]; /* gather: patch-relative byte offset of tap k */
+    __shared__ int s_shift[TC_MAX_TAPS];
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     uint8_t *smem_al = smem_raw + (smem_base - smem_u32(smem_raw));
     const uint32_t a_base = smem_base, b_base = smem_base + p.stages * p.a_stage_bytes;
     const int nsteps = p.ntaps * p.ksteps_per_tap;
-    const long long tiles_per_img = (long long)p.m_tiles * p.n_tiles;
-    const long long total = tiles_per_img * p.n_img;
+    const int tiles_per_img = p.m_tiles * p.n_tiles;
     /* gather-mode shared regions behind the weight tile */
-    uint8_t *g_patch = smem_al + (size_t)p.stages * p.a_stage_bytes + p.b_stage_bytes;
+    uint8_t *g_patch = smem_al + (size_t)p.stages * p.a_stage_bytes + p.b_stage_bytes; /* gather: B is one resident block */
     int *g_poff = reinterpret_cast<int *>(g_patch + 4096); /* per patch word: offset inside the input copy */
     int *g_pyx = g_poff + 1024;                            /* per patch word: patch row << 16 | byte column */
 
@@ -242,6 +257,7 @@ k_conv_tc(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUte
     for (int i = threadIdx.x; i < TC_MAX_CO; i += blockDim.x)
         s_cm[i] = (int32_t)((uint32_t)((p.bias && i < p.Co) ? p.bias[i] : 0) + (FAST ? 0x4B400000u : 0u));
     for (int i = threadIdx.x; i < 512; i += blockDim.x) s_lutw[i] = p.lutw[i];
+    if (threadIdx.x < TC_MAX_TAPS) s_shift[threadIdx.x] = p.a_shift[threadIdx.x];
     if (GATHER) {
         const int PP = p.gPWW * 4;
         for (int k = threadIdx.x; k < 128; k += blockDim.x) {
@@ -268,10 +284,9 @@ k_conv_tc(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUte
         const float cs = p.cs;
         const int sel8 = p.nhwc_sel * 8;
         int tl = 0;
-        for (long long tile = blockIdx.x; tile < total; tile += gridDim.x, tl++) {
-            const int img = (int)(tile / tiles_per_img);
-            const int rem = (int)(tile - (long long)img * tiles_per_img);
-            const int mt = rem / p.n_tiles, n_blk = rem - mt * p.n_tiles;
+        for (TileIter ti(blockIdx.x, gridDim.x, tiles_per_img); ti.img < p.n_img; ti.next(), tl++) {
+            const int img = ti.img;
+            const int mt = p.n_tiles == 1 ? ti.rem : ti.rem / p.n_tiles, n_blk = ti.rem - mt * p.n_tiles;
             const int buf = tl & 1, n0 = n_blk * p.n_tile;
             int oh, ow;
             bool valid;
@@ -282,7 +297,7 @@ k_conv_tc(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUte
                 valid = oh < p.Ho && ow < p.Wo;
             } else {
                 const int q = mt * TC_BM + r;
-                oh = q / p.Wp; ow = q - oh * p.Wp;
+                oh = (int)__umulhi((unsigned)q, p.wp_magic); ow = q - oh * p.Wp; /* q / Wp, exact for q * Wp < 2^32 (checked on the host) */
                 valid = q < p.mflat && ow < p.Wo;
             }
             uint8_t *pix_base = p.out_base + (unsigned long long)img * p.slot_stride + (oh * p.Wo + ow);
@@ -319,18 +334,19 @@ k_conv_tc(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUte
     } else if (warp == TC_WARP_MMA) {
         if (lane == 0) { /* ===== MMA issuer ===== */
             const uint32_t k_sbo = 8u * (uint32_t)p.bk;
-            if (GATHER) mbar_wait(smem_u32(&bar_b), 0);
-            int it = 0, tl = 0;
-            for (long long tile = blockIdx.x; tile < total; tile += gridDim.x, tl++) {
+            const bool b_res = GATHER || p.b_resident;
+            if (b_res) mbar_wait(smem_u32(&bar_b), 0);
+            int s = 0, ph = 0, tl = 0;
+            for (TileIter ti(blockIdx.x, gridDim.x, tiles_per_img); ti.img < p.n_img; ti.next(), tl++) {
                 const int buf = tl & 1;
                 mbar_wait(smem_u32(&bar_tmem_empty[buf]), ((tl >> 1) & 1) ^ 1); /* epilogue drained this accumulator */
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 const uint32_t acc = tmem_d + (uint32_t)(buf * p.n_tile);
-                for (int i = 0; i < nsteps; i++, it++) {
-                    const int s = it % p.stages, ph = (it / p.stages) & 1;
+                for (int i = 0; i < nsteps; i++) {
                     mbar_wait(smem_u32(&bar_full[s]), ph);
                     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                    const uint32_t a_addr = a_base + s * p.a_stage_bytes, b_addr = GATHER ? b_base : b_base + s * p.b_stage_bytes;
+                    const uint32_t a_addr = a_base + s * p.a_stage_bytes;
+                    const uint32_t b_addr = b_res ? b_base + i * p.b_stage_bytes : b_base + s * p.b_stage_bytes;
                     for (int j = 0; j < p.bk / 32; j++) {
                         /* A MN-major, 128B swizzle: 32 K-rows of 128 bytes = 4 atoms of 8 rows, 1024 B apart;
                          * K-major operands: rows of bk bytes, 8-row groups 8*bk apart, advance 32 B per MMA */
@@ -340,28 +356,35 @@ k_conv_tc(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUte
                         umma_i8(acc, da, db, p.idesc, (uint32_t)((i | j) != 0));
                     }
                     umma_commit(smem_u32(&bar_empty[s])); /* frees the stage when these MMAs retire */
+                    if (++s == p.stages) { s = 0; ph ^= 1; }
                 }
                 umma_commit(smem_u32(&bar_tmem_full[buf]));
             }
         }
     } else if (!GATHER) {
         if (warp == TC_WARP_PROD && lane == 0) { /* ===== TMA producer ===== */
-            const uint32_t tx = p.tx_bytes;
-            int it = 0;
-            for (long long tile = blockIdx.x; tile < total; tile += gridDim.x) {
-                const int img = (int)(tile / tiles_per_img);
-                const int rem = (int)(tile - (long long)img * tiles_per_img);
-                const int mt = rem / p.n_tiles, n0 = (rem - mt * p.n_tiles) * p.n_tile;
-                const int q0 = mt * TC_BM;
-                for (int i = 0; i < nsteps; i++, it++) {
-                    const int s = it % p.stages, ph = (it / p.stages) & 1;
-                    const int tap = i / p.ksteps_per_tap, kb = i - tap * p.ksteps_per_tap;
-                    mbar_wait(smem_u32(&bar_empty[s]), ph ^ 1);
-                    const uint32_t full = smem_u32(&bar_full[s]);
-                    mbar_expect_tx(full, tx);
-                    if (p.a_kmajor) tma_load_3d(a_base + s * p.a_stage_bytes, &mapA, full, kb * p.bk, q0 + p.a_shift[tap], p.img0 + img);
-                    else tma_load_3d(a_base + s * p.a_stage_bytes, &mapA, full, q0, kb * p.bk, p.img0 + img);
-                    tma_load_3d(b_base + s * p.b_stage_bytes, &mapB, full, kb * p.bk, n0, tap);
+            if (p.b_resident) { /* the whole repacked weight matrix of this N tile set stays in shared memory */
+                mbar_expect_tx(smem_u32(&bar_b), (uint32_t)(nsteps * p.n_tile * p.bk));
+                for (int tap = 0, i = 0; tap < p.ntaps; tap++)
+                    for (int kb = 0; kb < p.ksteps_per_tap; kb++, i++)
+                        tma_load_3d(b_base + i * p.b_stage_bytes, &mapB, smem_u32(&bar_b), kb * p.bk, 0, tap);
+            }
+            const uint32_t tx = p.b_resident ? p.a_stage_bytes : p.tx_bytes;
+            int s = 0, ph = 1; /* waits on the empty barriers start with the opposite parity */
+            for (TileIter ti(blockIdx.x, gridDim.x, tiles_per_img); ti.img < p.n_img; ti.next()) {
+                const int mt = p.n_tiles == 1 ? ti.rem : ti.rem / p.n_tiles, n0 = (ti.rem - mt * p.n_tiles) * p.n_tile;
+                const int q0 = mt * TC_BM, zc = p.img0 + ti.img;
+                for (int tap = 0; tap < p.ntaps; tap++) {
+                    const int qa = q0 + s_shift[tap];
+                    for (int kb = 0; kb < p.ksteps_per_tap; kb++) {
+                        mbar_wait(smem_u32(&bar_empty[s]), ph);
+                        const uint32_t full = smem_u32(&bar_full[s]);
+                        mbar_expect_tx(full, tx);
+                        if (p.a_kmajor) tma_load_3d(a_base + s * p.a_stage_bytes, &mapA, full, kb * p.bk, qa, zc);
+                        else tma_load_3d(a_base + s * p.a_stage_bytes, &mapA, full, q0, kb * p.bk, zc);
+                        if (!p.b_resident) tma_load_3d(b_base + s * p.b_stage_bytes, &mapB, full, kb * p.bk, n0, tap);
+                        if (++s == p.stages) { s = 0; ph ^= 1; }
+                    }
                 }
             }
         }
@@ -377,9 +400,7 @@ k_conv_tc(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUte
         const int tb = ((pr >> p.tw_shift) * p.gS) * PP + (pr & ((1 << p.tw_shift) - 1)) * p.gS; /* this pixel's origin in the patch */
         const int kwords = (p.gKt + 3) >> 2;
         uint32_t pre[8];
-        auto prefetch = [&](long long tile) {
-            const int img = (int)(tile / tiles_per_img);
-            const int mt = (int)(tile - (long long)img * tiles_per_img); /* n_tiles == 1 in gather mode */
+        auto prefetch = [&](int img, int mt) { /* n_tiles == 1 in gather mode: tile inside the image = M tile */
             const int ty = mt / p.tiles_x, tx = mt - ty * p.tiles_x;
             const int y0 = ty * th * p.gS - p.gpt, xs = (tx << p.tw_shift) * p.gS - p.gpl - p.gdx;
             const uint8_t *src = p.g_src + (unsigned long long)img * p.g_stride + ((long long)y0 * p.gW + xs);
@@ -393,17 +414,18 @@ k_conv_tc(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUte
                 }
             }
         };
-        int it = 0;
-        if ((long long)blockIdx.x < total) prefetch(blockIdx.x);
-        for (long long tile = blockIdx.x; tile < total; tile += gridDim.x, it++) {
-            const int s = it % p.stages, ph = (it / p.stages) & 1;
+        int s = 0, ph = 1;
+        TileIter ti(blockIdx.x, gridDim.x, tiles_per_img);
+        if (ti.img < p.n_img) prefetch(ti.img, ti.rem);
+        for (; ti.img < p.n_img;) {
             asm volatile("bar.sync 2, 128;" ::: "memory"); /* the previous tile's rows have been built: the patch may be replaced */
 #pragma unroll
             for (int i = 0; i < 8; i++)
                 if (pr + 128 * i < nwords) reinterpret_cast<uint32_t *>(g_patch)[pr + 128 * i] = pre[i];
             asm volatile("bar.sync 2, 128;" ::: "memory");
-            if (tile + gridDim.x < total) prefetch(tile + gridDim.x); /* in flight while this tile's rows are built */
-            mbar_wait(smem_u32(&bar_empty[s]), ph ^ 1);
+            ti.next();
+            if (ti.img < p.n_img) prefetch(ti.img, ti.rem); /* in flight while this tile's rows are built */
+            mbar_wait(smem_u32(&bar_empty[s]), ph);
             uint8_t *row = smem_al + (size_t)s * p.a_stage_bytes + pr * 128;
             const uint8_t *pb = g_patch + tb;
             for (int c = 0; c < 8; c++) {
@@ -435,6 +457,7 @@ k_conv_tc(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUte
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); /* generic-proxy writes -> visible to the MMA's async proxy */
             __syncwarp();
             if (lane == 0) mbar_arrive(smem_u32(&bar_full[s]));
+            if (++s == p.stages) { s = 0; ph ^= 1; }
         }
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -717,13 +740,22 @@ bool tc_plan(const Op &o, const ArenaGeom &ag, uint8_t *scratch, size_t scratch_
     while (p.tmem_cols < 2 * p.n_tile) p.tmem_cols <<= 1; /* two accumulators */
     t->ctas_per_sm = p.tmem_cols > 256 ? 1 : 2;
     const int budget = t->ctas_per_sm == 1 ? 200 * 1024 : 100 * 1024;
+    const int nsteps = g.ntaps * p.ksteps_per_tap;
     if (gather) { /* + 4 KiB patch + 8 KiB patch-word tables */
         p.stages = std::max(2, std::min(8, (budget - (int)p.b_stage_bytes - 12288 - 1024) / (int)p.a_stage_bytes));
         t->smem = 1024 + (size_t)p.stages * p.a_stage_bytes + p.b_stage_bytes + 12288;
     } else {
-        const int stage_bytes = (int)(p.a_stage_bytes + p.b_stage_bytes);
-        p.stages = std::max(2, std::min(8, budget / stage_bytes));
-        t->smem = 1024 + (size_t)p.stages * stage_bytes;
+        /* small weight matrices stay resident in shared memory for the whole (persistent) launch: one TMA per k-step */
+        const size_t b_all = (size_t)nsteps * p.b_stage_bytes;
+        p.b_resident = (p.n_tiles == 1 && b_all <= (size_t)budget / 2) ? 1 : 0;
+        if (p.b_resident) {
+            p.stages = std::max(2, std::min(8, (budget - (int)b_all) / (int)p.a_stage_bytes));
+            t->smem = 1024 + (size_t)p.stages * p.a_stage_bytes + b_all;
+        } else {
+            const int stage_bytes = (int)(p.a_stage_bytes + p.b_stage_bytes);
+            p.stages = std::max(2, std::min(8, budget / stage_bytes));
+            t->smem = 1024 + (size_t)p.stages * stage_bytes;
+        }
     }
     /* keep residency at ctas_per_sm: a further CTA would fit the registers but stall in tcgen05.alloc */
     t->smem = std::max<size_t>(t->smem, t->ctas_per_sm == 1 ? 120 * 1024 : 80 * 1024);
@@ -744,6 +776,8 @@ bool tc_plan(const Op &o, const ArenaGeom &ag, uint8_t *scratch, size_t scratch_
     p.cs = o.f0;
     p.slot_stride = ag.slot_stride;
     p.m_tiles = (p.mflat + TC_BM - 1) / TC_BM;
+    p.wp_magic = (unsigned)((1ull << 32) / (unsigned)g.Wp) + 1u;
+    if ((unsigned long long)p.mflat * (unsigned)g.Wp >= (1ull << 32) || (long long)p.m_tiles * p.n_tiles * ag.capacity >= (1ll << 31)) { delete t; return false; }
     if (gather) {
         const int tw = 1 << g.tw_shift, th = TC_BM >> g.tw_shift;
         p.tw_shift = g.tw_shift;
