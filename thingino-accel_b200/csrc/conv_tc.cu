@@ -126,6 +126,33 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+          "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+          "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+          "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+/* wait used by warps that are not on the critical path (epilogue, gather producers): back off between polls so the
+ * spin does not take issue slots from the warps doing the work */
+__device__ __forceinline__ void mbar_wait_relaxed(uint32_t bar, uint32_t parity) {
+    for (;;) {
+        uint32_t done;
+        asm volatile(
+            "{\n\t"
+            ".reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t"
+            "}\n" : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+        if (done) break;
+        __nanosleep(64);
+    }
+}
+
 /* UMMA shared-memory matrix descriptor (cute/arch/mma_sm100_desc.hpp layout):
  * [0,14) start>>4, [16,30) LBO>>4, [32,46) SBO>>4, [46,48) version=1, [61,64) layout type */
 __device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes, uint32_t layout) {
@@ -175,43 +202,45 @@ struct TileIter {
 };
 
 /* ---- epilogue of one unit: 16 accumulator columns (output channels) of this thread's pixel -----------------
- * NST = number of NCHW output streams stored (table bytes 0..NST-1), NHWC = also pack the `sel8/8`-th table byte of
- * the 16 channels into one 16-byte store of the consumer's channel-innermost copy.  o0..o2 point at channel c0 of
+ * NST = number of NCHW output streams stored (table bytes 0..NST-1), NHWC = also pack table byte 3 of every 16
+ * channels into one 16-byte store of the consumer's channel-innermost copy.  o0..o2 point at channel c0 of
  * this pixel; nch = how many of the 16 channels exist (16 = all, <= 0 = none / pixel outside the image). */
-template <bool FAST, int NST, bool NHWC>
-__device__ __forceinline__ void epilogue_unit(const uint32_t (&v)[16], const int32_t *cm, const uint32_t *lutw, float cs,
-                                              uint8_t *o0, uint8_t *o1, uint8_t *o2, long long plane, int nch, uint8_t *nh,
-                                              int sel8) {
+template <bool FAST, int NST, bool NHWC, int W>
+__device__ __forceinline__ void epilogue_unit(const uint32_t (&v)[W], const int32_t *cm, const uint32_t *lutw, float cs,
+                                              uint8_t *o0, uint8_t *o1, uint8_t *o2, long long plane, int nch, uint8_t *nh) {
     if (nch <= 0) return;
-    uint32_t pk[4] = {0u, 0u, 0u, 0u};
     const int4 *cmv = reinterpret_cast<const int4 *>(cm);
-    if (nch >= 16) {
+    if (nch >= W) {
 #pragma unroll
-        for (int j4 = 0; j4 < 4; j4++) {
-            const int4 c4 = cmv[j4];
-            const int cc[4] = {c4.x, c4.y, c4.z, c4.w};
+        for (int j16 = 0; j16 < W / 16; j16++) {
+            uint32_t pk[4] = {0u, 0u, 0u, 0u};
 #pragma unroll
-            for (int k = 0; k < 4; k++) {
-                const uint32_t w = lutw[requant_index<FAST>((int32_t)(v[j4 * 4 + k] + (uint32_t)cc[k]), cs)];
-                if (NST > 0) { *o0 = (uint8_t)w; o0 += plane; }
-                if (NST > 1) { *o1 = (uint8_t)(w >> 8); o1 += plane; }
-                if (NST > 2) { *o2 = (uint8_t)(w >> 16); o2 += plane; }
-                if (NHWC) pk[j4] |= ((w >> sel8) & 0xFFu) << (8 * k);
+            for (int j4 = 0; j4 < 4; j4++) {
+                const int4 c4 = cmv[j16 * 4 + j4];
+                const int cc[4] = {c4.x, c4.y, c4.z, c4.w};
+#pragma unroll
+                for (int k = 0; k < 4; k++) {
+                    const uint32_t w = lutw[requant_index<FAST>((int32_t)(v[j16 * 16 + j4 * 4 + k] + (uint32_t)cc[k]), cs)];
+                    if (NST > 0) { *o0 = (uint8_t)w; o0 += plane; }
+                    if (NST > 1) { *o1 = (uint8_t)(w >> 8); o1 += plane; }
+                    if (NST > 2) { *o2 = (uint8_t)(w >> 16); o2 += plane; }
+                    /* the side-output stream sits in the top byte of the table word: one byte permute per channel */
+                    if (NHWC) pk[j4] = __byte_perm(pk[j4], w, k == 0 ? 0x3217 : (k == 1 ? 0x3270 : (k == 2 ? 0x3710 : 0x7210)));
+                }
             }
+            if (NHWC) *reinterpret_cast<uint4 *>(nh + j16 * 16) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
         }
-    } else { /* ragged last unit (e.g. 255 head channels) */
+    } else { /* ragged last unit (e.g. 255 head channels); a side-output consumer always has Ci = Co, a multiple of 32 */
 #pragma unroll
-        for (int j = 0; j < 16; j++) {
-            const uint32_t w = lutw[requant_index<FAST>((int32_t)(v[j] + (uint32_t)cm[j]), cs)];
+        for (int j = 0; j < W; j++) {
             if (j < nch) {
+                const uint32_t w = lutw[requant_index<FAST>((int32_t)(v[j] + (uint32_t)cm[j]), cs)];
                 if (NST > 0) o0[(long long)j * plane] = (uint8_t)w;
                 if (NST > 1) o1[(long long)j * plane] = (uint8_t)(w >> 8);
                 if (NST > 2) o2[(long long)j * plane] = (uint8_t)(w >> 16);
             }
-            if (NHWC) pk[j >> 2] |= ((w >> sel8) & 0xFFu) << (8 * (j & 3));
         }
     }
-    if (NHWC) *reinterpret_cast<uint4 *>(nh) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
 }
 
 /* ---- the kernel ----------------------------------------------------------------
@@ -279,10 +308,11 @@ k_conv_tc(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUte
         /* ===== epilogue: TMEM -> registers -> requant index -> word table -> stores ===== */
         const int quad = warp & 3, half = warp >> 2;
         const int r = quad * 32 + lane; /* accumulator row = pixel of the tile */
-        const int n_units = p.n_tile >> 4;
+        /* 32 accumulator columns per TMEM load where that still leaves both warps of a lane quadrant busy */
+        const bool unit32 = p.n_tile >= 64 && (p.n_tile & 31) == 0;
+        const int n_units = unit32 ? p.n_tile >> 5 : p.n_tile >> 4;
         const long long plane = p.plane;
         const float cs = p.cs;
-        const int sel8 = p.nhwc_sel * 8;
         int tl = 0;
         for (TileIter ti(blockIdx.x, gridDim.x, tiles_per_img); ti.img < p.n_img; ti.next(), tl++) {
             const int img = ti.img;
@@ -310,25 +340,41 @@ k_conv_tc(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUte
                 } else dp = (long long)oh * p.nhwc_Wp + ow + p.nhwc_pl;
                 nh = p.nhwc_base + (unsigned long long)img * p.nhwc_stride + dp * p.nhwc_C;
             }
-            mbar_wait(smem_u32(&bar_tmem_full[buf]), (tl >> 1) & 1);
+            uint8_t *b0 = pix_base + p.out_off[0], *b1 = pix_base + p.out_off[1], *b2 = pix_base + p.out_off[2];
+            const int co_left = valid ? p.Co - n0 : 0; /* channels of this N tile that exist for this pixel (<= 0: nothing to store) */
+            mbar_wait_relaxed(smem_u32(&bar_tmem_full[buf]), (tl >> 1) & 1);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             const uint32_t acc = tmem_d + ((uint32_t)(quad * 32) << 16) + (uint32_t)(buf * p.n_tile);
             if (half >= n_units) { /* nothing to read for this warp: release the accumulator at once */
                 __syncwarp();
                 if (lane == 0) mbar_arrive(smem_u32(&bar_tmem_empty[buf]));
             }
-            for (int u = half; u < n_units; u += 2) {
-                uint32_t v[16];
-                tmem_ld16(acc + (uint32_t)(u * 16), v);
-                if (u + 2 >= n_units) { /* last read of this accumulator by this warp: hand it back */
-                    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(smem_u32(&bar_tmem_empty[buf]));
+            if (unit32) {
+                for (int u = half; u < n_units; u += 2) {
+                    uint32_t v[32];
+                    tmem_ld32(acc + (uint32_t)(u * 32), v);
+                    if (u + 2 >= n_units) { /* last read of this accumulator by this warp: hand it back */
+                        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(smem_u32(&bar_tmem_empty[buf]));
+                    }
+                    const int c0 = u * 32;
+                    const long long coff = (long long)(n0 + c0) * plane;
+                    epilogue_unit<FAST, NST, NHWC, 32>(v, s_cm + n0 + c0, s_lutw, cs, b0 + coff, b1 + coff, b2 + coff, plane, co_left - c0, nh + n0 + c0);
                 }
-                const int c0 = n0 + u * 16;
-                const long long coff = (long long)c0 * plane;
-                epilogue_unit<FAST, NST, NHWC>(v, s_cm + c0, s_lutw, cs, pix_base + p.out_off[0] + coff, pix_base + p.out_off[1] + coff,
-                                               pix_base + p.out_off[2] + coff, plane, valid ? p.Co - c0 : 0, nh + c0, sel8);
+            } else {
+                for (int u = half; u < n_units; u += 2) {
+                    uint32_t v[16];
+                    tmem_ld16(acc + (uint32_t)(u * 16), v);
+                    if (u + 2 >= n_units) {
+                        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(smem_u32(&bar_tmem_empty[buf]));
+                    }
+                    const int c0 = u * 16;
+                    const long long coff = (long long)(n0 + c0) * plane;
+                    epilogue_unit<FAST, NST, NHWC, 16>(v, s_cm + n0 + c0, s_lutw, cs, b0 + coff, b1 + coff, b2 + coff, plane, co_left - c0, nh + n0 + c0);
+                }
             }
         }
     } else if (warp == TC_WARP_MMA) {
@@ -425,7 +471,7 @@ k_conv_tc(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUte
             asm volatile("bar.sync 2, 128;" ::: "memory");
             ti.next();
             if (ti.img < p.n_img) prefetch(ti.img, ti.rem); /* in flight while this tile's rows are built */
-            mbar_wait(smem_u32(&bar_empty[s]), ph);
+            mbar_wait_relaxed(smem_u32(&bar_empty[s]), ph);
             uint8_t *row = smem_al + (size_t)s * p.a_stage_bytes + pr * 128;
             const uint8_t *pb = g_patch + tb;
             for (int c = 0; c < 8; c++) {
@@ -542,6 +588,7 @@ struct TcPlanImpl {
     uint32_t *d_lutw = nullptr; /* epilogue word table */
     int nst = 0;                /* NCHW streams stored */
     int stream_byte[3] = {-1, -1, -1}; /* table byte of stream Z / S / Y (plain conv: Y is stream 0), -1 = not in the table */
+    int nhwc_stream = -1;              /* stream whose value also fills table byte 3 (side output), -1 = none */
     TcKernel kernel = nullptr;
     size_t smem = 0;
     int ctas_per_sm = 2;
@@ -663,7 +710,7 @@ bool tc_linkable(const Op &o) { const TcGeom g = tc_geometry(o); return g.ok && 
 /* the word table of the epilogue: index = sign << 8 | magnitude (0..128); byte k = value of output stream k.
  * Stream order: a fused conv stores [Z, S, Y] (Z = SiLU product, the stream almost every consumer reads, sits in the
  * low byte), a plain conv stores [Y]. */
-static void build_lutw(const Op &o, const uint8_t *h_cpool, const int stream_byte[3], uint32_t *t) {
+static void build_lutw(const Op &o, const uint8_t *h_cpool, const int stream_byte[3], int nhwc_stream, uint32_t *t) {
     const int8_t *ls = o.lut_s >= 0 ? reinterpret_cast<const int8_t *>(h_cpool + o.lut_s) : nullptr;
     const int8_t *lz = o.lut_z >= 0 ? reinterpret_cast<const int8_t *>(h_cpool + o.lut_z) : nullptr;
     for (int idx = 0; idx < 512; idx++) {
@@ -676,6 +723,7 @@ static void build_lutw(const Op &o, const uint8_t *h_cpool, const int stream_byt
         uint32_t w = 0;
         for (int k = 0; k < 3; k++)
             if (stream_byte[k] >= 0) w |= (uint32_t)val[k] << (8 * stream_byte[k]);
+        if (nhwc_stream >= 0) w |= (uint32_t)val[nhwc_stream] << 24; /* at most 3 stored streams use bytes 0..2 */
         t[idx] = w;
     }
 }
@@ -804,8 +852,8 @@ bool tc_plan(const Op &o, const ArenaGeom &ag, uint8_t *scratch, size_t scratch_
         const TcGeom cg = tc_geometry(*consumer);
         const int sidx = o.fused_layers > 0 ? o.nhwc_stream : 0; /* stream index in {Z,S,Y} order; a plain conv only has Y = 0 */
         if (!cg.ok || (cg.prepass != 1 && cg.prepass != 2) || sidx < 0 || sidx > 2 || consumer->ic != o.oc) { delete t; return false; }
-        if (t->stream_byte[sidx] < 0) t->stream_byte[sidx] = t->nst; /* not stored in the arena: next free table byte (nst <= 2 then) */
-        p.nhwc_sel = t->stream_byte[sidx];
+        t->nhwc_stream = sidx; /* its value goes into the top byte of every table word */
+        p.nhwc_sel = 3;
         p.nhwc_mode = cg.prepass; p.nhwc_Wp = cg.Wp; p.nhwc_plane = cg.plane; p.nhwc_pt = consumer->pt; p.nhwc_pl = consumer->pl;
         p.nhwc_C = consumer->ic;
         p.nhwc_base = linked + consumer->copy_off;
@@ -825,7 +873,7 @@ bool tc_plan(const Op &o, const ArenaGeom &ag, uint8_t *scratch, size_t scratch_
     /* weights: [tap][co_pad][Ci] K-major, and the epilogue table */
     const size_t wr_bytes = (size_t)g.ntaps * co_pad * ci_eff;
     uint32_t lutw[512];
-    build_lutw(o, ag.h_cpool, t->stream_byte, lutw);
+    build_lutw(o, ag.h_cpool, t->stream_byte, t->nhwc_stream, lutw);
     if (cudaMalloc(&t->d_wr, wr_bytes) != cudaSuccess || cudaMalloc(&t->d_lutw, sizeof lutw) != cudaSuccess) {
         cudaFree(t->d_wr); delete t; return false;
     }
