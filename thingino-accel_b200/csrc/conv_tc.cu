@@ -40,11 +40,8 @@ namespace marsb200 {
 
 #define TC_MAX_TAPS 36
 #define TC_BM 128
-#define TC_EPI_WARPS 8   /* warps 0..7: epilogue, two per TMEM lane quadrant (quadrant = warp & 3) */
-#define TC_WARP_MMA 8    /* TMEM allocator + MMA issuer (one elected lane) */
-#define TC_WARP_PROD 9   /* TMA producer (lane 0); gather mode: warps 9..12 build the A tile in shared memory */
-#define TC_THREADS_TMA 320
-#define TC_THREADS_GATHER 416
+/* warp roles: warps 0..EPI-1 epilogue (EPI = 8, or 16 when one CTA owns the SM; quadrant = warp & 3), warp EPI = TMEM
+ * allocator + MMA issuer (one elected lane), warp EPI+1 = TMA producer (lane 0) -- gather mode: warps EPI+1..EPI+4 */
 #define TC_MAX_CO 1024
 
 struct TcParams {
@@ -69,6 +66,7 @@ struct TcParams {
     uint8_t *nhwc_base;
     unsigned long long nhwc_stride;
     unsigned wp_magic;       /* floor(2^32 / Wp) + 1 */
+    int halo, halo_min, halo_rb, halo_nb; /* kxk stride 1: one A load per (tile, k block) covers all taps: rows q0+halo_min .., halo_nb boxes of halo_rb rows */
     int b_resident;          /* all weight blocks of the (single) N tile stay in shared memory for the whole launch */
     int img0, n_img;         /* first image (TMA coordinate of the slot dimension), images of this launch */
     /* gather mode: A rows are built from a private NCHW copy of the input (small Ci, e.g. the 6x6 stride-2 stem) */
@@ -126,6 +124,21 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
+/* split form: issue the load, and later wait for it; the wait takes the destination registers as in/out operands so
+ * that no use of them can be scheduled before it */
+__device__ __forceinline__ void tmem_ld16_issue(uint32_t taddr, uint32_t (&v)[16]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];\n"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+          "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+        : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld_wait(uint32_t (&v)[16]) {
+    asm volatile("tcgen05.wait::ld.sync.aligned;"
+                 : "+r"(v[0]), "+r"(v[1]), "+r"(v[2]), "+r"(v[3]), "+r"(v[4]), "+r"(v[5]), "+r"(v[6]), "+r"(v[7]), "+r"(v[8]),
+                   "+r"(v[9]), "+r"(v[10]), "+r"(v[11]), "+r"(v[12]), "+r"(v[13]), "+r"(v[14]), "+r"(v[15])
+                 :: "memory");
+}
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
     asm volatile(
         "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
@@ -159,7 +172,6 @@ __device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo_bytes
     return (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16) |
            ((uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32) | ((uint64_t)1 << 46) | ((uint64_t)layout << 61);
 }
-
 /* ---- requantisation ------------------------------------------------------------
  * reference src/mars/mxu_conv.c:663-666: r = (int32)(sc + (sc >= 0 ? 0.5f : -0.5f)), sc = (float)acc * cs, clamped to
  * int8, with the x86 cvttss2si rule (NaN and |v| >= 2^31 become INT_MIN, hence -128).  Both variants return the index
@@ -251,8 +263,8 @@ __device__ __forceinline__ void epilogue_unit(const uint32_t (&v)[W], const int3
  * GATHER (small Ci, e.g. the 6x6 stride-2 stem): M tiles are tw x th output pixels; four producer warps stage the
  * input patch of the tile in shared memory (next tile's patch is in flight in registers meanwhile) and build the
  * 128-byte K rows of the A operand from it, in the 128B-swizzled K-major layout TMA would have produced. */
-template <bool FAST, bool GATHER, int NST, bool NHWC>
-__global__ void __launch_bounds__(GATHER ? TC_THREADS_GATHER : TC_THREADS_TMA, 2)
+template <bool FAST, bool GATHER, int NST, bool NHWC, int EPI>
+__global__ void __launch_bounds__((EPI + (GATHER ? 5 : 2)) * 32, EPI == 8 ? 2 : 1)
 k_conv_tc(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, const TcParams p) {
     extern __shared__ uint8_t smem_raw[];
     __shared__ __align__(8) uint64_t bar_full[8], bar_empty[8], bar_tmem_full[2], bar_tmem_empty[2], bar_b;
@@ -275,11 +287,12 @@ k_conv_tc(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUte
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < p.stages; s++) { mbar_init(smem_u32(&bar_full[s]), GATHER ? 4 : 1); mbar_init(smem_u32(&bar_empty[s]), 1); }
-        for (int b = 0; b < 2; b++) { mbar_init(smem_u32(&bar_tmem_full[b]), 1); mbar_init(smem_u32(&bar_tmem_empty[b]), TC_EPI_WARPS); }
+        for (int b = 0; b < 2; b++) { mbar_init(smem_u32(&bar_tmem_full[b]), 1); mbar_init(smem_u32(&bar_tmem_empty[b]), EPI); }
         mbar_init(smem_u32(&bar_b), 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (warp == TC_WARP_MMA) { /* TMEM allocation is a warp-wide operation; this warp also frees it */
+    constexpr int WARP_MMA = EPI, WARP_PROD = EPI + 1; /* then: TMA producer (lane 0) or four gather producer warps */
+    if (warp == WARP_MMA) { /* TMEM allocation is a warp-wide operation; this warp also frees it */
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_slot)), "r"((uint32_t)p.tmem_cols) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
@@ -304,80 +317,96 @@ k_conv_tc(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUte
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem_d = tmem_base_slot;
 
-    if (warp < TC_EPI_WARPS) {
-        /* ===== epilogue: TMEM -> registers -> requant index -> word table -> stores ===== */
-        const int quad = warp & 3, half = warp >> 2;
+    if (warp < EPI) {
+        /* ===== epilogue: TMEM -> registers -> requant index -> word table -> stores =====
+         * A warp's work items are (tile, 16-column unit) pairs; the TMEM load of item k+1 is issued before item k
+         * is processed, so the load latency (and, at a tile boundary, the wait for the next accumulator) hides
+         * behind the arithmetic and the stores of the current item. */
+        const int quad = warp & 3, part = warp >> 2, parts = EPI >> 2;
         const int r = quad * 32 + lane; /* accumulator row = pixel of the tile */
-        /* 32 accumulator columns per TMEM load where that still leaves both warps of a lane quadrant busy */
-        const bool unit32 = p.n_tile >= 64 && (p.n_tile & 31) == 0;
-        const int n_units = unit32 ? p.n_tile >> 5 : p.n_tile >> 4;
+        const int n_units = p.n_tile >> 4;
         const long long plane = p.plane;
         const float cs = p.cs;
-        int tl = 0;
-        for (TileIter ti(blockIdx.x, gridDim.x, tiles_per_img); ti.img < p.n_img; ti.next(), tl++) {
-            const int img = ti.img;
-            const int mt = p.n_tiles == 1 ? ti.rem : ti.rem / p.n_tiles, n_blk = ti.rem - mt * p.n_tiles;
-            const int buf = tl & 1, n0 = n_blk * p.n_tile;
-            int oh, ow;
-            bool valid;
-            if (GATHER) {
-                const int ty = mt / p.tiles_x, tx = mt - ty * p.tiles_x;
-                oh = ty * (TC_BM >> p.tw_shift) + (r >> p.tw_shift);
-                ow = (tx << p.tw_shift) + (r & ((1 << p.tw_shift) - 1));
-                valid = oh < p.Ho && ow < p.Wo;
-            } else {
-                const int q = mt * TC_BM + r;
-                oh = (int)__umulhi((unsigned)q, p.wp_magic); ow = q - oh * p.Wp; /* q / Wp, exact for q * Wp < 2^32 (checked on the host) */
-                valid = q < p.mflat && ow < p.Wo;
-            }
-            uint8_t *pix_base = p.out_base + (unsigned long long)img * p.slot_stride + (oh * p.Wo + ow);
-            uint8_t *nh = nullptr;
-            if (NHWC) {
-                long long dp;
-                if (p.nhwc_mode == 2) {
-                    const int yy = oh + p.nhwc_pt, xx = ow + p.nhwc_pl;
-                    dp = (long long)(((yy & 1) << 1) | (xx & 1)) * p.nhwc_plane + (long long)(yy >> 1) * p.nhwc_Wp + (xx >> 1);
-                } else dp = (long long)oh * p.nhwc_Wp + ow + p.nhwc_pl;
-                nh = p.nhwc_base + (unsigned long long)img * p.nhwc_stride + dp * p.nhwc_C;
-            }
-            uint8_t *b0 = pix_base + p.out_off[0], *b1 = pix_base + p.out_off[1], *b2 = pix_base + p.out_off[2];
-            const int co_left = valid ? p.Co - n0 : 0; /* channels of this N tile that exist for this pixel (<= 0: nothing to store) */
-            mbar_wait_relaxed(smem_u32(&bar_tmem_full[buf]), (tl >> 1) & 1);
-            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            const uint32_t acc = tmem_d + ((uint32_t)(quad * 32) << 16) + (uint32_t)(buf * p.n_tile);
-            if (half >= n_units) { /* nothing to read for this warp: release the accumulator at once */
+        const uint32_t acc_lane = tmem_d + ((uint32_t)(quad * 32) << 16);
+        if (part >= n_units) { /* narrow N tile: nothing to read for this warp, it only releases the accumulators */
+            int tl = 0;
+            for (TileIter ti(blockIdx.x, gridDim.x, tiles_per_img); ti.img < p.n_img; ti.next(), tl++) {
+                mbar_wait_relaxed(smem_u32(&bar_tmem_full[tl & 1]), (tl >> 1) & 1);
                 __syncwarp();
-                if (lane == 0) mbar_arrive(smem_u32(&bar_tmem_empty[buf]));
+                if (lane == 0) mbar_arrive(smem_u32(&bar_tmem_empty[tl & 1]));
             }
-            if (unit32) {
-                for (int u = half; u < n_units; u += 2) {
-                    uint32_t v[32];
-                    tmem_ld32(acc + (uint32_t)(u * 32), v);
-                    if (u + 2 >= n_units) { /* last read of this accumulator by this warp: hand it back */
-                        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-                        __syncwarp();
-                        if (lane == 0) mbar_arrive(smem_u32(&bar_tmem_empty[buf]));
-                    }
-                    const int c0 = u * 32;
-                    const long long coff = (long long)(n0 + c0) * plane;
-                    epilogue_unit<FAST, NST, NHWC, 32>(v, s_cm + n0 + c0, s_lutw, cs, b0 + coff, b1 + coff, b2 + coff, plane, co_left - c0, nh + n0 + c0);
+        } else {
+            TileIter ti(blockIdx.x, gridDim.x, tiles_per_img); /* current item: tile ti / tl, unit u */
+            int tl = 0, u = part;
+            /* per-tile values of the current item, recomputed when the tile changes */
+            int cached_tl = -1, n0 = 0, co_left = 0;
+            uint8_t *b0 = nullptr, *b1 = nullptr, *b2 = nullptr, *nh = nullptr;
+            uint32_t va[16], vb[16];
+            bool have = ti.img < p.n_img;
+            if (have) {
+                mbar_wait_relaxed(smem_u32(&bar_tmem_full[0]), 0);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                tmem_ld16_issue(acc_lane + (uint32_t)(u * 16), va);
+            }
+            auto step = [&](uint32_t (&vc)[16], uint32_t (&vn)[16]) {
+                /* the next item of this warp */
+                TileIter nti = ti;
+                int ntl = tl, nu = u + parts;
+                if (nu >= n_units) { nu = part; ntl++; nti.next(); }
+                const bool have_n = nti.img < p.n_img;
+                tmem_ld_wait(vc);
+                if (u + parts >= n_units) { /* last read of this accumulator by this warp: hand it back */
+                    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(smem_u32(&bar_tmem_empty[tl & 1]));
                 }
-            } else {
-                for (int u = half; u < n_units; u += 2) {
-                    uint32_t v[16];
-                    tmem_ld16(acc + (uint32_t)(u * 16), v);
-                    if (u + 2 >= n_units) {
-                        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-                        __syncwarp();
-                        if (lane == 0) mbar_arrive(smem_u32(&bar_tmem_empty[buf]));
+                if (have_n) {
+                    if (ntl != tl) {
+                        mbar_wait_relaxed(smem_u32(&bar_tmem_full[ntl & 1]), (ntl >> 1) & 1);
+                        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                     }
-                    const int c0 = u * 16;
-                    const long long coff = (long long)(n0 + c0) * plane;
-                    epilogue_unit<FAST, NST, NHWC, 16>(v, s_cm + n0 + c0, s_lutw, cs, b0 + coff, b1 + coff, b2 + coff, plane, co_left - c0, nh + n0 + c0);
+                    tmem_ld16_issue(acc_lane + (uint32_t)((ntl & 1) * p.n_tile + nu * 16), vn);
                 }
+                if (cached_tl != tl) {
+                    cached_tl = tl;
+                    const int mt = p.n_tiles == 1 ? ti.rem : ti.rem / p.n_tiles;
+                    n0 = (ti.rem - mt * p.n_tiles) * p.n_tile;
+                    int oh, ow;
+                    bool valid;
+                    if (GATHER) {
+                        const int ty = mt / p.tiles_x, tx = mt - ty * p.tiles_x;
+                        oh = ty * (TC_BM >> p.tw_shift) + (r >> p.tw_shift);
+                        ow = (tx << p.tw_shift) + (r & ((1 << p.tw_shift) - 1));
+                        valid = oh < p.Ho && ow < p.Wo;
+                    } else {
+                        const int q = mt * TC_BM + r;
+                        oh = (int)__umulhi((unsigned)q, p.wp_magic); ow = q - oh * p.Wp; /* q / Wp, exact for q * Wp < 2^32 (checked on the host) */
+                        valid = q < p.mflat && ow < p.Wo;
+                    }
+                    uint8_t *pix_base = p.out_base + (unsigned long long)ti.img * p.slot_stride + (oh * p.Wo + ow) + (long long)n0 * plane;
+                    b0 = pix_base + p.out_off[0]; b1 = pix_base + p.out_off[1]; b2 = pix_base + p.out_off[2];
+                    co_left = valid ? p.Co - n0 : 0; /* channels of this N tile that exist for this pixel (<= 0: nothing to store) */
+                    if (NHWC) {
+                        long long dp;
+                        if (p.nhwc_mode == 2) {
+                            const int yy = oh + p.nhwc_pt, xx = ow + p.nhwc_pl;
+                            dp = (long long)(((yy & 1) << 1) | (xx & 1)) * p.nhwc_plane + (long long)(yy >> 1) * p.nhwc_Wp + (xx >> 1);
+                        } else dp = (long long)oh * p.nhwc_Wp + ow + p.nhwc_pl;
+                        nh = p.nhwc_base + (unsigned long long)ti.img * p.nhwc_stride + dp * p.nhwc_C + n0;
+                    }
+                }
+                const int c0 = u * 16;
+                const long long coff = (long long)c0 * plane;
+                epilogue_unit<FAST, NST, NHWC, 16>(vc, s_cm + n0 + c0, s_lutw, cs, b0 + coff, b1 + coff, b2 + coff, plane, co_left - c0, nh + c0);
+                ti = nti; tl = ntl; u = nu; have = have_n;
+            };
+            while (have) {
+                step(va, vb);
+                if (!have) break;
+                step(vb, va);
             }
         }
-    } else if (warp == TC_WARP_MMA) {
+    } else if (warp == WARP_MMA) {
         if (lane == 0) { /* ===== MMA issuer ===== */
             const uint32_t k_sbo = 8u * (uint32_t)p.bk;
             const bool b_res = GATHER || p.b_resident;
@@ -388,6 +417,25 @@ k_conv_tc(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUte
                 mbar_wait(smem_u32(&bar_tmem_empty[buf]), ((tl >> 1) & 1) ^ 1); /* epilogue drained this accumulator */
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 const uint32_t acc = tmem_d + (uint32_t)(buf * p.n_tile);
+                if (p.halo) {
+                    for (int kb = 0; kb < p.ksteps_per_tap; kb++) {
+                        mbar_wait(smem_u32(&bar_full[s]), ph);
+                        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                        const uint32_t a_stage = a_base + s * p.a_stage_bytes;
+                        for (int tap = 0; tap < p.ntaps; tap++) {
+                            /* a tap = the same rows shifted: the operand simply starts (shift) rows further down.  The swizzle
+                             * is a function of the absolute shared-memory address (measured: a start address that is not a
+                             * multiple of the 8-row atom needs NO descriptor base offset), so TMA's layout is read back as is */
+                            const uint32_t a_addr = a_stage + (uint32_t)((s_shift[tap] - p.halo_min) * p.bk);
+                            const uint32_t b_addr = b_base + (tap * p.ksteps_per_tap + kb) * p.b_stage_bytes;
+                            for (int j = 0; j < p.bk / 32; j++)
+                                umma_i8(acc, umma_desc(a_addr + j * 32u, 16u, k_sbo, p.b_layout), umma_desc(b_addr + j * 32u, 16u, k_sbo, p.b_layout),
+                                        p.idesc, (uint32_t)((kb | tap | j) != 0));
+                        }
+                        umma_commit(smem_u32(&bar_empty[s]));
+                        if (++s == p.stages) { s = 0; ph ^= 1; }
+                    }
+                } else
                 for (int i = 0; i < nsteps; i++) {
                     mbar_wait(smem_u32(&bar_full[s]), ph);
                     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -408,7 +456,7 @@ k_conv_tc(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUte
             }
         }
     } else if (!GATHER) {
-        if (warp == TC_WARP_PROD && lane == 0) { /* ===== TMA producer ===== */
+        if (warp == WARP_PROD && lane == 0) { /* ===== TMA producer ===== */
             if (p.b_resident) { /* the whole repacked weight matrix of this N tile set stays in shared memory */
                 mbar_expect_tx(smem_u32(&bar_b), (uint32_t)(nsteps * p.n_tile * p.bk));
                 for (int tap = 0, i = 0; tap < p.ntaps; tap++)
@@ -420,6 +468,17 @@ k_conv_tc(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUte
             for (TileIter ti(blockIdx.x, gridDim.x, tiles_per_img); ti.img < p.n_img; ti.next()) {
                 const int mt = p.n_tiles == 1 ? ti.rem : ti.rem / p.n_tiles, n0 = (ti.rem - mt * p.n_tiles) * p.n_tile;
                 const int q0 = mt * TC_BM, zc = p.img0 + ti.img;
+                if (p.halo) {
+                    for (int kb = 0; kb < p.ksteps_per_tap; kb++) {
+                        mbar_wait(smem_u32(&bar_empty[s]), ph);
+                        const uint32_t full = smem_u32(&bar_full[s]);
+                        mbar_expect_tx(full, (uint32_t)(p.halo_nb * p.halo_rb * p.bk));
+                        for (int b = 0; b < p.halo_nb; b++)
+                            tma_load_3d(a_base + s * p.a_stage_bytes + b * p.halo_rb * p.bk, &mapA, full, kb * p.bk, q0 + p.halo_min + b * p.halo_rb, zc);
+                        if (++s == p.stages) { s = 0; ph ^= 1; }
+                    }
+                    continue;
+                }
                 for (int tap = 0; tap < p.ntaps; tap++) {
                     const int qa = q0 + s_shift[tap];
                     for (int kb = 0; kb < p.ksteps_per_tap; kb++) {
@@ -436,11 +495,11 @@ k_conv_tc(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUte
         }
     } else {
         /* ===== gather producer: 128 threads, one A row (output pixel) each ===== */
-        if (warp == TC_WARP_PROD && lane == 0) { /* the whole weight matrix once */
+        if (warp == WARP_PROD && lane == 0) { /* the whole weight matrix once */
             mbar_expect_tx(smem_u32(&bar_b), (uint32_t)(p.n_tile * 128));
             tma_load_3d(b_base, &mapB, smem_u32(&bar_b), 0, 0, 0);
         }
-        const int pr = (warp - TC_WARP_PROD) * 32 + lane;
+        const int pr = (warp - WARP_PROD) * 32 + lane;
         const int PP = p.gPWW * 4, nwords = p.gC * p.gPH * p.gPWW;
         const int th = TC_BM >> p.tw_shift;
         const int tb = ((pr >> p.tw_shift) * p.gS) * PP + (pr & ((1 << p.tw_shift) - 1)) * p.gS; /* this pixel's origin in the patch */
@@ -508,7 +567,7 @@ k_conv_tc(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUte
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
-    if (warp == TC_WARP_MMA) {
+    if (warp == WARP_MMA) {
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "r"((uint32_t)p.tmem_cols) : "memory");
     }
@@ -592,6 +651,7 @@ struct TcPlanImpl {
     TcKernel kernel = nullptr;
     size_t smem = 0;
     int ctas_per_sm = 2;
+    int epi = 8; /* epilogue warps per CTA */
 };
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
@@ -744,22 +804,24 @@ static bool fast_requant_ok(const Op &o, const ArenaGeom &ag) {
 }
 
 /* kernel variants: FAST requant x GATHER producer x number of stored NCHW streams x NHWC side output */
-template <bool FAST, bool GATHER>
+template <bool FAST, bool GATHER, int EPI>
 static TcKernel pick_kernel2(int nst, bool nhwc) {
     switch (nst * 2 + (nhwc ? 1 : 0)) {
-        case 0: return k_conv_tc<FAST, GATHER, 0, false>;
-        case 1: return k_conv_tc<FAST, GATHER, 0, true>;
-        case 2: return k_conv_tc<FAST, GATHER, 1, false>;
-        case 3: return k_conv_tc<FAST, GATHER, 1, true>;
-        case 4: return k_conv_tc<FAST, GATHER, 2, false>;
-        case 5: return k_conv_tc<FAST, GATHER, 2, true>;
-        case 6: return k_conv_tc<FAST, GATHER, 3, false>;
-        default: return k_conv_tc<FAST, GATHER, 3, true>;
+        case 0: return k_conv_tc<FAST, GATHER, 0, false, EPI>;
+        case 1: return k_conv_tc<FAST, GATHER, 0, true, EPI>;
+        case 2: return k_conv_tc<FAST, GATHER, 1, false, EPI>;
+        case 3: return k_conv_tc<FAST, GATHER, 1, true, EPI>;
+        case 4: return k_conv_tc<FAST, GATHER, 2, false, EPI>;
+        case 5: return k_conv_tc<FAST, GATHER, 2, true, EPI>;
+        case 6: return k_conv_tc<FAST, GATHER, 3, false, EPI>;
+        default: return k_conv_tc<FAST, GATHER, 3, true, EPI>;
     }
 }
-static TcKernel pick_kernel(bool fast, bool gather, int nst, bool nhwc) {
-    if (fast) return gather ? pick_kernel2<true, true>(nst, nhwc) : pick_kernel2<true, false>(nst, nhwc);
-    return gather ? pick_kernel2<false, true>(nst, nhwc) : pick_kernel2<false, false>(nst, nhwc);
+/* gather mode always runs two CTAs per SM (N tile <= 256 columns of TMEM in total), i.e. 8 epilogue warps */
+static TcKernel pick_kernel(bool fast, bool gather, int nst, bool nhwc, int epi) {
+    if (gather) return fast ? pick_kernel2<true, true, 8>(nst, nhwc) : pick_kernel2<false, true, 8>(nst, nhwc);
+    if (epi == 16) return fast ? pick_kernel2<true, false, 16>(nst, nhwc) : pick_kernel2<false, false, 16>(nst, nhwc);
+    return fast ? pick_kernel2<true, false, 8>(nst, nhwc) : pick_kernel2<false, false, 8>(nst, nhwc);
 }
 
 bool tc_plan(const Op &o, const ArenaGeom &ag, uint8_t *scratch, size_t scratch_stride, uint8_t *linked, size_t linked_stride,
@@ -796,6 +858,19 @@ bool tc_plan(const Op &o, const ArenaGeom &ag, uint8_t *scratch, size_t scratch_
         /* small weight matrices stay resident in shared memory for the whole (persistent) launch: one TMA per k-step */
         const size_t b_all = (size_t)nsteps * p.b_stage_bytes;
         p.b_resident = (p.n_tiles == 1 && b_all <= (size_t)budget / 2) ? 1 : 0;
+        /* kxk stride 1 over the padded channel-innermost copy: every tap is a row shift of the same pixel rows, so one
+         * load of the tile's rows plus its halo (128 + (kh-1)*Wp + kw-1 rows) serves all taps of a k block */
+        static const bool halo_enabled = !(getenv("MARS_TC_HALO") && atoi(getenv("MARS_TC_HALO")) == 0);
+        if (halo_enabled && g.prepass == 1 && p.b_resident && g.ntaps > 1) {
+            const int smin = -o.pt * g.Wp, smax = (o.kh - 1 - o.pt) * g.Wp + o.kw - 1;
+            const int R = TC_BM + smax - smin;
+            const int nb = (R + 255) / 256, rb = round_up((R + nb - 1) / nb, 8);
+            const uint32_t bytes = (uint32_t)round_up(nb * rb * p.bk, 1024);
+            if (rb <= 256 && (size_t)2 * bytes + b_all <= (size_t)budget) {
+                p.halo = 1; p.halo_min = smin; p.halo_rb = rb; p.halo_nb = nb;
+                p.a_stage_bytes = bytes;
+            }
+        }
         if (p.b_resident) {
             p.stages = std::max(2, std::min(8, (budget - (int)b_all) / (int)p.a_stage_bytes));
             t->smem = 1024 + (size_t)p.stages * p.a_stage_bytes + b_all;
@@ -891,16 +966,17 @@ bool tc_plan(const Op &o, const ArenaGeom &ag, uint8_t *scratch, size_t scratch_
                        (uint64_t)o.ih * o.iw, ag.slot_stride, TC_BM, (uint32_t)p.bk, CU_TENSOR_MAP_SWIZZLE_128B);
     else if (ok && !gather) /* NHWC copy: dims (C, pixels, images), K-major box {bk, 128} */
         ok = make_map3(&t->mapA, scratch, (uint64_t)ci_eff, (uint64_t)g.npix, (uint64_t)ag.capacity, (uint64_t)ci_eff,
-                       scratch_stride, (uint32_t)p.bk, TC_BM, ksw);
+                       scratch_stride, (uint32_t)p.bk, p.halo ? (uint32_t)p.halo_rb : TC_BM, ksw);
     else if (ok) t->mapA = CUtensorMap(); /* unused in gather mode */
     if (ok && o.copy_from >= 0 && linked && !gather && g.prepass != 0) {
         ok = make_map3(&t->mapA_linked, linked + o.copy_off, (uint64_t)ci_eff, (uint64_t)g.npix, (uint64_t)ag.capacity, (uint64_t)ci_eff,
-                       linked_stride, (uint32_t)p.bk, TC_BM, ksw);
+                       linked_stride, (uint32_t)p.bk, p.halo ? (uint32_t)p.halo_rb : TC_BM, ksw);
         t->has_linked = ok;
     }
     ok = ok && make_map3(&t->mapB, t->d_wr, (uint64_t)ci_eff, (uint64_t)co_pad, (uint64_t)g.ntaps, (uint64_t)ci_eff,
                          (uint64_t)co_pad * ci_eff, (uint32_t)p.bk, (uint32_t)p.n_tile, ksw);
-    t->kernel = pick_kernel(t->fast, gather, t->nst, p.nhwc_sel >= 0);
+    t->epi = (!gather && t->ctas_per_sm == 1) ? 16 : 8;
+    t->kernel = pick_kernel(t->fast, gather, t->nst, p.nhwc_sel >= 0, t->epi);
     ok = ok && cudaFuncSetAttribute((const void *)t->kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 210 * 1024) == cudaSuccess;
     if (!ok) { cudaFree(t->d_wr); cudaFree(t->d_lutw); delete t; return false; }
     plan->impl = t;
@@ -933,7 +1009,7 @@ bool tc_launch(const TcPlan &plan, uint8_t *slots_base, int first, int n, bool u
     static int sms = 0;
     if (!sms) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); if (sms <= 0) sms = 148; }
     const unsigned grid = (unsigned)std::min<long long>(total_tiles, (long long)sms * t->ctas_per_sm);
-    t->kernel<<<grid, t->prepass == 3 ? TC_THREADS_GATHER : TC_THREADS_TMA, t->smem, s>>>((use_linked && t->has_linked) ? t->mapA_linked : t->mapA, t->mapB, p);
+    t->kernel<<<grid, (t->epi + (t->prepass == 3 ? 5 : 2)) * 32, t->smem, s>>>((use_linked && t->has_linked) ? t->mapA_linked : t->mapA, t->mapB, p);
     (*launches)++;
     return cudaGetLastError() == cudaSuccess;
 }
