@@ -81,7 +81,7 @@ class ClockSampler(threading.Thread):
                 for bit, nm in names.items():
                     if r & bit:
                         self.reasons.add(nm)
-                time.sleep(0.05)
+                time.sleep(0.002)
         except Exception as e:  # nvml missing: record that, do not fail the bench
             self.reasons.add("nvml_unavailable:%s" % type(e).__name__)
 

@@ -45,9 +45,11 @@ def launches(src, dst, marker=None):
     dur = [float(r["Metric Value"].replace(",", "")) / 1e3 for r in rows]  # ns -> us
     lo, hi = 0, len(rows)
     if marker:
-        starts = [i for i, n in enumerate(names) if n.startswith(marker)]
-        if len(starts) >= 2:
-            lo, hi = starts[-2], starts[-1]
+        # a step ends with the marker kernel (e.g. k_nms_center); take the first complete step after the warm-up steps
+        ends = [i for i, n in enumerate(names) if n.startswith(marker)]
+        which = int(sys.argv[5]) if len(sys.argv) > 5 else 1
+        if len(ends) > which:
+            lo, hi = ends[which - 1] + 1, ends[which] + 1
     agg = collections.OrderedDict()
     for n, d in zip(names[lo:hi], dur[lo:hi]):
         a = agg.setdefault(n, [0, 0.0])
@@ -57,7 +59,7 @@ def launches(src, dst, marker=None):
     with open(dst, "w") as f:
         f.write("# ncu launch list summary (%s)\n\n" % src)
         f.write("Source: `ncu --metrics gpu__time_duration.sum --clock-control none` (cold-cache, serialised launches: compare shares).\n")
-        f.write("Launches %d..%d of %d (one full step%s); total %.1f us.\n\n" % (lo, hi, len(rows), " delimited by `%s`" % marker if marker else "", tot))
+        f.write("Launches %d..%d of %d (one full step%s); total %.1f us.\n\n" % (lo, hi, len(rows), " ending with `%s`" % marker if marker else "", tot))
         f.write("| kernel | launches | total us | share | avg us |\n|---|---:|---:|---:|---:|\n")
         for n, a in sorted(agg.items(), key=lambda kv: -kv[1][1]):
             f.write("| `%s` | %d | %.1f | %.1f%% | %.1f |\n" % (n, a[0], a[1], 100 * a[1] / tot, a[1] / a[0]))
