@@ -304,7 +304,9 @@ k_conv_tc(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUte
         const int PP = p.gPWW * 4;
         for (int k = threadIdx.x; k < 128; k += blockDim.x) {
             const int ci = k / (p.gKH * p.gKW), r = k - ci * p.gKH * p.gKW, y = r / p.gKW, x = r - y * p.gKW;
-            s_koff[k] = k < p.gKt ? (ci * p.gPH + y) * PP + x + p.gdx : 0;
+            const int off = k < p.gKt ? (ci * p.gPH + y) * PP + x + p.gdx : 0;
+            if (!p.g_align2) s_koff[k] = off;
+            else if ((k & 1) == 0) s_koff[k >> 1] = off; /* one entry per byte pair (k, k+1) */
         }
         for (int i = threadIdx.x; i < p.gC * p.gPH * p.gPWW; i += blockDim.x) {
             const int ci = i / (p.gPH * p.gPWW), r = i - ci * p.gPH * p.gPWW, py = r / p.gPWW, wi = r - py * p.gPWW;
@@ -503,7 +505,7 @@ k_conv_tc(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUte
         const int PP = p.gPWW * 4, nwords = p.gC * p.gPH * p.gPWW;
         const int th = TC_BM >> p.tw_shift;
         const int tb = ((pr >> p.tw_shift) * p.gS) * PP + (pr & ((1 << p.tw_shift) - 1)) * p.gS; /* this pixel's origin in the patch */
-        const int kwords = (p.gKt + 3) >> 2;
+        const int nchunks = (p.gKt + 15) >> 4;
         uint32_t pre[8];
         auto prefetch = [&](int img, int mt) { /* n_tiles == 1 in gather mode: tile inside the image = M tile */
             const int ty = mt / p.tiles_x, tx = mt - ty * p.tiles_x;
@@ -533,31 +535,34 @@ k_conv_tc(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUte
             mbar_wait_relaxed(smem_u32(&bar_empty[s]), ph);
             uint8_t *row = smem_al + (size_t)s * p.a_stage_bytes + pr * 128;
             const uint8_t *pb = g_patch + tb;
-            for (int c = 0; c < 8; c++) {
-                uint32_t wds[4] = {0u, 0u, 0u, 0u};
-                if (c * 4 < kwords) {
-                    if (p.g_align2) { /* taps come in aligned byte pairs (even stride, even kernel width): 2-byte loads */
+            /* K columns >= Kt meet zero weights (k_repack_rows pads B with zeros), so whatever bytes sit there are
+             * harmless: table entries beyond Kt point at offset 0 and 16-byte chunks beyond Kt are not written at all */
+            if (p.g_align2) { /* taps come in aligned byte pairs (even stride, even kernel width): 2-byte loads */
 #pragma unroll
-                        for (int g = 0; g < 4; g++) {
-                            const int4 o4 = reinterpret_cast<const int4 *>(s_koff)[c * 4 + g];
-                            if (c * 4 + g < kwords) {
-                                const uint32_t lo = *reinterpret_cast<const uint16_t *>(pb + o4.x);
-                                const uint32_t hi = (c * 16 + g * 4 + 2 < p.gKt) ? *reinterpret_cast<const uint16_t *>(pb + o4.z) : 0u;
-                                wds[g] = lo | (hi << 16);
-                            }
-                        }
-                    } else {
-#pragma unroll
-                        for (int g = 0; g < 4; g++) {
-                            const int4 o4 = reinterpret_cast<const int4 *>(s_koff)[c * 4 + g];
-                            const int off[4] = {o4.x, o4.y, o4.z, o4.w};
-#pragma unroll
-                            for (int b = 0; b < 4; b++)
-                                if (c * 16 + g * 4 + b < p.gKt) wds[g] |= (uint32_t)pb[off[b]] << (8 * b);
-                        }
+                for (int c = 0; c < 8; c++) {
+                    if (c < nchunks) {
+                        const int4 pa = reinterpret_cast<const int4 *>(s_koff)[c * 2], pc = reinterpret_cast<const int4 *>(s_koff)[c * 2 + 1];
+                        uint4 wv;
+                        wv.x = (uint32_t)*reinterpret_cast<const uint16_t *>(pb + pa.x) | ((uint32_t)*reinterpret_cast<const uint16_t *>(pb + pa.y) << 16);
+                        wv.y = (uint32_t)*reinterpret_cast<const uint16_t *>(pb + pa.z) | ((uint32_t)*reinterpret_cast<const uint16_t *>(pb + pa.w) << 16);
+                        wv.z = (uint32_t)*reinterpret_cast<const uint16_t *>(pb + pc.x) | ((uint32_t)*reinterpret_cast<const uint16_t *>(pb + pc.y) << 16);
+                        wv.w = (uint32_t)*reinterpret_cast<const uint16_t *>(pb + pc.z) | ((uint32_t)*reinterpret_cast<const uint16_t *>(pb + pc.w) << 16);
+                        *reinterpret_cast<uint4 *>(row + ((c ^ (pr & 7)) << 4)) = wv;
                     }
                 }
-                *reinterpret_cast<uint4 *>(row + ((c ^ (pr & 7)) << 4)) = make_uint4(wds[0], wds[1], wds[2], wds[3]);
+            } else {
+#pragma unroll
+                for (int c = 0; c < 8; c++) {
+                    if (c < nchunks) {
+                        uint32_t wds[4];
+#pragma unroll
+                        for (int g = 0; g < 4; g++) {
+                            const int4 o4 = reinterpret_cast<const int4 *>(s_koff)[c * 4 + g];
+                            wds[g] = (uint32_t)pb[o4.x] | ((uint32_t)pb[o4.y] << 8) | ((uint32_t)pb[o4.z] << 16) | ((uint32_t)pb[o4.w] << 24);
+                        }
+                        *reinterpret_cast<uint4 *>(row + ((c ^ (pr & 7)) << 4)) = make_uint4(wds[0], wds[1], wds[2], wds[3]);
+                    }
+                }
             }
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); /* generic-proxy writes -> visible to the MMA's async proxy */
             __syncwarp();

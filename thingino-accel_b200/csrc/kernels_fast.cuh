@@ -90,12 +90,118 @@ __global__ void __launch_bounds__(256) k_shift_copy(ArenaView v, KOp o, int peri
     }
 }
 
+/* In-place NCHW 1x1 conv (see k_conv1x1_nchw_inplace in kernels_exact.cuh for why one thread per pixel walking the output
+ * channels in order is exact) with the pixel's channel vector in REGISTERS: CI4 packed words per thread, weights and
+ * biases in shared memory read as 16-byte broadcasts, dp4a accumulation (exact int32, order-free).  The feedback
+ * "pass oc reads planes ic < oc in their output form" becomes a byte insert into word oc/4, a compile-time register
+ * index because the loop over output-channel groups is fully unrolled.  blockDim.x = 128 pixels;
+ * smem = (Co * CI4 + Co) * 4 bytes. */
+template <int CI4>
+__global__ void __launch_bounds__(128) k_conv1x1_inplace_reg(ArenaView v, KOp o) {
+    extern __shared__ uint32_t smem_w[];
+    const Img im = make_img(v, blockIdx.y);
+    uint32_t *ws = smem_w;                                        /* [oc][CI4] */
+    int32_t *bs = reinterpret_cast<int32_t *>(smem_w + o.oc * CI4); /* [oc] */
+    const int64_t P = (int64_t)o.oh * o.ow;
+    const int64_t p = (int64_t)blockIdx.x * 128 + threadIdx.x;
+    const uint8_t *in = im.s_minus_W + o.in0;
+    const uint32_t *w = reinterpret_cast<const uint32_t *>(im.w + o.w); /* weights lie in the blob, 4-byte aligned (checked on the host) */
+    for (int i = threadIdx.x; i < o.oc * CI4; i += 128) ws[i] = w[i];
+    for (int i = threadIdx.x; i < o.oc; i += 128) bs[i] = bias_i32<false>(im, o, i);
+    uint32_t x[CI4];
+    if (p < P) {
+#pragma unroll
+        for (int k = 0; k < CI4; k++) {
+            const uint8_t *q = in + (int64_t)(4 * k) * P + p;
+            x[k] = (uint32_t)q[0] | ((uint32_t)q[P] << 8) | ((uint32_t)q[2 * P] << 16) | ((uint32_t)q[3 * P] << 24);
+        }
+    }
+    __syncthreads();
+    if (p >= P) return;
+    uint8_t *out = wr_ptr(im, o.out) + p;
+    const float cs = o.f0;
+#pragma unroll
+    for (int g = 0; g < CI4; g++) { /* output channels 4g .. 4g+3 feed back into word g */
+        if (4 * g >= o.oc) break;
+#pragma unroll
+        for (int r = 0; r < 4; r++) {
+            const int oc = 4 * g + r;
+            if (oc < o.oc) {
+                int acc = bs[oc];
+                const uint4 *wr = reinterpret_cast<const uint4 *>(ws + oc * CI4);
+#pragma unroll
+                for (int k4 = 0; k4 < CI4 / 4; k4++) {
+                    const uint4 w4 = wr[k4];
+                    acc = __dp4a((int)x[4 * k4], (int)w4.x, acc); acc = __dp4a((int)x[4 * k4 + 1], (int)w4.y, acc);
+                    acc = __dp4a((int)x[4 * k4 + 2], (int)w4.z, acc); acc = __dp4a((int)x[4 * k4 + 3], (int)w4.w, acc);
+                }
+                const int8_t y = requant_conv(acc, cs);
+                out[(int64_t)oc * P] = (uint8_t)y;
+                x[g] = (x[g] & ~(0xFFu << (8 * r))) | ((uint32_t)(uint8_t)y << (8 * r));
+            }
+        }
+    }
+    for (int oc = 4 * CI4; oc < o.oc; oc++) { /* more outputs than inputs: no feedback beyond plane ic-1 */
+        int acc = bs[oc];
+        const uint4 *wr = reinterpret_cast<const uint4 *>(ws + oc * CI4);
+#pragma unroll
+        for (int k4 = 0; k4 < CI4 / 4; k4++) {
+            const uint4 w4 = wr[k4];
+            acc = __dp4a((int)x[4 * k4], (int)w4.x, acc); acc = __dp4a((int)x[4 * k4 + 1], (int)w4.y, acc);
+            acc = __dp4a((int)x[4 * k4 + 2], (int)w4.z, acc); acc = __dp4a((int)x[4 * k4 + 3], (int)w4.w, acc);
+        }
+        out[(int64_t)oc * P] = (uint8_t)requant_conv(acc, cs);
+    }
+}
+
+static inline bool inplace_reg_ok(const ArenaView &v, const KOp &o) {
+    return (o.ic == 32 || o.ic == 64 || o.ic == 128) && o.w >= 0 && (o.w & 3) == 0 &&
+           o.w + (int64_t)o.oc * o.ic <= (int64_t)v.W && (size_t)o.oc * (o.ic / 4 + 1) * 4 <= 160 * 1024;
+}
+static inline void launch_inplace_reg(const ArenaView &v, const KOp &o, int n_img, cudaStream_t s) {
+    const unsigned P = (unsigned)o.oh * o.ow;
+    dim3 g((P + 127) / 128, n_img);
+    const size_t smem = (size_t)o.oc * (o.ic / 4 + 1) * 4;
+    static bool attr = false;
+    if (!attr) {
+        cudaFuncSetAttribute(k_conv1x1_inplace_reg<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
+        cudaFuncSetAttribute(k_conv1x1_inplace_reg<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
+        cudaFuncSetAttribute(k_conv1x1_inplace_reg<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
+        attr = true;
+    }
+    if (o.ic == 32) k_conv1x1_inplace_reg<8><<<g, 128, smem, s>>>(v, o);
+    else if (o.ic == 64) k_conv1x1_inplace_reg<16><<<g, 128, smem, s>>>(v, o);
+    else k_conv1x1_inplace_reg<32><<<g, 128, smem, s>>>(v, o);
+}
+
 static inline unsigned fast_grid(uint64_t items, unsigned per_block = 256) {
     uint64_t b = (items + per_block - 1) / per_block;
     return (unsigned)std::max<uint64_t>(1, std::min<uint64_t>(b, 148 * 16));
 }
 
 /* ---- selection + launch ---------------------------------------------------------- */
+/* shifted flat copy whose source and destination are only 4-byte aligned relative to each other: 16-byte stores on the
+ * destination's alignment, four 4-byte loads each; head and tail words one by one.  n4 = words to copy. */
+__global__ void __launch_bounds__(256) k_shift_copy_d16(ArenaView v, KOp o) {
+    const Img im = make_img(v, blockIdx.y);
+    uint32_t *out = reinterpret_cast<uint32_t *>(im.s_minus_W + o.out + o.coff);
+    const uint32_t *in = reinterpret_cast<const uint32_t *>(im.s_minus_W + o.in0);
+    const int64_t n4 = (int64_t)o.n >> 2;
+    const int head = (int)((16 - (reinterpret_cast<uintptr_t>(out) & 15)) & 15) >> 2; /* words before the first aligned 16 bytes */
+    const int64_t nv = n4 > head ? (n4 - head) >> 2 : 0;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nv; i += (int64_t)gridDim.x * blockDim.x) {
+        const uint32_t *sp = in + head + 4 * i;
+        reinterpret_cast<uint4 *>(out + head)[i] = make_uint4(sp[0], sp[1], sp[2], sp[3]);
+    }
+    if (blockIdx.x == 0) {
+        if ((int)threadIdx.x < head && threadIdx.x < n4) out[threadIdx.x] = in[threadIdx.x];
+        const int64_t done = head + 4 * nv;
+        if (done + threadIdx.x < n4) out[done + threadIdx.x] = in[done + threadIdx.x];
+        const int64_t b = (n4 << 2) + threadIdx.x; /* tail bytes */
+        if (b < (int64_t)o.n) reinterpret_cast<uint8_t *>(out)[b] = reinterpret_cast<const uint8_t *>(in)[b];
+    }
+}
+
 static inline bool aligned16(int64_t x) { return (x & 15) == 0; }
 
 static inline bool fast_flat_ok(const ArenaView &v, const KOp &o) {
@@ -157,7 +263,8 @@ static inline bool fast_spatial_ok(const ArenaView &v, const KOp &o) {
 }
 static inline void launch_fast_spatial(const ArenaView &v, const KOp &o, int n_img, cudaStream_t s) {
     if (o.kind == OP_MAXPOOL || o.kind == OP_UPSAMPLE) {
-        dim3 g(fast_grid((uint64_t)o.oh * o.ow * (o.ic >> 2)), n_img);
+        /* one output word per thread: the loads of a thread are dependent, so parallelism comes from the number of warps */
+        dim3 g((unsigned)(((uint64_t)o.oh * o.ow * (o.ic >> 2) + 255) / 256), n_img);
         k_spatial_vec4<<<g, 256, 0, s>>>(v, o);
         return;
     }
@@ -171,6 +278,7 @@ static inline void launch_fast_spatial(const ArenaView &v, const KOp &o, int n_i
     else if (((rel_d | rel_s) & 3) == 0 && (!periodic || (o.coff & 3) == 0)) vec = 4;
     dim3 g(fast_grid(o.n / vec), n_img);
     if (vec == 16) k_shift_copy<16><<<g, 256, 0, s>>>(v, o, periodic);
+    else if (vec == 4 && !periodic && o.n >= 1024) k_shift_copy_d16<<<dim3(fast_grid(o.n / 16), n_img), 256, 0, s>>>(v, o);
     else if (vec == 4) k_shift_copy<4><<<g, 256, 0, s>>>(v, o, periodic);
     else k_shift_copy<1><<<g, 256, 0, s>>>(v, o, periodic);
 }

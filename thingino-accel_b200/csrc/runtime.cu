@@ -374,6 +374,9 @@ static mars_error_t launch_op(Model *m, size_t op_index, int first, int n, bool 
                     m->launches++;
                 }
             }
+        } else if (o.mode == EXEC_PIXEL_SERIAL && o.kind == OP_CONV_I8_NCHW && m->opt_level >= 1 && inplace_reg_ok(v, k)) {
+            launch_inplace_reg(v, k, n, s);
+            m->launches++;
         } else if (o.mode == EXEC_PIXEL_SERIAL && o.kind == OP_CONV_I8_NCHW) {
             dim3 g(blocks_for(P, 128), n);
             const size_t smem = (size_t)o.ic * 128 + (size_t)o.oc * o.ic;
