@@ -67,6 +67,8 @@ struct TcParams {
     unsigned long long nhwc_stride;
     unsigned wp_magic;       /* floor(2^32 / Wp) + 1 */
     int halo, halo_min, halo_rb, halo_nb; /* kxk stride 1: one A load per (tile, k block) covers all taps: rows q0+halo_min .., halo_nb boxes of halo_rb rows */
+    int acc_bufs;            /* TMEM accumulator ring depth (tmem_cols / n_tile, at most 8) */
+    int dbg;                 /* tuning aid (MARS_TC_DEBUG): 1 = epilogue computes but does not store, 2 = epilogue only drains TMEM */
     int b_resident;          /* all weight blocks of the (single) N tile stay in shared memory for the whole launch */
     int img0, n_img;         /* first image (TMA coordinate of the slot dimension), images of this launch */
     /* gather mode: A rows are built from a private NCHW copy of the input (small Ci, e.g. the 6x6 stride-2 stem) */
@@ -111,6 +113,19 @@ __device__ __forceinline__ void umma_i8(uint32_t tmem_d, uint64_t desc_a, uint64
         "setp.ne.b32 p, %4, 0;\n\t"
         "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, {%5, %5, %5, %5}, p;\n\t"
         "}\n" ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate), "r"(0u) : "memory");
+}
+/* same with the two 64-bit shared-memory descriptors given as 32-bit halves (the high halves are loop invariants) */
+__device__ __forceinline__ void umma_i8_parts(uint32_t tmem_d, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi, uint32_t idesc,
+                                              uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        ".reg .b64 da, db;\n\t"
+        "setp.ne.b32 p, %6, 0;\n\t"
+        "mov.b64 da, {%1, %2};\n\t"
+        "mov.b64 db, {%3, %4};\n\t"
+        "tcgen05.mma.cta_group::1.kind::i8 [%0], da, db, %5, {%7, %7, %7, %7}, p;\n\t"
+        "}\n" ::"r"(tmem_d), "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate), "r"(0u) : "memory");
 }
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
@@ -166,6 +181,19 @@ __device__ __forceinline__ void mbar_wait_relaxed(uint32_t bar, uint32_t parity)
     }
 }
 
+/* shared-memory loads through a 32-bit shared address kept in a register (the generic->shared conversion of a
+ * __shared__ object is otherwise re-materialised at every use in the epilogue's hot loop) */
+__device__ __forceinline__ uint32_t lds_u32(uint32_t addr) {
+    uint32_t v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ int4 lds_v4(uint32_t addr) {
+    int4 v;
+    asm volatile("ld.shared.v4.s32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
+    return v;
+}
+
 /* UMMA shared-memory matrix descriptor (cute/arch/mma_sm100_desc.hpp layout):
  * [0,14) start>>4, [16,30) LBO>>4, [32,46) SBO>>4, [46,48) version=1, [61,64) layout type */
 __device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes, uint32_t layout) {
@@ -218,21 +246,20 @@ struct TileIter {
  * channels into one 16-byte store of the consumer's channel-innermost copy.  o0..o2 point at channel c0 of
  * this pixel; nch = how many of the 16 channels exist (16 = all, <= 0 = none / pixel outside the image). */
 template <bool FAST, int NST, bool NHWC, int W>
-__device__ __forceinline__ void epilogue_unit(const uint32_t (&v)[W], const int32_t *cm, const uint32_t *lutw, float cs,
+__device__ __forceinline__ void epilogue_unit(const uint32_t (&v)[W], uint32_t cm, uint32_t lutw, float cs,
                                               uint8_t *o0, uint8_t *o1, uint8_t *o2, long long plane, int nch, uint8_t *nh) {
-    if (nch <= 0) return;
-    const int4 *cmv = reinterpret_cast<const int4 *>(cm);
+    if (nch <= 0) return; /* cm, lutw: shared addresses of the unit's bias words and of the word table */
     if (nch >= W) {
 #pragma unroll
         for (int j16 = 0; j16 < W / 16; j16++) {
             uint32_t pk[4] = {0u, 0u, 0u, 0u};
 #pragma unroll
             for (int j4 = 0; j4 < 4; j4++) {
-                const int4 c4 = cmv[j16 * 4 + j4];
+                const int4 c4 = lds_v4(cm + (uint32_t)(j16 * 4 + j4) * 16u);
                 const int cc[4] = {c4.x, c4.y, c4.z, c4.w};
 #pragma unroll
                 for (int k = 0; k < 4; k++) {
-                    const uint32_t w = lutw[requant_index<FAST>((int32_t)(v[j16 * 16 + j4 * 4 + k] + (uint32_t)cc[k]), cs)];
+                    const uint32_t w = lds_u32(lutw + 4u * requant_index<FAST>((int32_t)(v[j16 * 16 + j4 * 4 + k] + (uint32_t)cc[k]), cs));
                     if (NST > 0) { *o0 = (uint8_t)w; o0 += plane; }
                     if (NST > 1) { *o1 = (uint8_t)(w >> 8); o1 += plane; }
                     if (NST > 2) { *o2 = (uint8_t)(w >> 16); o2 += plane; }
@@ -246,7 +273,7 @@ __device__ __forceinline__ void epilogue_unit(const uint32_t (&v)[W], const int3
 #pragma unroll
         for (int j = 0; j < W; j++) {
             if (j < nch) {
-                const uint32_t w = lutw[requant_index<FAST>((int32_t)(v[j] + (uint32_t)cm[j]), cs)];
+                const uint32_t w = lds_u32(lutw + 4u * requant_index<FAST>((int32_t)(v[j] + lds_u32(cm + 4u * j)), cs));
                 if (NST > 0) o0[(long long)j * plane] = (uint8_t)w;
                 if (NST > 1) o1[(long long)j * plane] = (uint8_t)(w >> 8);
                 if (NST > 2) o2[(long long)j * plane] = (uint8_t)(w >> 16);
@@ -267,7 +294,7 @@ template <bool FAST, bool GATHER, int NST, bool NHWC, int EPI>
 __global__ void __launch_bounds__((EPI + (GATHER ? 5 : 2)) * 32, EPI == 8 ? 2 : 1)
 k_conv_tc(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, const TcParams p) {
     extern __shared__ uint8_t smem_raw[];
-    __shared__ __align__(8) uint64_t bar_full[8], bar_empty[8], bar_tmem_full[2], bar_tmem_empty[2], bar_b;
+    __shared__ __align__(8) uint64_t bar_full[8], bar_empty[8], bar_tmem_full[8], bar_tmem_empty[8], bar_b;
     __shared__ uint32_t tmem_base_slot;
     __shared__ __align__(16) int32_t s_cm[TC_MAX_CO];   /* bias (+ the int->float magic when FAST) */
     __shared__ __align__(16) uint32_t s_lutw[512];
@@ -287,7 +314,7 @@ k_conv_tc(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUte
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < p.stages; s++) { mbar_init(smem_u32(&bar_full[s]), GATHER ? 4 : 1); mbar_init(smem_u32(&bar_empty[s]), 1); }
-        for (int b = 0; b < 2; b++) { mbar_init(smem_u32(&bar_tmem_full[b]), 1); mbar_init(smem_u32(&bar_tmem_empty[b]), EPI); }
+        for (int b = 0; b < p.acc_bufs; b++) { mbar_init(smem_u32(&bar_tmem_full[b]), 1); mbar_init(smem_u32(&bar_tmem_empty[b]), EPI); }
         mbar_init(smem_u32(&bar_b), 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -299,7 +326,8 @@ k_conv_tc(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUte
     for (int i = threadIdx.x; i < TC_MAX_CO; i += blockDim.x)
         s_cm[i] = (int32_t)((uint32_t)((p.bias && i < p.Co) ? p.bias[i] : 0) + (FAST ? 0x4B400000u : 0u));
     for (int i = threadIdx.x; i < 512; i += blockDim.x) s_lutw[i] = p.lutw[i];
-    if (threadIdx.x < TC_MAX_TAPS) s_shift[threadIdx.x] = p.a_shift[threadIdx.x];
+    /* per tap: flat pixel shift (TMA coordinate); halo mode: start of the tap's rows inside the stage, in 16-byte units */
+    if (threadIdx.x < TC_MAX_TAPS) s_shift[threadIdx.x] = p.halo ? ((p.a_shift[threadIdx.x] - p.halo_min) * p.bk) >> 4 : p.a_shift[threadIdx.x];
     if (GATHER) {
         const int PP = p.gPWW * 4;
         for (int k = threadIdx.x; k < 128; k += blockDim.x) {
@@ -327,67 +355,82 @@ k_conv_tc(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUte
         const int quad = warp & 3, part = warp >> 2, parts = EPI >> 2;
         const int r = quad * 32 + lane; /* accumulator row = pixel of the tile */
         const int n_units = p.n_tile >> 4;
-        const long long plane = p.plane;
+        const long long plane = p.dbg == 1 ? 128 : p.plane;
         const float cs = p.cs;
         const uint32_t acc_lane = tmem_d + ((uint32_t)(quad * 32) << 16);
+        const uint32_t sa_lut = smem_u32(s_lutw), sa_cm = smem_u32(s_cm);
+        const uint32_t sa_full = smem_u32(&bar_tmem_full[0]), sa_empty = smem_u32(&bar_tmem_empty[0]);
+        const bool flat = !GATHER && p.Wp == p.Wo && !NHWC; /* no pad columns: the tile row index IS the pixel index */
+        uint8_t *const obase = p.out_base + r; /* + image * slot_stride + pixel + channel * plane + stream offset */
         if (part >= n_units) { /* narrow N tile: nothing to read for this warp, it only releases the accumulators */
-            int tl = 0;
-            for (TileIter ti(blockIdx.x, gridDim.x, tiles_per_img); ti.img < p.n_img; ti.next(), tl++) {
-                mbar_wait_relaxed(smem_u32(&bar_tmem_full[tl & 1]), (tl >> 1) & 1);
+            int ab = 0, aph = 0; /* accumulator ring position and phase */
+            for (TileIter ti(blockIdx.x, gridDim.x, tiles_per_img); ti.img < p.n_img; ti.next()) {
+                mbar_wait_relaxed(sa_full + 8u * ab, aph);
                 __syncwarp();
-                if (lane == 0) mbar_arrive(smem_u32(&bar_tmem_empty[tl & 1]));
+                if (lane == 0) mbar_arrive(sa_empty + 8u * ab);
+                if (++ab == p.acc_bufs) { ab = 0; aph ^= 1; }
             }
         } else {
             TileIter ti(blockIdx.x, gridDim.x, tiles_per_img); /* current item: tile ti / tl, unit u */
-            int tl = 0, u = part;
+            int tl = 0, u = part, ab = 0, aph = 0; /* ab / aph: accumulator ring position and phase of the current item's tile */
             /* per-tile values of the current item, recomputed when the tile changes */
             int cached_tl = -1, n0 = 0, co_left = 0;
             uint8_t *b0 = nullptr, *b1 = nullptr, *b2 = nullptr, *nh = nullptr;
             uint32_t va[16], vb[16];
             bool have = ti.img < p.n_img;
             if (have) {
-                mbar_wait_relaxed(smem_u32(&bar_tmem_full[0]), 0);
+                mbar_wait_relaxed(sa_full, 0);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 tmem_ld16_issue(acc_lane + (uint32_t)(u * 16), va);
             }
             auto step = [&](uint32_t (&vc)[16], uint32_t (&vn)[16]) {
                 /* the next item of this warp */
                 TileIter nti = ti;
-                int ntl = tl, nu = u + parts;
-                if (nu >= n_units) { nu = part; ntl++; nti.next(); }
+                int ntl = tl, nu = u + parts, nab = ab, naph = aph;
+                if (nu >= n_units) {
+                    nu = part; ntl++; nti.next();
+                    if (++nab == p.acc_bufs) { nab = 0; naph ^= 1; }
+                }
                 const bool have_n = nti.img < p.n_img;
                 tmem_ld_wait(vc);
                 if (u + parts >= n_units) { /* last read of this accumulator by this warp: hand it back */
                     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
                     __syncwarp();
-                    if (lane == 0) mbar_arrive(smem_u32(&bar_tmem_empty[tl & 1]));
+                    if (lane == 0) mbar_arrive(sa_empty + 8u * ab);
                 }
                 if (have_n) {
                     if (ntl != tl) {
-                        mbar_wait_relaxed(smem_u32(&bar_tmem_full[ntl & 1]), (ntl >> 1) & 1);
+                        mbar_wait_relaxed(sa_full + 8u * nab, naph);
                         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                     }
-                    tmem_ld16_issue(acc_lane + (uint32_t)((ntl & 1) * p.n_tile + nu * 16), vn);
+                    tmem_ld16_issue(acc_lane + (uint32_t)(nab * p.n_tile + nu * 16), vn);
                 }
                 if (cached_tl != tl) {
                     cached_tl = tl;
                     const int mt = p.n_tiles == 1 ? ti.rem : ti.rem / p.n_tiles;
                     n0 = (ti.rem - mt * p.n_tiles) * p.n_tile;
-                    int oh, ow;
+                    int oh = 0, ow = 0, pix;
                     bool valid;
-                    if (GATHER) {
-                        const int ty = mt / p.tiles_x, tx = mt - ty * p.tiles_x;
-                        oh = ty * (TC_BM >> p.tw_shift) + (r >> p.tw_shift);
-                        ow = (tx << p.tw_shift) + (r & ((1 << p.tw_shift) - 1));
-                        valid = oh < p.Ho && ow < p.Wo;
+                    if (flat) {
+                        pix = mt * TC_BM; /* + r, folded into obase */
+                        valid = pix + r < p.mflat;
                     } else {
-                        const int q = mt * TC_BM + r;
-                        oh = (int)__umulhi((unsigned)q, p.wp_magic); ow = q - oh * p.Wp; /* q / Wp, exact for q * Wp < 2^32 (checked on the host) */
-                        valid = q < p.mflat && ow < p.Wo;
+                        if (GATHER) {
+                            const int ty = mt / p.tiles_x, tx = mt - ty * p.tiles_x;
+                            oh = ty * (TC_BM >> p.tw_shift) + (r >> p.tw_shift);
+                            ow = (tx << p.tw_shift) + (r & ((1 << p.tw_shift) - 1));
+                            valid = oh < p.Ho && ow < p.Wo;
+                        } else {
+                            const int q = mt * TC_BM + r;
+                            oh = (int)__umulhi((unsigned)q, p.wp_magic); ow = q - oh * p.Wp; /* q / Wp, exact for q * Wp < 2^32 (checked on the host) */
+                            valid = q < p.mflat && ow < p.Wo;
+                        }
+                        pix = oh * p.Wo + ow - r;
                     }
-                    uint8_t *pix_base = p.out_base + (unsigned long long)ti.img * p.slot_stride + (oh * p.Wo + ow) + (long long)n0 * plane;
+                    uint8_t *pix_base = obase + ((unsigned long long)ti.img * p.slot_stride + (long long)n0 * plane + pix);
                     b0 = pix_base + p.out_off[0]; b1 = pix_base + p.out_off[1]; b2 = pix_base + p.out_off[2];
                     co_left = valid ? p.Co - n0 : 0; /* channels of this N tile that exist for this pixel (<= 0: nothing to store) */
+                    if (p.dbg == 1) { b0 = b1 = b2 = obase + p.out_off[0] + (long long)n0 * plane; } /* every tile stores to the same small window */
                     if (NHWC) {
                         long long dp;
                         if (p.nhwc_mode == 2) {
@@ -399,8 +442,9 @@ k_conv_tc(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUte
                 }
                 const int c0 = u * 16;
                 const long long coff = (long long)c0 * plane;
-                epilogue_unit<FAST, NST, NHWC, 16>(vc, s_cm + n0 + c0, s_lutw, cs, b0 + coff, b1 + coff, b2 + coff, plane, co_left - c0, nh + c0);
-                ti = nti; tl = ntl; u = nu; have = have_n;
+                if (p.dbg == 2) { if (vc[0] == 0x12345678u && vc[7] == 0x9abcdef0u) b0[0] = 1; }
+                else epilogue_unit<FAST, NST, NHWC, 16>(vc, sa_cm + 4u * (uint32_t)(n0 + c0), sa_lut, cs, b0 + coff, b1 + coff, b2 + coff, plane, co_left - c0, nh + c0);
+                ti = nti; tl = ntl; u = nu; ab = nab; aph = naph; have = have_n;
             };
             while (have) {
                 step(va, vb);
@@ -409,88 +453,105 @@ k_conv_tc(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUte
             }
         }
     } else if (warp == WARP_MMA) {
-        if (lane == 0) { /* ===== MMA issuer ===== */
-            const uint32_t k_sbo = 8u * (uint32_t)p.bk;
-            const bool b_res = GATHER || p.b_resident;
+        if (lane == 0) { /* ===== MMA issuer =====
+            * One thread per CTA runs this loop once per k-step of every tile, so its instruction count bounds the tile
+            * rate of the small layers: everything loop-invariant (descriptor halves, barrier addresses, strides in
+            * 16-byte descriptor units) is computed up front and the descriptors are advanced by additions. */
+            const uint32_t k_sbo16 = (8u * (uint32_t)p.bk) >> 4;
+            /* descriptor high word: SBO >> 4 at [32,46), version 1 at [46,48), layout type at [61,64) */
+            const uint32_t hi_k = k_sbo16 | (1u << 14) | (p.b_layout << 29);
+            const uint32_t hi_a = p.a_kmajor ? hi_k : ((1024u >> 4) | (1u << 14) | (2u << 29));
+            /* low word: start address >> 4 at [0,14), LBO >> 4 at [16,30) (16 bytes for the K-major operands) */
+            const uint32_t a_lo0 = (a_base >> 4) | (p.a_kmajor ? (1u << 16) : 0u), a_st16 = p.a_stage_bytes >> 4;
+            const uint32_t b_lo0 = (b_base >> 4) | (1u << 16), b_st16 = p.b_stage_bytes >> 4;
+            /* per MMA (K = 32): K-major operands advance 32 bytes inside the swizzle atom; the MN-major A (NCHW planes,
+             * 128B swizzle) advances 32 K-rows of 128 bytes = 4 atoms of 8 rows */
+            const uint32_t a_j16 = p.a_kmajor ? 2u : 256u;
+            const int nj = p.bk >> 5, stages = p.stages, acc_bufs = p.acc_bufs, n_tile = p.n_tile, n_img = p.n_img;
+            const int ntaps = p.ntaps, ksteps = p.ksteps_per_tap;
+            const uint32_t idesc = p.idesc;
+            const bool b_res = GATHER || p.b_resident, halo = p.halo != 0;
+            const uint32_t sa_full = smem_u32(&bar_full[0]), sa_empty = smem_u32(&bar_empty[0]);
+            const uint32_t sa_tfull = smem_u32(&bar_tmem_full[0]), sa_tempty = smem_u32(&bar_tmem_empty[0]);
             if (b_res) mbar_wait(smem_u32(&bar_b), 0);
-            int s = 0, ph = 0, tl = 0;
-            for (TileIter ti(blockIdx.x, gridDim.x, tiles_per_img); ti.img < p.n_img; ti.next(), tl++) {
-                const int buf = tl & 1;
-                mbar_wait(smem_u32(&bar_tmem_empty[buf]), ((tl >> 1) & 1) ^ 1); /* epilogue drained this accumulator */
+            int s = 0, ph = 0, buf = 0, aph = 1; /* waits on the accumulator-empty barriers start with the opposite parity */
+            for (TileIter ti(blockIdx.x, gridDim.x, tiles_per_img); ti.img < n_img; ti.next()) {
+                mbar_wait(sa_tempty + 8u * buf, aph); /* epilogue drained this accumulator */
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                const uint32_t acc = tmem_d + (uint32_t)(buf * p.n_tile);
-                if (p.halo) {
-                    for (int kb = 0; kb < p.ksteps_per_tap; kb++) {
-                        mbar_wait(smem_u32(&bar_full[s]), ph);
+                const uint32_t acc = tmem_d + (uint32_t)(buf * n_tile);
+                uint32_t accum = 0;
+                if (halo) {
+                    /* a tap = the same rows shifted: the operand simply starts (shift) rows further down.  The swizzle is a
+                     * function of the absolute shared-memory address (measured: a start address that is not a multiple of
+                     * the 8-row atom needs NO descriptor base offset), so TMA's layout is read back as is */
+                    for (int kb = 0; kb < ksteps; kb++) {
+                        mbar_wait(sa_full + 8u * s, ph);
                         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                        const uint32_t a_stage = a_base + s * p.a_stage_bytes;
-                        for (int tap = 0; tap < p.ntaps; tap++) {
-                            /* a tap = the same rows shifted: the operand simply starts (shift) rows further down.  The swizzle
-                             * is a function of the absolute shared-memory address (measured: a start address that is not a
-                             * multiple of the 8-row atom needs NO descriptor base offset), so TMA's layout is read back as is */
-                            const uint32_t a_addr = a_stage + (uint32_t)((s_shift[tap] - p.halo_min) * p.bk);
-                            const uint32_t b_addr = b_base + (tap * p.ksteps_per_tap + kb) * p.b_stage_bytes;
-                            for (int j = 0; j < p.bk / 32; j++)
-                                umma_i8(acc, umma_desc(a_addr + j * 32u, 16u, k_sbo, p.b_layout), umma_desc(b_addr + j * 32u, 16u, k_sbo, p.b_layout),
-                                        p.idesc, (uint32_t)((kb | tap | j) != 0));
+                        const uint32_t a_st = a_lo0 + s * a_st16;
+                        uint32_t b_lo = b_lo0 + kb * b_st16;
+                        for (int tap = 0; tap < ntaps; tap++, b_lo += ksteps * b_st16) {
+                            const uint32_t a_lo = a_st + (uint32_t)s_shift[tap]; /* halo mode: row shift in 16-byte units */
+                            for (int j = 0; j < nj; j++) { umma_i8_parts(acc, a_lo + 2u * j, hi_k, b_lo + 2u * j, hi_k, idesc, accum); accum = 1; }
                         }
-                        umma_commit(smem_u32(&bar_empty[s]));
-                        if (++s == p.stages) { s = 0; ph ^= 1; }
+                        umma_commit(sa_empty + 8u * s);
+                        if (++s == stages) { s = 0; ph ^= 1; }
                     }
-                } else
-                for (int i = 0; i < nsteps; i++) {
-                    mbar_wait(smem_u32(&bar_full[s]), ph);
-                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                    const uint32_t a_addr = a_base + s * p.a_stage_bytes;
-                    const uint32_t b_addr = b_res ? b_base + i * p.b_stage_bytes : b_base + s * p.b_stage_bytes;
-                    for (int j = 0; j < p.bk / 32; j++) {
-                        /* A MN-major, 128B swizzle: 32 K-rows of 128 bytes = 4 atoms of 8 rows, 1024 B apart;
-                         * K-major operands: rows of bk bytes, 8-row groups 8*bk apart, advance 32 B per MMA */
-                        const uint64_t da = p.a_kmajor ? umma_desc(a_addr + j * 32u, 16u, k_sbo, p.b_layout)
-                                                       : umma_desc(a_addr + j * 4096u, 0, 1024u, 2u);
-                        const uint64_t db = umma_desc(b_addr + j * 32u, 16u, k_sbo, p.b_layout);
-                        umma_i8(acc, da, db, p.idesc, (uint32_t)((i | j) != 0));
+                } else {
+                    for (int i = 0; i < nsteps; i++) {
+                        mbar_wait(sa_full + 8u * s, ph);
+                        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                        const uint32_t a_lo = a_lo0 + s * a_st16, b_lo = b_lo0 + (b_res ? i : s) * b_st16;
+                        for (int j = 0; j < nj; j++) { umma_i8_parts(acc, a_lo + a_j16 * j, hi_a, b_lo + 2u * j, hi_k, idesc, accum); accum = 1; }
+                        umma_commit(sa_empty + 8u * s); /* frees the stage when these MMAs retire */
+                        if (++s == stages) { s = 0; ph ^= 1; }
                     }
-                    umma_commit(smem_u32(&bar_empty[s])); /* frees the stage when these MMAs retire */
-                    if (++s == p.stages) { s = 0; ph ^= 1; }
                 }
-                umma_commit(smem_u32(&bar_tmem_full[buf]));
+                umma_commit(sa_tfull + 8u * buf);
+                if (++buf == acc_bufs) { buf = 0; aph ^= 1; }
             }
         }
     } else if (!GATHER) {
-        if (warp == WARP_PROD && lane == 0) { /* ===== TMA producer ===== */
-            if (p.b_resident) { /* the whole repacked weight matrix of this N tile set stays in shared memory */
-                mbar_expect_tx(smem_u32(&bar_b), (uint32_t)(nsteps * p.n_tile * p.bk));
-                for (int tap = 0, i = 0; tap < p.ntaps; tap++)
-                    for (int kb = 0; kb < p.ksteps_per_tap; kb++, i++)
-                        tma_load_3d(b_base + i * p.b_stage_bytes, &mapB, smem_u32(&bar_b), kb * p.bk, 0, tap);
+        if (warp == WARP_PROD && lane == 0) { /* ===== TMA producer (same care for the per-step instruction count) ===== */
+            const int bk = p.bk, ntaps = p.ntaps, ksteps = p.ksteps_per_tap, stages = p.stages, n_img = p.n_img, n_tiles = p.n_tiles;
+            const uint32_t a_stb = p.a_stage_bytes, b_stb = p.b_stage_bytes;
+            const bool b_res = p.b_resident != 0, a_km = p.a_kmajor != 0;
+            const uint32_t sa_full = smem_u32(&bar_full[0]), sa_empty = smem_u32(&bar_empty[0]);
+            if (b_res) { /* the whole repacked weight matrix of this N tile set stays in shared memory */
+                mbar_expect_tx(smem_u32(&bar_b), (uint32_t)(nsteps * p.n_tile * bk));
+                for (int tap = 0, i = 0; tap < ntaps; tap++)
+                    for (int kb = 0; kb < ksteps; kb++, i++)
+                        tma_load_3d(b_base + i * b_stb, &mapB, smem_u32(&bar_b), kb * bk, 0, tap);
             }
-            const uint32_t tx = p.b_resident ? p.a_stage_bytes : p.tx_bytes;
             int s = 0, ph = 1; /* waits on the empty barriers start with the opposite parity */
-            for (TileIter ti(blockIdx.x, gridDim.x, tiles_per_img); ti.img < p.n_img; ti.next()) {
-                const int mt = p.n_tiles == 1 ? ti.rem : ti.rem / p.n_tiles, n0 = (ti.rem - mt * p.n_tiles) * p.n_tile;
-                const int q0 = mt * TC_BM, zc = p.img0 + ti.img;
-                if (p.halo) {
-                    for (int kb = 0; kb < p.ksteps_per_tap; kb++) {
-                        mbar_wait(smem_u32(&bar_empty[s]), ph);
-                        const uint32_t full = smem_u32(&bar_full[s]);
-                        mbar_expect_tx(full, (uint32_t)(p.halo_nb * p.halo_rb * p.bk));
-                        for (int b = 0; b < p.halo_nb; b++)
-                            tma_load_3d(a_base + s * p.a_stage_bytes + b * p.halo_rb * p.bk, &mapA, full, kb * p.bk, q0 + p.halo_min + b * p.halo_rb, zc);
-                        if (++s == p.stages) { s = 0; ph ^= 1; }
-                    }
-                    continue;
-                }
-                for (int tap = 0; tap < p.ntaps; tap++) {
-                    const int qa = q0 + s_shift[tap];
-                    for (int kb = 0; kb < p.ksteps_per_tap; kb++) {
-                        mbar_wait(smem_u32(&bar_empty[s]), ph);
-                        const uint32_t full = smem_u32(&bar_full[s]);
+            if (p.halo) {
+                const int nb = p.halo_nb, rb = p.halo_rb, hmin = p.halo_min;
+                const uint32_t tx = (uint32_t)(nb * rb * bk), box_b = (uint32_t)(rb * bk);
+                for (TileIter ti(blockIdx.x, gridDim.x, tiles_per_img); ti.img < n_img; ti.next()) {
+                    const int q0 = ti.rem * TC_BM + hmin, zc = p.img0 + ti.img; /* n_tiles == 1 with resident weights */
+                    for (int kb = 0; kb < ksteps; kb++) {
+                        mbar_wait(sa_empty + 8u * s, ph);
+                        const uint32_t full = sa_full + 8u * s, dst = a_base + s * a_stb;
                         mbar_expect_tx(full, tx);
-                        if (p.a_kmajor) tma_load_3d(a_base + s * p.a_stage_bytes, &mapA, full, kb * p.bk, qa, zc);
-                        else tma_load_3d(a_base + s * p.a_stage_bytes, &mapA, full, q0, kb * p.bk, zc);
-                        if (!p.b_resident) tma_load_3d(b_base + s * p.b_stage_bytes, &mapB, full, kb * p.bk, n0, tap);
-                        if (++s == p.stages) { s = 0; ph ^= 1; }
+                        for (int b = 0; b < nb; b++) tma_load_3d(dst + b * box_b, &mapA, full, kb * bk, q0 + b * rb, zc);
+                        if (++s == stages) { s = 0; ph ^= 1; }
+                    }
+                }
+            } else {
+                const uint32_t tx = b_res ? a_stb : p.tx_bytes;
+                for (TileIter ti(blockIdx.x, gridDim.x, tiles_per_img); ti.img < n_img; ti.next()) {
+                    const int mt = n_tiles == 1 ? ti.rem : ti.rem / n_tiles, n0 = (ti.rem - mt * n_tiles) * p.n_tile;
+                    const int q0 = mt * TC_BM, zc = p.img0 + ti.img;
+                    for (int tap = 0; tap < ntaps; tap++) {
+                        const int qa = q0 + s_shift[tap];
+                        for (int kb = 0; kb < ksteps; kb++) {
+                            mbar_wait(sa_empty + 8u * s, ph);
+                            const uint32_t full = sa_full + 8u * s;
+                            mbar_expect_tx(full, tx);
+                            if (a_km) tma_load_3d(a_base + s * a_stb, &mapA, full, kb * bk, qa, zc);
+                            else tma_load_3d(a_base + s * a_stb, &mapA, full, q0, kb * bk, zc);
+                            if (!b_res) tma_load_3d(b_base + s * b_stb, &mapB, full, kb * bk, n0, tap);
+                            if (++s == stages) { s = 0; ph ^= 1; }
+                        }
                     }
                 }
             }
@@ -851,9 +912,12 @@ bool tc_plan(const Op &o, const ArenaGeom &ag, uint8_t *scratch, size_t scratch_
     p.a_stage_bytes = (uint32_t)(TC_BM * p.bk);
     p.b_stage_bytes = (uint32_t)round_up(p.n_tile * p.bk, 1024);
     p.tx_bytes = p.a_stage_bytes + (uint32_t)(p.n_tile * p.bk);
-    p.tmem_cols = 32;
-    while (p.tmem_cols < 2 * p.n_tile) p.tmem_cols <<= 1; /* two accumulators */
-    t->ctas_per_sm = p.tmem_cols > 256 ? 1 : 2;
+    /* accumulator ring in TMEM: two CTAs per SM share the 512 columns when two accumulators fit into 256 of them; the
+     * ring is as deep as the columns allow (up to 8), which decouples the MMA issuer from the epilogue's hand-back latency */
+    t->ctas_per_sm = 2 * p.n_tile > 256 ? 1 : 2;
+    p.tmem_cols = t->ctas_per_sm == 1 ? 512 : 256;
+    p.acc_bufs = std::min(8, p.tmem_cols / p.n_tile);
+    { static const int force = getenv("MARS_TC_ACC_BUFS") ? atoi(getenv("MARS_TC_ACC_BUFS")) : 0; if (force >= 2) p.acc_bufs = std::min(p.acc_bufs, force); }
     const int budget = t->ctas_per_sm == 1 ? 200 * 1024 : 100 * 1024;
     const int nsteps = g.ntaps * p.ksteps_per_tap;
     if (gather) { /* + 4 KiB patch + 8 KiB patch-word tables */
@@ -927,6 +991,7 @@ bool tc_plan(const Op &o, const ArenaGeom &ag, uint8_t *scratch, size_t scratch_
     }
     for (int k = 0; k < 3; k++)
         if (stream_off[k] >= 0) { t->stream_byte[k] = t->nst; p.out_off[t->nst++] = stream_off[k] - (int64_t)ag.W; }
+    p.dbg = getenv("MARS_TC_DEBUG") ? atoi(getenv("MARS_TC_DEBUG")) : 0;
     p.nhwc_sel = -1;
     if (consumer && linked) { /* this op's epilogue also writes the consumer's channel-innermost input copy */
         const TcGeom cg = tc_geometry(*consumer);

@@ -30,7 +30,7 @@ rows = [p for p in prof if p["calls"]]
 rows.sort(key=lambda p: -p["ms"])
 acc = sum(p["ms"] for p in rows)
 print("sum of op intervals %.2f ms/step" % (acc / steps))
-for p in rows[:45]:
+for p in rows[:int(sys.argv[3]) if len(sys.argv) > 3 else 45]:
     macs = p["oc"] * p["oh"] * p["ow"] * p["ic"] * p["kh"] * p["kw"] * B if p["kind"] in (1, 2, 3, 4) else 0
     ms = p["ms"] / p["calls"]
     print("op %3d L%3d %-14s impl=%d mode=%d ic=%4d oc=%4d o=%3dx%3d k=%d fused=%d  %8.3f ms  %5.1f%%  %s" % (
