@@ -68,7 +68,7 @@ struct TcParams {
     unsigned wp_magic;       /* floor(2^32 / Wp) + 1 */
     int halo, halo_min, halo_rb, halo_nb; /* kxk stride 1: one A load per (tile, k block) covers all taps: rows q0+halo_min .., halo_nb boxes of halo_rb rows */
     int acc_bufs;            /* TMEM accumulator ring depth (tmem_cols / n_tile, at most 8) */
-    int dbg;                 /* tuning aid (MARS_TC_DEBUG): 1 = epilogue computes but does not store, 2 = epilogue only drains TMEM */
+    int dbg;                 /* tuning aid (MARS_TC_DEBUG): 2 = epilogue only drains TMEM, 3 = 2 + no per-step TMA loads, 4 = 2 + no MMAs */
     int b_resident;          /* all weight blocks of the (single) N tile stay in shared memory for the whole launch */
     int img0, n_img;         /* first image (TMA coordinate of the slot dimension), images of this launch */
     /* gather mode: A rows are built from a private NCHW copy of the input (small Ci, e.g. the 6x6 stride-2 stem) */
@@ -346,6 +346,7 @@ k_conv_tc(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUte
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem_d = tmem_base_slot;
+    if (p.dbg == 6) goto teardown; /* tuning aid: prologue + teardown only */
 
     if (warp < EPI) {
         /* ===== epilogue: TMEM -> registers -> requant index -> word table -> stores =====
@@ -362,7 +363,7 @@ k_conv_tc(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUte
         const uint32_t sa_full = smem_u32(&bar_tmem_full[0]), sa_empty = smem_u32(&bar_tmem_empty[0]);
         const bool flat = !GATHER && p.Wp == p.Wo && !NHWC; /* no pad columns: the tile row index IS the pixel index */
         uint8_t *const obase = p.out_base + r; /* + image * slot_stride + pixel + channel * plane + stream offset */
-        if (part >= n_units) { /* narrow N tile: nothing to read for this warp, it only releases the accumulators */
+        if (part >= n_units || p.dbg == 7) { /* narrow N tile: nothing to read for this warp, it only releases the accumulators */
             int ab = 0, aph = 0; /* accumulator ring position and phase */
             for (TileIter ti(blockIdx.x, gridDim.x, tiles_per_img); ti.img < p.n_img; ti.next()) {
                 mbar_wait_relaxed(sa_full + 8u * ab, aph);
@@ -442,7 +443,7 @@ k_conv_tc(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUte
                 }
                 const int c0 = u * 16;
                 const long long coff = (long long)c0 * plane;
-                if (p.dbg == 2) { if (vc[0] == 0x12345678u && vc[7] == 0x9abcdef0u) b0[0] = 1; }
+                if (p.dbg >= 2) { if (vc[0] == 0x12345678u && vc[7] == 0x9abcdef0u) b0[0] = 1; }
                 else epilogue_unit<FAST, NST, NHWC, 16>(vc, sa_cm + 4u * (uint32_t)(n0 + c0), sa_lut, cs, b0 + coff, b1 + coff, b2 + coff, plane, co_left - c0, nh + c0);
                 ti = nti; tl = ntl; u = nu; ab = nab; aph = naph; have = have_n;
             };
@@ -501,7 +502,7 @@ k_conv_tc(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUte
                         mbar_wait(sa_full + 8u * s, ph);
                         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                         const uint32_t a_lo = a_lo0 + s * a_st16, b_lo = b_lo0 + (b_res ? i : s) * b_st16;
-                        for (int j = 0; j < nj; j++) { umma_i8_parts(acc, a_lo + a_j16 * j, hi_a, b_lo + 2u * j, hi_k, idesc, accum); accum = 1; }
+                        if (p.dbg != 4) for (int j = 0; j < nj; j++) { umma_i8_parts(acc, a_lo + a_j16 * j, hi_a, b_lo + 2u * j, hi_k, idesc, accum); accum = 1; }
                         umma_commit(sa_empty + 8u * s); /* frees the stage when these MMAs retire */
                         if (++s == stages) { s = 0; ph ^= 1; }
                     }
@@ -531,6 +532,7 @@ k_conv_tc(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUte
                     for (int kb = 0; kb < ksteps; kb++) {
                         mbar_wait(sa_empty + 8u * s, ph);
                         const uint32_t full = sa_full + 8u * s, dst = a_base + s * a_stb;
+                        if (p.dbg == 3) { mbar_arrive(full); if (++s == stages) { s = 0; ph ^= 1; } continue; }
                         mbar_expect_tx(full, tx);
                         for (int b = 0; b < nb; b++) tma_load_3d(dst + b * box_b, &mapA, full, kb * bk, q0 + b * rb, zc);
                         if (++s == stages) { s = 0; ph ^= 1; }
@@ -546,6 +548,7 @@ k_conv_tc(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUte
                         for (int kb = 0; kb < ksteps; kb++) {
                             mbar_wait(sa_empty + 8u * s, ph);
                             const uint32_t full = sa_full + 8u * s;
+                            if (p.dbg == 3) { mbar_arrive(full); if (++s == stages) { s = 0; ph ^= 1; } continue; }
                             mbar_expect_tx(full, tx);
                             if (a_km) tma_load_3d(a_base + s * a_stb, &mapA, full, kb * bk, qa, zc);
                             else tma_load_3d(a_base + s * a_stb, &mapA, full, q0, kb * bk, zc);
@@ -631,6 +634,7 @@ k_conv_tc(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUte
             if (++s == p.stages) { s = 0; ph ^= 1; }
         }
     }
+teardown:
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     if (warp == WARP_MMA) {
