@@ -284,3 +284,56 @@ def test_f32_model_layerwise(pkg, ob):
     assert checked > 40
     gm.close()
     om.close()
+
+
+@pytest.mark.parametrize("depthwise", [False, True])
+@pytest.mark.parametrize("opt", [1, 3])
+def test_generated_nanodet_like(pkg, ob, depthwise, opt):
+    """BASELINE config 5 shape (synthetic NanoDet-m-like graph, 320x320 int8): depthwise + pointwise blocks, concat,
+    upsample, 1x1 heads.  depthwise=False is the reference's semantics (DEPTHWISE_CONV2D is a no-op,
+    src/mars/mars_runtime.c:1168-1170); True is the restated depthwise (parity unpinned, oracle restatement)."""
+    blob = pkg.marsfile.build_nanodet_like(size=320, seed=7).to_bytes()
+    n = 3
+    gm = pkg.MarsModel(blob, arena_bytes=16 << 20, batch=n)
+    gm.set_opt_level(opt)
+    gm.set_depthwise_mode(1 if depthwise else 0)
+    oms = [ob.OracleModel(blob, arena_bytes=16 << 20, depthwise=depthwise) for _ in range(n)]
+    for step in range(2):  # two frames per stream through the same slots (stale bytes carry over, as in the reference)
+        xs = np.stack([np.random.default_rng(s * 1_000_003 + step).integers(-128, 128, size=3 * 320 * 320, dtype=np.int8) for s in range(n)])
+        gm.upload_inputs(0, n, xs, xs.shape[1])
+        gm.run_resident(0, n)
+        outs = gm.download_outputs(0, n)
+        for i, om in enumerate(oms):
+            om.set_input(xs[i])
+            om.run()
+            at, cnt = first_diff(outs[i], om.output_bytes())
+            assert cnt == 0, "frame %d stream %d: %d output bytes differ, first at %d" % (step, i, cnt, at)
+            if opt <= 2:
+                got = gm.arena_download(i)
+                at, cnt = first_diff(got, om.arena()[: got.size])
+                assert cnt == 0, "frame %d stream %d: %d arena bytes differ, first at %d" % (step, i, cnt, at)
+    gm.close()
+
+
+def test_generated_yolov5_f32_within_tolerance(pkg, ob):
+    """BASELINE config 4 shape (synthetic yolov5-shaped float32 model): convolutions run in the reference's exact
+    accumulation order, SIGMOID uses the device expf -> logits within 1e-3 relative of the reference's (north_star
+    tolerance), same NaN pattern (the head's output tensor holds stale work-buffer bytes)."""
+    blob = pkg.marsfile.build_yolov5(width=0.25, size=160, seed=6, f32=True).to_bytes()
+    arena = 64 << 20
+    gm = pkg.MarsModel(blob, arena_bytes=arena)
+    om = ob.OracleModel(blob, arena_bytes=arena)
+    x = np.random.default_rng(2).random(3 * 160 * 160).astype(np.float32)
+    for run in range(2):
+        gm.set_input(x)
+        gm.run()
+        om.set_input(x)
+        om.run()
+        a, b = gm.output_bytes().view(np.float32), om.output_bytes().view(np.float32)
+        assert np.array_equal(np.isnan(a), np.isnan(b))
+        fin = np.isfinite(b)
+        assert fin.any() and np.array_equal(np.isfinite(a), fin)
+        rel = np.abs(a[fin] - b[fin]) / np.maximum(np.abs(b[fin]), 1e-6)
+        assert rel.max() <= 1e-3, "run %d: max relative error %g" % (run, rel.max())
+    gm.close()
+    om.close()

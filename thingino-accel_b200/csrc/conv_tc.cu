@@ -67,7 +67,9 @@ struct TcParams {
     unsigned long long nhwc_stride;
     unsigned wp_magic;       /* floor(2^32 / Wp) + 1 */
     int halo, halo_min, halo_rb, halo_nb; /* kxk stride 1: one A load per (tile, k block) covers all taps: rows q0+halo_min .., halo_nb boxes of halo_rb rows */
-    int acc_bufs;            /* TMEM accumulator ring depth (tmem_cols / n_tile, at most 8) */
+    int acc_bufs;            /* TMEM accumulator ring depth */
+    int grp, m_groups;       /* M tiles (128 rows each) per pipeline step and accumulator hand-over; groups per image */
+    uint32_t a_tile_bytes;   /* bytes of one M tile's A block per k-step (a_stage_bytes = grp of them, or the halo region) */
     int dbg;                 /* tuning aid (MARS_TC_DEBUG): 2 = epilogue only drains TMEM, 3 = 2 + no per-step TMA loads, 4 = 2 + no MMAs */
     int b_resident;          /* all weight blocks of the (single) N tile stay in shared memory for the whole launch */
     int img0, n_img;         /* first image (TMA coordinate of the slot dimension), images of this launch */
@@ -92,6 +94,17 @@ __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+#ifdef MARS_SPIN_WAIT
+    uint32_t done;
+    do {
+        asm volatile(
+            "{\n\t"
+            ".reg .pred p;\n\t"
+            "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t"
+            "}\n" : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+    } while (!done);
+#else
     asm volatile(
         "{\n\t"
         ".reg .pred p;\n\t"
@@ -101,6 +114,7 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
         "bra WAIT_LOOP;\n\t"
         "WAIT_DONE:\n\t"
         "}\n" ::"r"(bar), "r"(parity) : "memory");
+#endif
 }
 __device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap *map, uint32_t bar, int c0, int c1, int c2) {
     asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
@@ -173,11 +187,17 @@ __device__ __forceinline__ void mbar_wait_relaxed(uint32_t bar, uint32_t parity)
         asm volatile(
             "{\n\t"
             ".reg .pred p;\n\t"
+#ifdef MARS_SPIN_WAIT
+            "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+#else
             "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+#endif
             "selp.u32 %0, 1, 0, p;\n\t"
             "}\n" : "=r"(done) : "r"(bar), "r"(parity) : "memory");
         if (done) break;
+#ifndef MARS_SPIN_WAIT
         __nanosleep(64);
+#endif
     }
 }
 
@@ -306,7 +326,7 @@ k_conv_tc(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUte
     uint8_t *smem_al = smem_raw + (smem_base - smem_u32(smem_raw));
     const uint32_t a_base = smem_base, b_base = smem_base + p.stages * p.a_stage_bytes;
     const int nsteps = p.ntaps * p.ksteps_per_tap;
-    const int tiles_per_img = p.m_tiles * p.n_tiles;
+    const int tiles_per_img = p.m_groups * p.n_tiles; /* scheduling unit = a group of p.grp M tiles x one N tile */
     /* gather-mode shared regions behind the weight tile */
     uint8_t *g_patch = smem_al + (size_t)p.stages * p.a_stage_bytes + p.b_stage_bytes; /* gather: B is one resident block */
     int *g_poff = reinterpret_cast<int *>(g_patch + 4096); /* per patch word: offset inside the input copy */
@@ -356,13 +376,14 @@ k_conv_tc(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUte
         const int quad = warp & 3, part = warp >> 2, parts = EPI >> 2;
         const int r = quad * 32 + lane; /* accumulator row = pixel of the tile */
         const int n_units = p.n_tile >> 4;
-        const long long plane = p.dbg == 1 ? 128 : p.plane;
+        const long long plane = p.plane;
         const float cs = p.cs;
         const uint32_t acc_lane = tmem_d + ((uint32_t)(quad * 32) << 16);
         const uint32_t sa_lut = smem_u32(s_lutw), sa_cm = smem_u32(s_cm);
         const uint32_t sa_full = smem_u32(&bar_tmem_full[0]), sa_empty = smem_u32(&bar_tmem_empty[0]);
         const bool flat = !GATHER && p.Wp == p.Wo && !NHWC; /* no pad columns: the tile row index IS the pixel index */
         uint8_t *const obase = p.out_base + r; /* + image * slot_stride + pixel + channel * plane + stream offset */
+        const int G = p.grp, gcols = p.grp * p.n_tile;
         if (part >= n_units || p.dbg == 7) { /* narrow N tile: nothing to read for this warp, it only releases the accumulators */
             int ab = 0, aph = 0; /* accumulator ring position and phase */
             for (TileIter ti(blockIdx.x, gridDim.x, tiles_per_img); ti.img < p.n_img; ti.next()) {
@@ -372,10 +393,11 @@ k_conv_tc(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUte
                 if (++ab == p.acc_bufs) { ab = 0; aph ^= 1; }
             }
         } else {
-            TileIter ti(blockIdx.x, gridDim.x, tiles_per_img); /* current item: tile ti / tl, unit u */
-            int tl = 0, u = part, ab = 0, aph = 0; /* ab / aph: accumulator ring position and phase of the current item's tile */
-            /* per-tile values of the current item, recomputed when the tile changes */
-            int cached_tl = -1, n0 = 0, co_left = 0;
+            /* current item: group ti (ring slot ab / phase aph), M tile g of the group, unit u */
+            TileIter ti(blockIdx.x, gridDim.x, tiles_per_img);
+            int tl = 0, g = 0, u = part, ab = 0, aph = 0;
+            /* per-M-tile values of the current item, recomputed when the M tile changes */
+            int cached_key = -1, n0 = 0, co_left = 0;
             uint8_t *b0 = nullptr, *b1 = nullptr, *b2 = nullptr, *nh = nullptr;
             uint32_t va[16], vb[16];
             bool have = ti.img < p.n_img;
@@ -387,14 +409,17 @@ k_conv_tc(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUte
             auto step = [&](uint32_t (&vc)[16], uint32_t (&vn)[16]) {
                 /* the next item of this warp */
                 TileIter nti = ti;
-                int ntl = tl, nu = u + parts, nab = ab, naph = aph;
+                int ntl = tl, ng = g, nu = u + parts, nab = ab, naph = aph;
                 if (nu >= n_units) {
-                    nu = part; ntl++; nti.next();
-                    if (++nab == p.acc_bufs) { nab = 0; naph ^= 1; }
+                    nu = part;
+                    if (++ng == G) {
+                        ng = 0; ntl++; nti.next();
+                        if (++nab == p.acc_bufs) { nab = 0; naph ^= 1; }
+                    }
                 }
                 const bool have_n = nti.img < p.n_img;
                 tmem_ld_wait(vc);
-                if (u + parts >= n_units) { /* last read of this accumulator by this warp: hand it back */
+                if (ntl != tl || !have_n) { /* last read of this accumulator group by this warp: hand it back */
                     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
                     __syncwarp();
                     if (lane == 0) mbar_arrive(sa_empty + 8u * ab);
@@ -404,12 +429,13 @@ k_conv_tc(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUte
                         mbar_wait_relaxed(sa_full + 8u * nab, naph);
                         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                     }
-                    tmem_ld16_issue(acc_lane + (uint32_t)(nab * p.n_tile + nu * 16), vn);
+                    tmem_ld16_issue(acc_lane + (uint32_t)(nab * gcols + ng * p.n_tile + nu * 16), vn);
                 }
-                if (cached_tl != tl) {
-                    cached_tl = tl;
-                    const int mt = p.n_tiles == 1 ? ti.rem : ti.rem / p.n_tiles;
-                    n0 = (ti.rem - mt * p.n_tiles) * p.n_tile;
+                if (cached_key != tl * 8 + g) {
+                    cached_key = tl * 8 + g;
+                    const int mg = p.n_tiles == 1 ? ti.rem : ti.rem / p.n_tiles;
+                    n0 = (ti.rem - mg * p.n_tiles) * p.n_tile;
+                    const int mt = mg * G + g;
                     int oh = 0, ow = 0, pix;
                     bool valid;
                     if (flat) {
@@ -431,7 +457,6 @@ k_conv_tc(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUte
                     uint8_t *pix_base = obase + ((unsigned long long)ti.img * p.slot_stride + (long long)n0 * plane + pix);
                     b0 = pix_base + p.out_off[0]; b1 = pix_base + p.out_off[1]; b2 = pix_base + p.out_off[2];
                     co_left = valid ? p.Co - n0 : 0; /* channels of this N tile that exist for this pixel (<= 0: nothing to store) */
-                    if (p.dbg == 1) { b0 = b1 = b2 = obase + p.out_off[0] + (long long)n0 * plane; } /* every tile stores to the same small window */
                     if (NHWC) {
                         long long dp;
                         if (p.nhwc_mode == 2) {
@@ -445,7 +470,7 @@ k_conv_tc(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUte
                 const long long coff = (long long)c0 * plane;
                 if (p.dbg >= 2) { if (vc[0] == 0x12345678u && vc[7] == 0x9abcdef0u) b0[0] = 1; }
                 else epilogue_unit<FAST, NST, NHWC, 16>(vc, sa_cm + 4u * (uint32_t)(n0 + c0), sa_lut, cs, b0 + coff, b1 + coff, b2 + coff, plane, co_left - c0, nh + c0);
-                ti = nti; tl = ntl; u = nu; ab = nab; aph = naph; have = have_n;
+                ti = nti; tl = ntl; g = ng; u = nu; ab = nab; aph = naph; have = have_n;
             };
             while (have) {
                 step(va, vb);
@@ -468,7 +493,8 @@ k_conv_tc(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUte
             /* per MMA (K = 32): K-major operands advance 32 bytes inside the swizzle atom; the MN-major A (NCHW planes,
              * 128B swizzle) advances 32 K-rows of 128 bytes = 4 atoms of 8 rows */
             const uint32_t a_j16 = p.a_kmajor ? 2u : 256u;
-            const int nj = p.bk >> 5, stages = p.stages, acc_bufs = p.acc_bufs, n_tile = p.n_tile, n_img = p.n_img;
+            const int nj = p.bk >> 5, stages = p.stages, acc_bufs = p.acc_bufs, n_tile = p.n_tile, n_img = p.n_img, G = p.grp;
+            const uint32_t a_tile16 = p.a_tile_bytes >> 4, g_rows16 = (uint32_t)(TC_BM * p.bk) >> 4;
             const int ntaps = p.ntaps, ksteps = p.ksteps_per_tap;
             const uint32_t idesc = p.idesc;
             const bool b_res = GATHER || p.b_resident, halo = p.halo != 0;
@@ -479,8 +505,7 @@ k_conv_tc(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUte
             for (TileIter ti(blockIdx.x, gridDim.x, tiles_per_img); ti.img < n_img; ti.next()) {
                 mbar_wait(sa_tempty + 8u * buf, aph); /* epilogue drained this accumulator */
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                const uint32_t acc = tmem_d + (uint32_t)(buf * n_tile);
-                uint32_t accum = 0;
+                const uint32_t acc = tmem_d + (uint32_t)(buf * G * n_tile);
                 if (halo) {
                     /* a tap = the same rows shifted: the operand simply starts (shift) rows further down.  The swizzle is a
                      * function of the absolute shared-memory address (measured: a start address that is not a multiple of
@@ -489,10 +514,13 @@ k_conv_tc(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUte
                         mbar_wait(sa_full + 8u * s, ph);
                         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                         const uint32_t a_st = a_lo0 + s * a_st16;
-                        uint32_t b_lo = b_lo0 + kb * b_st16;
-                        for (int tap = 0; tap < ntaps; tap++, b_lo += ksteps * b_st16) {
-                            const uint32_t a_lo = a_st + (uint32_t)s_shift[tap]; /* halo mode: row shift in 16-byte units */
-                            for (int j = 0; j < nj; j++) { umma_i8_parts(acc, a_lo + 2u * j, hi_k, b_lo + 2u * j, hi_k, idesc, accum); accum = 1; }
+                        for (int g = 0; g < G; g++) { /* M tile g of the group starts 128 rows further down the same stage */
+                            uint32_t b_lo = b_lo0 + kb * b_st16;
+                            for (int tap = 0; tap < ntaps; tap++, b_lo += ksteps * b_st16) {
+                                const uint32_t a_lo = a_st + g * g_rows16 + (uint32_t)s_shift[tap]; /* halo mode: row shift in 16-byte units */
+                                for (int j = 0; j < nj; j++)
+                                    umma_i8_parts(acc + (uint32_t)(g * n_tile), a_lo + 2u * j, hi_k, b_lo + 2u * j, hi_k, idesc, (uint32_t)((kb | tap | j) != 0));
+                            }
                         }
                         umma_commit(sa_empty + 8u * s);
                         if (++s == stages) { s = 0; ph ^= 1; }
@@ -501,8 +529,11 @@ k_conv_tc(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUte
                     for (int i = 0; i < nsteps; i++) {
                         mbar_wait(sa_full + 8u * s, ph);
                         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                        const uint32_t a_lo = a_lo0 + s * a_st16, b_lo = b_lo0 + (b_res ? i : s) * b_st16;
-                        if (p.dbg != 4) for (int j = 0; j < nj; j++) { umma_i8_parts(acc, a_lo + a_j16 * j, hi_a, b_lo + 2u * j, hi_k, idesc, accum); accum = 1; }
+                        const uint32_t a_st = a_lo0 + s * a_st16, b_lo = b_lo0 + (b_res ? i : s) * b_st16;
+                        if (p.dbg != 4)
+                            for (int g = 0; g < G; g++)
+                                for (int j = 0; j < nj; j++)
+                                    umma_i8_parts(acc + (uint32_t)(g * n_tile), a_st + g * a_tile16 + a_j16 * j, hi_a, b_lo + 2u * j, hi_k, idesc, (uint32_t)((i | j) != 0));
                         umma_commit(sa_empty + 8u * s); /* frees the stage when these MMAs retire */
                         if (++s == stages) { s = 0; ph ^= 1; }
                     }
@@ -514,7 +545,8 @@ k_conv_tc(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUte
     } else if (!GATHER) {
         if (warp == WARP_PROD && lane == 0) { /* ===== TMA producer (same care for the per-step instruction count) ===== */
             const int bk = p.bk, ntaps = p.ntaps, ksteps = p.ksteps_per_tap, stages = p.stages, n_img = p.n_img, n_tiles = p.n_tiles;
-            const uint32_t a_stb = p.a_stage_bytes, b_stb = p.b_stage_bytes;
+            const uint32_t a_stb = p.a_stage_bytes, b_stb = p.b_stage_bytes, a_tb = p.a_tile_bytes;
+            const int G = p.grp;
             const bool b_res = p.b_resident != 0, a_km = p.a_kmajor != 0;
             const uint32_t sa_full = smem_u32(&bar_full[0]), sa_empty = smem_u32(&bar_empty[0]);
             if (b_res) { /* the whole repacked weight matrix of this N tile set stays in shared memory */
@@ -528,7 +560,7 @@ k_conv_tc(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUte
                 const int nb = p.halo_nb, rb = p.halo_rb, hmin = p.halo_min;
                 const uint32_t tx = (uint32_t)(nb * rb * bk), box_b = (uint32_t)(rb * bk);
                 for (TileIter ti(blockIdx.x, gridDim.x, tiles_per_img); ti.img < n_img; ti.next()) {
-                    const int q0 = ti.rem * TC_BM + hmin, zc = p.img0 + ti.img; /* n_tiles == 1 with resident weights */
+                    const int q0 = ti.rem * G * TC_BM + hmin, zc = p.img0 + ti.img; /* n_tiles == 1 with resident weights */
                     for (int kb = 0; kb < ksteps; kb++) {
                         mbar_wait(sa_empty + 8u * s, ph);
                         const uint32_t full = sa_full + 8u * s, dst = a_base + s * a_stb;
@@ -541,8 +573,8 @@ k_conv_tc(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUte
             } else {
                 const uint32_t tx = b_res ? a_stb : p.tx_bytes;
                 for (TileIter ti(blockIdx.x, gridDim.x, tiles_per_img); ti.img < n_img; ti.next()) {
-                    const int mt = n_tiles == 1 ? ti.rem : ti.rem / n_tiles, n0 = (ti.rem - mt * n_tiles) * p.n_tile;
-                    const int q0 = mt * TC_BM, zc = p.img0 + ti.img;
+                    const int mg = n_tiles == 1 ? ti.rem : ti.rem / n_tiles, n0 = (ti.rem - mg * n_tiles) * p.n_tile;
+                    const int q0 = mg * G * TC_BM, zc = p.img0 + ti.img;
                     for (int tap = 0; tap < ntaps; tap++) {
                         const int qa = q0 + s_shift[tap];
                         for (int kb = 0; kb < ksteps; kb++) {
@@ -550,8 +582,10 @@ k_conv_tc(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUte
                             const uint32_t full = sa_full + 8u * s;
                             if (p.dbg == 3) { mbar_arrive(full); if (++s == stages) { s = 0; ph ^= 1; } continue; }
                             mbar_expect_tx(full, tx);
-                            if (a_km) tma_load_3d(a_base + s * a_stb, &mapA, full, kb * bk, qa, zc);
-                            else tma_load_3d(a_base + s * a_stb, &mapA, full, q0, kb * bk, zc);
+                            for (int g = 0; g < G; g++) { /* rows beyond the tensor (last, partial group) are zero-filled */
+                                if (a_km) tma_load_3d(a_base + s * a_stb + g * a_tb, &mapA, full, kb * bk, qa + g * TC_BM, zc);
+                                else tma_load_3d(a_base + s * a_stb + g * a_tb, &mapA, full, q0 + g * TC_BM, kb * bk, zc);
+                            }
                             if (!b_res) tma_load_3d(b_base + s * b_stb, &mapB, full, kb * bk, n0, tap);
                             if (++s == stages) { s = 0; ph ^= 1; }
                         }
@@ -585,19 +619,21 @@ k_conv_tc(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUte
                 }
             }
         };
-        int s = 0, ph = 1;
+        int s = 0, ph = 1, g = 0;
+        const int G = p.grp;
         TileIter ti(blockIdx.x, gridDim.x, tiles_per_img);
-        if (ti.img < p.n_img) prefetch(ti.img, ti.rem);
+        if (ti.img < p.n_img) prefetch(ti.img, ti.rem * G);
         for (; ti.img < p.n_img;) {
             asm volatile("bar.sync 2, 128;" ::: "memory"); /* the previous tile's rows have been built: the patch may be replaced */
 #pragma unroll
             for (int i = 0; i < 8; i++)
                 if (pr + 128 * i < nwords) reinterpret_cast<uint32_t *>(g_patch)[pr + 128 * i] = pre[i];
             asm volatile("bar.sync 2, 128;" ::: "memory");
-            ti.next();
-            if (ti.img < p.n_img) prefetch(ti.img, ti.rem); /* in flight while this tile's rows are built */
-            mbar_wait_relaxed(smem_u32(&bar_empty[s]), ph);
-            uint8_t *row = smem_al + (size_t)s * p.a_stage_bytes + pr * 128;
+            const int gcur = g;
+            if (++g == G) { g = 0; ti.next(); }
+            if (ti.img < p.n_img) prefetch(ti.img, ti.rem * G + g); /* in flight while this tile's rows are built */
+            if (gcur == 0) mbar_wait_relaxed(smem_u32(&bar_empty[s]), ph); /* the stage holds the whole group */
+            uint8_t *row = smem_al + (size_t)s * p.a_stage_bytes + (size_t)gcur * p.a_tile_bytes + pr * 128;
             const uint8_t *pb = g_patch + tb;
             /* K columns >= Kt meet zero weights (k_repack_rows pads B with zeros), so whatever bytes sit there are
              * harmless: table entries beyond Kt point at offset 0 and 16-byte chunks beyond Kt are not written at all */
@@ -628,10 +664,12 @@ k_conv_tc(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUte
                     }
                 }
             }
-            asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); /* generic-proxy writes -> visible to the MMA's async proxy */
-            __syncwarp();
-            if (lane == 0) mbar_arrive(smem_u32(&bar_full[s]));
-            if (++s == p.stages) { s = 0; ph ^= 1; }
+            if (gcur == G - 1) {
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); /* generic-proxy writes -> visible to the MMA's async proxy */
+                __syncwarp();
+                if (lane == 0) mbar_arrive(smem_u32(&bar_full[s]));
+                if (++s == p.stages) { s = 0; ph ^= 1; }
+            }
         }
     }
 teardown:
@@ -913,18 +951,26 @@ bool tc_plan(const Op &o, const ArenaGeom &ag, uint8_t *scratch, size_t scratch_
     p.bk = ci_eff % 128 == 0 ? 128 : (ci_eff % 64 == 0 ? 64 : 32);
     p.ksteps_per_tap = ci_eff / p.bk;
     p.ntaps = g.ntaps;
-    p.a_stage_bytes = (uint32_t)(TC_BM * p.bk);
+    p.a_tile_bytes = (uint32_t)(TC_BM * p.bk);
     p.b_stage_bytes = (uint32_t)round_up(p.n_tile * p.bk, 1024);
-    p.tx_bytes = p.a_stage_bytes + (uint32_t)(p.n_tile * p.bk);
-    /* accumulator ring in TMEM: two CTAs per SM share the 512 columns when two accumulators fit into 256 of them; the
-     * ring is as deep as the columns allow (up to 8), which decouples the MMA issuer from the epilogue's hand-back latency */
+    /* Accumulators in TMEM: two CTAs per SM share the 512 columns when a double-buffered accumulator group fits into 256.
+     * Narrow N tiles are processed in groups of several M tiles per pipeline step: the per-step cost of the single-thread
+     * producer / MMA loops and of the barrier hand-overs (measured: ~0.7 us per step, whatever the tile holds) is then
+     * paid once per group. */
     t->ctas_per_sm = 2 * p.n_tile > 256 ? 1 : 2;
     p.tmem_cols = t->ctas_per_sm == 1 ? 512 : 256;
-    p.acc_bufs = std::min(8, p.tmem_cols / p.n_tile);
-    { static const int force = getenv("MARS_TC_ACC_BUFS") ? atoi(getenv("MARS_TC_ACC_BUFS")) : 0; if (force >= 2) p.acc_bufs = std::min(p.acc_bufs, force); }
+    p.grp = 1;
+    if (p.n_tiles == 1 && t->ctas_per_sm == 2) {
+        static const int gmax = getenv("MARS_TC_GROUP") ? std::max(1, atoi(getenv("MARS_TC_GROUP"))) : 4;
+        while (p.grp * 2 <= gmax && 2 * (p.grp * 2) * p.n_tile <= p.tmem_cols) p.grp *= 2;
+    }
+    p.acc_bufs = std::max(2, std::min(4, p.tmem_cols / (p.grp * p.n_tile)));
+    p.a_stage_bytes = p.grp * p.a_tile_bytes;
+    p.tx_bytes = p.a_stage_bytes + (uint32_t)(p.n_tile * p.bk);
     const int budget = t->ctas_per_sm == 1 ? 200 * 1024 : 100 * 1024;
     const int nsteps = g.ntaps * p.ksteps_per_tap;
     if (gather) { /* + 4 KiB patch + 8 KiB patch-word tables */
+        if (p.grp > 2) { p.grp = 2; p.a_stage_bytes = p.grp * p.a_tile_bytes; p.acc_bufs = std::max(2, std::min(4, p.tmem_cols / (p.grp * p.n_tile))); }
         p.stages = std::max(2, std::min(8, (budget - (int)p.b_stage_bytes - 12288 - 1024) / (int)p.a_stage_bytes));
         t->smem = 1024 + (size_t)p.stages * p.a_stage_bytes + p.b_stage_bytes + 12288;
     } else {
@@ -936,7 +982,7 @@ bool tc_plan(const Op &o, const ArenaGeom &ag, uint8_t *scratch, size_t scratch_
         static const bool halo_enabled = !(getenv("MARS_TC_HALO") && atoi(getenv("MARS_TC_HALO")) == 0);
         if (halo_enabled && g.prepass == 1 && p.b_resident && g.ntaps > 1) {
             const int smin = -o.pt * g.Wp, smax = (o.kh - 1 - o.pt) * g.Wp + o.kw - 1;
-            const int R = TC_BM + smax - smin;
+            const int R = p.grp * TC_BM + smax - smin;
             const int nb = (R + 255) / 256, rb = round_up((R + nb - 1) / nb, 8);
             const uint32_t bytes = (uint32_t)round_up(nb * rb * p.bk, 1024);
             if (rb <= 256 && (size_t)2 * bytes + b_all <= (size_t)budget) {
@@ -972,6 +1018,7 @@ bool tc_plan(const Op &o, const ArenaGeom &ag, uint8_t *scratch, size_t scratch_
     p.cs = o.f0;
     p.slot_stride = ag.slot_stride;
     p.m_tiles = (p.mflat + TC_BM - 1) / TC_BM;
+    p.m_groups = (p.m_tiles + p.grp - 1) / p.grp;
     p.wp_magic = (unsigned)((1ull << 32) / (unsigned)g.Wp) + 1u;
     if ((unsigned long long)p.mflat * (unsigned)g.Wp >= (1ull << 32) || (long long)p.m_tiles * p.n_tiles * ag.capacity >= (1ll << 31)) { delete t; return false; }
     if (gather) {
@@ -979,6 +1026,7 @@ bool tc_plan(const Op &o, const ArenaGeom &ag, uint8_t *scratch, size_t scratch_
         p.tw_shift = g.tw_shift;
         p.tiles_x = (o.ow + tw - 1) / tw;
         p.m_tiles = p.tiles_x * ((o.oh + th - 1) / th);
+        p.m_groups = (p.m_tiles + p.grp - 1) / p.grp;
         p.gPH = g.PH; p.gPWW = g.PWW; p.gdx = g.dx;
         p.g_align2 = (o.sh % 2 == 0 && o.kw % 2 == 0 && g.dx % 2 == 0) ? 1 : 0;
     }
@@ -1079,7 +1127,7 @@ bool tc_launch(const TcPlan &plan, uint8_t *slots_base, int first, int n, bool u
     p.n_img = n;
     if (t->prepass == 3) p.g_src = scr;
     if (p.nhwc_sel >= 0) p.nhwc_base += (size_t)first * p.nhwc_stride;
-    const long long total_tiles = (long long)p.m_tiles * p.n_tiles * n;
+    const long long total_tiles = (long long)p.m_groups * p.n_tiles * n;
     static int sms = 0;
     if (!sms) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); if (sms <= 0) sms = 148; }
     const unsigned grid = (unsigned)std::min<long long>(total_tiles, (long long)sms * t->ctas_per_sm);
