@@ -75,6 +75,13 @@ mars_error_t mars_b200_download_detections(mars_model_t *m, int first, int n, ma
 /* end to end from host buffers: H2D, all layers, decode, NMS, D2H (pipelined in chunks) */
 mars_error_t mars_b200_detect_batch(mars_model_t *m, int n, const void *inputs, size_t in_stride,
                                     mars_det_t *dets, int32_t *counts, int maxd, float nms_thresh);
+/* asynchronous form: queue a batch of up to capacity/2 images on half `pool` (0 or 1) of the slot pool and return;
+ * mars_b200_wait_batch(pool) blocks until its detections are in dets/counts.  Submitting to one half while the other
+ * computes overlaps the host->device copy and the read-back with the kernels.  Buffers must stay valid (pinned memory,
+ * e.g. nna_malloc, for true overlap) until the wait returns. */
+mars_error_t mars_b200_submit_batch(mars_model_t *m, int pool, int n, const void *inputs, size_t in_stride,
+                                    mars_det_t *dets, int32_t *counts, int maxd, float nms_thresh);
+mars_error_t mars_b200_wait_batch(mars_model_t *m, int pool);
 /* end to end from host buffers returning raw output tensor 0 per image */
 mars_error_t mars_b200_run_batch(mars_model_t *m, int n, const void *inputs, size_t in_stride,
                                  void *outputs, size_t out_stride);

@@ -337,3 +337,41 @@ def test_generated_yolov5_f32_within_tolerance(pkg, ob):
         assert rel.max() <= 1e-3, "run %d: max relative error %g" % (run, rel.max())
     gm.close()
     om.close()
+
+
+def test_submit_wait_batches_match_the_synchronous_path(pkg, ob):
+    """mars_b200_submit_batch / wait_batch (two halves of the slot pool, copies overlapping kernels) give the same
+    detection lists as the oracle, batch after batch, including a short last batch"""
+    blob = pkg.marsfile.build_yolov5(width=0.125, size=160, seed=9).to_bytes()
+    half, total = 3, 8
+    gm = pkg.MarsModel(blob, arena_bytes=8 << 20, batch=2 * half)
+    rng = np.random.default_rng(21)
+    xs = rng.integers(-128, 128, size=(total, 3 * 160 * 160), dtype=np.int8)
+    want = []
+    for i in range(total):
+        om = ob.OracleModel(blob, arena_bytes=8 << 20)
+        om.set_input(xs[i])
+        om.run()
+        o = om.output_bytes().view(np.int8)
+        want.append(ob.nms(ob.parse_output(o, o.size // 85, om.tensor_desc(om.output_index()).scale)))
+        om.close()
+    dets = [np.zeros((half, 1000), dtype=pkg.capi.DET_DTYPE) for _ in range(2)]
+    counts = [np.zeros(half, dtype=np.int32) for _ in range(2)]
+    batches = [(s, min(half, total - s)) for s in range(0, total, half)]
+
+    def check(k):
+        s, n = batches[k]
+        gm.wait_batch(k & 1)
+        for i in range(n):
+            w = want[s + i]
+            assert counts[k & 1][i] == len(w) and dets[k & 1][i, : len(w)].tobytes() == w.tobytes(), "batch %d image %d" % (k, i)
+
+    for k, (s, n) in enumerate(batches):
+        if k >= 2:
+            check(k - 2)  # the half is reused: its previous batch must have been collected
+        gm.submit_batch(k & 1, n, xs[s:s + n], xs.shape[1], dets[k & 1], counts[k & 1])
+    for k in range(max(0, len(batches) - 2), len(batches)):
+        check(k)
+    with pytest.raises(pkg.capi.MarsError):
+        gm.submit_batch(0, half + 1, xs, xs.shape[1], dets[0], counts[0])
+    gm.close()

@@ -151,6 +151,8 @@ SIGNATURES = {
     "mars_b200_step_resident": (C.c_int, [PM, C.c_int, C.c_int, C.c_float, C.c_int]),
     "mars_b200_download_detections": (C.c_int, [PM, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int]),
     "mars_b200_detect_batch": (C.c_int, [PM, C.c_int, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_int, C.c_float]),
+    "mars_b200_submit_batch": (C.c_int, [PM, C.c_int, C.c_int, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_int, C.c_float]),
+    "mars_b200_wait_batch": (C.c_int, [PM, C.c_int]),
     "mars_b200_run_batch": (C.c_int, [PM, C.c_int, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t]),
     "mars_b200_detections_device": (None, [PM, C.c_void_p, C.c_void_p, C.c_void_p]),
     "mars_b200_launch_count": (C.c_uint64, [PM]),
@@ -341,6 +343,14 @@ class MarsModel:
     def detect_batch(self, n, inputs, in_stride, dets, counts, maxd=1000, thresh=0.45):
         self._check(lib().mars_b200_detect_batch(self.m, n, _addr(inputs), in_stride, _addr(dets), _addr(counts), maxd, thresh),
                     "detect_batch")
+
+    def submit_batch(self, pool, n, inputs, in_stride, dets, counts, maxd=1000, thresh=0.45):
+        """queue a batch on half `pool` of the slot pool; buffers must stay alive until wait_batch(pool)"""
+        self._check(lib().mars_b200_submit_batch(self.m, pool, n, _addr(inputs), in_stride, _addr(dets), _addr(counts), maxd, thresh),
+                    "submit_batch")
+
+    def wait_batch(self, pool):
+        self._check(lib().mars_b200_wait_batch(self.m, pool), "wait_batch")
 
     def run_batch(self, n, inputs, in_stride, outputs, out_stride):
         self._check(lib().mars_b200_run_batch(self.m, n, _addr(inputs), in_stride, _addr(outputs), out_stride), "run_batch")

@@ -156,6 +156,8 @@ struct Model {
     cudaEvent_t ev_in[2] = {nullptr, nullptr}, ev_done[2] = {nullptr, nullptr}, ev_out[2] = {nullptr, nullptr};
     float last_ms = 0.0f;
     uint64_t launches = 0;
+    /* asynchronous batches (mars_b200_submit_batch / wait_batch): one in flight per half of the slot pool */
+    struct Pending { bool active = false; int n = 0, maxd = 0; int32_t *counts = nullptr; } pending[2];
     /* device-resident detections */
     mars_det_t *d_raw = nullptr, *d_det = nullptr;
     int32_t *d_raw_cnt = nullptr, *d_det_cnt = nullptr;
@@ -1094,6 +1096,67 @@ mars_error_t mars_b200_run_batch(mars_model_t *model, int n, const void *inputs,
     if (!m || !inputs || !outputs) return MARS_ERR_INVALID_FILE;
     CU_OK(cudaSetDevice(m->device), MARS_ERR_NNA_INIT_FAILED);
     return batch_pipeline(m, n, inputs, in_stride, outputs, out_stride, nullptr, nullptr, 0, 0.0f);
+}
+
+/* Asynchronous form of mars_b200_detect_batch: the slot pool is split into two halves ("pools" 0 and 1); a batch of up to
+ * capacity/2 images is queued on one half -- H2D on the copy stream, layers + decode + NMS on the compute stream, D2H of the
+ * detection records on the read-back stream -- and the call returns.  While it runs the caller submits the next batch to the
+ * other half, so the host->device copy of batch k+1 and the read-back of batch k-1 overlap the kernels of batch k.
+ * inputs / dets / counts must stay valid (and should be pinned, e.g. nna_malloc) until mars_b200_wait_batch(pool) returns. */
+mars_error_t mars_b200_submit_batch(mars_model_t *model, int pool, int n, const void *inputs, size_t in_stride, mars_det_t *dets,
+                                    int32_t *counts, int maxd, float nms_thresh) {
+    Model *m = as_model(model);
+    if (!m || !inputs || !dets || !counts || pool < 0 || pool > 1) return MARS_ERR_INVALID_FILE;
+    CU_OK(cudaSetDevice(m->device), MARS_ERR_NNA_INIT_FAILED);
+    const int half = m->capacity / 2;
+    if (half < 1 || n < 0 || n > half) {
+        set_last_error("submit_batch: %d images do not fit half of the slot pool (capacity %d; mars_b200_set_batch)", n, m->capacity);
+        return MARS_ERR_INVALID_TENSOR;
+    }
+    if (m->pending[pool].active) {
+        set_last_error("submit_batch: pool %d still has a batch in flight (mars_b200_wait_batch first)", pool);
+        return MARS_ERR_LAYER_FAILED;
+    }
+    if (maxd > 1000) maxd = 1000;
+    if (maxd < 0) maxd = 0;
+    const size_t in_bytes = io_bytes(&m->pub, 0);
+    if (in_stride < in_bytes) in_stride = in_bytes;
+    const int first = pool * half;
+    mars_error_t e = MARS_OK;
+    if (n > 0) {
+        /* the half is free: its previous batch was waited for (read-back complete) before this call */
+        e = copy_io(m, first, n, const_cast<void *>(inputs), in_stride, 0, m->h2d_stream);
+        if (e != MARS_OK) return e;
+        cudaEventRecord(m->ev_in[pool], m->h2d_stream);
+        cudaStreamWaitEvent(m->stream, m->ev_in[pool], 0);
+        e = enqueue_run(m, first, n);
+        if (e == MARS_OK) e = enqueue_detect(m, first, n, nms_thresh);
+        if (e != MARS_OK) { cudaStreamSynchronize(m->stream); return e; }
+        cudaEventRecord(m->ev_done[pool], m->stream);
+        cudaStreamWaitEvent(m->d2h_stream, m->ev_done[pool], 0);
+        e = copy_dets(m, first, n, dets, counts, maxd, m->d2h_stream);
+        if (e != MARS_OK) return e;
+    }
+    cudaEventRecord(m->ev_out[pool], m->d2h_stream);
+    m->pending[pool].active = true;
+    m->pending[pool].n = n; m->pending[pool].maxd = maxd; m->pending[pool].counts = counts;
+    return MARS_OK;
+}
+
+mars_error_t mars_b200_wait_batch(mars_model_t *model, int pool) {
+    Model *m = as_model(model);
+    if (!m || pool < 0 || pool > 1) return MARS_ERR_INVALID_FILE;
+    if (!m->pending[pool].active) return MARS_OK;
+    CU_OK(cudaSetDevice(m->device), MARS_ERR_NNA_INIT_FAILED);
+    cudaError_t ce = cudaEventSynchronize(m->ev_out[pool]);
+    Model::Pending &pd = m->pending[pool];
+    pd.active = false;
+    if (ce != cudaSuccess) {
+        set_last_error("wait_batch: %s", cudaGetErrorString(ce));
+        return MARS_ERR_LAYER_FAILED;
+    }
+    for (int i = 0; i < pd.n; i++) if (pd.counts[i] > pd.maxd) pd.counts[i] = pd.maxd;
+    return MARS_OK;
 }
 
 uint64_t mars_b200_launch_count(mars_model_t *model) {
