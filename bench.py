@@ -4,15 +4,16 @@
     python bench.py --gpus N --steps K --warmup W            # this framework (CUDA)
     python bench.py --impl reference --steps K --warmup W    # the reference's CPU path
 
-A step = one pass of the hot path (all .mars layers, YOLO decode, class-wise NMS) over one
-batch of synthetic images per GPU.  The model is the yolov5s-shaped graph written by
+A step = one pass of the hot path (all .mars layers, YOLO decode, class-wise NMS) over the global
+batch of BASELINE configs[2] -- 1024 synthetic 640x640 images, sharded 1024 / N per GPU (strong scaling).  The model is the yolov5s-shaped graph written by
 thingino-accel_b200/marsfile.py (the reference's yolov5s_int8.mars is a missing blob; same layer
 table as the shipped yolov5n_int8.mars at 2x width, SYNTHETIC weights, seed 5).
 
   value : whole-job images/s with the batch already resident in HBM (device time, CUDA events
           on the library's stream, max over ranks);
-  e2e   : the same through mars_b200_detect_batch() with HOST (pinned) buffers -- H2D of every
-          image and D2H of the detection lists inside the timed region;
+  e2e   : the same through mars_b200_submit_batch() / mars_b200_wait_batch() with HOST (pinned) buffers -- H2D of
+          every image and D2H of every detection list inside the timed region, 256 images per submit so that
+          the copies of one submit overlap the kernels of the previous one;
   roofline / cpu_baseline : see DESIGN.md section 6.
 
 Images shard across ranks (one process per GPU, no data-path collective); rank 0 gathers the
@@ -35,6 +36,7 @@ sys.path.insert(0, ROOT)
 from __graft_entry__ import load_package  # noqa: E402
 
 METRIC = "yolov5s_int8_640_images_per_s"
+GLOBAL_BATCH = 1024  # BASELINE configs[2]: "batch 1024 sharded across 1/2/4/8 B200" -> strong scaling, 1024 / N images per GPU per step
 WORKLOAD = "BASELINE configs[2]: yolov5s_int8.mars-shaped 640x640 int8, all layers + decode + NMS"
 MODEL_FILE = ("synthetic yolov5s-shaped .mars (2x-width copy of the shipped yolov5n_int8 layer table, writer seed 5); "
               "the reference's yolov5s_int8.mars is a missing blob")
@@ -160,7 +162,7 @@ def run_reference_arm(args):
     value = args.steps * cores / dt
     sample = "%d image(s) per step on each of %d processes (one per host core), yolov5s-shaped 640x640 int8, all layers + decode + NMS" % (1, cores)
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
+            "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "int8", "data": "synthetic",
             "config": {"workload": WORKLOAD, "model_file": MODEL_FILE, "images_per_step": cores, "image": "3x640x640 int8",
                        "arena_bytes": arena, "parallelism": "%d independent host processes, one image each per step" % cores},
@@ -247,7 +249,7 @@ def run_cuda_arm(args):
     pkg = load_package()
     L = pkg.lib()
     blob, arena = build_model_blob(pkg)
-    B = args.batch
+    B = args.batch if args.batch > 0 else max(1, GLOBAL_BATCH // world)
     gm = pkg.MarsModel(blob, arena_bytes=arena, device=local_rank, batch=B)
     in_bytes = gm.input_bytes
     # synthetic inputs in pinned host memory
@@ -257,8 +259,6 @@ def run_cuda_arm(args):
     imgs = synth_images(rank * B, uniq)
     for i in range(B):
         host_in[i] = imgs[i % uniq]
-    host_dets, _ = pinned_array(L, B * 1000 * 24)
-    host_cnt, _ = pinned_array(L, B * 4, np.int32)
     gm.upload_inputs(0, B, host_in, in_bytes)
 
     # device-side gather of detections (the one collective of the path)
@@ -325,20 +325,25 @@ def run_cuda_arm(args):
     # pinned host memory to HBM and reads its detection records back; batch k+1 is submitted before batch k is
     # waited for, so the copies overlap the kernels (two halves of a 2B-slot pool).  K steps are timed, pipeline
     # fill and drain included.
-    gm.set_batch(2 * B)
-    host_dets2, _ = pinned_array(L, B * 1000 * 24)
-    host_cnt2, _ = pinned_array(L, B * 4, np.int32)
-    outs = [(host_dets, host_cnt), (host_dets2, host_cnt2)]
-    pool_gather = [make_gatherer(0, B), make_gatherer(B, B)]  # the slot pool was re-allocated: new device addresses
+    SUB = min(B, 256)  # images per submit: two halves of a 2*SUB-slot pool; a step = B / SUB submits
+    nsub = (B + SUB - 1) // SUB
+    gm.set_batch(2 * SUB)
+    outs = []
+    for _ in range(2):
+        d, _p = pinned_array(L, SUB * 1000 * 24)
+        c, _p = pinned_array(L, SUB * 4, np.int32)
+        outs.append((d, c))
+    pool_gather = [make_gatherer(0, SUB), make_gatherer(SUB, SUB)]  # the slot pool was re-allocated: new device addresses
 
     def e2e_steps(k):
-        gm.submit_batch(0, B, host_in, in_bytes, outs[0][0], outs[0][1], 1000, NMS_THRESH)
-        for i in range(1, k):
-            gm.submit_batch(i & 1, B, host_in, in_bytes, outs[i & 1][0], outs[i & 1][1], 1000, NMS_THRESH)
-            gm.wait_batch((i - 1) & 1)
-            pool_gather[(i - 1) & 1].run()
-        gm.wait_batch((k - 1) & 1)
-        pool_gather[(k - 1) & 1].run()
+        jobs = [(j * SUB, min(SUB, B - j * SUB)) for _ in range(k) for j in range(nsub)]
+        for i, (first, n) in enumerate(jobs):
+            gm.submit_batch(i & 1, n, host_in[first:first + n], in_bytes, outs[i & 1][0], outs[i & 1][1], 1000, NMS_THRESH)
+            if i >= 1:
+                gm.wait_batch((i - 1) & 1)
+                pool_gather[(i - 1) & 1].run()
+        gm.wait_batch((len(jobs) - 1) & 1)
+        pool_gather[(len(jobs) - 1) & 1].run()
 
     e2e_steps(2)
     barrier()
@@ -347,7 +352,7 @@ def run_cuda_arm(args):
     barrier()
     e2e_ms = maxr((time.perf_counter() - t0) * 1e3) / args.steps
     e2e_value = world * B / (e2e_ms * 1e-3)
-    checksum = int(host_cnt.sum())
+    checksum = int(outs[0][1].sum()) + int(outs[1][1].sum())
 
     peaks, peak_note = load_peaks()
     roof, shares = roofline_from_profile(prof, B, peaks, peak_note)
@@ -366,11 +371,12 @@ def run_cuda_arm(args):
             cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": kind,
                    "sample": "1 image on each of %d host processes (%.1f s), same model and input recipe" % (cores, dt)}
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
-                "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int8",
+                "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "int8",
                 "data": "synthetic",
                 "config": {"workload": WORKLOAD, "model_file": MODEL_FILE, "images_per_step": B * world,
                            "global_batch": B * world, "per_gpu_batch": B, "image": "3x640x640 int8", "arena_bytes": arena,
-                           "parallelism": "images sharded, dp%d, detections gathered to rank 0 over NCCL" % world,
+                           "parallelism": "images sharded, dp%d (global batch %d, strong scaling), detections gathered to rank 0 over NCCL" % (world, B * world),
+                           "e2e_submit_images": SUB,
                            "l2": "working set %.1f GB per GPU >> 126 MB L2 (no flush needed)" % (B * gm.slot_stride / 1e9)},
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": B * in_bytes * world,
                         "d2h_bytes_per_step": (B * 1000 * 24 + B * 4) * world, "ms_per_step": e2e_ms},
@@ -389,7 +395,8 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="cuda", choices=["cuda", "reference"])
-    ap.add_argument("--batch", type=int, default=int(os.environ.get("MARS_BENCH_BATCH", "128")), help="images per GPU per step")
+    ap.add_argument("--batch", type=int, default=int(os.environ.get("MARS_BENCH_BATCH", "0")),
+                    help="images per GPU per step (default: 1024 / number of GPUs)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
