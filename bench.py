@@ -358,6 +358,14 @@ def run_cuda_arm(args):
     roof, shares = roofline_from_profile(prof, B, peaks, peak_note)
     if roof:
         roof["ms_per_step_with_op_events"] = prof_ms_per_step
+        # DRAM bytes per launch of the dominant kernel group from the committed ncu capture (profiles/), scaled to this batch
+        tpath = os.path.join(ROOT, "profiles", "r01_traffic_conv_tc.json")
+        if roof["kernel"] == "conv_tcgen05_i8" and os.path.exists(tpath):
+            tr = json.load(open(tpath))
+            roof["traffic"] = tr["dram_bytes_per_image"] * B / tr["launches_per_step"]
+            roof["traffic_source"] = "profiles/r01_traffic_conv_tc.json (ncu dram__bytes_read.sum + dram__bytes_write.sum, %d images/GPU, per launch)" % tr["batch_per_gpu"]
+            roof["hbm_gbs_achieved"] = roof["traffic"] / (roof["avg_launch_ms"] * 1e-3) / 1e9
+            roof["hbm_frac"] = roof["hbm_gbs_achieved"] / peaks["hbm_gbs"]
 
     line = None
     if rank == 0:
