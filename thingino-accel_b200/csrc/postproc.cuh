@@ -199,22 +199,25 @@ struct NmsShared {
     NmsSortShared sort;
     float x[MARS_MAX_DETS], y[MARS_MAX_DETS], w[MARS_MAX_DETS], h[MARS_MAX_DETS];
     int cls[MARS_MAX_DETS];
-    unsigned mask[MARS_MAX_DETS][32]; /* row i, bit j: sorted element j > i has i's class and IoU(i, j) > thresh */
     unsigned removed[32];
     int warp_sums[32];
 };
 
-/* dets_in/dets_out: [det_stride] per image; counts in/out per image.  blockDim.x = NMS_THREADS, dynamic smem = sizeof(NmsShared).
+/* dets_in/dets_out: [det_stride] per image; counts in/out per image.  blockDim.x = NMS_THREADS, dynamic smem = sizeof(NmsShared);
+ * mask_scratch: MARS_MAX_DETS x 32 words per image (row i, bit j: sorted element j > i has i's class and IoU(i, j) > thresh) --
+ * kept in global memory (L2-resident, written and read once) so that two blocks fit one SM: the sort is a chain of barriers and
+ * leaves the SM mostly idle, a second image fills the gaps.
  * Greedy suppression (mars_yolo_test.c:113-123) as a bit matrix: all pair tests in parallel (class test first, the IoU
  * with its two divisions only for same-class pairs), then one warp walks i ascending and ORs row i into the removed
  * set iff i is still alive -- the same result as the sequential double loop. */
-__global__ void __launch_bounds__(NMS_THREADS) k_nms_center(const mars_det_t *dets_in, const int32_t *counts_in,
-                                                            mars_det_t *dets_out, int32_t *counts_out, int det_stride,
-                                                            float thresh) {
+__global__ void __launch_bounds__(NMS_THREADS, 2) k_nms_center(const mars_det_t *dets_in, const int32_t *counts_in,
+                                                               mars_det_t *dets_out, int32_t *counts_out, int det_stride,
+                                                               float thresh, unsigned *mask_scratch) {
     extern __shared__ __align__(16) uint8_t nms_smem[];
     NmsShared &sh = *reinterpret_cast<NmsShared *>(nms_smem);
     const mars_det_t *in = dets_in + (size_t)blockIdx.x * det_stride;
     mars_det_t *out = dets_out + (size_t)blockIdx.x * det_stride;
+    unsigned *mask = mask_scratch + (size_t)blockIdx.x * MARS_MAX_DETS * 32;
     int n = counts_in[blockIdx.x];
     if (n > MARS_MAX_DETS) n = MARS_MAX_DETS;
     const int j = threadIdx.x, lane = j & 31, wid = j >> 5;
@@ -239,14 +242,14 @@ __global__ void __launch_bounds__(NMS_THREADS) k_nms_center(const mars_det_t *de
                 s = iou_center(a, b) > thresh;
             }
             const unsigned bits = __ballot_sync(0xffffffffu, s);
-            if (lane == 0) sh.mask[i][w] = bits;
+            if (lane == 0) mask[i * 32 + w] = bits;
         }
     }
     __syncthreads();
     if (wid == 0) {
         unsigned removed = 0u; /* lane w: bits of elements [32w, 32w+32) */
         for (int i = 0; i < n; i++) {
-            const unsigned row = (lane >= (i >> 5) && lane < nwords) ? sh.mask[i][lane] : 0u;
+            const unsigned row = (lane >= (i >> 5) && lane < nwords) ? mask[i * 32 + lane] : 0u;
             const unsigned word = __shfl_sync(0xffffffffu, removed, i >> 5);
             if (!((word >> (i & 31)) & 1u)) removed |= row;
         }
@@ -262,14 +265,15 @@ __global__ void __launch_bounds__(NMS_THREADS) k_nms_center(const mars_det_t *de
 }
 
 static inline cudaError_t launch_nms_center(const mars_det_t *dets_in, const int32_t *counts_in, mars_det_t *dets_out,
-                                            int32_t *counts_out, int det_stride, float thresh, int n_img, cudaStream_t s) {
+                                            int32_t *counts_out, int det_stride, float thresh, int n_img, unsigned *mask_scratch,
+                                            cudaStream_t s) {
     static bool attr = false;
     if (!attr) {
         cudaError_t e = cudaFuncSetAttribute(k_nms_center, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(NmsShared));
         if (e != cudaSuccess) return e;
         attr = true;
     }
-    k_nms_center<<<n_img, NMS_THREADS, sizeof(NmsShared), s>>>(dets_in, counts_in, dets_out, counts_out, det_stride, thresh);
+    k_nms_center<<<n_img, NMS_THREADS, sizeof(NmsShared), s>>>(dets_in, counts_in, dets_out, counts_out, det_stride, thresh, mask_scratch);
     return cudaGetLastError();
 }
 

@@ -161,6 +161,7 @@ struct Model {
     /* device-resident detections */
     mars_det_t *d_raw = nullptr, *d_det = nullptr;
     int32_t *d_raw_cnt = nullptr, *d_det_cnt = nullptr;
+    unsigned *d_nms_mask = nullptr; /* capacity x 1024 x 32 words: suppression bit matrices */
     DecodeTables *d_tab = nullptr;
     float tab_scale = 0.0f;
     bool tab_valid = false;
@@ -192,7 +193,7 @@ static void model_release(Model *m) {
     tc_release(m->tc);
     for (auto e : m->prof_ev) cudaEventDestroy(e);
     cudaFree(m->d_weights); cudaFree(m->d_slots); cudaFree(m->d_scratch); cudaFree(m->d_cpool); cudaFree(m->d_tc_scratch); cudaFree(m->d_linked);
-    cudaFree(m->d_raw); cudaFree(m->d_det); cudaFree(m->d_raw_cnt); cudaFree(m->d_det_cnt); cudaFree(m->d_tab);
+    cudaFree(m->d_raw); cudaFree(m->d_det); cudaFree(m->d_raw_cnt); cudaFree(m->d_det_cnt); cudaFree(m->d_tab); cudaFree(m->d_nms_mask);
     if (m->h_arena) cudaFreeHost(m->h_arena);
     if (m->ev0) cudaEventDestroy(m->ev0);
     if (m->ev1) cudaEventDestroy(m->ev1);
@@ -231,13 +232,16 @@ static mars_error_t set_capacity(Model *m, int capacity) {
     }
     CU_OK(cudaMalloc(&nraw, (size_t)capacity * MARS_MAX_DETS * sizeof(mars_det_t)), MARS_ERR_ALLOC_FAILED);
     CU_OK(cudaMalloc(&ndet, (size_t)capacity * MARS_MAX_DETS * sizeof(mars_det_t)), MARS_ERR_ALLOC_FAILED);
+    unsigned *nmask = nullptr;
+    CU_OK(cudaMalloc(&nmask, (size_t)capacity * MARS_MAX_DETS * 32 * sizeof(unsigned)), MARS_ERR_ALLOC_FAILED);
     CU_OK(cudaMalloc(&nrc, (size_t)capacity * sizeof(int32_t)), MARS_ERR_ALLOC_FAILED);
     CU_OK(cudaMalloc(&ndc, (size_t)capacity * sizeof(int32_t)), MARS_ERR_ALLOC_FAILED);
     CU_OK(cudaMemsetAsync(nrc, 0, (size_t)capacity * sizeof(int32_t), m->stream), MARS_ERR_ALLOC_FAILED);
     CU_OK(cudaMemsetAsync(ndc, 0, (size_t)capacity * sizeof(int32_t), m->stream), MARS_ERR_ALLOC_FAILED);
     CU_OK(cudaStreamSynchronize(m->stream), MARS_ERR_LAYER_FAILED);
     cudaFree(m->d_slots); cudaFree(m->d_scratch); cudaFree(m->d_raw); cudaFree(m->d_det);
-    cudaFree(m->d_raw_cnt); cudaFree(m->d_det_cnt);
+    cudaFree(m->d_raw_cnt); cudaFree(m->d_det_cnt); cudaFree(m->d_nms_mask);
+    m->d_nms_mask = nmask;
     m->d_slots = ns; m->d_scratch = nscr; m->d_raw = nraw; m->d_det = ndet; m->d_raw_cnt = nrc; m->d_det_cnt = ndc;
     m->capacity = capacity;
     m->pub.ddr_paddr = m->d_slots;
@@ -516,7 +520,8 @@ static mars_error_t enqueue_detect(Model *m, int first, int n, float thresh) {
                                             m->d_raw + (size_t)first * MARS_MAX_DETS, m->d_raw_cnt + first, 1000,
                                             MARS_MAX_DETS);
     CU_OK(launch_nms_center(m->d_raw + (size_t)first * MARS_MAX_DETS, m->d_raw_cnt + first, m->d_det + (size_t)first * MARS_MAX_DETS,
-                            m->d_det_cnt + first, MARS_MAX_DETS, thresh, n, m->stream), MARS_ERR_LAYER_FAILED);
+                            m->d_det_cnt + first, MARS_MAX_DETS, thresh, n, m->d_nms_mask + (size_t)first * MARS_MAX_DETS * 32, m->stream),
+          MARS_ERR_LAYER_FAILED);
     m->launches += 2;
     CU_OK(cudaGetLastError(), MARS_ERR_LAYER_FAILED);
     return MARS_OK;
