@@ -252,6 +252,56 @@ __global__ void __launch_bounds__(256) k_spatial_vec4(ArenaView v, KOp o) {
     }
 }
 
+/* stride-1 maxpool, separable: a block stages a strip of input rows in shared memory, takes the horizontal window
+ * maximum (kw loads per word instead of kh*kw), then the vertical one.  Rows are iw*ic bytes = RW words; windows are
+ * clipped at the right / bottom edge and pads are ignored, exactly like maxpool_point.  grid = (strips, images),
+ * smem = 2 * (TH + kh - 1) * RW words. */
+__global__ void __launch_bounds__(256) k_maxpool_sep(ArenaView v, KOp o, int TH) {
+    extern __shared__ uint32_t mp_smem[];
+    const Img im = make_img(v, blockIdx.y);
+    const uint32_t *in = reinterpret_cast<const uint32_t *>(im.s_minus_W + o.in0);
+    uint32_t *out = reinterpret_cast<uint32_t *>(im.s_minus_W + o.out);
+    const int c4 = o.ic >> 2, RW = o.iw * c4, OW = o.ow * c4;
+    const int r0 = blockIdx.x * TH, nout = min(TH, o.oh - r0), nin = min(nout + o.kh - 1, o.ih - r0);
+    uint32_t *raw = mp_smem, *hm = mp_smem + (TH + o.kh - 1) * RW;
+    for (int t = threadIdx.x; t < nin * RW; t += blockDim.x) raw[t] = in[(int64_t)r0 * RW + t];
+    __syncthreads();
+    for (int t = threadIdx.x; t < nin * OW; t += blockDim.x) { /* horizontal: output column x covers input columns x .. x+kw-1 */
+        const int y = t / OW, xw = t - y * OW, x = xw / c4;
+        const int kx = min(o.kw, o.iw - x);
+        uint32_t r = 0x80808080u;
+        const uint32_t *p = raw + y * RW + xw;
+        for (int k = 0; k < kx; k++) r = __vmaxs4(r, p[k * c4]);
+        hm[y * OW + xw] = r;
+    }
+    __syncthreads();
+    for (int t = threadIdx.x; t < nout * OW; t += blockDim.x) { /* vertical: output row y covers input rows y .. y+kh-1 */
+        const int y = t / OW, xw = t - y * OW;
+        const int ky = min(o.kh, nin - y);
+        uint32_t r = 0x80808080u;
+        for (int k = 0; k < ky; k++) r = __vmaxs4(r, hm[(y + k) * OW + xw]);
+        out[(int64_t)(r0 + y) * OW + xw] = r;
+    }
+}
+
+/* nearest upsample by an integer factor with exact output size: one thread per INPUT word, s*s output words */
+__global__ void __launch_bounds__(256) k_upsample_rep(ArenaView v, KOp o) {
+    const Img im = make_img(v, blockIdx.y);
+    const uint32_t *in = reinterpret_cast<const uint32_t *>(im.s_minus_W + o.in0);
+    uint32_t *out = reinterpret_cast<uint32_t *>(im.s_minus_W + o.out);
+    const int c4 = o.ic >> 2;
+    const int64_t total = (int64_t)o.ih * o.iw * c4, orow = (int64_t)o.ow * c4;
+    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
+        const int c = (int)(t % c4);
+        const int64_t p = t / c4;
+        const int ih = (int)(p / o.iw), iw = (int)(p - (int64_t)ih * o.iw);
+        const uint32_t w = in[t];
+        uint32_t *dst = out + ((int64_t)ih * o.sh) * orow + ((int64_t)iw * o.sw) * c4 + c;
+        for (int dy = 0; dy < o.sh; dy++)
+            for (int dx = 0; dx < o.sw; dx++) dst[dy * orow + (int64_t)dx * c4] = w;
+    }
+}
+
 static inline bool fast_spatial_ok(const ArenaView &v, const KOp &o) {
     if (o.mode != EXEC_PARALLEL || o.out < (int64_t)v.W) return false;
     if (o.kind == OP_CONCAT) return o.in0 >= (int64_t)v.W && o.ic == o.oc && o.n >= 64;
@@ -262,6 +312,23 @@ static inline bool fast_spatial_ok(const ArenaView &v, const KOp &o) {
     return false;
 }
 static inline void launch_fast_spatial(const ArenaView &v, const KOp &o, int n_img, cudaStream_t s) {
+    if (o.kind == OP_MAXPOOL && o.sh == 1 && o.sw == 1 && o.kh >= 1 && o.kw >= 1 && o.oh <= o.ih && o.ow <= o.iw) {
+        const int RW = o.iw * (o.ic >> 2);
+        int TH = 32;
+        while (TH > 1 && (size_t)2 * (TH + o.kh - 1) * RW * 4 > 96 * 1024) TH >>= 1;
+        if ((size_t)2 * (TH + o.kh - 1) * RW * 4 <= 96 * 1024) {
+            static bool attr = false;
+            if (!attr) { cudaFuncSetAttribute(k_maxpool_sep, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024); attr = true; }
+            dim3 g((o.oh + TH - 1) / TH, n_img);
+            k_maxpool_sep<<<g, 256, (size_t)2 * (TH + o.kh - 1) * RW * 4, s>>>(v, o, TH);
+            return;
+        }
+    }
+    if (o.kind == OP_UPSAMPLE && o.oh == o.ih * o.sh && o.ow == o.iw * o.sw) {
+        dim3 g((unsigned)std::min<uint64_t>(((uint64_t)o.ih * o.iw * (o.ic >> 2) + 255) / 256, 148 * 64), n_img);
+        k_upsample_rep<<<g, 256, 0, s>>>(v, o);
+        return;
+    }
     if (o.kind == OP_MAXPOOL || o.kind == OP_UPSAMPLE) {
         /* one output word per thread: the loads of a thread are dependent, so parallelism comes from the number of warps */
         dim3 g((unsigned)(((uint64_t)o.oh * o.ow * (o.ic >> 2) + 255) / 256), n_img);

@@ -148,7 +148,19 @@ __device__ __forceinline__ int exchange_sort_block(NmsSortShared &sh, float myk,
     sh.key[0][j] = myk;
     sh.idx[0][j] = (uint16_t)j;
     __syncthreads();
+    bool parked = false;
     for (int i = 0; i + 1 < n; i++) {
+        /* a warp whose positions are all final (below i) or beyond n only keeps the barrier count: it publishes
+         * neutral values once and then skips the arithmetic of every further pass */
+        if ((wid + 1) * 32 <= i || wid * 32 >= n) {
+            if (!parked) {
+                if (lane == 0) { sh.wmax[wid] = NEG_INF; sh.wlast[wid] = -1; }
+                parked = true;
+            }
+            __syncthreads();
+            if (!sh.skip[i & 1]) __syncthreads();
+            continue;
+        }
         const bool act = j >= i && j < n;
         const float v = (act && myk == myk) ? myk : NEG_INF;
         float inc = v; /* inclusive prefix max inside the warp */
