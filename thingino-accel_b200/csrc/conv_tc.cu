@@ -329,7 +329,7 @@ k_conv_tc(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUte
     const int tiles_per_img = p.m_groups * p.n_tiles; /* scheduling unit = a group of p.grp M tiles x one N tile */
     /* gather-mode shared regions behind the weight tile */
     uint8_t *g_patch = smem_al + (size_t)p.stages * p.a_stage_bytes + p.b_stage_bytes; /* gather: B is one resident block */
-    int *g_poff = reinterpret_cast<int *>(g_patch + 4096); /* per patch word: offset inside the input copy */
+    int *g_poff = reinterpret_cast<int *>(g_patch + 3 * 4096); /* three patch buffers, then per patch word: offset inside the input */
     int *g_pyx = g_poff + 1024;                            /* per patch word: patch row << 16 | byte column */
 
     if (threadIdx.x == 0) {
@@ -604,37 +604,42 @@ k_conv_tc(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUte
         const int th = TC_BM >> p.tw_shift;
         const int tb = ((pr >> p.tw_shift) * p.gS) * PP + (pr & ((1 << p.tw_shift) - 1)) * p.gS; /* this pixel's origin in the patch */
         const int nchunks = (p.gKt + 15) >> 4;
-        uint32_t pre[8];
-        auto prefetch = [&](int img, int mt) { /* n_tiles == 1 in gather mode: tile inside the image = M tile */
+        /* the input patch of a tile travels global -> shared with cp.async (zero fill outside the image), three
+         * patch buffers deep: while the rows of tile t are built, the patches of tiles t+1 and t+2 are in flight */
+        const uint32_t patch_sa = smem_u32(g_patch);
+        auto issue = [&](int img, int mt, int buf) { /* n_tiles == 1 in gather mode: tile inside the image = M tile */
             const int ty = mt / p.tiles_x, tx = mt - ty * p.tiles_x;
             const int y0 = ty * th * p.gS - p.gpt, xs = (tx << p.tw_shift) * p.gS - p.gpl - p.gdx;
             const uint8_t *src = p.g_src + (unsigned long long)img * p.g_stride + ((long long)y0 * p.gW + xs);
 #pragma unroll
             for (int i = 0; i < 8; i++) {
                 const int wi = pr + 128 * i;
-                pre[i] = 0u;
                 if (wi < nwords) {
                     const int yx = g_pyx[wi], y = y0 + (yx >> 16), x = xs + (yx & 0xFFFF);
-                    if ((unsigned)y < (unsigned)p.gH && (unsigned)x < (unsigned)p.gW) pre[i] = *reinterpret_cast<const uint32_t *>(src + g_poff[wi]);
+                    const bool ok = (unsigned)y < (unsigned)p.gH && (unsigned)x < (unsigned)p.gW;
+                    const uint8_t *a = ok ? src + g_poff[wi] : p.g_src;
+                    asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(patch_sa + (uint32_t)(buf * 4096 + wi * 4)), "l"(a), "r"(ok ? 4 : 0) : "memory");
                 }
             }
         };
-        int s = 0, ph = 1, g = 0;
+        int s = 0, ph = 1, g = 0, gi = 0, t = 0;
         const int G = p.grp;
-        TileIter ti(blockIdx.x, gridDim.x, tiles_per_img);
-        if (ti.img < p.n_img) prefetch(ti.img, ti.rem * G);
-        for (; ti.img < p.n_img;) {
-            asm volatile("bar.sync 2, 128;" ::: "memory"); /* the previous tile's rows have been built: the patch may be replaced */
-#pragma unroll
-            for (int i = 0; i < 8; i++)
-                if (pr + 128 * i < nwords) reinterpret_cast<uint32_t *>(g_patch)[pr + 128 * i] = pre[i];
-            asm volatile("bar.sync 2, 128;" ::: "memory");
+        TileIter ti(blockIdx.x, gridDim.x, tiles_per_img), tii = ti; /* consume / issue positions */
+        for (int k = 0; k < 2; k++) {
+            if (tii.img < p.n_img) { issue(tii.img, tii.rem * G + gi, k); if (++gi == G) { gi = 0; tii.next(); } }
+            asm volatile("cp.async.commit_group;" ::: "memory");
+        }
+        for (; ti.img < p.n_img; t++) {
+            asm volatile("bar.sync 2, 128;" ::: "memory"); /* everyone has built the rows of tile t-1: its patch buffer is free */
+            if (tii.img < p.n_img) { issue(tii.img, tii.rem * G + gi, (t + 2) % 3); if (++gi == G) { gi = 0; tii.next(); } }
+            asm volatile("cp.async.commit_group;" ::: "memory");
+            asm volatile("cp.async.wait_group 2;" ::: "memory"); /* this thread's part of tile t's patch has landed ... */
+            asm volatile("bar.sync 2, 128;" ::: "memory");        /* ... and everybody else's */
             const int gcur = g;
             if (++g == G) { g = 0; ti.next(); }
-            if (ti.img < p.n_img) prefetch(ti.img, ti.rem * G + g); /* in flight while this tile's rows are built */
             if (gcur == 0) mbar_wait_relaxed(smem_u32(&bar_empty[s]), ph); /* the stage holds the whole group */
             uint8_t *row = smem_al + (size_t)s * p.a_stage_bytes + (size_t)gcur * p.a_tile_bytes + pr * 128;
-            const uint8_t *pb = g_patch + tb;
+            const uint8_t *pb = g_patch + (t % 3) * 4096 + tb;
             /* K columns >= Kt meet zero weights (k_repack_rows pads B with zeros), so whatever bytes sit there are
              * harmless: table entries beyond Kt point at offset 0 and 16-byte chunks beyond Kt are not written at all */
             if (p.g_align2) { /* taps come in aligned byte pairs (even stride, even kernel width): 2-byte loads */
@@ -760,6 +765,7 @@ struct TcPlanImpl {
     size_t smem = 0;
     int ctas_per_sm = 2;
     int epi = 8; /* epilogue warps per CTA */
+    bool gather_direct = false; /* gather mode reads the input tensor in the arena itself (no private copy needed) */
 };
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
@@ -969,10 +975,10 @@ bool tc_plan(const Op &o, const ArenaGeom &ag, uint8_t *scratch, size_t scratch_
     p.tx_bytes = p.a_stage_bytes + (uint32_t)(p.n_tile * p.bk);
     const int budget = t->ctas_per_sm == 1 ? 200 * 1024 : 100 * 1024;
     const int nsteps = g.ntaps * p.ksteps_per_tap;
-    if (gather) { /* + 4 KiB patch + 8 KiB patch-word tables */
+    if (gather) { /* + 3 x 4 KiB patch ring + 8 KiB patch-word tables */
         if (p.grp > 2) { p.grp = 2; p.a_stage_bytes = p.grp * p.a_tile_bytes; p.acc_bufs = std::max(2, std::min(4, p.tmem_cols / (p.grp * p.n_tile))); }
-        p.stages = std::max(2, std::min(8, (budget - (int)p.b_stage_bytes - 12288 - 1024) / (int)p.a_stage_bytes));
-        t->smem = 1024 + (size_t)p.stages * p.a_stage_bytes + p.b_stage_bytes + 12288;
+        p.stages = std::max(2, std::min(8, (budget - (int)p.b_stage_bytes - 20480 - 1024) / (int)p.a_stage_bytes));
+        t->smem = 1024 + (size_t)p.stages * p.a_stage_bytes + p.b_stage_bytes + 20480;
     } else {
         /* small weight matrices stay resident in shared memory for the whole (persistent) launch: one TMA per k-step */
         const size_t b_all = (size_t)nsteps * p.b_stage_bytes;
@@ -1062,6 +1068,12 @@ bool tc_plan(const Op &o, const ArenaGeom &ag, uint8_t *scratch, size_t scratch_
     t->src_slot0 = ag.d_slots + (o.in0 - (int64_t)ag.W);
     t->scratch = scratch; t->scratch_stride = scratch_stride; t->slot_stride = ag.slot_stride;
     if (gather) {
+        /* the private input copy is only needed when a stored output stream overwrites the input tensor (round-robin work
+         * buffers) while other tiles still have to read it */
+        const int64_t in_lo = o.in0 - (int64_t)ag.W, in_hi = in_lo + (int64_t)o.ic * o.ih * o.iw;
+        t->gather_direct = true;
+        for (int k = 0; k < t->nst; k++)
+            if (p.out_off[k] < in_hi && in_lo < p.out_off[k] + (int64_t)o.oc * o.oh * o.ow) t->gather_direct = false;
         p.g_src = scratch; p.g_stride = scratch_stride;
         p.gC = o.ic; p.gH = o.ih; p.gW = o.iw; p.gS = o.sh; p.gpt = o.pt; p.gpl = o.pl; p.gKH = o.kh; p.gKW = o.kw;
         p.gKt = o.ic * o.kh * o.kw;
@@ -1111,11 +1123,11 @@ bool tc_launch(const TcPlan &plan, uint8_t *slots_base, int first, int n, bool u
     if (!t) return false;
     const uint8_t *src = t->src_slot0 + (size_t)first * t->slot_stride;
     uint8_t *scr = t->scratch + (size_t)first * t->scratch_stride;
-    if (t->prepass == 3) {
+    if (t->prepass == 3 && !t->gather_direct) {
         /* private copy of the input tensor: the fused outputs may overwrite the input's work buffer */
         if (cudaMemcpy2DAsync(scr, t->scratch_stride, src, t->slot_stride, (size_t)t->C * t->H * t->W, (size_t)n,
                               cudaMemcpyDeviceToDevice, s) != cudaSuccess) return false;
-    } else if (t->prepass && !(use_linked && t->has_linked)) {
+    } else if (t->prepass && t->prepass != 3 && !(use_linked && t->has_linked)) {
         dim3 g((t->npix + 31) / 32, (t->C + 31) / 32, n);
         k_to_nhwc<<<g, 256, 0, s>>>(src, t->slot_stride, scr, t->scratch_stride, t->C, t->H, t->W, t->p.Wp, t->plane, t->npix,
                                     t->prepass == 2, t->pt, t->pl);
@@ -1125,7 +1137,10 @@ bool tc_launch(const TcPlan &plan, uint8_t *slots_base, int first, int n, bool u
     p.out_base = slots_base + (size_t)first * t->slot_stride;
     p.img0 = first;
     p.n_img = n;
-    if (t->prepass == 3) p.g_src = scr;
+    if (t->prepass == 3) {
+        if (t->gather_direct) { p.g_src = src; p.g_stride = t->slot_stride; }
+        else p.g_src = scr;
+    }
     if (p.nhwc_sel >= 0) p.nhwc_base += (size_t)first * p.nhwc_stride;
     const long long total_tiles = (long long)p.m_groups * p.n_tiles * n;
     static int sms = 0;
