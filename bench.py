@@ -245,6 +245,8 @@ def run_cuda_arm(args):
         raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback (use --impl reference for the CPU arm)")
     torch.cuda.set_device(local_rank)
     if world > 1:
+        if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"  # the version banner goes to stdout, which carries exactly one JSON line
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     pkg = load_package()
     L = pkg.lib()
@@ -390,7 +392,7 @@ def run_cuda_arm(args):
                         "d2h_bytes_per_step": (B * 1000 * 24 + B * 4) * world, "ms_per_step": e2e_ms},
                 "gpu_launches": int(launches), "wall_ms_per_step": wall_ms / args.steps, "clocks": clocks,
                 "roofline": roof, "kernel_time_shares": shares, "cpu_baseline": cpu, "detections_checksum": checksum}
-        print(json.dumps(line))
+        print(json.dumps(line), flush=True)
     gm.close()
     if world > 1:
         dist.destroy_process_group()
