@@ -1,32 +1,30 @@
 /*
- * conv_tc.cu -- int8 convolution as a TMA-fed implicit GEMM on tcgen05 (sm_100a).
+ * conv_tc.cu -- int8 convolution as an implicit GEMM on tcgen05 (sm_100a), persistent and warp-specialised.
  *
- * Replaces the reference's conv2d_int8_mxu (src/mars/mxu_conv.c:630-670; MIPS variant
- * :144-408 built on the 64-byte S4MACSSB dot product) for hazard-free NCHW/OIHW layers.
+ * Replaces the reference's conv2d_int8_mxu (src/mars/mxu_conv.c:630-670; MIPS variant :144-408 built on the
+ * 64-byte S4MACSSB dot product) for hazard-free NCHW/OIHW layers, together with the SIGMOID and MUL layers the
+ * planner folded into it (src/mars/mars_runtime.c:724-838).  DESIGN.md section 5.1 is the long form.
  *
- *   GEMM view   D[M = pixels][N = out channels] = A[M][K] * B[N][K],  K = taps x in channels.
- *   A operand   1x1 convs: the NCHW activation planes themselves -- one K-row = 128 consecutive
- *               pixels of one input channel (MN-major A, legal for kind::i8), loaded by TMA
- *               straight from the arena with the 128-byte swizzle.
- *               kxk convs: a kernel tap (kh,kw) is a FLAT pixel shift, so the k-loop walks
- *               (tap, channel block) with no im2col buffer.  TMA faults ("illegal instruction",
- *               measured on B200) when the innermost box coordinate is not 16-byte aligned, so
- *               the 1-pixel shifts cannot be applied to NCHW planes; a small pre-pass kernel
- *               writes a channel-innermost (NHWC) copy instead -- rows padded with k-1 zero
- *               columns for stride 1 (the flat shift then never wraps into real pixels), a 2x2
- *               phase split for stride 2 (every tap becomes a stride-1 shift inside one phase
- *               plane) -- and A is K-major like B.  The copy is also what allows the fused
- *               outputs below to overwrite the layer's own input buffer, as the reference's
- *               work-buffer aliasing demands.
- *   B operand   weights repacked once at load to [tap][Co][Ci] (K-major), TMA + swizzle.
- *   D           int32 in TMEM (128 lanes = pixels, N columns); read back with tcgen05.ld.
- *   epilogue    + int32 bias (wrap-around), fp32 requantisation with the x86 float->int rule
- *               (SURVEY A.1), then -- when the planner fused the following SIGMOID and MUL
- *               layers -- two 256-entry tables give the sigmoid and the SiLU product of the
- *               same element; all observable tensors are stored NCHW.
- *   roles       warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer (one elected
- *               lane), warps 2..5 = epilogue (one TMEM lane quadrant each).  One output tile
- *               per CTA, two CTAs per SM so one tile's epilogue overlaps the other's mainloop.
+ *   GEMM view   D[M = 128 pixels][N = out channels] = A[M][K] * B[N][K],  K = taps x in channels.
+ *   A operand   1x1 convs: the NCHW activation planes themselves -- one K-row = 128 consecutive pixels of one
+ *               input channel (MN-major A, legal for kind::i8), loaded by TMA straight from the arena (128B swizzle).
+ *               kxk convs: a kernel tap (kh,kw) is a FLAT pixel shift.  TMA faults ("illegal instruction", measured
+ *               on B200) when the innermost box coordinate is not 16-byte aligned, so 1-pixel shifts cannot be
+ *               applied to NCHW planes; A comes from a channel-innermost (NHWC) copy instead -- rows padded with k-1
+ *               zero columns for stride 1, a 2x2 phase split for stride 2 -- and is K-major like B.  The copy is
+ *               written by the PRODUCING conv's epilogue when there is one (Op::copy_from), by the k_to_nhwc
+ *               pre-pass otherwise; it is also what lets fused outputs overwrite the layer's own input buffer, as
+ *               the reference's work-buffer aliasing demands.  Stride 1 with resident weights: one load of the
+ *               unit's rows plus halo serves all taps as row-shifted operands ("halo" mode).
+ *               small Ci (6x6 stride-2 stem): producer warps build the K rows in shared memory ("gather" mode).
+ *   B operand   weights repacked once at load to [tap][Co][Ci] (K-major); resident in shared memory when small.
+ *   D           int32 in TMEM (128 lanes = pixels, N columns per M tile, ring of accumulator groups).
+ *   epilogue    + int32 bias (wrap-around), requantisation with the x86 float->int rule, one lookup
+ *               in a 512-entry word table holding the clamped int8 and its fused followers, NCHW byte stores and
+ *               the optional channel-innermost side output.
+ *   roles       warps 0..EPI-1 epilogue (two or four per TMEM lane quadrant), warp EPI = TMEM allocator + MMA
+ *               issuer (one lane), warp EPI+1 = TMA producer (one lane) or EPI+1..EPI+4 = gather producers.
+ *               CTA b walks work units b, b+grid, ... ; two CTAs per SM unless the N tile needs all of TMEM.
  */
 #include <cuda.h>
 #include <cuda_runtime.h>
@@ -144,15 +142,6 @@ __device__ __forceinline__ void umma_i8_parts(uint32_t tmem_d, uint32_t a_lo, ui
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
-__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];\n"
-        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
-          "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
-        : "r"(taddr));
-    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-}
-
 /* split form: issue the load, and later wait for it; the wait takes the destination registers as in/out operands so
  * that no use of them can be scheduled before it */
 __device__ __forceinline__ void tmem_ld16_issue(uint32_t taddr, uint32_t (&v)[16]) {
@@ -167,17 +156,6 @@ __device__ __forceinline__ void tmem_ld_wait(uint32_t (&v)[16]) {
                  : "+r"(v[0]), "+r"(v[1]), "+r"(v[2]), "+r"(v[3]), "+r"(v[4]), "+r"(v[5]), "+r"(v[6]), "+r"(v[7]), "+r"(v[8]),
                    "+r"(v[9]), "+r"(v[10]), "+r"(v[11]), "+r"(v[12]), "+r"(v[13]), "+r"(v[14]), "+r"(v[15])
                  :: "memory");
-}
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n"
-        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
-          "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
-          "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
-          "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
-        : "r"(taddr));
-    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 /* wait used by warps that are not on the critical path (epilogue, gather producers): back off between polls so the
  * spin does not take issue slots from the warps doing the work */
