@@ -116,7 +116,11 @@ MICRO = [
     ("conv", dict(k=3, s=1, c=32, co=48, h=40, w=40, padding=1)), ("conv", dict(k=3, s=2, c=64, co=128, h=40, w=40)),
     ("conv", dict(k=3, s=2, c=32, co=64, h=34, w=30, padding=1)), ("conv", dict(k=3, s=1, c=96, co=16, h=9, w=50, no_bias=True)),
     ("conv", dict(k=3, s=1, c=32, co=32, h=24, w=24, padding=0)),
-    # im2col + tcgen05 (small Ci, >= 4096 output pixels)
+    # halo loads with 2 / 1 / 4 M tiles per group, 5x5 taps, narrow N tiles (one 16-column unit), N = 48
+    ("conv", dict(k=3, s=1, c=64, co=64, h=30, w=26)), ("conv", dict(k=3, s=1, c=32, co=128, h=24, w=20)),
+    ("conv", dict(k=5, s=1, c=32, co=32, h=20, w=20)), ("conv", dict(k=1, s=1, c=32, co=16, h=64, w=64)),
+    ("conv", dict(k=1, s=1, c=64, co=48, h=50, w=50)), ("conv", dict(k=3, s=1, c=128, co=128, h=40, w=40)),
+    # gather producer + tcgen05 (small Ci, >= 4096 output pixels)
     ("conv", dict(k=6, s=2, c=3, co=32, h=128, w=128)), ("conv", dict(k=3, s=1, c=8, co=24, h=70, w=66, padding=1)),
     ("conv", dict(k=3, s=2, c=5, co=17, h=130, w=140)),
 ]
