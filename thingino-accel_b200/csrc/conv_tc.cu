@@ -301,8 +301,9 @@ k_conv_tc(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUte
     int *g_pyx = g_poff + 1024;                            /* per patch word: patch row << 16 | byte column */
 
     if (threadIdx.x == 0) {
-        for (int s = 0; s < p.stages; s++) { mbar_init(smem_u32(&bar_full[s]), GATHER ? 4 : 1); mbar_init(smem_u32(&bar_empty[s]), 1); }
-        for (int b = 0; b < p.acc_bufs; b++) { mbar_init(smem_u32(&bar_tmem_full[b]), 1); mbar_init(smem_u32(&bar_tmem_empty[b]), EPI); }
+        /* one MMA-issuing lane per M tile of a group: each commits (arrives) on its own */
+        for (int s = 0; s < p.stages; s++) { mbar_init(smem_u32(&bar_full[s]), GATHER ? 4 : 1); mbar_init(smem_u32(&bar_empty[s]), p.grp); }
+        for (int b = 0; b < p.acc_bufs; b++) { mbar_init(smem_u32(&bar_tmem_full[b]), p.grp); mbar_init(smem_u32(&bar_tmem_empty[b]), EPI); }
         mbar_init(smem_u32(&bar_b), 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -352,7 +353,7 @@ k_conv_tc(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUte
         const bool flat = !GATHER && p.Wp == p.Wo && !NHWC; /* no pad columns: the tile row index IS the pixel index */
         uint8_t *const obase = p.out_base + r; /* + image * slot_stride + pixel + channel * plane + stream offset */
         const int G = p.grp, gcols = p.grp * p.n_tile;
-        if (part >= n_units || p.dbg == 7) { /* narrow N tile: nothing to read for this warp, it only releases the accumulators */
+        if (part >= n_units || p.dbg == 7 || p.dbg == 9) { /* narrow N tile: nothing to read for this warp, it only releases the accumulators */
             int ab = 0, aph = 0; /* accumulator ring position and phase */
             for (TileIter ti(blockIdx.x, gridDim.x, tiles_per_img); ti.img < p.n_img; ti.next()) {
                 mbar_wait_relaxed(sa_full + 8u * ab, aph);
@@ -447,10 +448,12 @@ k_conv_tc(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUte
             }
         }
     } else if (warp == WARP_MMA) {
-        if (lane == 0) { /* ===== MMA issuer =====
-            * One thread per CTA runs this loop once per k-step of every tile, so its instruction count bounds the tile
-            * rate of the small layers: everything loop-invariant (descriptor halves, barrier addresses, strides in
-            * 16-byte descriptor units) is computed up front and the descriptors are advanced by additions. */
+        if (lane < p.grp) { /* ===== MMA issuers: lane g issues the MMAs of M tile g of every group =====
+            * Issuing one small MMA costs a thread ~300 cycles (measured: 9 taps x K=32, N=32 are issue-bound, not
+            * tensor-bound), so the M tiles of a group -- independent accumulators -- are issued by different lanes of this
+            * warp, each committing (arriving) on its own.  All MMAs of one accumulator stay on one lane, i.e. in order.
+            * Everything loop-invariant (descriptor halves, barrier addresses, strides in 16-byte descriptor units) is
+            * computed up front and the descriptors are advanced by additions. */
             const uint32_t k_sbo16 = (8u * (uint32_t)p.bk) >> 4;
             /* descriptor high word: SBO >> 4 at [32,46), version 1 at [46,48), layout type at [61,64) */
             const uint32_t hi_k = k_sbo16 | (1u << 14) | (p.b_layout << 29);
@@ -482,7 +485,8 @@ k_conv_tc(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUte
                         mbar_wait(sa_full + 8u * s, ph);
                         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                         const uint32_t a_st = a_lo0 + s * a_st16;
-                        for (int g = 0; g < G; g++) { /* M tile g of the group starts 128 rows further down the same stage */
+                        { /* M tile g of the group starts 128 rows further down the same stage */
+                            const int g = lane;
                             uint32_t b_lo = b_lo0 + kb * b_st16;
                             for (int tap = 0; tap < ntaps; tap++, b_lo += ksteps * b_st16) {
                                 const uint32_t a_lo = a_st + g * g_rows16 + (uint32_t)s_shift[tap]; /* halo mode: row shift in 16-byte units */
@@ -498,10 +502,9 @@ k_conv_tc(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUte
                         mbar_wait(sa_full + 8u * s, ph);
                         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                         const uint32_t a_st = a_lo0 + s * a_st16, b_lo = b_lo0 + (b_res ? i : s) * b_st16;
-                        if (p.dbg != 4)
-                            for (int g = 0; g < G; g++)
-                                for (int j = 0; j < nj; j++)
-                                    umma_i8_parts(acc + (uint32_t)(g * n_tile), a_st + g * a_tile16 + a_j16 * j, hi_a, b_lo + 2u * j, hi_k, idesc, (uint32_t)((i | j) != 0));
+                        if (p.dbg != 4 && p.dbg != 9)
+                            for (int j = 0; j < nj; j++)
+                                    umma_i8_parts(acc + (uint32_t)(lane * n_tile), a_st + lane * a_tile16 + a_j16 * j, hi_a, b_lo + 2u * j, hi_k, idesc, (uint32_t)((i | j) != 0));
                         umma_commit(sa_empty + 8u * s); /* frees the stage when these MMAs retire */
                         if (++s == stages) { s = 0; ph ^= 1; }
                     }
@@ -532,7 +535,7 @@ k_conv_tc(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUte
                     for (int kb = 0; kb < ksteps; kb++) {
                         mbar_wait(sa_empty + 8u * s, ph);
                         const uint32_t full = sa_full + 8u * s, dst = a_base + s * a_stb;
-                        if (p.dbg == 3) { mbar_arrive(full); if (++s == stages) { s = 0; ph ^= 1; } continue; }
+                        if (p.dbg == 3 || p.dbg == 9) { mbar_arrive(full); if (++s == stages) { s = 0; ph ^= 1; } continue; }
                         mbar_expect_tx(full, tx);
                         for (int b = 0; b < nb; b++) tma_load_3d(dst + b * box_b, &mapA, full, kb * bk, q0 + b * rb, zc);
                         if (++s == stages) { s = 0; ph ^= 1; }
@@ -548,7 +551,7 @@ k_conv_tc(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUte
                         for (int kb = 0; kb < ksteps; kb++) {
                             mbar_wait(sa_empty + 8u * s, ph);
                             const uint32_t full = sa_full + 8u * s;
-                            if (p.dbg == 3) { mbar_arrive(full); if (++s == stages) { s = 0; ph ^= 1; } continue; }
+                            if (p.dbg == 3 || p.dbg == 9) { mbar_arrive(full); if (++s == stages) { s = 0; ph ^= 1; } continue; }
                             mbar_expect_tx(full, tx);
                             for (int g = 0; g < G; g++) { /* rows beyond the tensor (last, partial group) are zero-filled */
                                 if (a_km) tma_load_3d(a_base + s * a_stb + g * a_tb, &mapA, full, kb * bk, qa + g * TC_BM, zc);
