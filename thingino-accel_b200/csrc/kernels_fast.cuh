@@ -202,6 +202,43 @@ __global__ void __launch_bounds__(256) k_shift_copy_d16(ArenaView v, KOp o) {
     }
 }
 
+/* in-place concat input = periodic replication: A[out + j] = A[out + (j mod s)] for s <= j < n + s, with the
+ * first s bytes (never written here) as the pattern.  Written as a fill: the pattern is expanded in shared memory to
+ * L = lcm(s, 16) bytes, so every 16-byte aligned destination vector is one aligned 16-byte read of it; write-only traffic.
+ * grid = (chunks, images), smem = L bytes. */
+__global__ void __launch_bounds__(256) k_fill_periodic(ArenaView v, KOp o, int L) {
+    extern __shared__ __align__(16) uint8_t fp_pat[];
+    const Img im = make_img(v, blockIdx.y);
+    uint8_t *base = im.s_minus_W + o.out; /* pattern at [0, s), destination [s, s + n) */
+    const int s = o.coff;
+    for (int k = threadIdx.x; k < L; k += blockDim.x) fp_pat[k] = base[k % s];
+    __syncthreads();
+    const int64_t lo = s, hi = (int64_t)s + (int64_t)o.n;
+    /* 16-byte vectors relative to `base` rounded down: base itself is 16-byte aligned? not necessarily -> align on the address */
+    const uintptr_t b0 = reinterpret_cast<uintptr_t>(base);
+    const int64_t a_lo = (int64_t)(((b0 + lo + 15) & ~(uintptr_t)15) - b0), a_hi = (int64_t)(((b0 + hi) & ~(uintptr_t)15) - b0);
+    if (a_lo < a_hi) {
+        const int64_t nv = (a_hi - a_lo) >> 4;
+        for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nv; i += (int64_t)gridDim.x * blockDim.x) {
+            const int64_t j = a_lo + (i << 4); /* offset from base; the pattern phase of byte j is j mod s */
+            const int ph = (int)(j % L);
+            uint4 w;
+            if ((ph & 15) == 0) w = *reinterpret_cast<const uint4 *>(fp_pat + ph);
+            else { /* base not 16-byte aligned relative to the period: assemble bytewise (rare) */
+                uint8_t t[16];
+                for (int b = 0; b < 16; b++) t[b] = fp_pat[(ph + b) % L];
+                w = *reinterpret_cast<const uint4 *>(t);
+            }
+            *reinterpret_cast<uint4 *>(base + j) = w;
+        }
+    }
+    if (blockIdx.x == 0) { /* ragged ends */
+        const int64_t e_lo = a_lo < a_hi ? a_lo : hi, s_hi = a_lo < a_hi ? a_hi : hi;
+        for (int64_t j = lo + threadIdx.x; j < e_lo; j += blockDim.x) base[j] = fp_pat[j % L];
+        for (int64_t j = s_hi + threadIdx.x; j < hi; j += blockDim.x) base[j] = fp_pat[j % L];
+    }
+}
+
 static inline bool aligned16(int64_t x) { return (x & 15) == 0; }
 
 static inline bool fast_flat_ok(const ArenaView &v, const KOp &o) {
@@ -336,6 +373,15 @@ static inline void launch_fast_spatial(const ArenaView &v, const KOp &o, int n_i
         return;
     }
     const int periodic = o.kind == OP_CONCAT_PERIODIC;
+    if (periodic && o.coff > 0 && o.n >= 4096) {
+        int g = o.coff, b = 16;
+        while (b) { int t = g % b; g = b; b = t; } /* gcd(coff, 16) */
+        const long long L = (long long)o.coff / g * 16;
+        if (L <= 16384) {
+            k_fill_periodic<<<dim3(fast_grid(o.n >> 4), n_img), 256, (size_t)L, s>>>(v, o, (int)L);
+            return;
+        }
+    }
     const int64_t dst = o.out + o.coff, src = periodic ? o.out : o.in0;
     /* slot bases are 1 KiB aligned and W-relative offsets keep their low bits: alignment of the
      * arena offsets minus W is what counts, and v.W is subtracted from both alike */
