@@ -321,21 +321,19 @@ __global__ void __launch_bounds__(256) k_maxpool_sep(ArenaView v, KOp o, int TH)
     }
 }
 
-/* nearest upsample by an integer factor with exact output size: one thread per INPUT word, s*s output words */
+/* nearest upsample (reference src/mars/mars_runtime.c:1027-1040: ih = min(oh / sh, ih - 1), same for columns): one block
+ * per (output row, image); a thread produces consecutive output words (fully coalesced stores), reading the input row
+ * through L1.  Divisions by multiplication. */
 __global__ void __launch_bounds__(256) k_upsample_rep(ArenaView v, KOp o) {
     const Img im = make_img(v, blockIdx.y);
-    const uint32_t *in = reinterpret_cast<const uint32_t *>(im.s_minus_W + o.in0);
-    uint32_t *out = reinterpret_cast<uint32_t *>(im.s_minus_W + o.out);
-    const int c4 = o.ic >> 2;
-    const int64_t total = (int64_t)o.ih * o.iw * c4, orow = (int64_t)o.ow * c4;
-    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
-        const int c = (int)(t % c4);
-        const int64_t p = t / c4;
-        const int ih = (int)(p / o.iw), iw = (int)(p - (int64_t)ih * o.iw);
-        const uint32_t w = in[t];
-        uint32_t *dst = out + ((int64_t)ih * o.sh) * orow + ((int64_t)iw * o.sw) * c4 + c;
-        for (int dy = 0; dy < o.sh; dy++)
-            for (int dx = 0; dx < o.sw; dx++) dst[dy * orow + (int64_t)dx * c4] = w;
+    const int c4 = o.ic >> 2, orw = o.ow * c4;
+    const uint32_t *in = reinterpret_cast<const uint32_t *>(im.s_minus_W + o.in0) + (int64_t)min((int)blockIdx.x / o.sh, o.ih - 1) * o.iw * c4;
+    uint32_t *out = reinterpret_cast<uint32_t *>(im.s_minus_W + o.out) + (int64_t)blockIdx.x * orw;
+    const unsigned m_c4 = 0xFFFFFFFFu / (unsigned)c4 + 1u, m_sw = 0xFFFFFFFFu / (unsigned)o.sw + 1u; /* floor(a / d) = umulhi(a, m) */
+    for (int w = threadIdx.x; w < orw; w += blockDim.x) {
+        const int xo = (int)__umulhi((unsigned)w, m_c4), c = w - xo * c4;
+        const int xi = min(o.sw == 1 ? xo : (int)__umulhi((unsigned)xo, m_sw), o.iw - 1);
+        out[w] = in[xi * c4 + c];
     }
 }
 
@@ -361,9 +359,8 @@ static inline void launch_fast_spatial(const ArenaView &v, const KOp &o, int n_i
             return;
         }
     }
-    if (o.kind == OP_UPSAMPLE && o.oh == o.ih * o.sh && o.ow == o.iw * o.sw) {
-        dim3 g((unsigned)std::min<uint64_t>(((uint64_t)o.ih * o.iw * (o.ic >> 2) + 255) / 256, 148 * 64), n_img);
-        k_upsample_rep<<<g, 256, 0, s>>>(v, o);
+    if (o.kind == OP_UPSAMPLE && o.oh <= 65535 && (long long)o.ow * (o.ic >> 2) < 65536) {
+        k_upsample_rep<<<dim3(o.oh, n_img), 256, 0, s>>>(v, o);
         return;
     }
     if (o.kind == OP_MAXPOOL || o.kind == OP_UPSAMPLE) {
