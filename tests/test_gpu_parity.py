@@ -120,6 +120,10 @@ MICRO = [
     ("conv", dict(k=3, s=1, c=64, co=64, h=30, w=26)), ("conv", dict(k=3, s=1, c=32, co=128, h=24, w=20)),
     ("conv", dict(k=5, s=1, c=32, co=32, h=20, w=20)), ("conv", dict(k=1, s=1, c=32, co=16, h=64, w=64)),
     ("conv", dict(k=1, s=1, c=64, co=48, h=50, w=50)), ("conv", dict(k=3, s=1, c=128, co=128, h=40, w=40)),
+    # the stem shape (6x6 stride 2, pads 0 or 2, <= 4 channels): space-to-depth copy read as overlapping K rows
+    ("conv", dict(k=6, s=2, c=3, co=32, h=128, w=128, pad=2)), ("conv", dict(k=6, s=2, c=3, co=32, h=128, w=128, pad=2, padding=1)),
+    ("conv", dict(k=6, s=2, c=3, co=16, h=130, w=136, pad=2)), ("conv", dict(k=6, s=2, c=4, co=48, h=128, w=160, pad=2, padding=1)),
+    ("conv", dict(k=6, s=2, c=2, co=128, h=160, w=128, pad=2)), ("conv", dict(k=6, s=2, c=1, co=32, h=256, w=64, pad=2, no_bias=True)),
     # gather producer + tcgen05 (small Ci, >= 4096 output pixels)
     ("conv", dict(k=6, s=2, c=3, co=32, h=128, w=128)), ("conv", dict(k=3, s=1, c=8, co=24, h=70, w=66, padding=1)),
     ("conv", dict(k=3, s=2, c=5, co=17, h=130, w=140)),

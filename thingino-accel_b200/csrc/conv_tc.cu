@@ -16,7 +16,9 @@
  *               pre-pass otherwise; it is also what lets fused outputs overwrite the layer's own input buffer, as
  *               the reference's work-buffer aliasing demands.  Stride 1 with resident weights: one load of the
  *               unit's rows plus halo serves all taps as row-shifted operands ("halo" mode).
- *               small Ci (6x6 stride-2 stem): producer warps build the K rows in shared memory ("gather" mode).
+ *               6x6 stride-2 stem (Ci <= 4): 3x3 over the space-to-depth image; 16-byte pixels read through a no-swizzle
+ *               descriptor as overlapping 32-byte K rows ("s2d" mode).  Other small-Ci shapes: producer warps build
+ *               the K rows in shared memory ("gather" mode).
  *   B operand   weights repacked once at load to [tap][Co][Ci] (K-major); resident in shared memory when small.
  *   D           int32 in TMEM (128 lanes = pixels, N columns per M tile, ring of accumulator groups).
  *   epilogue    + int32 bias (wrap-around), requantisation with the x86 float->int rule, one lookup
@@ -64,6 +66,8 @@ struct TcParams {
     uint8_t *nhwc_base;
     unsigned long long nhwc_stride;
     unsigned wp_magic;       /* floor(2^32 / Wp) + 1 */
+    int a_row_bytes;         /* bytes of one A row in a halo stage: bk, or 16 in s2d mode */
+    int toep;                /* s2d mode: A rows are 16-byte pixels read as overlapping 32-byte K rows (no swizzle) */
     int halo, halo_min, halo_rb, halo_nb; /* kxk stride 1: one A load per (tile, k block) covers all taps: rows q0+halo_min .., halo_nb boxes of halo_rb rows */
     int acc_bufs;            /* TMEM accumulator ring depth */
     int grp, m_groups;       /* M tiles (128 rows each) per pipeline step and accumulator hand-over; groups per image */
@@ -316,7 +320,7 @@ k_conv_tc(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUte
         s_cm[i] = (int32_t)((uint32_t)((p.bias && i < p.Co) ? p.bias[i] : 0) + (FAST ? 0x4B400000u : 0u));
     for (int i = threadIdx.x; i < 512; i += blockDim.x) s_lutw[i] = p.lutw[i];
     /* per tap: flat pixel shift (TMA coordinate); halo mode: start of the tap's rows inside the stage, in 16-byte units */
-    if (threadIdx.x < TC_MAX_TAPS) s_shift[threadIdx.x] = p.halo ? ((p.a_shift[threadIdx.x] - p.halo_min) * p.bk) >> 4 : p.a_shift[threadIdx.x];
+    if (threadIdx.x < TC_MAX_TAPS) s_shift[threadIdx.x] = p.halo ? ((p.a_shift[threadIdx.x] - p.halo_min) * p.a_row_bytes) >> 4 : p.a_shift[threadIdx.x];
     if (GATHER) {
         const int PP = p.gPWW * 4;
         for (int k = threadIdx.x; k < 128; k += blockDim.x) {
@@ -457,7 +461,9 @@ k_conv_tc(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUte
             const uint32_t k_sbo16 = (8u * (uint32_t)p.bk) >> 4;
             /* descriptor high word: SBO >> 4 at [32,46), version 1 at [46,48), layout type at [61,64) */
             const uint32_t hi_k = k_sbo16 | (1u << 14) | (p.b_layout << 29);
-            const uint32_t hi_a = p.a_kmajor ? hi_k : ((1024u >> 4) | (1u << 14) | (2u << 29));
+            /* s2d mode: canonical no-swizzle K-major layout with SBO = 128 (8 rows of 16 bytes) and LBO = 16: element (r, k) at
+             * byte 16 r + k, i.e. a 32-byte K row is the pixel's 16 channels followed by the NEXT pixel's */
+            const uint32_t hi_a = p.toep ? ((128u >> 4) | (1u << 14)) : (p.a_kmajor ? hi_k : ((1024u >> 4) | (1u << 14) | (2u << 29)));
             /* low word: start address >> 4 at [0,14), LBO >> 4 at [16,30) (16 bytes for the K-major operands) */
             const uint32_t a_lo0 = (a_base >> 4) | (p.a_kmajor ? (1u << 16) : 0u), a_st16 = p.a_stage_bytes >> 4;
             const uint32_t b_lo0 = (b_base >> 4) | (1u << 16), b_st16 = p.b_stage_bytes >> 4;
@@ -465,7 +471,7 @@ k_conv_tc(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUte
              * 128B swizzle) advances 32 K-rows of 128 bytes = 4 atoms of 8 rows */
             const uint32_t a_j16 = p.a_kmajor ? 2u : 256u;
             const int nj = p.bk >> 5, stages = p.stages, acc_bufs = p.acc_bufs, n_tile = p.n_tile, n_img = p.n_img, G = p.grp;
-            const uint32_t a_tile16 = p.a_tile_bytes >> 4, g_rows16 = (uint32_t)(TC_BM * p.bk) >> 4;
+            const uint32_t a_tile16 = p.a_tile_bytes >> 4, g_rows16 = (uint32_t)(TC_BM * p.a_row_bytes) >> 4;
             const int ntaps = p.ntaps, ksteps = p.ksteps_per_tap;
             const uint32_t idesc = p.idesc;
             const bool b_res = GATHER || p.b_resident, halo = p.halo != 0;
@@ -491,7 +497,7 @@ k_conv_tc(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUte
                             for (int tap = 0; tap < ntaps; tap++, b_lo += ksteps * b_st16) {
                                 const uint32_t a_lo = a_st + g * g_rows16 + (uint32_t)s_shift[tap]; /* halo mode: row shift in 16-byte units */
                                 for (int j = 0; j < nj; j++)
-                                    umma_i8_parts(acc + (uint32_t)(g * n_tile), a_lo + 2u * j, hi_k, b_lo + 2u * j, hi_k, idesc, (uint32_t)((kb | tap | j) != 0));
+                                    umma_i8_parts(acc + (uint32_t)(g * n_tile), a_lo + 2u * j, hi_a, b_lo + 2u * j, hi_k, idesc, (uint32_t)((kb | tap | j) != 0));
                             }
                         }
                         umma_commit(sa_empty + 8u * s);
@@ -529,7 +535,7 @@ k_conv_tc(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUte
             int s = 0, ph = 1; /* waits on the empty barriers start with the opposite parity */
             if (p.halo) {
                 const int nb = p.halo_nb, rb = p.halo_rb, hmin = p.halo_min;
-                const uint32_t tx = (uint32_t)(nb * rb * bk), box_b = (uint32_t)(rb * bk);
+                const uint32_t tx = (uint32_t)(nb * rb * p.a_row_bytes), box_b = (uint32_t)(rb * p.a_row_bytes);
                 for (TileIter ti(blockIdx.x, gridDim.x, tiles_per_img); ti.img < n_img; ti.next()) {
                     const int q0 = ti.rem * G * TC_BM + hmin, zc = p.img0 + ti.img; /* n_tiles == 1 with resident weights */
                     for (int kb = 0; kb < ksteps; kb++) {
@@ -696,6 +702,36 @@ __global__ void __launch_bounds__(256) k_to_nhwc(const uint8_t *src_base, unsign
         if (pix < npix && c < C) dst[(long long)pix * C + c] = tile[tx][ty + 8 * k];
     }
 }
+/* ---- s2d mode (6x6 stride-2 pad-2 conv with <= 4 input channels = 3x3 stride-1 pad-1 conv over the 2x2 space-to-depth
+ * image): P[(y+1)*Wp + (x+1)][16] = the 2x2 input block (2y+py, 2x+px) of every channel, byte c' = ci*4 + py*2 + px,
+ * zero border and zero beyond 4*C bytes.  One thread per P pixel. */
+__global__ void __launch_bounds__(256) k_s2d16(const uint8_t *src_base, unsigned long long src_stride, uint8_t *dst_base,
+                                               unsigned long long dst_stride, int C, int H, int W, int Wp, int npix) {
+    const uint8_t *src = src_base + (unsigned long long)blockIdx.y * src_stride;
+    uint4 *dst = reinterpret_cast<uint4 *>(dst_base + (unsigned long long)blockIdx.y * dst_stride);
+    const int pix = blockIdx.x * blockDim.x + threadIdx.x;
+    if (pix >= npix) return;
+    const int yy = pix / Wp, y = yy - 1, x = pix - yy * Wp - 1;
+    uint32_t w[4] = {0u, 0u, 0u, 0u};
+    if (y >= 0 && 2 * y + 1 < H && x >= 0 && 2 * x + 1 < W) {
+        for (int ci = 0; ci < C; ci++) {
+            const uint8_t *r0 = src + ((long long)ci * H + 2 * y) * W + 2 * x;
+            w[ci] = (uint32_t)*reinterpret_cast<const uint16_t *>(r0) | ((uint32_t)*reinterpret_cast<const uint16_t *>(r0 + W) << 16);
+        }
+    }
+    dst[pix] = make_uint4(w[0], w[1], w[2], w[3]);
+}
+/* OIHW 6x6 weights -> [t = ky2*2 + pair][Co_pad][32]: K byte k = (pixel kx2 = 2*pair + k/16, channel byte c' = k%16) */
+__global__ void k_repack_s2d(const int8_t *w, int8_t *dst, int Co, int Co_pad, int Ci) {
+    const long long total = 6ll * Co_pad * 32;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int k = (int)(i % 32), co = (int)((i / 32) % Co_pad), t = (int)(i / (32ll * Co_pad));
+        const int ky2 = t >> 1, kx2 = 2 * (t & 1) + (k >> 4), cp = k & 15, ci = cp >> 2, py = (cp >> 1) & 1, px = cp & 1;
+        int8_t v = 0;
+        if (co < Co && ci < Ci && kx2 < 3) v = w[(((long long)co * Ci + ci) * 6 + (2 * ky2 + py)) * 6 + (2 * kx2 + px)];
+        dst[i] = v;
+    }
+}
 /* OIHW rows (Kt bytes) -> [Co_pad][Kp], zero padded */
 __global__ void k_repack_rows(const int8_t *w, int8_t *dst, int Co, int Co_pad, int Kt, int Kp) {
     long long total = (long long)Co_pad * Kp;
@@ -780,7 +816,7 @@ static int round_up(int x, int a) { return (x + a - 1) / a * a; }
 /* geometry shared by tc_scratch_need and tc_plan */
 struct TcGeom {
     bool ok = false;
-    int prepass = 0; /* 0: A from the arena (1x1); 1: NHWC copy, rows padded (stride 1); 2: NHWC 2x2 phase split (stride 2);
+    int prepass = 0; /* 4: space-to-depth copy with 16-byte pixels (stem); 0: A from the arena (1x1); 1: NHWC copy, rows padded (stride 1); 2: NHWC 2x2 phase split (stride 2);
                         3: gather -- A rows built in shared memory from a private NCHW copy of the input (small Ci) */
     int Wp = 0, plane = 0, npix = 0, ntaps = 0, Kp = 0;
     int tw_shift = 0, PH = 0, PWW = 0, dx = 0; /* gather: M tile shape and input patch geometry */
@@ -793,6 +829,16 @@ static TcGeom tc_geometry(const Op &o) {
     if (o.oh <= 0 || o.ow <= 0 || o.ih <= 0 || o.iw <= 0 || o.ic <= 0) return g;
     if (round_up(o.oc, 16) > TC_MAX_CO) return g;
     if (o.ic < 32 || o.ic % 32 || o.kh != o.kw) {
+        /* the YOLOv5 stem shape: 6x6 stride 2 pad 2 over <= 4 channels == 3x3 stride 1 pad 1 over the 2x2 space-to-depth image */
+        static const bool s2d_enabled = !(getenv("MARS_TC_S2D") && atoi(getenv("MARS_TC_S2D")) == 0);
+        if (s2d_enabled && o.sh == 2 && o.sw == 2 && o.kh == 6 && o.kw == 6 && (o.pt == 0 || o.pt == 2) && (o.pl == 0 || o.pl == 2) &&
+            o.ic <= 4 && o.ih % 2 == 0 && o.iw % 2 == 0 && o.oh <= o.ih / 2 && o.ow <= o.iw / 2 && round_up(o.oc, 16) <= 128 &&
+            (long long)o.oh * o.ow >= 4096) {
+            g.prepass = 4; g.Wp = o.iw / 2 + 2; g.plane = (o.ih / 2 + 2) * g.Wp; g.npix = g.plane; g.ntaps = 6; g.Kp = 32;
+            g.scratch_bytes = (size_t)g.npix * 16;
+            g.ok = true;
+            return g;
+        }
         /* small / odd channel counts: one 128-byte K row per pixel, built in shared memory from a staged input patch */
         const int Kt = o.ic * o.kh * o.kw;
         if (Kt > 128 || o.kh > 255 || o.kw > 255 || (long long)o.oh * o.ow < 4096 || round_up(o.oc, 16) > 256) return g;
@@ -918,8 +964,8 @@ bool tc_plan(const Op &o, const ArenaGeom &ag, uint8_t *scratch, size_t scratch_
     TcPlanImpl *t = new TcPlanImpl();
     TcParams &p = t->p;
     memset(&p, 0, sizeof p);
-    const bool gather = g.prepass == 3;
-    const int ci_eff = gather ? g.Kp : o.ic; /* K extent of one tap */
+    const bool gather = g.prepass == 3, s2d = g.prepass == 4;
+    const int ci_eff = (gather || s2d) ? g.Kp : o.ic; /* K extent of one tap */
     p.Co = o.oc; p.Ho = o.oh; p.Wo = o.ow; p.Wp = g.Wp; p.mflat = o.oh * g.Wp; p.plane = o.oh * o.ow;
     const int co_pad = round_up(o.oc, 16);
     p.n_tile = co_pad <= 256 ? co_pad : (co_pad % 256 == 0 ? 256 : 128);
@@ -929,6 +975,8 @@ bool tc_plan(const Op &o, const ArenaGeom &ag, uint8_t *scratch, size_t scratch_
     p.ksteps_per_tap = ci_eff / p.bk;
     p.ntaps = g.ntaps;
     p.a_tile_bytes = (uint32_t)(TC_BM * p.bk);
+    p.a_row_bytes = s2d ? 16 : p.bk;
+    p.toep = s2d ? 1 : 0;
     p.b_stage_bytes = (uint32_t)round_up(p.n_tile * p.bk, 1024);
     /* Accumulators in TMEM: two CTAs per SM share the 512 columns when a double-buffered accumulator group fits into 256.
      * Narrow N tiles are processed in groups of several M tiles per pipeline step: the per-step cost of the single-thread
@@ -957,16 +1005,22 @@ bool tc_plan(const Op &o, const ArenaGeom &ag, uint8_t *scratch, size_t scratch_
         /* kxk stride 1 over the padded channel-innermost copy: every tap is a row shift of the same pixel rows, so one
          * load of the tile's rows plus its halo (128 + (kh-1)*Wp + kw-1 rows) serves all taps of a k block */
         static const bool halo_enabled = !(getenv("MARS_TC_HALO") && atoi(getenv("MARS_TC_HALO")) == 0);
-        if (halo_enabled && g.prepass == 1 && p.b_resident && g.ntaps > 1) {
-            const int smin = -o.pt * g.Wp, smax = (o.kh - 1 - o.pt) * g.Wp + o.kw - 1;
+        if (s2d && !p.b_resident) { delete t; return false; }
+        if ((halo_enabled && g.prepass == 1 && p.b_resident && g.ntaps > 1) || s2d) {
+            /* s2d: the copy has a one-pixel zero border, so tap (ky2, pair) of output pixel q = oh*Wp + ow starts at row
+             * q + (ky2 + 1 - pt/2)*Wp + (2*pair + 1 - pl/2) and reads two pixels; taps that leave the image hit the border, the
+             * next row's border column, or rows beyond the copy (zero-filled by TMA) */
+            const int s2d_min = (1 - o.pt / 2) * g.Wp + (1 - o.pl / 2);
+            const int smin = s2d ? s2d_min : -o.pt * g.Wp, smax = s2d ? s2d_min + 2 * g.Wp + 3 : (o.kh - 1 - o.pt) * g.Wp + o.kw - 1;
             const int R = p.grp * TC_BM + smax - smin;
             const int nb = (R + 255) / 256, rb = round_up((R + nb - 1) / nb, 8);
-            const uint32_t bytes = (uint32_t)round_up(nb * rb * p.bk, 1024);
+            const uint32_t bytes = (uint32_t)round_up(nb * rb * p.a_row_bytes, 1024);
             if (rb <= 256 && (size_t)2 * bytes + b_all <= (size_t)budget) {
                 p.halo = 1; p.halo_min = smin; p.halo_rb = rb; p.halo_nb = nb;
                 p.a_stage_bytes = bytes;
             }
         }
+        if (s2d && !p.halo) { delete t; return false; }
         if (p.b_resident) {
             p.stages = std::max(2, std::min(8, (budget - (int)b_all) / (int)p.a_stage_bytes));
             t->smem = 1024 + (size_t)p.stages * p.a_stage_bytes + b_all;
@@ -983,7 +1037,8 @@ bool tc_plan(const Op &o, const ArenaGeom &ag, uint8_t *scratch, size_t scratch_
     p.b_layout = p.bk == 128 ? 2u : (p.bk == 64 ? 4u : 6u);
     p.a_kmajor = g.prepass != 0;
     if (!p.a_kmajor) p.idesc |= 1u << 15; /* A MN-major */
-    for (int kh = 0; kh < (gather ? 1 : o.kh); kh++)
+    if (s2d) for (int t6 = 0; t6 < 6; t6++) p.a_shift[t6] = ((t6 >> 1) + 1 - o.pt / 2) * g.Wp + 2 * (t6 & 1) + 1 - o.pl / 2;
+    for (int kh = 0; kh < ((gather || s2d) ? (s2d ? 0 : 1) : o.kh); kh++)
         for (int kw = 0; kw < (gather ? 1 : o.kw); kw++) {
             const int tap = kh * o.kw + kw;
             if (g.prepass == 0 || gather) p.a_shift[tap] = 0;
@@ -1059,7 +1114,9 @@ bool tc_plan(const Op &o, const ArenaGeom &ag, uint8_t *scratch, size_t scratch_
     }
     cudaMemcpy(t->d_lutw, lutw, sizeof lutw, cudaMemcpyHostToDevice);
     p.lutw = t->d_lutw;
-    if (gather)
+    if (s2d)
+        k_repack_s2d<<<64, 256>>>(reinterpret_cast<const int8_t *>(ag.d_weights + o.w), t->d_wr, o.oc, co_pad, o.ic);
+    else if (gather)
         k_repack_rows<<<256, 256>>>(reinterpret_cast<const int8_t *>(ag.d_weights + o.w), t->d_wr, o.oc, co_pad, o.ic * o.kh * o.kw, g.Kp);
     else
         k_repack_weights<<<256, 256>>>(reinterpret_cast<const int8_t *>(ag.d_weights + o.w), t->d_wr, o.oc, co_pad, o.ic, g.ntaps);
@@ -1069,6 +1126,9 @@ bool tc_plan(const Op &o, const ArenaGeom &ag, uint8_t *scratch, size_t scratch_
     if (ok && g.prepass == 0)
         ok = make_map3(&t->mapA, (void *)t->src_slot0, (uint64_t)o.ih * o.iw, (uint64_t)o.ic, (uint64_t)ag.capacity,
                        (uint64_t)o.ih * o.iw, ag.slot_stride, TC_BM, (uint32_t)p.bk, CU_TENSOR_MAP_SWIZZLE_128B);
+    else if (ok && s2d) /* 16-byte pixels, linear rows (no swizzle): the MMA reads them as overlapping 32-byte K rows */
+        ok = make_map3(&t->mapA, scratch, 16, (uint64_t)g.npix, (uint64_t)ag.capacity, 16, scratch_stride, 16, (uint32_t)p.halo_rb,
+                       CU_TENSOR_MAP_SWIZZLE_NONE);
     else if (ok && !gather) /* NHWC copy: dims (C, pixels, images), K-major box {bk, 128} */
         ok = make_map3(&t->mapA, scratch, (uint64_t)ci_eff, (uint64_t)g.npix, (uint64_t)ag.capacity, (uint64_t)ci_eff,
                        scratch_stride, (uint32_t)p.bk, p.halo ? (uint32_t)p.halo_rb : TC_BM, ksw);
@@ -1098,6 +1158,9 @@ bool tc_launch(const TcPlan &plan, uint8_t *slots_base, int first, int n, bool u
         /* private copy of the input tensor: the fused outputs may overwrite the input's work buffer */
         if (cudaMemcpy2DAsync(scr, t->scratch_stride, src, t->slot_stride, (size_t)t->C * t->H * t->W, (size_t)n,
                               cudaMemcpyDeviceToDevice, s) != cudaSuccess) return false;
+    } else if (t->prepass == 4) {
+        k_s2d16<<<dim3((t->npix + 255) / 256, n), 256, 0, s>>>(src, t->slot_stride, scr, t->scratch_stride, t->C, t->H, t->W, t->p.Wp, t->npix);
+        (*launches)++;
     } else if (t->prepass && t->prepass != 3 && !(use_linked && t->has_linked)) {
         dim3 g((t->npix + 31) / 32, (t->C + 31) / 32, n);
         k_to_nhwc<<<g, 256, 0, s>>>(src, t->slot_stride, scr, t->scratch_stride, t->C, t->H, t->W, t->p.Wp, t->plane, t->npix,

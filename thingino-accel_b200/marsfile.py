@@ -494,7 +494,7 @@ def build_single_layer(kind, **kw):
     if kind == "conv":
         k, s, co = kw.get("k", 3), kw.get("s", 1), kw.get("co", 16)
         padding = kw.get("padding", PAD_EXPLICIT)
-        pad = k // 2
+        pad = kw.get("pad", k // 2)
         if padding == PAD_VALID:
             ho, wo = (h - k) // s + 1, (w - k) // s + 1
         else:

@@ -1,3 +1,3 @@
-for mode in 1 2; do for kw in '{"k":3,"s":1,"c":32,"co":32,"h":20,"w":20}' '{"k":3,"s":1,"c":64,"co":64,"h":20,"w":20}' '{"k":3,"s":1,"c":128,"co":32,"h":20,"w":20}' '{"k":3,"s":1,"c":128,"co":32,"h":6,"w":14}'; do
-  echo "== halo=$mode $kw"; MARS_TC_HALO=$mode timeout 60 python tools/tc_probe.py "$kw" 2>&1 | tail -1
-done; done
+for kw in '{"k":6,"s":2,"c":3,"co":32,"h":128,"w":128,"pad":2}' '{"k":6,"s":2,"c":3,"co":32,"h":128,"w":128,"padding":1,"pad":2}' '{"k":6,"s":2,"c":3,"co":16,"h":130,"w":136,"pad":2}' '{"k":6,"s":2,"c":4,"co":48,"h":128,"w":160,"padding":1,"pad":2}' '{"k":6,"s":2,"c":2,"co":128,"h":160,"w":128,"pad":2}'; do
+  echo "== $kw"; timeout 60 python tools/tc_probe.py "$kw" 2>&1 | tail -2 | cut -c1-330
+done
