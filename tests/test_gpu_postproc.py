@@ -40,6 +40,31 @@ def test_postprocess_random_vs_oracle(pkg, ob):
     assert len(pkg.capi.nms(np.zeros(0, dtype=pkg.capi.DET_DTYPE))) == 0
 
 
+def test_nms_arbitrary_class_ids_and_special_scores(pkg, ob):
+    """class ids outside the member-bitset range take the all-pairs path; NaN / inf / tied scores keep the C loop's order"""
+    rng = np.random.default_rng(77)
+    for trial in range(8):
+        n = int(rng.choice([1, 2, 31, 32, 33, 500, 1000, 1024]))
+        d = np.zeros(n, dtype=pkg.capi.DET_DTYPE)
+        d["x"] = rng.integers(0, 64, n).astype(np.float32)
+        d["y"] = rng.integers(0, 64, n).astype(np.float32)
+        d["w"] = rng.integers(1, 40, n).astype(np.float32)
+        d["h"] = rng.integers(1, 40, n).astype(np.float32)
+        d["conf"] = (rng.integers(0, 12, n) / 12).astype(np.float32)  # heavy ties
+        if trial % 2:
+            d["cls"] = rng.choice(np.array([-7, -1, 0, 3, 126, 127, 5000], dtype=np.int32), n)
+        else:
+            d["cls"] = rng.integers(-1, 127, n).astype(np.int32)
+        if trial >= 4 and n > 8:
+            k = rng.integers(0, n, 6)
+            d["conf"][k[:2]] = np.nan
+            d["conf"][k[2:4]] = np.inf
+            d["conf"][k[4:]] = -np.inf
+        for th in (0.45, 0.0):
+            a, b = ob.nms(d.copy(), th), pkg.capi.nms(d.copy(), th)
+            assert a.tobytes() == b.tobytes(), (trial, n, th, len(a), len(b))
+
+
 def test_corner_nms_scale_and_anchor_decode(pkg, ob):
     rng = np.random.default_rng(6)
     boxes = np.zeros(500, dtype=pkg.capi.BOX_DTYPE)

@@ -14,6 +14,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdlib.h>
 
 #include "kernels_exact.cuh"
 
@@ -206,64 +207,250 @@ __device__ __forceinline__ int exchange_sort_block(NmsSortShared &sh, float myk,
     return myi;
 }
 
+
+/*
+ * The same exchange-sort permutation, one WARP per image and no barriers (the default path; the block-wide version
+ * above is kept as a cross-check, MARS_NMS_BLOCKSORT=1).
+ *
+ * Lane L holds positions [32L, 32L+32) in registers (key k[], input index x[]); the 32 positions of the lane that
+ * contains the current pass index i are spread one per lane (Bk, Bx: "the block"), so that the hand d[i] is a shuffle
+ * from lane i % 32 and nothing is indexed dynamically.  Pass i, as in exchange_sort_block, rotates the chain of strict
+ * prefix-maximum records of d[i..n): every record takes its predecessor's element, the first record takes the hand and
+ * position i takes the last record's element.  The chain is found in two levels:
+ *   block    : prefix max over the 32 lanes (retired positions hold -inf and are inert);
+ *   registers: each lane keeps the first-occurrence maximum (lm, lmx) of its 32 positions; a prefix max over the lanes
+ *              (seeded with the block's outgoing maximum) tells which lanes contain records and what enters them, and those
+ *              lanes walk their registers with the literal compare-and-swap of the C loop.
+ * The element leaving the last record is final: it is written to order[i] and never looked at again.
+ * NaN keys never compare greater (never records); a NaN hand makes every comparison fail, so the pass moves nothing.
+ */
+__global__ void __launch_bounds__(32) k_nms_sort_warp(const mars_det_t *dets_in, const int32_t *counts_in, int det_stride,
+                                                      unsigned *scratch, size_t scratch_stride_words) {
+    const int img = blockIdx.x, lane = threadIdx.x;
+    const mars_det_t *in = dets_in + (size_t)img * det_stride;
+    uint16_t *order = reinterpret_cast<uint16_t *>(scratch + (size_t)img * scratch_stride_words + (size_t)MARS_MAX_DETS * 32);
+    int n = counts_in[img];
+    if (n > MARS_MAX_DETS) n = MARS_MAX_DETS;
+    const float NEG_INF = -__int_as_float(0x7f800000), POS_INF = __int_as_float(0x7f800000);
+    const unsigned FULL = 0xffffffffu;
+    float k[32];
+    int x[32];
+#pragma unroll
+    for (int t = 0; t < 32; t++) {
+        const int p = lane * 32 + t;
+        k[t] = p < n ? in[p].conf : NEG_INF;
+        x[t] = p;
+    }
+    float lm = NEG_INF, Bk = NEG_INF;
+    int lmx = 0, Bx = 0;
+    const unsigned below = (1u << lane) - 1u;
+    for (int i = 0; i < n; i++) {
+        const int L0 = i >> 5, t = i & 31;
+        if (t == 0) {
+            /* lane L0's registers become the block; the lane itself is dead from now on */
+#pragma unroll
+            for (int u = 0; u < 32; u++) {
+                const float vk = __shfl_sync(FULL, k[u], L0);
+                const int vx = __shfl_sync(FULL, x[u], L0);
+                if (lane == u) { Bk = vk; Bx = vx; }
+                if (lane == L0) k[u] = NEG_INF;
+            }
+            if (lane == L0) lm = NEG_INF;
+            if (i == 0) { /* first-occurrence maxima of the register lanes */
+#pragma unroll
+                for (int u = 0; u < 32; u++)
+                    if (k[u] > lm) { lm = k[u]; lmx = x[u]; }
+            }
+        }
+        const float hk = __shfl_sync(FULL, Bk, t);
+        const int hx = __shfl_sync(FULL, Bx, t);
+        if (lane == t) Bk = NEG_INF; /* position i retires */
+        const float run0 = (hk != hk) ? POS_INF : hk;
+        /* ---- records inside the block ---- */
+        float inc = (Bk == Bk) ? Bk : NEG_INF;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const float y = __shfl_up_sync(FULL, inc, d);
+            if (lane >= d) inc = fmaxf(inc, y);
+        }
+        float exc = __shfl_up_sync(FULL, inc, 1);
+        exc = fmaxf(lane ? exc : NEG_INF, run0);
+        const bool brec = Bk > exc;
+        const unsigned bm = __ballot_sync(FULL, brec);
+        const int blast = bm ? 31 - __clz(bm) : 0;
+        const unsigned blower = bm & below;
+        const int bsrc = blower ? 31 - __clz(blower) : 0;
+        float ok = __shfl_sync(FULL, Bk, blast);
+        int ox = __shfl_sync(FULL, Bx, blast);
+        const float pk = __shfl_sync(FULL, Bk, bsrc);
+        const int px = __shfl_sync(FULL, Bx, bsrc);
+        if (!bm) { ok = run0; ox = hx; } /* the hand itself leaves the block */
+        if (brec) { Bk = blower ? pk : hk; Bx = blower ? px : hx; }
+        /* ---- records in the register lanes ---- */
+        float inc2 = lm;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const float y = __shfl_up_sync(FULL, inc2, d);
+            if (lane >= d) inc2 = fmaxf(inc2, y);
+        }
+        float e2 = __shfl_up_sync(FULL, inc2, 1);
+        e2 = fmaxf(lane ? e2 : NEG_INF, ok);
+        const bool has = lm > e2;
+        const unsigned hm = __ballot_sync(FULL, has);
+        float wk = ok;
+        int wx = ox;
+        if (hm) { /* uniform */
+            const unsigned hlower = hm & below;
+            const int hsrc = hlower ? 31 - __clz(hlower) : 0;
+            const int ix = __shfl_sync(FULL, lmx, hsrc);
+            float run_k = e2;
+            int run_x = hlower ? ix : ox;
+            float nlm = NEG_INF;
+            int nlx = 0;
+#pragma unroll
+            for (int u = 0; u < 32; u++) {
+                const bool sw = k[u] > run_k;
+                const float nk = sw ? run_k : k[u];
+                const int nx = sw ? run_x : x[u];
+                run_k = sw ? k[u] : run_k;
+                run_x = sw ? x[u] : run_x;
+                k[u] = nk; x[u] = nx;
+                const bool q = nk > nlm;
+                nlm = q ? nk : nlm;
+                nlx = q ? nx : nlx;
+            }
+            lm = nlm; lmx = nlx;
+            const int hlast = 31 - __clz(hm);
+            wk = __shfl_sync(FULL, run_k, hlast);
+            wx = __shfl_sync(FULL, run_x, hlast);
+        }
+        (void)wk;
+        if (lane == 0) order[i] = (uint16_t)wx;
+    }
+}
+
+/* words of per-image scratch: the suppression bit matrix, then the sorted order (uint16 per position) */
+#define NMS_SCRATCH_WORDS ((size_t)MARS_MAX_DETS * 32 + MARS_MAX_DETS / 2)
+
 /* dynamic shared memory of k_nms_center */
+#define NMS_CLASS_ROWS 128 /* class ids -1..126 get a member bitset; anything else takes the dense pair loop */
 struct NmsShared {
     NmsSortShared sort;
-    float x[MARS_MAX_DETS], y[MARS_MAX_DETS], w[MARS_MAX_DETS], h[MARS_MAX_DETS];
+    float x0[MARS_MAX_DETS], y0[MARS_MAX_DETS], x1[MARS_MAX_DETS], y1[MARS_MAX_DETS], area[MARS_MAX_DETS];
     int cls[MARS_MAX_DETS];
+    unsigned members[NMS_CLASS_ROWS][32]; /* bit j of row c: sorted element j has class c - 1 */
     unsigned removed[32];
     int warp_sums[32];
+    int dense;
 };
 
+/* IoU of reference src/mars/mars_yolo_test.c:115-121 from the per-element corners and areas (each operation rounded
+ * separately, exactly as when it is evaluated per pair: the corner and area expressions only involve one box) */
+__device__ __forceinline__ float iou_pre(float ax0, float ay0, float ax1, float ay1, float aarea, float bx0, float by0, float bx1,
+                                         float by1, float barea) {
+    const float x1 = fmaxf(ax0, bx0), y1 = fmaxf(ay0, by0), x2 = fminf(ax1, bx1), y2 = fminf(ay1, by1);
+    const float inter = __fmul_rn(fmaxf(0.0f, __fsub_rn(x2, x1)), fmaxf(0.0f, __fsub_rn(y2, y1)));
+    return __fdiv_rn(inter, __fadd_rn(__fsub_rn(__fadd_rn(aarea, barea), inter), 1e-6f));
+}
+
 /* dets_in/dets_out: [det_stride] per image; counts in/out per image.  blockDim.x = NMS_THREADS, dynamic smem = sizeof(NmsShared);
- * mask_scratch: MARS_MAX_DETS x 32 words per image (row i, bit j: sorted element j > i has i's class and IoU(i, j) > thresh) --
- * kept in global memory (L2-resident, written and read once) so that two blocks fit one SM: the sort is a chain of barriers and
- * leaves the SM mostly idle, a second image fills the gaps.
- * Greedy suppression (mars_yolo_test.c:113-123) as a bit matrix: all pair tests in parallel (class test first, the IoU
- * with its two divisions only for same-class pairs), then one warp walks i ascending and ORs row i into the removed
- * set iff i is still alive -- the same result as the sequential double loop. */
+ * mask_scratch: NMS_SCRATCH_WORDS per image: MARS_MAX_DETS x 32 words (row i, bit j: sorted element j > i has i's class and
+ * IoU(i, j) > thresh; kept in global memory, L2-resident, written and read once, so that two blocks fit one SM), then the
+ * sorted order written by k_nms_sort_warp.
+ * Greedy suppression (mars_yolo_test.c:113-123) as a bit matrix.  Only same-class pairs can suppress: a member bitset per
+ * class turns row i into "members of i's class behind i" -- one word per lane -- and each lane evaluates the IoU of the
+ * few bits set in its word.  Then one warp walks i ascending and ORs row i into the removed set iff i is still alive --
+ * the same result as the sequential double loop. */
 __global__ void __launch_bounds__(NMS_THREADS, 2) k_nms_center(const mars_det_t *dets_in, const int32_t *counts_in,
                                                                mars_det_t *dets_out, int32_t *counts_out, int det_stride,
-                                                               float thresh, unsigned *mask_scratch) {
+                                                               float thresh, unsigned *mask_scratch, int presorted) {
     extern __shared__ __align__(16) uint8_t nms_smem[];
     NmsShared &sh = *reinterpret_cast<NmsShared *>(nms_smem);
     const mars_det_t *in = dets_in + (size_t)blockIdx.x * det_stride;
     mars_det_t *out = dets_out + (size_t)blockIdx.x * det_stride;
-    unsigned *mask = mask_scratch + (size_t)blockIdx.x * MARS_MAX_DETS * 32;
+    unsigned *const mask = mask_scratch + (size_t)blockIdx.x * NMS_SCRATCH_WORDS;
+    const uint16_t *order = reinterpret_cast<const uint16_t *>(mask + (size_t)MARS_MAX_DETS * 32);
     int n = counts_in[blockIdx.x];
     if (n > MARS_MAX_DETS) n = MARS_MAX_DETS;
     const int j = threadIdx.x, lane = j & 31, wid = j >> 5;
     const float NEG_INF = -__int_as_float(0x7f800000);
-    const int src = exchange_sort_block(sh.sort, j < n ? in[j].conf : NEG_INF, n);
+    /* sorted position j holds input element src: from k_nms_sort_warp, or (cross-check path) sorted here by the block */
+    const int src = presorted ? (j < n ? order[j] : j) : exchange_sort_block(sh.sort, j < n ? in[j].conf : NEG_INF, n);
+    for (int q = j; q < NMS_CLASS_ROWS * 32; q += NMS_THREADS) (&sh.members[0][0])[q] = 0u;
+    if (j == 0) sh.dense = 0;
     mars_det_t me;
     if (j < n) {
         me = in[src];
-        sh.x[j] = me.x; sh.y[j] = me.y; sh.w[j] = me.w; sh.h[j] = me.h; sh.cls[j] = me.cls;
+        const float hw = __fdiv_rn(me.w, 2.0f), hh = __fdiv_rn(me.h, 2.0f);
+        sh.x0[j] = __fsub_rn(me.x, hw); sh.x1[j] = __fadd_rn(me.x, hw);
+        sh.y0[j] = __fsub_rn(me.y, hh); sh.y1[j] = __fadd_rn(me.y, hh);
+        sh.area[j] = __fmul_rn(me.w, me.h);
+        sh.cls[j] = me.cls;
+    }
+    __syncthreads();
+    if (j < n) {
+        const unsigned c = (unsigned)(me.cls + 1);
+        if (c < NMS_CLASS_ROWS) atomicOr(&sh.members[c][wid], 1u << lane);
+        else sh.dense = 1;
     }
     __syncthreads();
     const int nwords = (n + 31) >> 5;
-    for (int i = wid; i < n; i += NMS_THREADS / 32) { /* one warp per row, lane = bit */
-        mars_det_t a;
-        a.x = sh.x[i]; a.y = sh.y[i]; a.w = sh.w[i]; a.h = sh.h[i]; a.conf = 0.0f; a.cls = sh.cls[i];
-        for (int w = i >> 5; w < nwords; w++) {
-            const int jj = w * 32 + lane;
-            bool s = false;
-            if (jj > i && jj < n && sh.cls[jj] == a.cls) {
-                mars_det_t b;
-                b.x = sh.x[jj]; b.y = sh.y[jj]; b.w = sh.w[jj]; b.h = sh.h[jj]; b.conf = 0.0f; b.cls = a.cls;
-                s = iou_center(a, b) > thresh;
+    if (!sh.dense) {
+        for (int i = wid; i < n; i += NMS_THREADS / 32) { /* one warp per row, lane = word of the row */
+            const int w0 = i >> 5;
+            unsigned cand = (lane >= w0 && lane < nwords) ? sh.members[sh.cls[i] + 1][lane] : 0u;
+            if (lane == w0) cand &= ~((2u << (i & 31)) - 1u); /* only elements behind i */
+            unsigned bits = 0u;
+            if (__any_sync(0xffffffffu, cand != 0u)) {
+                const float ax0 = sh.x0[i], ay0 = sh.y0[i], ax1 = sh.x1[i], ay1 = sh.y1[i], aarea = sh.area[i];
+                while (cand) {
+                    const int b = __ffs(cand) - 1;
+                    cand &= cand - 1u;
+                    const int jj = lane * 32 + b;
+                    if (iou_pre(ax0, ay0, ax1, ay1, aarea, sh.x0[jj], sh.y0[jj], sh.x1[jj], sh.y1[jj], sh.area[jj]) > thresh) bits |= 1u << b;
+                }
             }
-            const unsigned bits = __ballot_sync(0xffffffffu, s);
-            if (lane == 0) mask[i * 32 + w] = bits;
+            if (lane >= w0 && lane < nwords) mask[i * 32 + lane] = bits;
+        }
+    } else {
+        for (int i = wid; i < n; i += NMS_THREADS / 32) { /* arbitrary class ids: one warp per row, lane = bit, all pairs */
+            const float ax0 = sh.x0[i], ay0 = sh.y0[i], ax1 = sh.x1[i], ay1 = sh.y1[i], aarea = sh.area[i];
+            const int acls = sh.cls[i];
+            for (int w = i >> 5; w < nwords; w++) {
+                const int jj = w * 32 + lane;
+                bool sup = false;
+                if (jj > i && jj < n && sh.cls[jj] == acls)
+                    sup = iou_pre(ax0, ay0, ax1, ay1, aarea, sh.x0[jj], sh.y0[jj], sh.x1[jj], sh.y1[jj], sh.area[jj]) > thresh;
+                const unsigned bits = __ballot_sync(0xffffffffu, sup);
+                if (lane == 0) mask[i * 32 + w] = bits;
+            }
         }
     }
     __syncthreads();
     if (wid == 0) {
-        unsigned removed = 0u; /* lane w: bits of elements [32w, 32w+32) */
-        for (int i = 0; i < n; i++) {
-            const unsigned row = (lane >= (i >> 5) && lane < nwords) ? mask[i * 32 + lane] : 0u;
-            const unsigned word = __shfl_sync(0xffffffffu, removed, i >> 5);
-            if (!((word >> (i & 31)) & 1u)) removed |= row;
+        /* lane w: bits of elements [32w, 32w+32).  The walk is serial in i but the rows do not depend on it: they are
+         * fetched sixteen at a time (independent L2 loads in flight together), the next sixteen while these are used. */
+        unsigned removed = 0u;
+        constexpr int CH = 16;
+        unsigned cur_rows[CH], nxt_rows[CH];
+        auto fetch = [&](unsigned (&rows)[CH], int base) {
+#pragma unroll
+            for (int q = 0; q < CH; q++) {
+                const int i = base + q;
+                rows[q] = (i < n && lane >= (i >> 5) && lane < nwords) ? mask[i * 32 + lane] : 0u;
+            }
+        };
+        fetch(cur_rows, 0);
+        for (int base = 0; base < n; base += CH) {
+            fetch(nxt_rows, base + CH);
+#pragma unroll
+            for (int q = 0; q < CH; q++) {
+                const int i = base + q; /* rows beyond n are zero */
+                const unsigned word = __shfl_sync(0xffffffffu, removed, (i >> 5) & 31);
+                if (!((word >> (i & 31)) & 1u)) removed |= cur_rows[q];
+            }
+#pragma unroll
+            for (int q = 0; q < CH; q++) cur_rows[q] = nxt_rows[q];
         }
         sh.removed[lane] = removed;
     }
@@ -277,15 +464,18 @@ __global__ void __launch_bounds__(NMS_THREADS, 2) k_nms_center(const mars_det_t 
 }
 
 static inline cudaError_t launch_nms_center(const mars_det_t *dets_in, const int32_t *counts_in, mars_det_t *dets_out,
-                                            int32_t *counts_out, int det_stride, float thresh, int n_img, unsigned *mask_scratch,
-                                            cudaStream_t s) {
+                                            int32_t *counts_out, int det_stride, float thresh, int n_img, unsigned *scratch /* NMS_SCRATCH_WORDS per image */,
+                                            cudaStream_t s, int *launches = nullptr) {
     static bool attr = false;
+    static const bool block_sort = getenv("MARS_NMS_BLOCKSORT") && atoi(getenv("MARS_NMS_BLOCKSORT")) != 0;
     if (!attr) {
         cudaError_t e = cudaFuncSetAttribute(k_nms_center, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(NmsShared));
         if (e != cudaSuccess) return e;
         attr = true;
     }
-    k_nms_center<<<n_img, NMS_THREADS, sizeof(NmsShared), s>>>(dets_in, counts_in, dets_out, counts_out, det_stride, thresh, mask_scratch);
+    if (!block_sort) k_nms_sort_warp<<<n_img, 32, 0, s>>>(dets_in, counts_in, det_stride, scratch, NMS_SCRATCH_WORDS);
+    k_nms_center<<<n_img, NMS_THREADS, sizeof(NmsShared), s>>>(dets_in, counts_in, dets_out, counts_out, det_stride, thresh, scratch, block_sort ? 0 : 1);
+    if (launches) *launches = block_sort ? 1 : 2;
     return cudaGetLastError();
 }
 

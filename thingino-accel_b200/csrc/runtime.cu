@@ -233,7 +233,7 @@ static mars_error_t set_capacity(Model *m, int capacity) {
     CU_OK(cudaMalloc(&nraw, (size_t)capacity * MARS_MAX_DETS * sizeof(mars_det_t)), MARS_ERR_ALLOC_FAILED);
     CU_OK(cudaMalloc(&ndet, (size_t)capacity * MARS_MAX_DETS * sizeof(mars_det_t)), MARS_ERR_ALLOC_FAILED);
     unsigned *nmask = nullptr;
-    CU_OK(cudaMalloc(&nmask, (size_t)capacity * MARS_MAX_DETS * 32 * sizeof(unsigned)), MARS_ERR_ALLOC_FAILED);
+    CU_OK(cudaMalloc(&nmask, (size_t)capacity * NMS_SCRATCH_WORDS * sizeof(unsigned)), MARS_ERR_ALLOC_FAILED);
     CU_OK(cudaMalloc(&nrc, (size_t)capacity * sizeof(int32_t)), MARS_ERR_ALLOC_FAILED);
     CU_OK(cudaMalloc(&ndc, (size_t)capacity * sizeof(int32_t)), MARS_ERR_ALLOC_FAILED);
     CU_OK(cudaMemsetAsync(nrc, 0, (size_t)capacity * sizeof(int32_t), m->stream), MARS_ERR_ALLOC_FAILED);
@@ -311,6 +311,8 @@ static mars_error_t compile_model(Model *m) {
     }
     m->prof_ms.assign(m->prog.ops.size(), 0.0);
     m->prof_calls.assign(m->prog.ops.size(), 0);
+    /* tables, the zeroed link area and the repacked weights are complete before a (non-blocking) stream uses them */
+    CU_OK(cudaDeviceSynchronize(), MARS_ERR_LAYER_FAILED);
     m->compiled = true;
     return MARS_OK;
 }
@@ -516,13 +518,14 @@ static mars_error_t enqueue_detect(Model *m, int first, int n, float thresh) {
     mars_error_t e = ensure_tables(m, d.scale);
     if (e != MARS_OK) return e;
     const int8_t *data = reinterpret_cast<const int8_t *>(dev_addr(m, m->toff[oi], first));
+    int nms_launches = 1;
     k_parse_output<<<n, 256, 0, m->stream>>>(data, m->slot_stride, d.shape[1], d.scale, m->d_tab,
                                             m->d_raw + (size_t)first * MARS_MAX_DETS, m->d_raw_cnt + first, 1000,
                                             MARS_MAX_DETS);
     CU_OK(launch_nms_center(m->d_raw + (size_t)first * MARS_MAX_DETS, m->d_raw_cnt + first, m->d_det + (size_t)first * MARS_MAX_DETS,
-                            m->d_det_cnt + first, MARS_MAX_DETS, thresh, n, m->d_nms_mask + (size_t)first * MARS_MAX_DETS * 32, m->stream),
+                            m->d_det_cnt + first, MARS_MAX_DETS, thresh, n, m->d_nms_mask + (size_t)first * NMS_SCRATCH_WORDS, m->stream, &nms_launches),
           MARS_ERR_LAYER_FAILED);
-    m->launches += 2;
+    m->launches += 1 + nms_launches;
     CU_OK(cudaGetLastError(), MARS_ERR_LAYER_FAILED);
     return MARS_OK;
 }
