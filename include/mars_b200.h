@@ -63,6 +63,11 @@ size_t mars_b200_input_bytes(mars_model_t *m);
 size_t mars_b200_output_bytes(mars_model_t *m);
 /* host -> slots [first, first+n): n inputs, `stride` bytes apart in host memory */
 mars_error_t mars_b200_upload_inputs(mars_model_t *m, int first, int n, const void *host, size_t stride);
+/* Pre-processing in front of mars_run (what the reference's caller does on the CPU, src/mars/mars_yolo_test.c:40-77 and
+ * :157-165): n RGB8 frames of w x h pixels in host memory, frame_stride bytes apart, are letterboxed on the GPU into input
+ * tensor 0 of slots [first, first+n): stbir_resize_uint8 (include/stb/stb_image_resize.h) semantics bit for bit, gray border
+ * -17, px - 128, NCHW or NHWC as the tensor's format field says.  Replaces load_image + mars_b200_upload_inputs. */
+mars_error_t mars_b200_preprocess_batch(mars_model_t *m, int first, int n, const uint8_t *frames, size_t frame_stride, int w, int h);
 /* slots -> host: output tensor 0 of n images */
 mars_error_t mars_b200_download_outputs(mars_model_t *m, int first, int n, void *host, size_t stride);
 /* run all layers for slots [first, first+n) with inputs already resident in HBM */
@@ -106,6 +111,14 @@ size_t mars_b200_tensor_offset(mars_model_t *m, uint32_t index);
 uint64_t mars_b200_launch_count(mars_model_t *m);
 /* CUDA-event time of the last mars_b200_run_resident / detect_resident, milliseconds */
 float mars_b200_last_gpu_ms(mars_model_t *m);
+
+/* ---- YOLO pre-process on host buffers ------------------------------------ */
+/* load_image of reference src/mars/mars_yolo_test.c:40-77 without the file decode: rgb = h x w x 3 bytes in,
+ * out = tw x th x 3 int8 (three planes, or interleaved when nhwc != 0).  Returns 0 on success, -1 on failure. */
+int mars_b200_letterbox(const uint8_t *rgb, int w, int h, int tw, int th, int nhwc, int8_t *out);
+/* host half of the above (no GPU needed): the (source sample, coefficient) taps each of the out_size output samples of one
+ * axis sums, in the order stbir_resize_uint8 adds them.  start[out_size + 1]; returns the tap count (> cap: nothing copied). */
+int mars_b200_resize_taps(int in_size, int out_size, int32_t *start, int32_t *src, float *w, int cap);
 
 /* ---- YOLO post-process on host buffers ----------------------------------- */
 /* parse_output of reference src/mars/mars_yolo_test.c:80-104 (conf threshold 0.25) */

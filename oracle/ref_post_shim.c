@@ -17,6 +17,16 @@ int oracle_ref_parse_output(const int8_t *data, int npred, float scale, void *de
 int oracle_ref_nms(void *dets, int n, float thresh) { return nms((det_t *)dets, n, thresh); }
 int oracle_ref_det_size(void) { return (int)sizeof(det_t); }
 
+/* the reference's own load_image() (:40-77): stb_image decode of the file (tests write a binary PPM), stbir letterbox
+ * resize, int8 packing.  out = tw*th*3 bytes. */
+int oracle_ref_load_image(const char *path, int tw, int th, int nhwc, int8_t *out, int *ow, int *oh) {
+    int8_t *p = load_image(path, tw, th, nhwc, ow, oh);
+    if (!p) return -1;
+    memcpy(out, p, (size_t)tw * th * 3);
+    free(p);
+    return 0;
+}
+
 /* run one layer through the reference's own mars_run(): a shallow copy of the
  * model whose layer table starts at layer i and has length 1. */
 int oracle_ref_run_layer(mars_model_t *m, uint32_t i) {

@@ -130,6 +130,9 @@ class RefRuntime:
             lib.oracle_ref_parse_output.argtypes = [C.c_void_p, C.c_int, C.c_float, C.c_void_p, C.c_int]
             lib.oracle_ref_nms.restype = C.c_int
             lib.oracle_ref_nms.argtypes = [C.c_void_p, C.c_int, C.c_float]
+            if hasattr(lib, "oracle_ref_load_image"):
+                lib.oracle_ref_load_image.restype = C.c_int
+                lib.oracle_ref_load_image.argtypes = [C.c_char_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_int)]
             lib.oracle_ref_cpp_nms.restype = C.c_int
             lib.oracle_ref_cpp_nms.argtypes = [C.c_void_p, C.c_int, C.c_float]
             lib.oracle_ref_cpp_iou.restype = C.c_float
@@ -212,6 +215,25 @@ def ref_nms(dets: np.ndarray, thresh=0.45) -> np.ndarray:
     d = np.ascontiguousarray(dets.copy())
     n = lib.oracle_ref_nms(d.ctypes.data, len(d), thresh)
     return d[:n].copy()
+
+
+def ref_load_image(rgb: np.ndarray, tw: int, th: int, nhwc: bool) -> np.ndarray:
+    """the reference's own load_image() (src/mars/mars_yolo_test.c:40-77) on an [h, w, 3] uint8 frame: the frame goes
+    through a binary PPM file so that the unmodified function (stb_image decode included) runs.  Returns tw*th*3 int8."""
+    import tempfile
+    lib = RefRuntime.lib()
+    rgb = np.ascontiguousarray(rgb, dtype=np.uint8)
+    h, w, _ = rgb.shape
+    out = np.zeros(tw * th * 3, dtype=np.int8)
+    ow, oh = C.c_int(0), C.c_int(0)
+    with tempfile.NamedTemporaryFile(suffix=".ppm") as f:
+        f.write(b"P6\n%d %d\n255\n" % (w, h))
+        f.write(rgb.tobytes())
+        f.flush()
+        rc = lib.oracle_ref_load_image(f.name.encode(), tw, th, 1 if nhwc else 0, out.ctypes.data, C.byref(ow), C.byref(oh))
+    if rc != 0 or (ow.value, oh.value) != (w, h):
+        raise RuntimeError("reference load_image failed (rc %d, %dx%d)" % (rc, ow.value, oh.value))
+    return out
 
 
 def pattern_p0(nbytes: int) -> np.ndarray:

@@ -146,6 +146,7 @@ SIGNATURES = {
     "mars_b200_output_bytes": (C.c_size_t, [PM]),
     "mars_b200_upload_inputs": (C.c_int, [PM, C.c_int, C.c_int, C.c_void_p, C.c_size_t]),
     "mars_b200_download_outputs": (C.c_int, [PM, C.c_int, C.c_int, C.c_void_p, C.c_size_t]),
+    "mars_b200_preprocess_batch": (C.c_int, [PM, C.c_int, C.c_int, C.c_void_p, C.c_size_t, C.c_int, C.c_int]),
     "mars_b200_run_resident": (C.c_int, [PM, C.c_int, C.c_int]),
     "mars_b200_detect_resident": (C.c_int, [PM, C.c_int, C.c_int, C.c_float]),
     "mars_b200_step_resident": (C.c_int, [PM, C.c_int, C.c_int, C.c_float, C.c_int]),
@@ -164,6 +165,8 @@ SIGNATURES = {
     "mars_b200_tensor_offset": (C.c_size_t, [PM, C.c_uint32]),
     "mars_yolo_parse_output": (C.c_int, [C.c_void_p, C.c_int, C.c_float, C.c_void_p, C.c_int]),
     "mars_yolo_nms": (C.c_int, [C.c_void_p, C.c_int, C.c_float]),
+    "mars_b200_letterbox": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
+    "mars_b200_resize_taps": (C.c_int, [C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]),
     "mars_yolo_nms_boxes": (C.c_int, [C.c_void_p, C.c_int, C.c_float]),
     "mars_yolo_scale_detections": (None, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]),
     "mars_yolo_decode_anchor_grid": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_float, C.c_int, C.c_float, C.c_void_p, C.c_int, C.c_int]),
@@ -315,6 +318,15 @@ class MarsModel:
     def upload_inputs(self, first, n, host, stride=0):
         self._check(lib().mars_b200_upload_inputs(self.m, first, n, _addr(host), stride), "upload_inputs")
 
+    def preprocess(self, first, frames):
+        """frames: [n, h, w, 3] uint8 (host) -> letterboxed into input tensor 0 of slots [first, first+n) on the device
+        (reference src/mars/mars_yolo_test.c:40-77); returns the GPU milliseconds of the copy + kernels"""
+        f = np.ascontiguousarray(frames, dtype=np.uint8)
+        n, h, w, c = f.shape
+        assert c == 3
+        self._check(lib().mars_b200_preprocess_batch(self.m, first, n, f.ctypes.data, h * w * 3, w, h), "preprocess_batch")
+        return float(lib().mars_b200_last_gpu_ms(self.m))
+
     def download_outputs(self, first, n, host=None, stride=0):
         if host is None:
             host = np.zeros((n, self.out_bytes), dtype=np.uint8)
@@ -394,6 +406,31 @@ class MarsModel:
             self.close()
         except Exception:
             pass
+
+
+# ---- pre-process on host arrays ------------------------------------------------------
+def letterbox(rgb, tw, th, nhwc=False):
+    """[h, w, 3] uint8 frame -> tw*th*3 int8 network input (runs on the device; reference load_image minus the decode)"""
+    f = np.ascontiguousarray(rgb, dtype=np.uint8)
+    h, w, _ = f.shape
+    out = np.zeros(tw * th * 3, dtype=np.int8)
+    if lib().mars_b200_letterbox(f.ctypes.data, w, h, tw, th, 1 if nhwc else 0, out.ctypes.data) != 0:
+        raise RuntimeError("mars_b200_letterbox failed: " + last_error())
+    return out
+
+
+def resize_taps(in_size, out_size):
+    """host half of the pre-processing (no GPU): (start[out+1], src[], w[]) tap lists of one axis"""
+    start = np.zeros(out_size + 1, dtype=np.int32)
+    cap = 16 * max(in_size, out_size) + 64
+    while True:
+        src, w = np.zeros(cap, dtype=np.int32), np.zeros(cap, dtype=np.float32)
+        n = lib().mars_b200_resize_taps(in_size, out_size, start.ctypes.data, src.ctypes.data, w.ctypes.data, cap)
+        if n < 0:
+            raise ValueError("resize_taps(%d, %d)" % (in_size, out_size))
+        if n <= cap:
+            return start, src[:n].copy(), w[:n].copy()
+        cap = n
 
 
 # ---- post-process on host arrays (runs on the device) ---------------------------------

@@ -34,6 +34,7 @@
 #include "kernels_fast.cuh"
 #include "mars_internal.h"
 #include "postproc.cuh"
+#include "preproc.cuh"
 
 namespace marsb200 {
 
@@ -158,6 +159,12 @@ struct Model {
     uint64_t launches = 0;
     /* asynchronous batches (mars_b200_submit_batch / wait_batch): one in flight per half of the slot pool */
     struct Pending { bool active = false; int n = 0, maxd = 0; int32_t *counts = nullptr; } pending[2];
+    /* letterbox pre-processing (mars_b200_preprocess_batch): tap lists of the last geometry, frame staging, float rows */
+    LetterboxPlan pre_plan;
+    uint8_t *d_frames = nullptr;
+    size_t frames_cap = 0;
+    float *d_preH = nullptr;
+    size_t preH_cap = 0;
     /* device-resident detections */
     mars_det_t *d_raw = nullptr, *d_det = nullptr;
     int32_t *d_raw_cnt = nullptr, *d_det_cnt = nullptr;
@@ -202,6 +209,9 @@ static void model_release(Model *m) {
         if (m->ev_done[i]) cudaEventDestroy(m->ev_done[i]);
         if (m->ev_out[i]) cudaEventDestroy(m->ev_out[i]);
     }
+    letterbox_plan_release(&m->pre_plan);
+    cudaFree(m->d_frames);
+    cudaFree(m->d_preH);
     if (m->stream) cudaStreamDestroy(m->stream);
     if (m->h2d_stream) cudaStreamDestroy(m->h2d_stream);
     if (m->d2h_stream) cudaStreamDestroy(m->d2h_stream);
@@ -946,6 +956,62 @@ mars_error_t mars_b200_download_outputs(mars_model_t *model, int first, int n, v
     mars_error_t e = copy_io(m, first, n, host, stride, 1, m->stream);
     if (e != MARS_OK) return e;
     CU_OK(cudaStreamSynchronize(m->stream), MARS_ERR_LAYER_FAILED);
+    return MARS_OK;
+}
+
+/* Pre-processing in front of mars_run, as the reference's caller does it on the CPU (src/mars/mars_yolo_test.c:40-77 and
+ * :157-165): n RGB8 frames of w x h pixels (host memory, frame_stride bytes apart, >= w*h*3) are letterboxed into input
+ * tensor 0 of slots [first, first+n) -- stbir_resize_uint8 semantics, gray border -17, px - 128, NCHW or NHWC as the
+ * tensor's format field says.  Synchronous like mars_b200_upload_inputs. */
+mars_error_t mars_b200_preprocess_batch(mars_model_t *model, int first, int n, const uint8_t *frames, size_t frame_stride, int w, int h) {
+    Model *m = as_model(model);
+    if (!m || !frames) return MARS_ERR_INVALID_FILE;
+    CU_OK(cudaSetDevice(m->device), MARS_ERR_NNA_INIT_FAILED);
+    if (!range_ok(m, first, n)) return MARS_ERR_INVALID_TENSOR;
+    if (m->pub.header.num_inputs < 1) return MARS_ERR_INVALID_TENSOR;
+    const uint32_t ti = m->pub.header.input_tensor_ids[0];
+    if (ti >= m->pub.header.num_tensors || m->toff[ti] < m->weights_size) return MARS_ERR_INVALID_TENSOR;
+    const mars_tensor_t &d = m->pub.tensors[ti].desc;
+    if (d.dtype != MARS_DTYPE_INT8 || d.ndims < 4 || w <= 0 || h <= 0) {
+        set_last_error("preprocess: input 0 must be a 4-d int8 tensor (reference src/mars/mars_yolo_test.c:157-159)");
+        return MARS_ERR_INVALID_TENSOR;
+    }
+    const int nhwc = d.format == MARS_FORMAT_NHWC;
+    const int th = nhwc ? d.shape[1] : d.shape[2], tw = nhwc ? d.shape[2] : d.shape[3];
+    if (th <= 0 || tw <= 0 || (size_t)tw * th * 3 > m->buffer_size) return MARS_ERR_INVALID_TENSOR;
+    const size_t frame_bytes = (size_t)w * h * 3;
+    if (frame_stride < frame_bytes) frame_stride = frame_bytes;
+    if (!letterbox_plan_build(w, h, tw, th, &m->pre_plan)) {
+        set_last_error("preprocess: cannot letterbox %dx%d into %dx%d", w, h, tw, th);
+        return MARS_ERR_INVALID_TENSOR;
+    }
+    const size_t h_per = (size_t)h * m->pre_plan.g.nw * 3 * sizeof(float);
+    int chunk = (int)std::max<size_t>(1, std::min<size_t>((size_t)n, ((size_t)256 << 20) / std::max<size_t>(h_per, 1)));
+    if ((size_t)chunk * frame_bytes > m->frames_cap) {
+        cudaFree(m->d_frames);
+        m->d_frames = nullptr; m->frames_cap = 0;
+        CU_OK(cudaMalloc(&m->d_frames, (size_t)chunk * frame_bytes), MARS_ERR_ALLOC_FAILED);
+        m->frames_cap = (size_t)chunk * frame_bytes;
+    }
+    if ((size_t)chunk * h_per > m->preH_cap) {
+        cudaFree(m->d_preH);
+        m->d_preH = nullptr; m->preH_cap = 0;
+        CU_OK(cudaMalloc(&m->d_preH, (size_t)chunk * h_per), MARS_ERR_ALLOC_FAILED);
+        m->preH_cap = (size_t)chunk * h_per;
+    }
+    cudaEventRecord(m->ev0, m->stream);
+    for (int done = 0; done < n; done += chunk) {
+        const int c = std::min(chunk, n - done);
+        CU_OK(cudaMemcpy2DAsync(m->d_frames, frame_bytes, frames + (size_t)done * frame_stride, frame_stride, frame_bytes, (size_t)c,
+                                cudaMemcpyHostToDevice, m->stream), MARS_ERR_LAYER_FAILED);
+        CU_OK(launch_letterbox(m->pre_plan, m->d_frames, frame_bytes, c, m->d_preH,
+                               reinterpret_cast<int8_t *>(dev_addr(m, m->toff[ti], first + done)), m->slot_stride, nhwc, m->stream),
+              MARS_ERR_LAYER_FAILED);
+        m->launches += 2;
+    }
+    cudaEventRecord(m->ev1, m->stream);
+    CU_OK(cudaStreamSynchronize(m->stream), MARS_ERR_LAYER_FAILED);
+    cudaEventElapsedTime(&m->last_ms, m->ev0, m->ev1);
     return MARS_OK;
 }
 
