@@ -12,7 +12,7 @@ table as the shipped yolov5n_int8.mars at 2x width, SYNTHETIC weights, seed 5).
   value : whole-job images/s with the batch already resident in HBM (device time, CUDA events
           on the library's stream, max over ranks);
   e2e   : the same through mars_b200_submit_batch() / mars_b200_wait_batch() with HOST (pinned) buffers -- H2D of
-          every image and D2H of every detection list inside the timed region, 256 images per submit so that
+          every image and D2H of every detection list inside the timed region, up to 512 images per submit so that
           the copies of one submit overlap the kernels of the previous one;
   roofline / cpu_baseline : see DESIGN.md section 6.
 
@@ -327,7 +327,7 @@ def run_cuda_arm(args):
     # pinned host memory to HBM and reads its detection records back; batch k+1 is submitted before batch k is
     # waited for, so the copies overlap the kernels (two halves of a 2B-slot pool).  K steps are timed, pipeline
     # fill and drain included.
-    SUB = min(B, 256)  # images per submit: two halves of a 2*SUB-slot pool; a step = B / SUB submits
+    SUB = min(B, int(os.environ.get("MARS_BENCH_SUB", "512")))  # images per submit: two halves of a 2*SUB-slot pool; a step = B / SUB submits
     nsub = (B + SUB - 1) // SUB
     gm.set_batch(2 * SUB)
     outs = []
