@@ -262,42 +262,39 @@ __global__ void __launch_bounds__(32) k_nms_sort_warp(const mars_det_t *dets_in,
                     if (k[u] > lm) { lm = k[u]; lmx = x[u]; }
             }
         }
+        /* The pass is one dependent chain (scan -> who holds records -> walk -> next pass's maxima), so it is written for
+         * latency: both prefix-max scans run interleaved and start before the hand is known (only their seeds depend on it),
+         * and the walk keeps four independent one-operation chains (running key, running index, new maximum, its index). */
         const float hk = __shfl_sync(FULL, Bk, t);
         const int hx = __shfl_sync(FULL, Bx, t);
         if (lane == t) Bk = NEG_INF; /* position i retires */
-        const float run0 = (hk != hk) ? POS_INF : hk;
-        /* ---- records inside the block ---- */
-        float inc = (Bk == Bk) ? Bk : NEG_INF;
+        float inc = (Bk == Bk) ? Bk : NEG_INF; /* block: records among the 32 spread positions */
+        float inc2 = lm;                       /* register lanes: which lanes hold records */
 #pragma unroll
         for (int d = 1; d < 32; d <<= 1) {
             const float y = __shfl_up_sync(FULL, inc, d);
-            if (lane >= d) inc = fmaxf(inc, y);
+            const float y2 = __shfl_up_sync(FULL, inc2, d);
+            if (lane >= d) { inc = fmaxf(inc, y); inc2 = fmaxf(inc2, y2); }
         }
         float exc = __shfl_up_sync(FULL, inc, 1);
+        float e2 = __shfl_up_sync(FULL, inc2, 1);
+        const float bmax = __shfl_sync(FULL, inc, 31); /* maximum of the whole block */
+        const float run0 = (hk != hk) ? POS_INF : hk;
         exc = fmaxf(lane ? exc : NEG_INF, run0);
+        const float ok = fmaxf(bmax, run0); /* key that leaves the block: its last record's, or the hand's */
+        e2 = fmaxf(lane ? e2 : NEG_INF, ok);
         const bool brec = Bk > exc;
+        const bool has = lm > e2;
         const unsigned bm = __ballot_sync(FULL, brec);
+        const unsigned hm = __ballot_sync(FULL, has);
         const int blast = bm ? 31 - __clz(bm) : 0;
         const unsigned blower = bm & below;
         const int bsrc = blower ? 31 - __clz(blower) : 0;
-        float ok = __shfl_sync(FULL, Bk, blast);
         int ox = __shfl_sync(FULL, Bx, blast);
         const float pk = __shfl_sync(FULL, Bk, bsrc);
         const int px = __shfl_sync(FULL, Bx, bsrc);
-        if (!bm) { ok = run0; ox = hx; } /* the hand itself leaves the block */
+        if (!bm) ox = hx; /* the hand itself leaves the block */
         if (brec) { Bk = blower ? pk : hk; Bx = blower ? px : hx; }
-        /* ---- records in the register lanes ---- */
-        float inc2 = lm;
-#pragma unroll
-        for (int d = 1; d < 32; d <<= 1) {
-            const float y = __shfl_up_sync(FULL, inc2, d);
-            if (lane >= d) inc2 = fmaxf(inc2, y);
-        }
-        float e2 = __shfl_up_sync(FULL, inc2, 1);
-        e2 = fmaxf(lane ? e2 : NEG_INF, ok);
-        const bool has = lm > e2;
-        const unsigned hm = __ballot_sync(FULL, has);
-        float wk = ok;
         int wx = ox;
         if (hm) { /* uniform */
             const unsigned hlower = hm & below;
@@ -309,22 +306,21 @@ __global__ void __launch_bounds__(32) k_nms_sort_warp(const mars_det_t *dets_in,
             int nlx = 0;
 #pragma unroll
             for (int u = 0; u < 32; u++) {
-                const bool sw = k[u] > run_k;
-                const float nk = sw ? run_k : k[u];
-                const int nx = sw ? run_x : x[u];
-                run_k = sw ? k[u] : run_k;
-                run_x = sw ? x[u] : run_x;
+                const float ku = k[u];
+                const int xu = x[u];
+                const bool sw = ku > run_k;          /* the C loop's comparison (false for NaN) */
+                const float nk = sw ? run_k : ku;
+                const int nx = sw ? run_x : xu;
+                run_k = fmaxf(run_k, ku);            /* == sw ? ku : run_k; run_k is never NaN and fmaxf ignores a NaN ku */
+                run_x = sw ? xu : run_x;
                 k[u] = nk; x[u] = nx;
                 const bool q = nk > nlm;
-                nlm = q ? nk : nlm;
+                nlm = fmaxf(nlm, nk);
                 nlx = q ? nx : nlx;
             }
             lm = nlm; lmx = nlx;
-            const int hlast = 31 - __clz(hm);
-            wk = __shfl_sync(FULL, run_k, hlast);
-            wx = __shfl_sync(FULL, run_x, hlast);
+            wx = __shfl_sync(FULL, run_x, 31 - __clz(hm));
         }
-        (void)wk;
         if (lane == 0) order[i] = (uint16_t)wx;
     }
 }
