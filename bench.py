@@ -169,7 +169,7 @@ def run_reference_arm(args):
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
-    print(json.dumps(line))
+    emit_line(json.dumps(line))
     return 0
 
 
@@ -235,6 +235,23 @@ def pinned_array(L, nbytes, dtype=np.uint8):
     return np.ctypeslib.as_array((C.c_uint8 * nbytes).from_address(p)).view(dtype), p
 
 
+def bind_to_gpu_numa_node(index):
+    """run this rank on the CPUs NVML reports as local to its GPU, so that the pinned staging buffers it allocates (first
+    touch) and the copy engine's reads stay on that socket; best effort"""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(index)
+        ncpu = os.cpu_count() or 1
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (ncpu + 63) // 64)
+        cpus = {64 * i + b for i, w in enumerate(words) for b in range(64) if (int(w) >> b) & 1}
+        cpus &= set(os.sched_getaffinity(0))
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+    except Exception:  # noqa: BLE001
+        pass
+
+
 def run_cuda_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -245,6 +262,7 @@ def run_cuda_arm(args):
         raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback (use --impl reference for the CPU arm)")
     torch.cuda.set_device(local_rank)
     if world > 1:
+        bind_to_gpu_numa_node(local_rank)  # (not at N = 1: the cpu_baseline leg uses every host core)
         if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
             os.environ["NCCL_DEBUG"] = "WARN"  # the version banner goes to stdout, which carries exactly one JSON line
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
@@ -268,12 +286,16 @@ def run_cuda_arm(args):
         def __init__(self, ptr, shape, typestr):
             self.__cuda_array_interface__ = {"shape": shape, "typestr": typestr, "data": (ptr, False), "version": 3}
 
+    # collectives are enqueued on the library's own compute stream: ordered after the kernels that wrote the records and
+    # before the next batch that overwrites them, without a host synchronisation in between
+    lib_stream = torch.cuda.ExternalStream(gm.compute_stream(), device=torch.device("cuda", local_rank)) if world > 1 else None
+
     def make_gatherer(first, n):
         """NCCL gather of the detection records of image slots [first, first+n) to rank 0"""
         dptr, cptr, dstride = gm.detections_device()
         det_t = torch.as_tensor(_Dev(dptr + first * dstride * 24, (n, dstride * 6), "<i4"), device="cuda")
         cnt_t = torch.as_tensor(_Dev(cptr + first * 4, (n,), "<i4"), device="cuda")
-        return pkg.shard.DetectionGather(det_t, cnt_t, dist if world > 1 else None)
+        return pkg.shard.DetectionGather(det_t, cnt_t, dist if world > 1 else None, stream=lib_stream)
 
     gather = make_gatherer(0, B).run
 
@@ -392,11 +414,29 @@ def run_cuda_arm(args):
                         "d2h_bytes_per_step": (B * 1000 * 24 + B * 4) * world, "ms_per_step": e2e_ms},
                 "gpu_launches": int(launches), "wall_ms_per_step": wall_ms / args.steps, "clocks": clocks,
                 "roofline": roof, "kernel_time_shares": shares, "cpu_baseline": cpu, "detections_checksum": checksum}
-        print(json.dumps(line), flush=True)
+        emit_line(json.dumps(line))
     gm.close()
     if world > 1:
         dist.destroy_process_group()
     return 0
+
+
+_RESULT_FD = None
+
+
+def claim_stdout():
+    """stdout carries exactly one JSON line: whatever libraries print (NCCL's version banner, torchrun notices) is sent
+    to stderr by pointing fd 1 at fd 2; the result line is written to the saved descriptor"""
+    global _RESULT_FD
+    if _RESULT_FD is None:
+        sys.stdout.flush()
+        _RESULT_FD = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit_line(text):
+    sys.stdout.flush()
+    os.write(_RESULT_FD if _RESULT_FD is not None else 1, (text + "\n").encode())
 
 
 def main():
@@ -409,9 +449,11 @@ def main():
                     help="images per GPU per step (default: 1024 / number of GPUs)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if not (args.impl != "reference" and args.gpus > 1 and world == 1):
+        claim_stdout()  # (the torchrun re-launch below hands its stdout to the ranks untouched)
     if args.impl == "reference":
         return run_reference_arm(args)
-    world = int(os.environ.get("WORLD_SIZE", "1"))
     if args.gpus > 1 and world == 1:
         # convenience: re-launch under torchrun (the driver launches torchrun itself)
         cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(args.gpus),

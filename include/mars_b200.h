@@ -107,6 +107,9 @@ void mars_b200_geometry(mars_model_t *m, size_t *out5);
 /* arena offset of tensor table entry `index` (reference planner, src/mars/mars_runtime.c:248-337) */
 size_t mars_b200_tensor_offset(mars_model_t *m, uint32_t index);
 
+/* the CUDA stream (cudaStream_t) the model's kernels run on; work enqueued there by the caller (e.g. an NCCL gather of the
+ * resident detection records) is ordered between the batches */
+void *mars_b200_compute_stream(mars_model_t *m);
 /* kernels launched by this model since load (the bench's gpu_launches claim) */
 uint64_t mars_b200_launch_count(mars_model_t *m);
 /* CUDA-event time of the last mars_b200_run_resident / detect_resident, milliseconds */

@@ -157,6 +157,7 @@ SIGNATURES = {
     "mars_b200_run_batch": (C.c_int, [PM, C.c_int, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t]),
     "mars_b200_detections_device": (None, [PM, C.c_void_p, C.c_void_p, C.c_void_p]),
     "mars_b200_launch_count": (C.c_uint64, [PM]),
+    "mars_b200_compute_stream": (C.c_void_p, [PM]),
     "mars_b200_last_gpu_ms": (C.c_float, [PM]),
     "mars_b200_set_profile": (None, [PM, C.c_int]),
     "mars_b200_num_ops": (C.c_int, [PM]),
@@ -344,6 +345,10 @@ class MarsModel:
     def step_resident(self, first, n, thresh=0.45, with_detect=True):
         self._check(lib().mars_b200_step_resident(self.m, first, n, thresh, 1 if with_detect else 0), "step_resident")
         return float(lib().mars_b200_last_gpu_ms(self.m))
+
+    def compute_stream(self):
+        """cudaStream_t handle (int) of the stream the model's kernels run on"""
+        return int(lib().mars_b200_compute_stream(self.m) or 0)
 
     def download_detections(self, first, n, maxd=1000):
         dets = np.zeros((n, maxd), dtype=DET_DTYPE)

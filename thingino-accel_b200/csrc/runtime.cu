@@ -1233,6 +1233,12 @@ mars_error_t mars_b200_wait_batch(mars_model_t *model, int pool) {
     return MARS_OK;
 }
 
+/* the CUDA stream (cudaStream_t) every kernel of this model is launched on: work a caller enqueues there -- e.g. an NCCL
+ * gather of the resident detection records -- is ordered after the batch that produced them and before the next one */
+void *mars_b200_compute_stream(mars_model_t *model) {
+    Model *m = as_model(model);
+    return m ? (void *)m->stream : nullptr;
+}
 uint64_t mars_b200_launch_count(mars_model_t *model) {
     Model *m = as_model(model);
     return m ? m->launches : 0;

@@ -30,9 +30,12 @@ class DetectionGather:
     All ranks must pass equally shaped tensors (pad the last shard).  World size 1: no-op.
     """
 
-    def __init__(self, det_t, cnt_t, dist=None, dst=0):
+    def __init__(self, det_t, cnt_t, dist=None, dst=0, stream=None):
         import torch
         self.det_t, self.cnt_t, self.dist, self.dst = det_t, cnt_t, dist, dst
+        # stream: a torch.cuda.Stream the collectives are ordered on (e.g. ExternalStream of the library's compute stream,
+        # so that the gather sits between the batch that wrote the records and the next one that overwrites them)
+        self.stream = stream
         self.active = dist is not None and dist.is_initialized() and dist.get_world_size() > 1
         self.world = dist.get_world_size() if self.active else 1
         self.rank = dist.get_rank() if self.active else 0
@@ -41,7 +44,14 @@ class DetectionGather:
         self.gc = [torch.empty_like(cnt_t) for _ in range(self.world)] if root else None
 
     def run(self):
-        if self.active:
+        if not self.active:
+            return
+        if self.stream is not None:
+            import torch
+            with torch.cuda.stream(self.stream):
+                self.dist.gather(self.cnt_t, self.gc, dst=self.dst)
+                self.dist.gather(self.det_t, self.gd, dst=self.dst)
+        else:
             self.dist.gather(self.cnt_t, self.gc, dst=self.dst)
             self.dist.gather(self.det_t, self.gd, dst=self.dst)
 
