@@ -359,8 +359,24 @@ def run_cuda_arm(args):
         outs.append((d, c))
     pool_gather = [make_gatherer(0, SUB), make_gatherer(SUB, SUB)]  # the slot pool was re-allocated: new device addresses
 
+    def step_jobs(ramp):
+        """(first image, count) submits covering the B images of one step.  The first step of a run ramps its submit size up
+        (SUB/8, SUB/8, SUB/4, SUB/2, SUB, ...): the kernels start after a short first copy instead of idling behind a full one"""
+        sizes, done = [], 0
+        s = max(1, SUB // 8) if ramp else SUB
+        first_pair = ramp
+        while done < B:
+            n = min(s, B - done)
+            sizes.append((done, n))
+            done += n
+            if first_pair:
+                first_pair = False  # the smallest size is used twice so that the sizes keep adding up to powers of two
+            elif s < SUB:
+                s = min(SUB, 2 * s)
+        return sizes
+
     def e2e_steps(k):
-        jobs = [(j * SUB, min(SUB, B - j * SUB)) for _ in range(k) for j in range(nsub)]
+        jobs = [j for st in range(k) for j in step_jobs(st == 0)]
         for i, (first, n) in enumerate(jobs):
             gm.submit_batch(i & 1, n, host_in[first:first + n], in_bytes, outs[i & 1][0], outs[i & 1][1], 1000, NMS_THRESH)
             if i >= 1:
@@ -408,7 +424,7 @@ def run_cuda_arm(args):
                 "config": {"workload": WORKLOAD, "model_file": MODEL_FILE, "images_per_step": B * world,
                            "global_batch": B * world, "per_gpu_batch": B, "image": "3x640x640 int8", "arena_bytes": arena,
                            "parallelism": "images sharded, dp%d (global batch %d, strong scaling), detections gathered to rank 0 over NCCL" % (world, B * world),
-                           "e2e_submit_images": SUB,
+                           "e2e_submit_images": SUB, "e2e_first_step_submits": [n for _f, n in step_jobs(True)],
                            "l2": "working set %.1f GB per GPU >> 126 MB L2 (no flush needed)" % (B * gm.slot_stride / 1e9)},
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": B * in_bytes * world,
                         "d2h_bytes_per_step": (B * 1000 * 24 + B * 4) * world, "ms_per_step": e2e_ms},
