@@ -705,21 +705,37 @@ __global__ void __launch_bounds__(256) k_to_nhwc(const uint8_t *src_base, unsign
 /* ---- s2d mode (6x6 stride-2 pad-2 conv with <= 4 input channels = 3x3 stride-1 pad-1 conv over the 2x2 space-to-depth
  * image): P[(y+1)*Wp + (x+1)][16] = the 2x2 input block (2y+py, 2x+px) of every channel, byte c' = ci*4 + py*2 + px,
  * zero border and zero beyond 4*C bytes.  One thread per P pixel. */
-__global__ void __launch_bounds__(256) k_s2d16(const uint8_t *src_base, unsigned long long src_stride, uint8_t *dst_base,
+__global__ void __launch_bounds__(256) k_s2d16(const uint8_t *__restrict__ src_base, unsigned long long src_stride, uint8_t *__restrict__ dst_base,
                                                unsigned long long dst_stride, int C, int H, int W, int Wp, int npix) {
     const uint8_t *src = src_base + (unsigned long long)blockIdx.y * src_stride;
     uint4 *dst = reinterpret_cast<uint4 *>(dst_base + (unsigned long long)blockIdx.y * dst_stride);
-    const int pix = blockIdx.x * blockDim.x + threadIdx.x;
-    if (pix >= npix) return;
-    const int yy = pix / Wp, y = yy - 1, x = pix - yy * Wp - 1;
-    uint32_t w[4] = {0u, 0u, 0u, 0u};
-    if (y >= 0 && 2 * y + 1 < H && x >= 0 && 2 * x + 1 < W) {
-        for (int ci = 0; ci < C; ci++) {
-            const uint8_t *r0 = src + ((long long)ci * H + 2 * y) * W + 2 * x;
-            w[ci] = (uint32_t)*reinterpret_cast<const uint16_t *>(r0) | ((uint32_t)*reinterpret_cast<const uint16_t *>(r0 + W) << 16);
+    /* four pixels per thread, 256 apart: all their loads are issued before the first store (the kernel is pure latency) */
+    constexpr int PPT = 4;
+    const int base = blockIdx.x * (256 * PPT) + threadIdx.x;
+    const unsigned wp_magic = 0xFFFFFFFFu / (unsigned)Wp + 1u; /* floor(a / Wp) = umulhi(a, magic), a < 2^31 / Wp (host-checked mflat bound) */
+    uint32_t w[PPT][4];
+#pragma unroll
+    for (int k = 0; k < PPT; k++) {
+        const int pix = base + k * 256;
+        w[k][0] = w[k][1] = w[k][2] = w[k][3] = 0u;
+        if (pix < npix) {
+            const int yy = (int)__umulhi((unsigned)pix, wp_magic), y = yy - 1, x = pix - yy * Wp - 1;
+            if (y >= 0 && 2 * y + 1 < H && x >= 0 && 2 * x + 1 < W) {
+#pragma unroll
+                for (int ci = 0; ci < 4; ci++) { /* the mode requires C <= 4 */
+                    if (ci < C) {
+                        const uint8_t *r0 = src + ((long long)ci * H + 2 * y) * W + 2 * x;
+                        w[k][ci] = (uint32_t)*reinterpret_cast<const uint16_t *>(r0) | ((uint32_t)*reinterpret_cast<const uint16_t *>(r0 + W) << 16);
+                    }
+                }
+            }
         }
     }
-    dst[pix] = make_uint4(w[0], w[1], w[2], w[3]);
+#pragma unroll
+    for (int k = 0; k < PPT; k++) {
+        const int pix = base + k * 256;
+        if (pix < npix) dst[pix] = make_uint4(w[k][0], w[k][1], w[k][2], w[k][3]);
+    }
 }
 /* OIHW 6x6 weights -> [t = ky2*2 + pair][Co_pad][32]: K byte k = (pixel kx2 = 2*pair + k/16, channel byte c' = k%16) */
 __global__ void k_repack_s2d(const int8_t *w, int8_t *dst, int Co, int Co_pad, int Ci) {
@@ -1159,7 +1175,7 @@ bool tc_launch(const TcPlan &plan, uint8_t *slots_base, int first, int n, bool u
         if (cudaMemcpy2DAsync(scr, t->scratch_stride, src, t->slot_stride, (size_t)t->C * t->H * t->W, (size_t)n,
                               cudaMemcpyDeviceToDevice, s) != cudaSuccess) return false;
     } else if (t->prepass == 4) {
-        k_s2d16<<<dim3((t->npix + 255) / 256, n), 256, 0, s>>>(src, t->slot_stride, scr, t->scratch_stride, t->C, t->H, t->W, t->p.Wp, t->npix);
+        k_s2d16<<<dim3((t->npix + 1023) / 1024, n), 256, 0, s>>>(src, t->slot_stride, scr, t->scratch_stride, t->C, t->H, t->W, t->p.Wp, t->npix);
         (*launches)++;
     } else if (t->prepass && t->prepass != 3 && !(use_linked && t->has_linked)) {
         dim3 g((t->npix + 31) / 32, (t->C + 31) / 32, n);
