@@ -321,6 +321,39 @@ __global__ void __launch_bounds__(256) k_maxpool_sep(ArenaView v, KOp o, int TH)
     }
 }
 
+/* 5x5 stride-1 maxpool (the SPPF pools): one thread per output column word walks down the rows with the horizontal maxima
+ * of the current and the next four rows in registers -- no shared memory, no barriers, long-lived threads whose loads for
+ * the following rows are in flight while the current row is reduced.  Same clipping as k_maxpool_sep (right / bottom edge,
+ * pads ignored; -128 is the identity).  grid = (column blocks, row chunks, images). */
+__global__ void __launch_bounds__(128) k_maxpool5_col(ArenaView v, KOp o, int rows_per_block) {
+    const Img im = make_img(v, blockIdx.z);
+    const int c4 = o.ic >> 2, RW = o.iw * c4, OW = o.ow * c4;
+    const int xw = blockIdx.x * 128 + threadIdx.x;
+    if (xw >= OW) return;
+    const int x = xw / c4, kx = min(5, o.iw - x);
+    const int y0 = blockIdx.y * rows_per_block, y1 = min(y0 + rows_per_block, o.oh);
+    const uint32_t *in = reinterpret_cast<const uint32_t *>(im.s_minus_W + o.in0) + (x * c4 + (xw - x * c4));
+    uint32_t *out = reinterpret_cast<uint32_t *>(im.s_minus_W + o.out) + xw;
+    const uint32_t NEG = 0x80808080u;
+    auto hmax = [&](int r) -> uint32_t { /* horizontal window maximum of input row r; rows past the bottom edge do not exist */
+        if (r >= o.ih) return NEG;
+        const uint32_t *p = in + (int64_t)r * RW;
+        uint32_t m = p[0];
+        if (kx > 1) m = __vmaxs4(m, p[c4]);
+        if (kx > 2) m = __vmaxs4(m, p[2 * c4]);
+        if (kx > 3) m = __vmaxs4(m, p[3 * c4]);
+        if (kx > 4) m = __vmaxs4(m, p[4 * c4]);
+        return m;
+    };
+    uint32_t h0 = hmax(y0), h1 = hmax(y0 + 1), h2 = hmax(y0 + 2), h3 = hmax(y0 + 3);
+#pragma unroll 4
+    for (int y = y0; y < y1; y++) {
+        const uint32_t h4 = hmax(y + 4);
+        out[(int64_t)y * OW] = __vmaxs4(__vmaxs4(__vmaxs4(h0, h1), __vmaxs4(h2, h3)), h4);
+        h0 = h1; h1 = h2; h2 = h3; h3 = h4;
+    }
+}
+
 /* nearest upsample (reference src/mars/mars_runtime.c:1027-1040: ih = min(oh / sh, ih - 1), same for columns): one block
  * per (output row, image); a thread produces consecutive output words (fully coalesced stores), reading the input row
  * through L1.  Divisions by multiplication. */
@@ -347,6 +380,11 @@ static inline bool fast_spatial_ok(const ArenaView &v, const KOp &o) {
     return false;
 }
 static inline void launch_fast_spatial(const ArenaView &v, const KOp &o, int n_img, cudaStream_t s) {
+    if (o.kind == OP_MAXPOOL && o.sh == 1 && o.sw == 1 && o.kh == 5 && o.kw == 5 && o.oh <= o.ih && o.ow <= o.iw && n_img <= 65535) {
+        const int OW = o.ow * (o.ic >> 2), rows = 64;
+        k_maxpool5_col<<<dim3((OW + 127) / 128, (o.oh + rows - 1) / rows, n_img), 128, 0, s>>>(v, o, rows);
+        return;
+    }
     if (o.kind == OP_MAXPOOL && o.sh == 1 && o.sw == 1 && o.kh >= 1 && o.kw >= 1 && o.oh <= o.ih && o.ow <= o.iw) {
         const int RW = o.iw * (o.ic >> 2);
         int TH = 32;
