@@ -165,6 +165,10 @@ struct Model {
     size_t frames_cap = 0;
     float *d_preH = nullptr;
     size_t preH_cap = 0;
+    /* captured steps (mars_b200_step_resident): one CUDA graph per (first, n, threshold, with_detect) seen twice */
+    struct StepGraph { int first, n, with_detect; uint32_t thresh_bits; int seen; cudaGraphExec_t exec; uint64_t launches; };
+    std::vector<StepGraph> graphs;
+    bool graphs_broken = false;
     /* device-resident detections */
     mars_det_t *d_raw = nullptr, *d_det = nullptr;
     int32_t *d_raw_cnt = nullptr, *d_det_cnt = nullptr;
@@ -193,10 +197,17 @@ static inline uint8_t *dev_addr(const Model *m, size_t off, int slot) {
     return off < m->weights_size ? m->d_weights + off : m->d_slots + (size_t)slot * m->slot_stride + (off - m->weights_size);
 }
 
+static void release_graphs(Model *m) {
+    for (auto &g : m->graphs)
+        if (g.exec) cudaGraphExecDestroy(g.exec);
+    m->graphs.clear();
+}
+
 static void model_release(Model *m) {
     if (!m) return;
     cudaSetDevice(m->device);
     if (m->stream) cudaStreamSynchronize(m->stream);
+    release_graphs(m);
     tc_release(m->tc);
     for (auto e : m->prof_ev) cudaEventDestroy(e);
     cudaFree(m->d_weights); cudaFree(m->d_slots); cudaFree(m->d_scratch); cudaFree(m->d_cpool); cudaFree(m->d_tc_scratch); cudaFree(m->d_linked);
@@ -270,6 +281,7 @@ static mars_error_t set_capacity(Model *m, int capacity) {
 
 static mars_error_t compile_model(Model *m) {
     if (m->compiled) return MARS_OK;
+    release_graphs(m); /* kernel parameters (slot addresses, tensor maps, tables) are about to change */
     Program p;
     mars_error_t e = compile_program(m->pub.header, m->pub.tensors, m->pub.layers, m->toff, m->weights_size,
                                      m->arena_size, m->opt_level, m->depthwise_mode, &p);
@@ -1070,15 +1082,72 @@ mars_error_t mars_b200_detect_resident(mars_model_t *model, int first, int n, fl
     return e;
 }
 
+/* The ~110 launches of a step replayed as one CUDA graph: the second time a (first, n, threshold) combination is seen the
+ * launch sequence is captured from the compute stream, afterwards it is replayed -- the kernels and their parameters are
+ * the same, only the host-side launch work and the inter-kernel launch latency go.  MARS_GRAPH=1 enables it; profiling
+ * (per-op events) and anything that cannot be captured fall back to plain launches. */
+static bool graphs_enabled() {
+    static const bool on = getenv("MARS_GRAPH") && atoi(getenv("MARS_GRAPH")) != 0; /* opt-in until measured on every batch size */
+    return on;
+}
+
+static mars_error_t enqueue_step(Model *m, int first, int n, float nms_thresh, int with_detect) {
+    mars_error_t e = enqueue_run(m, first, n);
+    if (e == MARS_OK && with_detect) e = enqueue_detect(m, first, n, nms_thresh);
+    return e;
+}
+
+static mars_error_t enqueue_step_graphed(Model *m, int first, int n, float nms_thresh, int with_detect) {
+    if (!graphs_enabled() || m->graphs_broken || m->profile || n <= 0) return enqueue_step(m, first, n, nms_thresh, with_detect);
+    uint32_t tb;
+    memcpy(&tb, &nms_thresh, 4);
+    Model::StepGraph *g = nullptr;
+    for (auto &c : m->graphs)
+        if (c.first == first && c.n == n && c.with_detect == with_detect && c.thresh_bits == tb) g = &c;
+    if (!g) {
+        if (m->graphs.size() >= 16) release_graphs(m);
+        m->graphs.push_back(Model::StepGraph{first, n, with_detect, tb, 0, nullptr, 0});
+        g = &m->graphs.back();
+    }
+    if (g->exec) {
+        if (cudaGraphLaunch(g->exec, m->stream) != cudaSuccess) { m->graphs_broken = true; return MARS_ERR_LAYER_FAILED; }
+        m->launches += g->launches;
+        return MARS_OK;
+    }
+    if (++g->seen < 2) return enqueue_step(m, first, n, nms_thresh, with_detect); /* first time: plain (also does the lazy one-time setup) */
+    const uint64_t before = m->launches;
+    cudaGraph_t graph = nullptr;
+    if (cudaStreamBeginCapture(m->stream, cudaStreamCaptureModeThreadLocal) != cudaSuccess) {
+        m->graphs_broken = true;
+        cudaGetLastError();
+        return enqueue_step(m, first, n, nms_thresh, with_detect);
+    }
+    mars_error_t e = enqueue_step(m, first, n, nms_thresh, with_detect);
+    const cudaError_t ce = cudaStreamEndCapture(m->stream, &graph);
+    if (e != MARS_OK || ce != cudaSuccess || !graph || cudaGraphInstantiate(&g->exec, graph, 0) != cudaSuccess) {
+        if (graph) cudaGraphDestroy(graph);
+        g->exec = nullptr;
+        m->graphs_broken = true;
+        cudaGetLastError();
+        m->launches = before;
+        return e != MARS_OK ? e : enqueue_step(m, first, n, nms_thresh, with_detect);
+    }
+    cudaGraphDestroy(graph);
+    g->launches = m->launches - before;
+    if (cudaGraphLaunch(g->exec, m->stream) != cudaSuccess) { m->graphs_broken = true; return MARS_ERR_LAYER_FAILED; }
+    return MARS_OK;
+}
+
 /* run + detect as one timed region (the bench's resident step) */
 mars_error_t mars_b200_step_resident(mars_model_t *model, int first, int n, float nms_thresh, int with_detect) {
     Model *m = as_model(model);
     if (!m) return MARS_ERR_INVALID_FILE;
     CU_OK(cudaSetDevice(m->device), MARS_ERR_NNA_INIT_FAILED);
     if (!range_ok(m, first, n)) return MARS_ERR_INVALID_TENSOR;
+    mars_error_t e = compile_model(m);
+    if (e != MARS_OK) return e;
     cudaEventRecord(m->ev0, m->stream);
-    mars_error_t e = enqueue_run(m, first, n);
-    if (e == MARS_OK && with_detect) e = enqueue_detect(m, first, n, nms_thresh);
+    e = enqueue_step_graphed(m, first, n, nms_thresh, with_detect);
     cudaEventRecord(m->ev1, m->stream);
     cudaError_t ce = cudaStreamSynchronize(m->stream);
     if (e == MARS_OK && ce != cudaSuccess) {
@@ -1203,8 +1272,7 @@ mars_error_t mars_b200_submit_batch(mars_model_t *model, int pool, int n, const 
         if (e != MARS_OK) return e;
         cudaEventRecord(m->ev_in[pool], m->h2d_stream);
         cudaStreamWaitEvent(m->stream, m->ev_in[pool], 0);
-        e = enqueue_run(m, first, n);
-        if (e == MARS_OK) e = enqueue_detect(m, first, n, nms_thresh);
+        e = enqueue_step_graphed(m, first, n, nms_thresh, 1);
         if (e != MARS_OK) { cudaStreamSynchronize(m->stream); return e; }
         cudaEventRecord(m->ev_done[pool], m->stream);
         cudaStreamWaitEvent(m->d2h_stream, m->ev_done[pool], 0);
