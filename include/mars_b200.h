@@ -119,6 +119,10 @@ float mars_b200_last_gpu_ms(mars_model_t *m);
 /* load_image of reference src/mars/mars_yolo_test.c:40-77 without the file decode: rgb = h x w x 3 bytes in,
  * out = tw x th x 3 int8 (three planes, or interleaved when nhwc != 0).  Returns 0 on success, -1 on failure. */
 int mars_b200_letterbox(const uint8_t *rgb, int w, int h, int tw, int th, int nhwc, int8_t *out);
+/* load_and_preprocess_image of reference examples/yolo_detect.cpp:72-130 without the file decode: the same resize into an
+ * RGBA uint8 frame, out = tw x th x 4 bytes (the reference fixes 640 x 640): 114 everywhere outside the image (alpha
+ * included), R, G, B, 0 inside.  Returns 0 on success, -1 on failure. */
+int mars_b200_letterbox_rgba(const uint8_t *rgb, int w, int h, int tw, int th, uint8_t *out);
 /* host half of the above (no GPU needed): the (source sample, coefficient) taps each of the out_size output samples of one
  * axis sums, in the order stbir_resize_uint8 adds them.  start[out_size + 1]; returns the tap count (> cap: nothing copied). */
 int mars_b200_resize_taps(int in_size, int out_size, int32_t *start, int32_t *src, float *w, int cap);

@@ -130,6 +130,9 @@ class RefRuntime:
             lib.oracle_ref_parse_output.argtypes = [C.c_void_p, C.c_int, C.c_float, C.c_void_p, C.c_int]
             lib.oracle_ref_nms.restype = C.c_int
             lib.oracle_ref_nms.argtypes = [C.c_void_p, C.c_int, C.c_float]
+            if hasattr(lib, "oracle_ref_cpp_preprocess"):
+                lib.oracle_ref_cpp_preprocess.restype = C.c_int
+                lib.oracle_ref_cpp_preprocess.argtypes = [C.c_char_p, C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_int)]
             if hasattr(lib, "oracle_ref_load_image"):
                 lib.oracle_ref_load_image.restype = C.c_int
                 lib.oracle_ref_load_image.argtypes = [C.c_char_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_int)]
@@ -233,6 +236,25 @@ def ref_load_image(rgb: np.ndarray, tw: int, th: int, nhwc: bool) -> np.ndarray:
         rc = lib.oracle_ref_load_image(f.name.encode(), tw, th, 1 if nhwc else 0, out.ctypes.data, C.byref(ow), C.byref(oh))
     if rc != 0 or (ow.value, oh.value) != (w, h):
         raise RuntimeError("reference load_image failed (rc %d, %dx%d)" % (rc, ow.value, oh.value))
+    return out
+
+
+def ref_preprocess_rgba(rgb: np.ndarray) -> np.ndarray:
+    """the reference's own load_and_preprocess_image() (examples/yolo_detect.cpp:72-130) on an [h, w, 3] uint8 frame, through a
+    binary PPM file.  Returns the 640*640*4 uint8 RGBA frame."""
+    import tempfile
+    lib = RefRuntime.lib()
+    rgb = np.ascontiguousarray(rgb, dtype=np.uint8)
+    h, w, _ = rgb.shape
+    out = np.zeros(640 * 640 * 4, dtype=np.uint8)
+    ow, oh = C.c_int(0), C.c_int(0)
+    with tempfile.NamedTemporaryFile(suffix=".ppm") as f:
+        f.write(b"P6\n%d %d\n255\n" % (w, h))
+        f.write(rgb.tobytes())
+        f.flush()
+        rc = lib.oracle_ref_cpp_preprocess(f.name.encode(), out.ctypes.data, C.byref(ow), C.byref(oh))
+    if rc != 0 or (ow.value, oh.value) != (w, h):
+        raise RuntimeError("reference load_and_preprocess_image failed (rc %d)" % rc)
     return out
 
 

@@ -25,6 +25,10 @@ CASES = [
 ]
 
 
+# RGBA frames of examples/yolo_detect.cpp:72-130 (always 640 x 640): (frame w, frame h, seed)
+RGBA_CASES = [(64, 48, 21), (800, 600, 22), (640, 640, 23), (1280, 720, 24), (333, 999, 25)]
+
+
 def frame(w, h, seed):
     """smooth ramps + noise, so that both interpolation and clamping matter"""
     rng = np.random.default_rng(seed)
@@ -43,5 +47,9 @@ if __name__ == "__main__":
         out["%dx%d_to_%dx%d_%s_s%d" % (w, h, tw, th, "nhwc" if nhwc else "nchw", seed)] = {
             "case": [w, h, tw, th, nhwc, seed], "sha256": hashlib.sha256(t.tobytes()).hexdigest(),
             "border": int((t == -17).sum())}
+    for (w, h, seed) in RGBA_CASES:
+        t = rb.ref_preprocess_rgba(frame(w, h, seed))
+        out["rgba_%dx%d_s%d" % (w, h, seed)] = {"rgba": [w, h, seed], "sha256": hashlib.sha256(t.tobytes()).hexdigest(),
+                                                "border": int((t.reshape(-1, 4)[:, 3] == 114).sum())}
     json.dump(out, open(os.path.join(HERE, "preproc.json"), "w"), indent=1, sort_keys=True)
     print("wrote %d cases" % len(out))

@@ -18,7 +18,9 @@ from util import GOLDEN_DIR
 sys.path.insert(0, GOLDEN_DIR)
 from make_preproc_golden import frame  # noqa: E402
 
-PRE = json.load(open(os.path.join(GOLDEN_DIR, "preproc.json")))
+PRE_ALL = json.load(open(os.path.join(GOLDEN_DIR, "preproc.json")))
+PRE = {k: v for k, v in PRE_ALL.items() if "case" in v}      # int8 tensors (src/mars/mars_yolo_test.c load_image)
+RGBA = {k: v for k, v in PRE_ALL.items() if "rgba" in v}     # RGBA frames (examples/yolo_detect.cpp load_and_preprocess_image)
 SMALL = [k for k, v in PRE.items() if v["case"][0] * v["case"][1] <= 10000]
 ALL = sorted(PRE)
 
@@ -38,7 +40,7 @@ def axis_sum(a, start, src, w):
     return out
 
 
-def letterbox_numpy(capi, rgb, tw, th, nhwc):
+def letterbox_numpy(capi, rgb, tw, th, nhwc, rgba=False):
     h, w, _ = rgb.shape
     scale = min(np.float32(tw) / np.float32(w), np.float32(th) / np.float32(h))
     nw, nh = int(np.float32(w) * scale), int(np.float32(h) * scale)
@@ -47,6 +49,11 @@ def letterbox_numpy(capi, rgb, tw, th, nhwc):
     H = axis_sum(dec.transpose(1, 0, 2), *capi.resize_taps(w, nw)).transpose(1, 0, 2)
     V = axis_sum(H, *capi.resize_taps(h, nh))
     u = ((np.clip(V, 0, 1) * np.float32(255.0)).astype(np.float64) + 0.5).astype(np.int64).astype(np.uint8)
+    if rgba:
+        out = np.full((th, tw, 4), 114, np.uint8)
+        out[py:py + nh, px:px + nw, :3] = u
+        out[py:py + nh, px:px + nw, 3] = 0
+        return out.reshape(-1)
     out = np.full((th, tw, 3), -17, np.int8)
     out[py:py + nh, px:px + nw] = (u.astype(np.int16) - 128).astype(np.int8)
     return (out if nhwc else out.transpose(2, 0, 1)).reshape(-1)
@@ -63,6 +70,19 @@ def test_reference_load_image_reproduces_the_golden_hashes(rb, tag):
 def test_host_tap_lists_reproduce_the_reference_resize(pkg, tag):
     w, h, tw, th, nhwc, seed = PRE[tag]["case"]
     assert sha(letterbox_numpy(pkg.capi, frame(w, h, seed), tw, th, nhwc)) == PRE[tag]["sha256"]
+
+
+@pytest.mark.parametrize("tag", sorted(RGBA))
+def test_reference_rgba_preprocess_reproduces_the_golden_hashes(rb, tag):
+    w, h, seed = RGBA[tag]["rgba"]
+    t = rb.ref_preprocess_rgba(frame(w, h, seed))
+    assert sha(t) == RGBA[tag]["sha256"] and int((t.reshape(-1, 4)[:, 3] == 114).sum()) == RGBA[tag]["border"]
+
+
+def test_host_tap_lists_reproduce_the_reference_rgba_frame(pkg):
+    tag = "rgba_64x48_s21"
+    w, h, seed = RGBA[tag]["rgba"]
+    assert sha(letterbox_numpy(pkg.capi, frame(w, h, seed), 640, 640, True, rgba=True)) == RGBA[tag]["sha256"]
 
 
 def test_tap_lists_are_well_formed(pkg):
@@ -82,6 +102,13 @@ def test_letterbox_kernel_matches_the_reference(pkg, tag):
     w, h, tw, th, nhwc, seed = PRE[tag]["case"]
     got = pkg.capi.letterbox(frame(w, h, seed), tw, th, bool(nhwc))
     assert sha(got) == PRE[tag]["sha256"]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("tag", sorted(RGBA))
+def test_rgba_letterbox_kernel_matches_the_reference(pkg, tag):
+    w, h, seed = RGBA[tag]["rgba"]
+    assert sha(pkg.capi.letterbox_rgba(frame(w, h, seed))) == RGBA[tag]["sha256"]
 
 
 @pytest.mark.gpu

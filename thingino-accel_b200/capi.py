@@ -167,6 +167,7 @@ SIGNATURES = {
     "mars_yolo_parse_output": (C.c_int, [C.c_void_p, C.c_int, C.c_float, C.c_void_p, C.c_int]),
     "mars_yolo_nms": (C.c_int, [C.c_void_p, C.c_int, C.c_float]),
     "mars_b200_letterbox": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
+    "mars_b200_letterbox_rgba": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
     "mars_b200_resize_taps": (C.c_int, [C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]),
     "mars_yolo_nms_boxes": (C.c_int, [C.c_void_p, C.c_int, C.c_float]),
     "mars_yolo_scale_detections": (None, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]),
@@ -420,7 +421,17 @@ def letterbox(rgb, tw, th, nhwc=False):
     h, w, _ = f.shape
     out = np.zeros(tw * th * 3, dtype=np.int8)
     if lib().mars_b200_letterbox(f.ctypes.data, w, h, tw, th, 1 if nhwc else 0, out.ctypes.data) != 0:
-        raise RuntimeError("mars_b200_letterbox failed: " + last_error())
+        raise RuntimeError("mars_b200_letterbox failed: " + lib().mars_b200_last_error().decode())
+    return out
+
+
+def letterbox_rgba(rgb, tw=640, th=640):
+    """[h, w, 3] uint8 frame -> tw*th*4 uint8 RGBA frame (reference examples/yolo_detect.cpp:72-130 minus the decode)"""
+    f = np.ascontiguousarray(rgb, dtype=np.uint8)
+    h, w, _ = f.shape
+    out = np.zeros(tw * th * 4, dtype=np.uint8)
+    if lib().mars_b200_letterbox_rgba(f.ctypes.data, w, h, tw, th, out.ctypes.data) != 0:
+        raise RuntimeError("mars_b200_letterbox_rgba failed: " + lib().mars_b200_last_error().decode())
     return out
 
 

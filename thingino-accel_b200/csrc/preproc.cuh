@@ -12,7 +12,7 @@
  * kernels one tap list per output index, in that order, so the device sums are bit-identical:
  *     k_pre_horizontal    : H[f][r][x][c] = sum_t (u8 / 255.0f) * wh[t]            (stb :1243-1282, :1441-1652)
  *     k_pre_vertical_pack : v = sum_t H[f][src_t][x][c] * wv[t]; u8 = (int)((double)(sat(v) * 255.0f) + 0.5);
- *                           out = (int8)(u8 - 128), border -17                      (stb :1692-1760, :1866-2061)
+ *                           out = (int8)(u8 - 128), border -17  -- or RGBA u8, border 114 (stb :1692-1760, :1866-2061)
  */
 #pragma once
 #include <cuda_runtime.h>
@@ -202,20 +202,25 @@ __global__ void __launch_bounds__(128) k_pre_horizontal(const uint8_t *frames, s
     o[0] = a0; o[1] = a1; o[2] = a2;
 }
 
-__device__ __forceinline__ int pre_encode(float v) {
+/* the resized sample as stb stores it: (unsigned char)(int)((double)(saturate(v) * 255.0f) + 0.5) */
+__device__ __forceinline__ int pre_encode_u8(float v) {
     const float s = v < 0 ? 0.0f : (v > 1 ? 1.0f : v);
-    const int u = __double2int_rz((double)__fmul_rn(s, 255.0f) + 0.5);
-    return (int)(int8_t)((int)(unsigned char)u - 128);
+    return (int)(unsigned char)__double2int_rz((double)__fmul_rn(s, 255.0f) + 0.5);
 }
 
-/* one thread per target pixel: grid (ceil(tw/128), th, n); dst = input tensor of slot 0 of the launch, slots slot_stride apart */
+/* packing of the target frame: the two int8 tensor layouts of mars_yolo_test.c:62-72 (px - 128, border -17), or the RGBA
+ * uint8 frame of examples/yolo_detect.cpp:104-124 (memset 114 -- alpha included -- then R, G, B, 0 inside the image) */
+enum { PRE_NCHW_I8 = 0, PRE_NHWC_I8 = 1, PRE_RGBA_U8 = 2 };
+
+/* one thread per target pixel: grid (ceil(tw/128), th, n); dst = target of frame 0 of the launch, frames slot_stride apart */
 __global__ void __launch_bounds__(128) k_pre_vertical_pack(const float *H, LetterboxGeom g, const int *vstart, const int *vsrc,
-                                                           const float *vw, int8_t *dst, size_t slot_stride, int nhwc) {
+                                                           const float *vw, int8_t *dst, size_t slot_stride, int mode) {
     const int dx = blockIdx.x * 128 + threadIdx.x, dy = blockIdx.y, f = blockIdx.z;
     if (dx >= g.tw) return;
-    int r0 = -17, r1 = -17, r2 = -17;
     const int x = dx - g.px, y = dy - g.py;
-    if (x >= 0 && x < g.nw && y >= 0 && y < g.nh) {
+    const bool inside = x >= 0 && x < g.nw && y >= 0 && y < g.nh;
+    int u0 = 0, u1 = 0, u2 = 0;
+    if (inside) {
         float a0 = 0.0f, a1 = 0.0f, a2 = 0.0f;
         for (int t = vstart[y]; t < vstart[y + 1]; t++) {
             const float *p = H + (((size_t)f * g.oh + vsrc[t]) * g.nw + x) * 3;
@@ -224,10 +229,16 @@ __global__ void __launch_bounds__(128) k_pre_vertical_pack(const float *H, Lette
             a1 = __fadd_rn(a1, __fmul_rn(p[1], c));
             a2 = __fadd_rn(a2, __fmul_rn(p[2], c));
         }
-        r0 = pre_encode(a0); r1 = pre_encode(a1); r2 = pre_encode(a2);
+        u0 = pre_encode_u8(a0); u1 = pre_encode_u8(a1); u2 = pre_encode_u8(a2);
     }
     int8_t *o = dst + (size_t)f * slot_stride;
-    if (nhwc) {
+    if (mode == PRE_RGBA_U8) {
+        uchar4 px = inside ? make_uchar4((unsigned char)u0, (unsigned char)u1, (unsigned char)u2, 0) : make_uchar4(114, 114, 114, 114);
+        reinterpret_cast<uchar4 *>(o)[(size_t)dy * g.tw + dx] = px;
+        return;
+    }
+    const int r0 = inside ? u0 - 128 : -17, r1 = inside ? u1 - 128 : -17, r2 = inside ? u2 - 128 : -17;
+    if (mode == PRE_NHWC_I8) {
         int8_t *q = o + ((size_t)dy * g.tw + dx) * 3;
         q[0] = (int8_t)r0; q[1] = (int8_t)r1; q[2] = (int8_t)r2;
     } else {
@@ -275,11 +286,11 @@ static inline bool letterbox_plan_build(int ow, int oh, int tw, int th, Letterbo
 
 /* frames (device) -> int8 tensors at dst + f * slot_stride, f < n; H = scratch of n * oh * nw * 3 floats */
 static inline cudaError_t launch_letterbox(const LetterboxPlan &p, const uint8_t *d_frames, size_t frame_stride, int n, float *d_H,
-                                           int8_t *dst, size_t slot_stride, int nhwc, cudaStream_t s) {
+                                           int8_t *dst, size_t slot_stride, int mode, cudaStream_t s) {
     const LetterboxGeom &g = p.g;
     k_pre_horizontal<<<dim3((g.nw + 127) / 128, g.oh, n), 128, 0, s>>>(d_frames, frame_stride, g.ow, g.oh, g.nw, p.d_hstart, p.d_hsrc,
                                                                        p.d_hw, d_H);
-    k_pre_vertical_pack<<<dim3((g.tw + 127) / 128, g.th, n), 128, 0, s>>>(d_H, g, p.d_vstart, p.d_vsrc, p.d_vw, dst, slot_stride, nhwc);
+    k_pre_vertical_pack<<<dim3((g.tw + 127) / 128, g.th, n), 128, 0, s>>>(d_H, g, p.d_vstart, p.d_vsrc, p.d_vw, dst, slot_stride, mode);
     return cudaGetLastError();
 }
 

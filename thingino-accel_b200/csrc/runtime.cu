@@ -1084,10 +1084,10 @@ mars_error_t mars_b200_detect_resident(mars_model_t *model, int first, int n, fl
 
 /* The ~110 launches of a step replayed as one CUDA graph: the second time a (first, n, threshold) combination is seen the
  * launch sequence is captured from the compute stream, afterwards it is replayed -- the kernels and their parameters are
- * the same, only the host-side launch work and the inter-kernel launch latency go.  MARS_GRAPH=1 enables it; profiling
+ * the same, only the host-side launch work and the inter-kernel launch latency go.  MARS_GRAPH=0 disables it; profiling
  * (per-op events) and anything that cannot be captured fall back to plain launches. */
 static bool graphs_enabled() {
-    static const bool on = getenv("MARS_GRAPH") && atoi(getenv("MARS_GRAPH")) != 0; /* opt-in until measured on every batch size */
+    static const bool on = !(getenv("MARS_GRAPH") && atoi(getenv("MARS_GRAPH")) == 0);
     return on;
 }
 
