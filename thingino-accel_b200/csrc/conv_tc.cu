@@ -1068,7 +1068,8 @@ bool tc_plan(const Op &o, const ArenaGeom &ag, uint8_t *scratch, size_t scratch_
     p.m_tiles = (p.mflat + TC_BM - 1) / TC_BM;
     p.m_groups = (p.m_tiles + p.grp - 1) / p.grp;
     p.wp_magic = (unsigned)((1ull << 32) / (unsigned)g.Wp) + 1u;
-    if ((unsigned long long)p.mflat * (unsigned)g.Wp >= (1ull << 32) || (long long)p.m_tiles * p.n_tiles * ag.capacity >= (1ll << 31)) { delete t; return false; }
+    /* (+ 2 rows: the s2d pre-pass divides pixel indices of the bordered image by Wp with the same multiply-high trick) */
+    if ((unsigned long long)(p.mflat + 2 * g.Wp) * (unsigned)g.Wp >= (1ull << 32) || (long long)p.m_tiles * p.n_tiles * ag.capacity >= (1ll << 31)) { delete t; return false; }
     if (gather) {
         const int tw = 1 << g.tw_shift, th = TC_BM >> g.tw_shift;
         p.tw_shift = g.tw_shift;
