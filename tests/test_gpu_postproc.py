@@ -65,6 +65,28 @@ def test_nms_arbitrary_class_ids_and_special_scores(pkg, ob):
             assert a.tobytes() == b.tobytes(), (trial, n, th, len(a), len(b))
 
 
+def test_large_batches_take_the_256_thread_suppression_kernel_with_identical_results(pkg):
+    """more than 592 images per launch switch the suppression to k_nms_suppress; every slot must match the small-batch path"""
+    from conftest import shipped
+    path = shipped("yolov5n_int8.mars")
+    rng = np.random.default_rng(9)
+    xs = rng.integers(-128, 128, size=(3, 3 * 640 * 640), dtype=np.int8)
+    small = pkg.MarsModel(path, batch=3)
+    small.upload_inputs(0, 3, xs, xs.shape[1])
+    small.step_resident(0, 3, 0.45, True)
+    d_ref, c_ref = small.download_detections(0, 3)
+    del small
+    n = 600
+    big = pkg.MarsModel(path, batch=n)
+    for i in range(n):
+        big.upload_inputs(i, 1, xs[i % 3], xs.shape[1])
+    big.step_resident(0, n, 0.45, True)
+    d, c = big.download_detections(0, n)
+    assert c_ref.min() > 0
+    for i in range(n):
+        assert c[i] == c_ref[i % 3] and d[i][:c[i]].tobytes() == d_ref[i % 3][:c[i]].tobytes(), i
+
+
 def test_corner_nms_scale_and_anchor_decode(pkg, ob):
     rng = np.random.default_rng(6)
     boxes = np.zeros(500, dtype=pkg.capi.BOX_DTYPE)

@@ -325,11 +325,12 @@ __global__ void __launch_bounds__(32) k_nms_sort_warp(const mars_det_t *dets_in,
     }
 }
 
-/* words of per-image scratch: the suppression bit matrix, then the sorted order (uint16 per position) */
-#define NMS_SCRATCH_WORDS ((size_t)MARS_MAX_DETS * 32 + MARS_MAX_DETS / 2)
+/* words of per-image scratch: the suppression bit matrix, the sorted order (uint16 per position), and the per-class member
+ * bitsets of k_nms_suppress (NMS_CLASS_ROWS x 32 words) */
+#define NMS_CLASS_ROWS 128 /* class ids -1..126 get a member bitset; anything else takes the dense pair loop */
+#define NMS_SCRATCH_WORDS ((size_t)MARS_MAX_DETS * 32 + MARS_MAX_DETS / 2 + NMS_CLASS_ROWS * 32)
 
 /* dynamic shared memory of k_nms_center */
-#define NMS_CLASS_ROWS 128 /* class ids -1..126 get a member bitset; anything else takes the dense pair loop */
 struct NmsShared {
     NmsSortShared sort;
     float x0[MARS_MAX_DETS], y0[MARS_MAX_DETS], x1[MARS_MAX_DETS], y1[MARS_MAX_DETS], area[MARS_MAX_DETS];
@@ -459,6 +460,139 @@ __global__ void __launch_bounds__(NMS_THREADS, 2) k_nms_center(const mars_det_t 
     if (j == 0) counts_out[blockIdx.x] = total;
 }
 
+/* ---- suppression for presorted images: 256 threads per image, ~24 KiB of shared memory ----------------------------------
+ * Same algorithm as the second half of k_nms_center (member bitsets -> bit matrix -> ordered walk -> ordered compaction),
+ * sized so that eight images share an SM and a whole 1024-image batch is resident at once: the per-class member bitsets live
+ * in the image's global scratch (L2), each thread owns four sorted positions, and the compaction rank comes from population
+ * counts over the removed set instead of a block scan. */
+#define NMS_SUP_THREADS 256
+struct NmsSupShared {
+    float x0[MARS_MAX_DETS], y0[MARS_MAX_DETS], x1[MARS_MAX_DETS], y1[MARS_MAX_DETS], area[MARS_MAX_DETS];
+    int cls[MARS_MAX_DETS];
+    unsigned removed[32];
+    int removed_before[32]; /* removed elements in words 0..w-1 */
+    int dense;
+};
+
+__global__ void __launch_bounds__(NMS_SUP_THREADS, 8) k_nms_suppress(const mars_det_t *dets_in, const int32_t *counts_in,
+                                                                     mars_det_t *dets_out, int32_t *counts_out, int det_stride,
+                                                                     float thresh, unsigned *scratch) {
+    __shared__ NmsSupShared sh;
+    const mars_det_t *in = dets_in + (size_t)blockIdx.x * det_stride;
+    mars_det_t *out = dets_out + (size_t)blockIdx.x * det_stride;
+    unsigned *const mask = scratch + (size_t)blockIdx.x * NMS_SCRATCH_WORDS;
+    const uint16_t *order = reinterpret_cast<const uint16_t *>(mask + (size_t)MARS_MAX_DETS * 32);
+    unsigned *const members = mask + (size_t)MARS_MAX_DETS * 32 + MARS_MAX_DETS / 2; /* [NMS_CLASS_ROWS][32] */
+    int n = counts_in[blockIdx.x];
+    if (n > MARS_MAX_DETS) n = MARS_MAX_DETS;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    constexpr int NW = NMS_SUP_THREADS / 32, PER = MARS_MAX_DETS / NMS_SUP_THREADS;
+    for (int q = tid; q < NMS_CLASS_ROWS * 32; q += NMS_SUP_THREADS) members[q] = 0u;
+    if (tid == 0) sh.dense = 0;
+    /* thread tid owns the sorted positions j = tid + k * 256 */
+#pragma unroll
+    for (int k = 0; k < PER; k++) {
+        const int j = tid + k * NMS_SUP_THREADS;
+        if (j < n) {
+            const mars_det_t me = in[order[j]];
+            const float hw = __fdiv_rn(me.w, 2.0f), hh = __fdiv_rn(me.h, 2.0f);
+            sh.x0[j] = __fsub_rn(me.x, hw); sh.x1[j] = __fadd_rn(me.x, hw);
+            sh.y0[j] = __fsub_rn(me.y, hh); sh.y1[j] = __fadd_rn(me.y, hh);
+            sh.area[j] = __fmul_rn(me.w, me.h);
+            sh.cls[j] = me.cls;
+        }
+    }
+    __syncthreads(); /* members zeroed (global writes of this block are visible to it after the barrier), dense flag reset */
+#pragma unroll
+    for (int k = 0; k < PER; k++) {
+        const int j = tid + k * NMS_SUP_THREADS;
+        if (j < n) {
+            const unsigned c = (unsigned)(sh.cls[j] + 1);
+            if (c < NMS_CLASS_ROWS) atomicOr(&members[c * 32 + (j >> 5)], 1u << (j & 31));
+            else sh.dense = 1;
+        }
+    }
+    __syncthreads();
+    const int nwords = (n + 31) >> 5;
+    if (!sh.dense) {
+        for (int i = wid; i < n; i += NW) { /* one warp per row, lane = word of the row */
+            const int w0 = i >> 5;
+            unsigned cand = (lane >= w0 && lane < nwords) ? members[(sh.cls[i] + 1) * 32 + lane] : 0u;
+            if (lane == w0) cand &= ~((2u << (i & 31)) - 1u); /* only elements behind i */
+            unsigned bits = 0u;
+            if (__any_sync(0xffffffffu, cand != 0u)) {
+                const float ax0 = sh.x0[i], ay0 = sh.y0[i], ax1 = sh.x1[i], ay1 = sh.y1[i], aarea = sh.area[i];
+                while (cand) {
+                    const int b = __ffs(cand) - 1;
+                    cand &= cand - 1u;
+                    const int jj = lane * 32 + b;
+                    if (iou_pre(ax0, ay0, ax1, ay1, aarea, sh.x0[jj], sh.y0[jj], sh.x1[jj], sh.y1[jj], sh.area[jj]) > thresh) bits |= 1u << b;
+                }
+            }
+            if (lane >= w0 && lane < nwords) mask[i * 32 + lane] = bits;
+        }
+    } else {
+        for (int i = wid; i < n; i += NW) { /* arbitrary class ids: lane = bit, all pairs */
+            const float ax0 = sh.x0[i], ay0 = sh.y0[i], ax1 = sh.x1[i], ay1 = sh.y1[i], aarea = sh.area[i];
+            const int acls = sh.cls[i];
+            for (int w = i >> 5; w < nwords; w++) {
+                const int jj = w * 32 + lane;
+                bool sup = false;
+                if (jj > i && jj < n && sh.cls[jj] == acls)
+                    sup = iou_pre(ax0, ay0, ax1, ay1, aarea, sh.x0[jj], sh.y0[jj], sh.x1[jj], sh.y1[jj], sh.area[jj]) > thresh;
+                const unsigned bits = __ballot_sync(0xffffffffu, sup);
+                if (lane == 0) mask[i * 32 + w] = bits;
+            }
+        }
+    }
+    __syncthreads();
+    if (wid == 0) {
+        unsigned removed = 0u; /* lane w: bits of elements [32w, 32w+32) */
+        constexpr int CH = 8;
+        unsigned cur_rows[CH], nxt_rows[CH];
+        auto fetch = [&](unsigned (&rows)[CH], int base) {
+#pragma unroll
+            for (int q = 0; q < CH; q++) {
+                const int i = base + q;
+                rows[q] = (i < n && lane >= (i >> 5) && lane < nwords) ? mask[i * 32 + lane] : 0u;
+            }
+        };
+        fetch(cur_rows, 0);
+        for (int base = 0; base < n; base += CH) {
+            fetch(nxt_rows, base + CH);
+#pragma unroll
+            for (int q = 0; q < CH; q++) {
+                const int i = base + q; /* rows beyond n are zero */
+                const unsigned word = __shfl_sync(0xffffffffu, removed, (i >> 5) & 31);
+                if (!((word >> (i & 31)) & 1u)) removed |= cur_rows[q];
+            }
+#pragma unroll
+            for (int q = 0; q < CH; q++) cur_rows[q] = nxt_rows[q];
+        }
+        /* exclusive prefix of the per-word removed counts */
+        const int cnt = __popc(removed);
+        int incl = cnt;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const int y = __shfl_up_sync(0xffffffffu, incl, d);
+            if (lane >= d) incl += y;
+        }
+        sh.removed[lane] = removed;
+        sh.removed_before[lane] = incl - cnt;
+        if (lane == 31) counts_out[blockIdx.x] = n - incl;
+    }
+    __syncthreads();
+    /* ordered compaction: a kept element moves up by the number of removed elements in front of it */
+#pragma unroll
+    for (int k = 0; k < PER; k++) {
+        const int j = tid + k * NMS_SUP_THREADS;
+        if (j < n) {
+            const unsigned word = sh.removed[j >> 5];
+            if (!((word >> (j & 31)) & 1u)) out[j - sh.removed_before[j >> 5] - __popc(word & ((1u << (j & 31)) - 1u))] = in[order[j]];
+        }
+    }
+}
+
 static inline cudaError_t launch_nms_center(const mars_det_t *dets_in, const int32_t *counts_in, mars_det_t *dets_out,
                                             int32_t *counts_out, int det_stride, float thresh, int n_img, unsigned *scratch /* NMS_SCRATCH_WORDS per image */,
                                             cudaStream_t s, int *launches = nullptr) {
@@ -469,8 +603,14 @@ static inline cudaError_t launch_nms_center(const mars_det_t *dets_in, const int
         if (e != cudaSuccess) return e;
         attr = true;
     }
-    if (!block_sort) k_nms_sort_warp<<<n_img, 32, 0, s>>>(dets_in, counts_in, det_stride, scratch, NMS_SCRATCH_WORDS);
-    k_nms_center<<<n_img, NMS_THREADS, sizeof(NmsShared), s>>>(dets_in, counts_in, dets_out, counts_out, det_stride, thresh, scratch, block_sort ? 0 : 1);
+    if (!block_sort) {
+        k_nms_sort_warp<<<n_img, 32, 0, s>>>(dets_in, counts_in, det_stride, scratch, NMS_SCRATCH_WORDS);
+        /* many images: eight 256-thread blocks per SM keep the whole batch resident (throughput); few images: 1024 threads
+         * per image finish each one sooner (latency) */
+        static const int force = getenv("MARS_NMS_SUPPRESS") ? atoi(getenv("MARS_NMS_SUPPRESS")) : -1; /* 1 / 0: always / never (tests) */
+        if (force == 1 || (force != 0 && n_img > 2 * 296)) k_nms_suppress<<<n_img, NMS_SUP_THREADS, 0, s>>>(dets_in, counts_in, dets_out, counts_out, det_stride, thresh, scratch);
+        else k_nms_center<<<n_img, NMS_THREADS, sizeof(NmsShared), s>>>(dets_in, counts_in, dets_out, counts_out, det_stride, thresh, scratch, 1);
+    } else k_nms_center<<<n_img, NMS_THREADS, sizeof(NmsShared), s>>>(dets_in, counts_in, dets_out, counts_out, det_stride, thresh, scratch, 0);
     if (launches) *launches = block_sort ? 1 : 2;
     return cudaGetLastError();
 }
