@@ -61,33 +61,45 @@ def synth_images(first, n):
 # clocks
 # ---------------------------------------------------------------------------------------
 class ClockSampler(threading.Thread):
-    """samples SM clock and throttle reasons of one GPU while the timed region runs"""
+    """samples SM clock and throttle reasons of one GPU while the timed region runs.  NVML is initialised in the
+    constructor (it can take longer than a short timed region), and a sample is also taken synchronously at start and stop."""
+
+    NAMES = {0x2: "applications_clocks_setting", 0x4: "sw_power_cap", 0x8: "hw_slowdown", 0x10: "sync_boost",
+             0x20: "sw_thermal_slowdown", 0x40: "hw_thermal_slowdown", 0x80: "hw_power_brake_slowdown",
+             0x100: "display_clock_setting"}
 
     def __init__(self, index):
         super().__init__(daemon=True)
         self.index, self.stop_flag, self.samples, self.reasons, self.max_mhz = index, False, [], set(), None
-
-    def run(self):
+        self.nv = self.h = self.get_reasons = None
         try:
             import pynvml as nv
             nv.nvmlInit()
-            h = nv.nvmlDeviceGetHandleByIndex(self.index)
-            self.max_mhz = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
-            get_reasons = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or nv.nvmlDeviceGetCurrentClocksThrottleReasons
-            names = {0x2: "applications_clocks_setting", 0x4: "sw_power_cap", 0x8: "hw_slowdown", 0x10: "sync_boost",
-                     0x20: "sw_thermal_slowdown", 0x40: "hw_thermal_slowdown", 0x80: "hw_power_brake_slowdown",
-                     0x100: "display_clock_setting"}
-            while not self.stop_flag:
-                self.samples.append(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM))
-                r = get_reasons(h)
-                for bit, nm in names.items():
-                    if r & bit:
-                        self.reasons.add(nm)
-                time.sleep(0.002)
+            self.nv, self.h = nv, nv.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = nv.nvmlDeviceGetMaxClockInfo(self.h, nv.NVML_CLOCK_SM)
+            self.get_reasons = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or nv.nvmlDeviceGetCurrentClocksThrottleReasons
         except Exception as e:  # nvml missing: record that, do not fail the bench
             self.reasons.add("nvml_unavailable:%s" % type(e).__name__)
 
+    def sample(self):
+        if self.nv is None:
+            return
+        try:
+            self.samples.append(self.nv.nvmlDeviceGetClockInfo(self.h, self.nv.NVML_CLOCK_SM))
+            r = self.get_reasons(self.h)
+            for bit, nm in self.NAMES.items():
+                if r & bit:
+                    self.reasons.add(nm)
+        except Exception as e:  # noqa: BLE001
+            self.reasons.add("nvml_error:%s" % type(e).__name__)
+
+    def run(self):
+        while not self.stop_flag:
+            self.sample()
+            time.sleep(0.002)
+
     def result(self):
+        self.sample()  # the GPU is still busy or just finished: one more sample under (near) load
         self.stop_flag = True
         self.join(timeout=2)
         s = sorted(self.samples)
@@ -313,11 +325,11 @@ def run_cuda_arm(args):
         return float(t.item())
 
     # ---- resident: W warm-up + K timed steps --------------------------------------------
+    sampler = ClockSampler(local_rank)  # NVML set up before the warm-up, sampling starts with the timed region
     for _ in range(max(args.warmup, 3)):
         gm.step_resident(0, B, NMS_THRESH, True)
         gather()
     barrier()
-    sampler = ClockSampler(local_rank)
     sampler.start()
     l0 = gm.launch_count
     dev_ms = 0.0
