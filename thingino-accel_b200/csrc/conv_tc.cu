@@ -670,8 +670,8 @@ teardown:
  * 32 pixels x 32 channels per block through shared memory: coalesced reads along pixels,
  * coalesced writes along channels. */
 __global__ void __launch_bounds__(256) k_to_nhwc(const uint8_t *src_base, unsigned long long src_stride, uint8_t *dst_base,
-                                                 unsigned long long dst_stride, int C, int H, int W, int Wp, int plane, int npix,
-                                                 int stride2, int pt, int pl) {
+                                                 unsigned long long dst_stride, int C, int Cp, int H, int W, int Wp, int plane, int npix,
+                                                 int stride2, int pt, int pl) { /* Cp >= C: bytes per pixel of the copy */
     __shared__ uint8_t tile[32][33];
     const uint8_t *src = src_base + (unsigned long long)blockIdx.z * src_stride;
     uint8_t *dst = dst_base + (unsigned long long)blockIdx.z * dst_stride;
@@ -699,7 +699,7 @@ __global__ void __launch_bounds__(256) k_to_nhwc(const uint8_t *src_base, unsign
 #pragma unroll
     for (int k = 0; k < 4; k++) {
         const int pix = p0 + ty + 8 * k, c = c0 + tx;
-        if (pix < npix && c < C) dst[(long long)pix * C + c] = tile[tx][ty + 8 * k];
+        if (pix < npix && c < Cp) dst[(long long)pix * Cp + c] = tile[tx][ty + 8 * k]; /* channels C..Cp-1: zeros (padded K) */
     }
 }
 /* ---- s2d mode (6x6 stride-2 pad-2 conv with <= 4 input channels = 3x3 stride-1 pad-1 conv over the 2x2 space-to-depth
@@ -775,7 +775,7 @@ struct TcPlanImpl {
     TcParams p;
     int prepass = 0;
     bool fast = false;
-    int C = 0, H = 0, W = 0, pt = 0, pl = 0, plane = 0, npix = 0;
+    int C = 0, Cp = 0, H = 0, W = 0, pt = 0, pl = 0, plane = 0, npix = 0; /* Cp: bytes per pixel of the channel-innermost copy */
     const uint8_t *src_slot0 = nullptr; /* input tensor in slot 0 */
     uint8_t *scratch = nullptr;
     size_t scratch_stride = 0, slot_stride = 0;
@@ -835,6 +835,7 @@ struct TcGeom {
     int prepass = 0; /* 4: space-to-depth copy with 16-byte pixels (stem); 0: A from the arena (1x1); 1: NHWC copy, rows padded (stride 1); 2: NHWC 2x2 phase split (stride 2);
                         3: gather -- A rows built in shared memory from a private NCHW copy of the input (small Ci) */
     int Wp = 0, plane = 0, npix = 0, ntaps = 0, Kp = 0;
+    int kpad = 0; /* prepass 0 with Ci not a multiple of 32: K extent padded with zeros (TMA fills the missing channel rows, the repacked weights hold zeros) */
     int tw_shift = 0, PH = 0, PWW = 0, dx = 0; /* gather: M tile shape and input patch geometry */
     size_t scratch_bytes = 0;
 };
@@ -844,6 +845,19 @@ static TcGeom tc_geometry(const Op &o) {
     if (o.oc < 16 || o.sh != o.sw || o.sh < 1 || o.kh < 1 || o.kw < 1) return g;
     if (o.oh <= 0 || o.ow <= 0 || o.ih <= 0 || o.iw <= 0 || o.ic <= 0) return g;
     if (round_up(o.oc, 16) > TC_MAX_CO) return g;
+    /* 1x1 stride-1 conv straight from the NCHW planes with any channel count >= 16 (ShuffleNet-style 58 / 116 / 232 / 464):
+     * the channel rows a k-step reads beyond Ci do not exist in the tensor map and arrive as zeros */
+    if (o.ic >= 16 && o.ic % 32 && o.kh == 1 && o.kw == 1 && o.sh == 1 && o.pt == 0 && o.pl == 0 && o.oh <= o.ih && o.ow == o.iw) {
+        g.ntaps = 1; g.Wp = o.iw;
+        g.kpad = o.ic > 64 ? round_up(o.ic, 128) : round_up(o.ic, 32);
+        if (((long long)o.ih * o.iw) % 16 == 0) { g.prepass = 0; g.scratch_bytes = 0; }
+        else { /* planes that TMA cannot address (stride not a multiple of 16 bytes, e.g. 10 x 10): channel-innermost copy, kpad bytes per pixel */
+            g.prepass = 1; g.plane = o.ih * g.Wp; g.npix = g.plane;
+            g.scratch_bytes = (size_t)g.npix * g.kpad;
+        }
+        g.ok = true;
+        return g;
+    }
     if (o.ic < 32 || o.ic % 32 || o.kh != o.kw) {
         /* the YOLOv5 stem shape: 6x6 stride 2 pad 2 over <= 4 channels == 3x3 stride 1 pad 1 over the 2x2 space-to-depth image */
         static const bool s2d_enabled = !(getenv("MARS_TC_S2D") && atoi(getenv("MARS_TC_S2D")) == 0);
@@ -903,8 +917,8 @@ size_t tc_scratch_need(const Op &o) {
 }
 bool tc_supported(const Op &o) {
     if (!tc_geometry(o).ok) return false;
-    const int co_pad = round_up(o.oc, 16);
-    return co_pad <= 256 || co_pad % 128 == 0;
+    return true; /* any Co up to TC_MAX_CO: above 256 the N tiles are 256 or 128 wide and the last one may be ragged (weight rows
+                  * beyond Co_pad do not exist in the tensor map and arrive as zeros; the epilogue skips their columns) */
 }
 int tc_n_tiles(int oc) {
     const int co_pad = round_up(oc, 16);
@@ -912,7 +926,7 @@ int tc_n_tiles(int oc) {
     return (co_pad + nt - 1) / nt;
 }
 bool tc_uses_copy(const Op &o) { return tc_geometry(o).prepass != 0; }
-bool tc_linkable(const Op &o) { const TcGeom g = tc_geometry(o); return g.ok && (g.prepass == 1 || g.prepass == 2); }
+bool tc_linkable(const Op &o) { const TcGeom g = tc_geometry(o); return g.ok && (g.prepass == 1 || g.prepass == 2) && !g.kpad; }
 
 /* the word table of the epilogue: index = sign << 8 | magnitude (0..128); byte k = value of output stream k.
  * Stream order: a fused conv stores [Z, S, Y] (Z = SiLU product, the stream almost every consumer reads, sits in the
@@ -981,11 +995,10 @@ bool tc_plan(const Op &o, const ArenaGeom &ag, uint8_t *scratch, size_t scratch_
     TcParams &p = t->p;
     memset(&p, 0, sizeof p);
     const bool gather = g.prepass == 3, s2d = g.prepass == 4;
-    const int ci_eff = (gather || s2d) ? g.Kp : o.ic; /* K extent of one tap */
+    const int ci_eff = (gather || s2d) ? g.Kp : (g.kpad ? g.kpad : o.ic); /* K extent of one tap */
     p.Co = o.oc; p.Ho = o.oh; p.Wo = o.ow; p.Wp = g.Wp; p.mflat = o.oh * g.Wp; p.plane = o.oh * o.ow;
     const int co_pad = round_up(o.oc, 16);
     p.n_tile = co_pad <= 256 ? co_pad : (co_pad % 256 == 0 ? 256 : 128);
-    if (co_pad > 256 && co_pad % 128) { delete t; return false; }
     p.n_tiles = (co_pad + p.n_tile - 1) / p.n_tile;
     p.bk = ci_eff % 128 == 0 ? 128 : (ci_eff % 64 == 0 ? 64 : 32);
     p.ksteps_per_tap = ci_eff / p.bk;
@@ -1106,7 +1119,7 @@ bool tc_plan(const Op &o, const ArenaGeom &ag, uint8_t *scratch, size_t scratch_
         p.nhwc_stride = linked_stride;
     }
     t->fast = fast_requant_ok(o, ag);
-    t->prepass = g.prepass; t->C = o.ic; t->H = o.ih; t->W = o.iw; t->pt = o.pt; t->pl = o.pl;
+    t->prepass = g.prepass; t->C = o.ic; t->Cp = ci_eff; t->H = o.ih; t->W = o.iw; t->pt = o.pt; t->pl = o.pl;
     t->plane = g.plane; t->npix = g.npix;
     t->src_slot0 = ag.d_slots + (o.in0 - (int64_t)ag.W);
     t->scratch = scratch; t->scratch_stride = scratch_stride; t->slot_stride = ag.slot_stride;
@@ -1135,6 +1148,8 @@ bool tc_plan(const Op &o, const ArenaGeom &ag, uint8_t *scratch, size_t scratch_
         k_repack_s2d<<<64, 256>>>(reinterpret_cast<const int8_t *>(ag.d_weights + o.w), t->d_wr, o.oc, co_pad, o.ic);
     else if (gather)
         k_repack_rows<<<256, 256>>>(reinterpret_cast<const int8_t *>(ag.d_weights + o.w), t->d_wr, o.oc, co_pad, o.ic * o.kh * o.kw, g.Kp);
+    else if (g.kpad) /* 1x1: OIHW rows are already K-major, pad them to the K extent */
+        k_repack_rows<<<256, 256>>>(reinterpret_cast<const int8_t *>(ag.d_weights + o.w), t->d_wr, o.oc, co_pad, o.ic, g.kpad);
     else
         k_repack_weights<<<256, 256>>>(reinterpret_cast<const int8_t *>(ag.d_weights + o.w), t->d_wr, o.oc, co_pad, o.ic, g.ntaps);
     bool ok = cudaDeviceSynchronize() == cudaSuccess;
@@ -1179,8 +1194,8 @@ bool tc_launch(const TcPlan &plan, uint8_t *slots_base, int first, int n, bool u
         k_s2d16<<<dim3((t->npix + 1023) / 1024, n), 256, 0, s>>>(src, t->slot_stride, scr, t->scratch_stride, t->C, t->H, t->W, t->p.Wp, t->npix);
         (*launches)++;
     } else if (t->prepass && t->prepass != 3 && !(use_linked && t->has_linked)) {
-        dim3 g((t->npix + 31) / 32, (t->C + 31) / 32, n);
-        k_to_nhwc<<<g, 256, 0, s>>>(src, t->slot_stride, scr, t->scratch_stride, t->C, t->H, t->W, t->p.Wp, t->plane, t->npix,
+        dim3 g((t->npix + 31) / 32, (t->Cp + 31) / 32, n);
+        k_to_nhwc<<<g, 256, 0, s>>>(src, t->slot_stride, scr, t->scratch_stride, t->C, t->Cp, t->H, t->W, t->p.Wp, t->plane, t->npix,
                                     t->prepass == 2, t->pt, t->pl);
         (*launches)++;
     }

@@ -13,17 +13,22 @@ B = int(sys.argv[1]) if len(sys.argv) > 1 else 128
 steps = int(sys.argv[2]) if len(sys.argv) > 2 else 3
 pkg = load_package()
 mf = pkg.marsfile
-blob = mf.build_yolov5(width=0.5, size=640, seed=5).to_bytes()
-gm = pkg.MarsModel(blob, arena_bytes=mf.ARENA_YOLOV5S_INT8, batch=B)
-x = np.random.default_rng(1000).integers(-128, 128, size=(1, 3 * 640 * 640), dtype=np.int8)
+import os
+if os.environ.get("PROFILE_MODEL") == "nanodet":  # BASELINE config 5 shape
+    blob, arena, side = mf.build_nanodet_like(size=320, seed=7).to_bytes(), 16 << 20, 320
+else:
+    blob, arena, side = mf.build_yolov5(width=0.5, size=640, seed=5).to_bytes(), mf.ARENA_YOLOV5S_INT8, 640
+gm = pkg.MarsModel(blob, arena_bytes=arena, batch=B)
+x = np.random.default_rng(1000).integers(-128, 128, size=(1, 3 * side * side), dtype=np.int8)
 for i in range(B):
     gm.upload_inputs(i, 1, x, x.shape[1])
+DETECT = os.environ.get("PROFILE_MODEL") != "nanodet"
 for _ in range(2):
-    gm.step_resident(0, B, 0.45, True)
+    gm.step_resident(0, B, 0.45, DETECT)
 gm.set_profile(True)
 tot = 0.0
 for _ in range(steps):
-    tot += gm.step_resident(0, B, 0.45, True)
+    tot += gm.step_resident(0, B, 0.45, DETECT)
 prof = gm.op_profile()
 print("batch %d: %.2f ms/step, %.1f img/s" % (B, tot / steps, B * steps / tot * 1e3))
 rows = [p for p in prof if p["calls"]]
