@@ -127,6 +127,12 @@ MICRO = [
     # gather producer + tcgen05 (small Ci, >= 4096 output pixels)
     ("conv", dict(k=6, s=2, c=3, co=32, h=128, w=128)), ("conv", dict(k=3, s=1, c=8, co=24, h=70, w=66, padding=1)),
     ("conv", dict(k=3, s=2, c=5, co=17, h=130, w=140)),
+    # channel counts that are not multiples of 32 on the tensor-core path: zero-padded K (TMA fill / padded copy), ragged N > 256
+    ("conv", dict(k=1, s=1, c=58, co=58, h=40, w=40)), ("conv", dict(k=1, s=1, c=116, co=232, h=10, w=10)),
+    ("conv", dict(k=1, s=1, c=232, co=464, h=10, w=10)), ("conv", dict(k=1, s=1, c=48, co=40, h=20, w=20)),
+    ("conv", dict(k=1, s=1, c=464, co=300, h=12, w=12)), ("conv", dict(k=3, s=1, c=48, co=32, h=20, w=20)),
+    ("conv", dict(k=3, s=2, c=24, co=40, h=40, w=40)), ("conv", dict(k=3, s=1, c=116, co=58, h=20, w=20, padding=1)),
+    ("conv", dict(k=5, s=1, c=40, co=272, h=12, w=14)),
 ]
 
 

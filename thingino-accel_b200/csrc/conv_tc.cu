@@ -756,14 +756,14 @@ __global__ void k_repack_rows(const int8_t *w, int8_t *dst, int Co, int Co_pad, 
         dst[i] = (co < Co && k < Kt) ? w[(long long)co * Kt + k] : (int8_t)0;
     }
 }
-/* OIHW -> [tap][Co_pad][Ci], rows beyond Co zero */
-__global__ void k_repack_weights(const int8_t *w, int8_t *dst, int Co, int Co_pad, int Ci, int ntaps) {
-    long long total = (long long)ntaps * Co_pad * Ci;
+/* OIHW -> [tap][Co_pad][Cip], rows beyond Co and columns beyond Ci zero */
+__global__ void k_repack_weights(const int8_t *w, int8_t *dst, int Co, int Co_pad, int Ci, int Cip, int ntaps) {
+    long long total = (long long)ntaps * Co_pad * Cip; /* Cip >= Ci: K extent per tap, columns beyond Ci zero */
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-        int ci = (int)(i % Ci);
-        long long r = i / Ci;
+        int ci = (int)(i % Cip);
+        long long r = i / Cip;
         int co = (int)(r % Co_pad), tap = (int)(r / Co_pad);
-        dst[i] = co < Co ? w[((long long)co * Ci + ci) * ntaps + tap] : (int8_t)0;
+        dst[i] = (co < Co && ci < Ci) ? w[((long long)co * Ci + ci) * ntaps + tap] : (int8_t)0;
     }
 }
 
@@ -859,6 +859,7 @@ static TcGeom tc_geometry(const Op &o) {
         return g;
     }
     if (o.ic < 32 || o.ic % 32 || o.kh != o.kw) {
+        auto small_k = [&]() -> bool {
         /* the YOLOv5 stem shape: 6x6 stride 2 pad 2 over <= 4 channels == 3x3 stride 1 pad 1 over the 2x2 space-to-depth image */
         static const bool s2d_enabled = !(getenv("MARS_TC_S2D") && atoi(getenv("MARS_TC_S2D")) == 0);
         if (s2d_enabled && o.sh == 2 && o.sw == 2 && o.kh == 6 && o.kw == 6 && (o.pt == 0 || o.pt == 2) && (o.pl == 0 || o.pl == 2) &&
@@ -867,12 +868,12 @@ static TcGeom tc_geometry(const Op &o) {
             g.prepass = 4; g.Wp = o.iw / 2 + 2; g.plane = (o.ih / 2 + 2) * g.Wp; g.npix = g.plane; g.ntaps = 6; g.Kp = 32;
             g.scratch_bytes = (size_t)g.npix * 16;
             g.ok = true;
-            return g;
+            return true;
         }
         /* small / odd channel counts: one 128-byte K row per pixel, built in shared memory from a staged input patch */
         const int Kt = o.ic * o.kh * o.kw;
-        if (Kt > 128 || o.kh > 255 || o.kw > 255 || (long long)o.oh * o.ow < 4096 || round_up(o.oc, 16) > 256) return g;
-        if (o.iw % 4 || o.pl < 0 || o.pt < 0) return g;
+        if (Kt > 128 || o.kh > 255 || o.kw > 255 || (long long)o.oh * o.ow < 4096 || round_up(o.oc, 16) > 256) return false;
+        if (o.iw % 4 || o.pl < 0 || o.pt < 0) return false;
         /* M tile = tw x (128/tw) output pixels: least padding, then the widest */
         long long best = -1;
         for (int sh = 7; sh >= 4; sh--) {
@@ -884,15 +885,22 @@ static TcGeom tc_geometry(const Op &o) {
             const long long padded = (long long)((o.ow + tw - 1) / tw) * tw * ((o.oh + th - 1) / th) * th;
             if (best < 0 || padded < best) { best = padded; g.tw_shift = sh; g.PH = PH; g.PWW = PWW; g.dx = dx; }
         }
-        if (best < 0) return g;
+        if (best < 0) return false;
         g.prepass = 3; g.Kp = 128; g.ntaps = 1; g.Wp = o.ow; g.npix = o.oh * o.ow;
         g.scratch_bytes = (size_t)o.ic * o.ih * o.iw;
         g.ok = true;
-        return g;
+        return true;
+            };
+        if (small_k()) return g;
+        /* larger K with a channel count that is not a multiple of 32: the general paths below over a channel-innermost copy
+         * whose pixels are padded to kpad bytes (zero channels), weights repacked with zero columns */
+        if (o.kh != o.kw || o.ic < 8) return TcGeom();
+        g = TcGeom();
+        g.kpad = round_up(o.ic, 32);
     }
     g.ntaps = o.kh * o.kw;
     if (g.ntaps > TC_MAX_TAPS) return g;
-    if (o.kh == 1 && o.sh == 1 && o.pt == 0 && o.pl == 0 && o.oh <= o.ih && o.ow == o.iw && ((long long)o.ih * o.iw) % 16 == 0) {
+    if (!g.kpad && o.kh == 1 && o.sh == 1 && o.pt == 0 && o.pl == 0 && o.oh <= o.ih && o.ow == o.iw && ((long long)o.ih * o.iw) % 16 == 0) {
         g.prepass = 0; g.Wp = o.iw;
     } else if (o.sh == 1) {
         if (o.pl >= o.kw || o.pt >= o.kh) return g;
@@ -906,7 +914,7 @@ static TcGeom tc_geometry(const Op &o) {
         g.plane = rows * g.Wp; g.npix = 4 * g.plane;
     } else return g;
     if (o.ow > g.Wp) return g;
-    g.scratch_bytes = g.prepass ? (size_t)g.npix * o.ic : 0;
+    g.scratch_bytes = g.prepass ? (size_t)g.npix * (g.kpad ? g.kpad : o.ic) : 0;
     g.ok = true;
     return g;
 }
@@ -1148,10 +1156,8 @@ bool tc_plan(const Op &o, const ArenaGeom &ag, uint8_t *scratch, size_t scratch_
         k_repack_s2d<<<64, 256>>>(reinterpret_cast<const int8_t *>(ag.d_weights + o.w), t->d_wr, o.oc, co_pad, o.ic);
     else if (gather)
         k_repack_rows<<<256, 256>>>(reinterpret_cast<const int8_t *>(ag.d_weights + o.w), t->d_wr, o.oc, co_pad, o.ic * o.kh * o.kw, g.Kp);
-    else if (g.kpad) /* 1x1: OIHW rows are already K-major, pad them to the K extent */
-        k_repack_rows<<<256, 256>>>(reinterpret_cast<const int8_t *>(ag.d_weights + o.w), t->d_wr, o.oc, co_pad, o.ic, g.kpad);
     else
-        k_repack_weights<<<256, 256>>>(reinterpret_cast<const int8_t *>(ag.d_weights + o.w), t->d_wr, o.oc, co_pad, o.ic, g.ntaps);
+        k_repack_weights<<<256, 256>>>(reinterpret_cast<const int8_t *>(ag.d_weights + o.w), t->d_wr, o.oc, co_pad, o.ic, ci_eff, g.ntaps);
     bool ok = cudaDeviceSynchronize() == cudaSuccess;
 
     const CUtensorMapSwizzle ksw = p.bk == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : (p.bk == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
