@@ -43,8 +43,8 @@ def test_postprocess_random_vs_oracle(pkg, ob):
 def test_nms_arbitrary_class_ids_and_special_scores(pkg, ob):
     """class ids outside the member-bitset range take the all-pairs path; NaN / inf / tied scores keep the C loop's order"""
     rng = np.random.default_rng(77)
-    for trial in range(8):
-        n = int(rng.choice([1, 2, 31, 32, 33, 500, 1000, 1024]))
+    sizes = [1, 2, 31, 32, 33, 64, 65, 128, 129, 200, 256, 257, 384, 385, 500, 512, 513, 768, 769, 896, 897, 1000, 1023, 1024]
+    for trial, n in enumerate(sizes):  # every layout of the warp sort (4 / 8 / 16 / 32 positions per lane) and each of its phase boundaries
         d = np.zeros(n, dtype=pkg.capi.DET_DTYPE)
         d["x"] = rng.integers(0, 64, n).astype(np.float32)
         d["y"] = rng.integers(0, 64, n).astype(np.float32)

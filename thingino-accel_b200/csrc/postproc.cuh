@@ -224,43 +224,40 @@ __device__ __forceinline__ int exchange_sort_block(NmsSortShared &sh, float myk,
  * The element leaving the last record is final: it is written to order[i] and never looked at again.
  * NaN keys never compare greater (never records); a NaN hand makes every comparison fail, so the pass moves nothing.
  */
-__global__ void __launch_bounds__(32) k_nms_sort_warp(const mars_det_t *dets_in, const int32_t *counts_in, int det_stride,
-                                                      unsigned *scratch, size_t scratch_stride_words) {
-    const int img = blockIdx.x, lane = threadIdx.x;
-    const mars_det_t *in = dets_in + (size_t)img * det_stride;
-    uint16_t *order = reinterpret_cast<uint16_t *>(scratch + (size_t)img * scratch_stride_words + (size_t)MARS_MAX_DETS * 32);
-    int n = counts_in[img];
-    if (n > MARS_MAX_DETS) n = MARS_MAX_DETS;
+/* passes [i0, i1) over a layout in which lane L holds the R consecutive positions base + L*R .. (R = 32, 16, 8 or 4; i0 - base
+ * is a multiple of 32).  A block of 32 positions is 32/R lanes wide. */
+template <int R>
+__device__ __forceinline__ void nms_sort_passes(float (&k)[R], int (&x)[R], int base, int i0, int i1, uint16_t *order, int lane) {
     const float NEG_INF = -__int_as_float(0x7f800000), POS_INF = __int_as_float(0x7f800000);
     const unsigned FULL = 0xffffffffu;
-    float k[32];
-    int x[32];
-#pragma unroll
-    for (int t = 0; t < 32; t++) {
-        const int p = lane * 32 + t;
-        k[t] = p < n ? in[p].conf : NEG_INF;
-        x[t] = p;
-    }
+    constexpr int LPB = 32 / R; /* lanes per block */
     float lm = NEG_INF, Bk = NEG_INF;
     int lmx = 0, Bx = 0;
     const unsigned below = (1u << lane) - 1u;
-    for (int i = 0; i < n; i++) {
-        const int L0 = i >> 5, t = i & 31;
+    for (int i = i0; i < i1; i++) {
+        const int t = (i - base) & 31;
         if (t == 0) {
-            /* lane L0's registers become the block; the lane itself is dead from now on */
+            /* the next 32 positions become the block; the lanes that held them are dead from now on */
+            const int l0 = ((i - base) >> 5) * LPB;
 #pragma unroll
-            for (int u = 0; u < 32; u++) {
-                const float vk = __shfl_sync(FULL, k[u], L0);
-                const int vx = __shfl_sync(FULL, x[u], L0);
-                if (lane == u) { Bk = vk; Bx = vx; }
-                if (lane == L0) k[u] = NEG_INF;
+            for (int sub = 0; sub < LPB; sub++) {
+#pragma unroll
+                for (int u = 0; u < R; u++) {
+                    const float vk = __shfl_sync(FULL, k[u], l0 + sub);
+                    const int vx = __shfl_sync(FULL, x[u], l0 + sub);
+                    if (lane == sub * R + u) { Bk = vk; Bx = vx; }
+                }
             }
-            if (lane == L0) lm = NEG_INF;
-            if (i == 0) { /* first-occurrence maxima of the register lanes */
+            if (lane >= l0 && lane < l0 + LPB) {
 #pragma unroll
-                for (int u = 0; u < 32; u++)
+                for (int u = 0; u < R; u++) k[u] = NEG_INF;
+            }
+            if (i == i0) { /* first-occurrence maxima of the register lanes of this phase */
+                lm = NEG_INF;
+#pragma unroll
+                for (int u = 0; u < R; u++)
                     if (k[u] > lm) { lm = k[u]; lmx = x[u]; }
-            }
+            } else if (lane >= l0 && lane < l0 + LPB) lm = NEG_INF;
         }
         /* The pass is one dependent chain (scan -> who holds records -> walk -> next pass's maxima), so it is written for
          * latency: both prefix-max scans run interleaved and start before the hand is known (only their seeds depend on it),
@@ -305,7 +302,7 @@ __global__ void __launch_bounds__(32) k_nms_sort_warp(const mars_det_t *dets_in,
             float nlm = NEG_INF;
             int nlx = 0;
 #pragma unroll
-            for (int u = 0; u < 32; u++) {
+            for (int u = 0; u < R; u++) {
                 const float ku = k[u];
                 const int xu = x[u];
                 const bool sw = ku > run_k;          /* the C loop's comparison (false for NaN) */
@@ -323,6 +320,59 @@ __global__ void __launch_bounds__(32) k_nms_sort_warp(const mars_det_t *dets_in,
         }
         if (lane == 0) order[i] = (uint16_t)wx;
     }
+}
+
+/* all passes from position `base` on, starting with R positions per lane: the first half of what is left is sorted with this
+ * layout, then the surviving upper 16 lanes are spread over the whole warp (R/2 positions per lane: the walk, the largest
+ * part of a pass, shrinks with the data) and the rest follows recursively */
+template <int R>
+__device__ __forceinline__ void nms_sort_from(float (&k)[R], int (&x)[R], int base, int n, uint16_t *order, int lane) {
+    constexpr int RMIN = 4;
+    const int stop = (R > RMIN) ? min(n, base + 16 * R) : n;
+    nms_sort_passes<R>(k, x, base, base, stop, order, lane);
+    if constexpr (R > RMIN) {
+        if (n > stop) { /* uniform */
+            float nk[R / 2];
+            int nx[R / 2];
+            const int src = 16 + (lane >> 1);
+#pragma unroll
+            for (int u = 0; u < R / 2; u++) {
+                const float a = __shfl_sync(0xffffffffu, k[u], src), b = __shfl_sync(0xffffffffu, k[u + R / 2], src);
+                const int ax = __shfl_sync(0xffffffffu, x[u], src), bx = __shfl_sync(0xffffffffu, x[u + R / 2], src);
+                nk[u] = (lane & 1) ? b : a;
+                nx[u] = (lane & 1) ? bx : ax;
+            }
+            nms_sort_from<R / 2>(nk, nx, base + 16 * R, n, order, lane);
+        }
+    }
+}
+
+template <int R>
+__device__ __forceinline__ void nms_sort_image(const mars_det_t *in, int n, uint16_t *order, int lane) {
+    const float NEG_INF = -__int_as_float(0x7f800000);
+    float k[R];
+    int x[R];
+#pragma unroll
+    for (int u = 0; u < R; u++) {
+        const int p = lane * R + u;
+        k[u] = p < n ? in[p].conf : NEG_INF;
+        x[u] = p;
+    }
+    nms_sort_from<R>(k, x, 0, n, order, lane);
+}
+
+__global__ void __launch_bounds__(32) k_nms_sort_warp(const mars_det_t *dets_in, const int32_t *counts_in, int det_stride,
+                                                      unsigned *scratch, size_t scratch_stride_words) {
+    const int img = blockIdx.x, lane = threadIdx.x;
+    const mars_det_t *in = dets_in + (size_t)img * det_stride;
+    uint16_t *order = reinterpret_cast<uint16_t *>(scratch + (size_t)img * scratch_stride_words + (size_t)MARS_MAX_DETS * 32);
+    int n = counts_in[img];
+    if (n > MARS_MAX_DETS) n = MARS_MAX_DETS;
+    /* fewest positions per lane that hold the image: short lists do not pay for a 1024-position layout */
+    if (n <= 128) nms_sort_image<4>(in, n, order, lane);
+    else if (n <= 256) nms_sort_image<8>(in, n, order, lane);
+    else if (n <= 512) nms_sort_image<16>(in, n, order, lane);
+    else nms_sort_image<32>(in, n, order, lane);
 }
 
 /* words of per-image scratch: the suppression bit matrix, the sorted order (uint16 per position), and the per-class member
