@@ -4,9 +4,13 @@
  *  k_parse_output : parse_output() of reference src/mars/mars_yolo_test.c:80-104 --
  *                   per-row objectness/class decode through host-built libm tables,
  *                   ORDER-PRESERVING compaction with the reference's hard cap;
- *  k_nms_center   : nms() of reference src/mars/mars_yolo_test.c:107-130 -- the exchange
+ *  k_nms_sort_warp, k_nms_suppress / k_nms_center :
+ *                   nms() of reference src/mars/mars_yolo_test.c:107-130 -- the exchange
  *                   sort is emulated pass by pass (its permutation under ties is NOT a
- *                   stable sort), then greedy same-class suppression;
+ *                   stable sort) by one warp per image, then greedy same-class
+ *                   suppression through per-class member bitsets and a bit matrix (256
+ *                   threads per image for large batches, 1024 for small ones; k_nms_center
+ *                   also holds the block-wide sort kept as a cross-check);
  *  k_nms_corner   : nms() of reference examples/yolo_detect.cpp:152-173 (corner boxes);
  *  k_anchor_decode: anchor-grid decode (mgk-decompiler/test_yolo_inference.py:136-202).
  * One thread block per image; blocks are independent (images shard with no exchange).
