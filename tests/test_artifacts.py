@@ -15,8 +15,15 @@ def last_json_line(path):
     return json.loads(lines[-1])
 
 
+def latest_prefix():
+    """rNNx of the most recent 1-GPU bench line (names sort by round, then by build letter)"""
+    names = sorted(os.path.basename(f) for f in glob.glob(os.path.join(ROOT, "profiles", "r*_bench_n1.json")))
+    assert names
+    return names[-1].split("_bench_")[0]
+
+
 def test_committed_bench_lines_follow_the_contract():
-    files = sorted(glob.glob(os.path.join(ROOT, "profiles", "r01i_bench_n*.json")))
+    files = sorted(glob.glob(os.path.join(ROOT, "profiles", latest_prefix() + "_bench_n*.json")))
     assert files
     for f in files:
         d = last_json_line(f)
@@ -30,6 +37,6 @@ def test_committed_bench_lines_follow_the_contract():
 
 
 def test_committed_reference_line():
-    d = last_json_line(os.path.join(ROOT, "profiles", "r01i_bench_reference_n1.json"))
+    d = last_json_line(os.path.join(ROOT, "profiles", latest_prefix() + "_bench_reference_n1.json"))
     assert d["impl"] == "reference" and d["value"] > 0 and d["cpu_baseline"]["kind"] in ("reference", "port")
     assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0
