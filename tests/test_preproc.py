@@ -85,6 +85,25 @@ def test_host_tap_lists_reproduce_the_reference_rgba_frame(pkg):
     assert sha(letterbox_numpy(pkg.capi, frame(w, h, seed), 640, 640, True, rgba=True)) == RGBA[tag]["sha256"]
 
 
+def test_host_tap_lists_random_sizes_against_the_reference_function(pkg, rb):
+    """enlarging, shrinking, one-pixel-off and mixed axes: the numpy sums over the product's tap lists equal the reference's
+    load_image for frame / tensor sizes drawn at random"""
+    rng = np.random.default_rng(12)
+    done = 0
+    while done < 24:
+        w, h = int(rng.integers(1, 90)), int(rng.integers(1, 90))
+        tw, th = int(rng.integers(8, 72)), int(rng.integers(8, 72))
+        scale = min(np.float32(tw) / np.float32(w), np.float32(th) / np.float32(h))
+        if int(np.float32(w) * scale) < 1 or int(np.float32(h) * scale) < 1:
+            continue
+        f = rng.integers(0, 256, (h, w, 3), dtype=np.uint8)
+        nhwc = bool(rng.integers(0, 2))
+        want = rb.ref_load_image(f, tw, th, nhwc)
+        got = letterbox_numpy(pkg.capi, f, tw, th, nhwc)
+        assert got.tobytes() == want.tobytes(), (w, h, tw, th, nhwc)
+        done += 1
+
+
 def test_tap_lists_are_well_formed(pkg):
     for (i, o) in [(1, 1), (1, 7), (7, 1), (640, 640), (1920, 640), (37, 64), (1000, 3)]:
         start, src, w = pkg.capi.resize_taps(i, o)
