@@ -56,7 +56,8 @@ struct TcParams {
     int a_shift[TC_MAX_TAPS];
     const int32_t *bias;     /* device pointer or null */
     float cs;
-    const uint32_t *lutw;    /* 512-entry word table: index = sign << 8 | magnitude, byte k = value of output stream k */
+    const uint32_t *lutw;    /* 256-entry word table: index = r + 128, byte k = value of output stream k, byte 3 = side-output stream */
+    uint32_t tab_off;        /* offset of the per-lane replicated copy ([256][32] words) in dynamic shared memory */
     uint8_t *out_base;       /* slot 0 of the launch */
     unsigned long long slot_stride;
     long long out_off[3];    /* slot-relative byte offset of output stream k (NCHW), -1 = not stored */
@@ -176,6 +177,18 @@ __device__ __forceinline__ void mbar_wait_relaxed(uint32_t bar, uint32_t parity)
     }
 }
 
+/* one non-blocking probe */
+__device__ __forceinline__ bool mbar_test(uint32_t bar, uint32_t parity) {
+    uint32_t done;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t"
+        "}\n" : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+    return done != 0;
+}
+
 /* shared-memory loads through a 32-bit shared address kept in a register (the generic->shared conversion of a
  * __shared__ object is otherwise re-materialised at every use in the epilogue's hot loop) */
 __device__ __forceinline__ uint32_t lds_u32(uint32_t addr) {
@@ -194,29 +207,38 @@ __device__ __forceinline__ int4 lds_v4(uint32_t addr) {
 
 /* ---- requantisation ------------------------------------------------------------
  * reference src/mars/mxu_conv.c:663-666: r = (int32)(sc + (sc >= 0 ? 0.5f : -0.5f)), sc = (float)acc * cs, clamped to
- * int8, with the x86 cvttss2si rule (NaN and |v| >= 2^31 become INT_MIN, hence -128).  Both variants return the index
- * sign << 8 | min(|r|, 128) into the per-op word table, which holds the clamped int8 and its fused followers.
+ * int8, with the x86 cvttss2si rule (NaN and |v| >= 2^31 become INT_MIN, hence -128).  Both variants return the clamped
+ * value r in [-128, 127]; the fused followers (sigmoid, SiLU product, byte-ReLU) are one lookup r -> word afterwards.
  *
- * FAST (chosen per layer on the host when max|acc| < 2^22 and |cs| < 512, so |sc| < 2^31 and nothing overflows):
- * no int<->float conversion instructions (they issue at a quarter of the FP32 rate):
- *   (float)acc = as_float(acc + 0x4B400000) - 1.5*2^23          exact for |acc| < 2^22
- *   |r| = floor(|sc| + 0.5f) = low bits of RZ(min(|sc| + 0.5f, 128) + 2^23)   (|sc| + 0.5f rounds exactly like sc +- 0.5f)
- * `t` arrives with the magic constant already folded into the bias. */
+ * FAST (chosen per layer on the host when max|acc| < 2^22 and |cs| < 512, so |sc| < 2^31 and nothing overflows): the
+ * int -> float conversion is an integer add of 0x4B400000 (folded into the bias word) and one float subtract,
+ *   (float)acc = as_float(acc + 0x4B400000) - 1.5 * 2^23          exact for |acc| < 2^22,
+ * done for two channels at a time with the packed FADD2 / FMUL2 of sm_100 (same IEEE rounding per half).  The final
+ * truncation + clamp is one F2I.S8.TRUNC (float -> int conversions saturate in PTX).  Measured (tools/epi_bench.cu,
+ * profiles/r02a_epi_bench.txt): 9.3 cycles per warp-element per scheduler against 11.9 for the round-1 sequence, which
+ * avoided the conversion with five integer-pipe instructions; the integer pipe (16 lanes per scheduler) is what limits
+ * the epilogue.  The +-0.5 add stays a scalar FADD: ptxas contracts mul.rn.f32x2 + add.rn.f32x2 into FFMA2 (one
+ * rounding), which is not the reference's arithmetic. */
 template <bool FAST>
-__device__ __forceinline__ uint32_t requant_index(int32_t t, float cs) {
+__device__ __forceinline__ void requant_pair(int32_t t0, int32_t t1, float cs, int &r0, int &r1) {
+    float s0, s1;
     if (FAST) {
-        const float f = __fsub_rn(__int_as_float(t), 12582912.0f);
-        const float sc = __fmul_rn(f, cs);
-        const float m = fminf(__fadd_rn(fabsf(sc), 0.5f), 128.0f);
-        const float u = __fadd_rz(m, 8388608.0f);
-        return (__float_as_uint(u) - 0x4B000000u) | ((__float_as_uint(sc) >> 23) & 0x100u);
+        unsigned long long a, b, c2;
+        asm("mov.b64 %0, {%1, %2};" : "=l"(a) : "r"(t0), "r"(t1));
+        asm("add.rn.f32x2 %0, %1, %2;" : "=l"(b) : "l"(a), "l"(0xCB400000CB400000ull)); /* - 12582912.0f, twice */
+        asm("mov.b64 %0, {%1, %1};" : "=l"(c2) : "f"(cs));
+        asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(a) : "l"(b), "l"(c2));
+        asm("mov.b64 {%0, %1}, %2;" : "=f"(s0), "=f"(s1) : "l"(a));
     } else {
-        const float scaled = __fmul_rn(__int2float_rn(t), cs);
-        const float biased = __fadd_rn(scaled, copysignf(0.5f, scaled)); /* scaled == +-0: both signs truncate to 0 */
-        int r;
-        asm("cvt.rzi.sat.s8.f32 %0, %1;" : "=r"(r) : "f"(biased)); /* truncate + clamp to [-128,127]; NaN -> 0 */
-        if (!(biased < 2147483648.0f)) r = -128;                    /* x86: +overflow and NaN -> INT_MIN -> -128 */
-        return r >= 0 ? (uint32_t)r : (0x100u | (uint32_t)(-r));
+        s0 = __fmul_rn(__int2float_rn(t0), cs);
+        s1 = __fmul_rn(__int2float_rn(t1), cs);
+    }
+    const float h0 = __fadd_rn(s0, copysignf(0.5f, s0)), h1 = __fadd_rn(s1, copysignf(0.5f, s1)); /* +-0: both signs truncate to 0 */
+    asm("cvt.rzi.s8.f32 %0, %1;" : "=r"(r0) : "f"(h0)); /* truncate + clamp to [-128, 127]; NaN -> 0 */
+    asm("cvt.rzi.s8.f32 %0, %1;" : "=r"(r1) : "f"(h1));
+    if (!FAST) { /* x86: +overflow and NaN -> INT_MIN -> -128 */
+        if (!(h0 < 2147483648.0f)) r0 = -128;
+        if (!(h1 < 2147483648.0f)) r1 = -128;
     }
 }
 
@@ -234,41 +256,58 @@ struct TileIter {
 };
 
 /* ---- epilogue of one unit: 16 accumulator columns (output channels) of this thread's pixel -----------------
- * NST = number of NCHW output streams stored (table bytes 0..NST-1), NHWC = also pack table byte 3 of every 16
- * channels into one 16-byte store of the consumer's channel-innermost copy.  o0..o2 point at channel c0 of
- * this pixel; nch = how many of the 16 channels exist (16 = all, <= 0 = none / pixel outside the image). */
-template <bool FAST, int NST, bool NHWC, int W>
-__device__ __forceinline__ void epilogue_unit(const uint32_t (&v)[W], uint32_t cm, uint32_t lutw, float cs,
+ * TAB = the op has fused followers: r indexes this lane's copy of the 256-entry word table (byte k = value of output
+ * stream k, byte 3 = the side-output stream); the table is replicated per lane ([256][32] words), so the data-dependent
+ * lookups of a warp never meet in a bank (the shared 512-entry table of round 1 cost ~3 wavefronts per lookup).
+ * NST = number of NCHW output streams stored (table bytes 0..NST-1), NHWC = also pack the side byte of every 16 channels
+ * into one 16-byte store of the consumer's channel-innermost copy.  o0..o2 point at channel c0 of this pixel; nch = how
+ * many of the 16 channels exist (16 = all, <= 0 = none / pixel outside the image). */
+template <bool FAST, bool TAB, int NST, bool NHWC>
+__device__ __forceinline__ void epilogue_unit(const uint32_t (&v)[16], uint32_t cm, uint32_t tab_lane, float cs,
                                               uint8_t *o0, uint8_t *o1, uint8_t *o2, long long plane, int nch, uint8_t *nh) {
-    if (nch <= 0) return; /* cm, lutw: shared addresses of the unit's bias words and of the word table */
-    if (nch >= W) {
+    if (nch <= 0) return; /* cm: shared address of the unit's bias words; tab_lane: shared address of entry r = 0 of this lane's table */
+    if (nch >= 16) {
+        uint32_t pk[4];
 #pragma unroll
-        for (int j16 = 0; j16 < W / 16; j16++) {
-            uint32_t pk[4] = {0u, 0u, 0u, 0u};
+        for (int j4 = 0; j4 < 4; j4++) {
+            const int4 c4 = lds_v4(cm + (uint32_t)j4 * 16u);
+            const int cc[4] = {c4.x, c4.y, c4.z, c4.w};
+            uint32_t w[4];
 #pragma unroll
-            for (int j4 = 0; j4 < 4; j4++) {
-                const int4 c4 = lds_v4(cm + (uint32_t)(j16 * 4 + j4) * 16u);
-                const int cc[4] = {c4.x, c4.y, c4.z, c4.w};
-#pragma unroll
-                for (int k = 0; k < 4; k++) {
-                    const uint32_t w = lds_u32(lutw + 4u * requant_index<FAST>((int32_t)(v[j16 * 16 + j4 * 4 + k] + (uint32_t)cc[k]), cs));
-                    if (NST > 0) { *o0 = (uint8_t)w; o0 += plane; }
-                    if (NST > 1) { *o1 = (uint8_t)(w >> 8); o1 += plane; }
-                    if (NST > 2) { *o2 = (uint8_t)(w >> 16); o2 += plane; }
-                    /* the side-output stream sits in the top byte of the table word: one byte permute per channel */
-                    if (NHWC) pk[j4] = __byte_perm(pk[j4], w, k == 0 ? 0x3217 : (k == 1 ? 0x3270 : (k == 2 ? 0x3710 : 0x7210)));
-                }
+            for (int k = 0; k < 4; k += 2) {
+                int r0, r1;
+                requant_pair<FAST>((int32_t)(v[j4 * 4 + k] + (uint32_t)cc[k]), (int32_t)(v[j4 * 4 + k + 1] + (uint32_t)cc[k + 1]), cs, r0, r1);
+                w[k] = TAB ? lds_u32(tab_lane + (uint32_t)(r0 * 128)) : (uint32_t)r0;
+                w[k + 1] = TAB ? lds_u32(tab_lane + (uint32_t)(r1 * 128)) : (uint32_t)r1;
             }
-            if (NHWC) *reinterpret_cast<uint4 *>(nh + j16 * 16) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                if (NST > 0) { *o0 = (uint8_t)w[k]; o0 += plane; }
+                if (NST > 1) { *o1 = (uint8_t)(w[k] >> 8); o1 += plane; }
+                if (NST > 2) { *o2 = (uint8_t)(w[k] >> 16); o2 += plane; }
+            }
+            if (NHWC) { /* the side-output stream sits in the top byte of the table word (plain conv: the value itself) */
+                const uint32_t sel = TAB ? 0x0073u : 0x0040u;
+                pk[j4] = __byte_perm(__byte_perm(w[0], w[1], sel), __byte_perm(w[2], w[3], sel), 0x5410);
+            }
         }
+        if (NHWC) *reinterpret_cast<uint4 *>(nh) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
     } else { /* ragged last unit (e.g. 255 head channels); a side-output consumer always has Ci = Co, a multiple of 32 */
 #pragma unroll
-        for (int j = 0; j < W; j++) {
+        for (int j = 0; j < 16; j += 2) {
             if (j < nch) {
-                const uint32_t w = lds_u32(lutw + 4u * requant_index<FAST>((int32_t)(v[j] + lds_u32(cm + 4u * j)), cs));
-                if (NST > 0) o0[(long long)j * plane] = (uint8_t)w;
-                if (NST > 1) o1[(long long)j * plane] = (uint8_t)(w >> 8);
-                if (NST > 2) o2[(long long)j * plane] = (uint8_t)(w >> 16);
+                int r0, r1;
+                requant_pair<FAST>((int32_t)(v[j] + lds_u32(cm + 4u * j)), (int32_t)(v[j + 1] + lds_u32(cm + 4u * j + 4u)), cs, r0, r1);
+                const uint32_t w0 = TAB ? lds_u32(tab_lane + (uint32_t)(r0 * 128)) : (uint32_t)r0;
+                const uint32_t w1 = TAB ? lds_u32(tab_lane + (uint32_t)(r1 * 128)) : (uint32_t)r1;
+                if (NST > 0) o0[(long long)j * plane] = (uint8_t)w0;
+                if (NST > 1) o1[(long long)j * plane] = (uint8_t)(w0 >> 8);
+                if (NST > 2) o2[(long long)j * plane] = (uint8_t)(w0 >> 16);
+                if (j + 1 < nch) {
+                    if (NST > 0) o0[(long long)(j + 1) * plane] = (uint8_t)w1;
+                    if (NST > 1) o1[(long long)(j + 1) * plane] = (uint8_t)(w1 >> 8);
+                    if (NST > 2) o2[(long long)(j + 1) * plane] = (uint8_t)(w1 >> 16);
+                }
             }
         }
     }
@@ -282,14 +321,13 @@ __device__ __forceinline__ void epilogue_unit(const uint32_t (&v)[W], uint32_t c
  * GATHER (small Ci, e.g. the 6x6 stride-2 stem): M tiles are tw x th output pixels; four producer warps stage the
  * input patch of the tile in shared memory (next tile's patch is in flight in registers meanwhile) and build the
  * 128-byte K rows of the A operand from it, in the 128B-swizzled K-major layout TMA would have produced. */
-template <bool FAST, bool GATHER, int NST, bool NHWC, int EPI>
+template <bool FAST, bool GATHER, bool TAB, int NST, bool NHWC, int EPI>
 __global__ void __launch_bounds__((EPI + (GATHER ? 5 : 2)) * 32, EPI == 8 ? 2 : 1)
 k_conv_tc(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, const TcParams p) {
     extern __shared__ uint8_t smem_raw[];
     __shared__ __align__(8) uint64_t bar_full[8], bar_empty[8], bar_tmem_full[8], bar_tmem_empty[8], bar_b;
     __shared__ uint32_t tmem_base_slot;
     __shared__ __align__(16) int32_t s_cm[TC_MAX_CO];   /* bias (+ the int->float magic when FAST) */
-    __shared__ __align__(16) uint32_t s_lutw[512];
     __shared__ __align__(16) int s_koff[GATHER ? 128 : 4]; /* gather: patch-relative byte offset of tap k */
     __shared__ int s_shift[TC_MAX_TAPS];
 
@@ -318,7 +356,10 @@ k_conv_tc(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUte
     }
     for (int i = threadIdx.x; i < TC_MAX_CO; i += blockDim.x)
         s_cm[i] = (int32_t)((uint32_t)((p.bias && i < p.Co) ? p.bias[i] : 0) + (FAST ? 0x4B400000u : 0u));
-    for (int i = threadIdx.x; i < 512; i += blockDim.x) s_lutw[i] = p.lutw[i];
+    if (TAB) { /* [256][32] words: every lane reads its own copy (bank = lane), so the data-dependent lookups never conflict */
+        uint32_t *tab = reinterpret_cast<uint32_t *>(smem_al + p.tab_off);
+        for (int i = threadIdx.x; i < 256 * 32; i += blockDim.x) tab[i] = __ldg(p.lutw + (i >> 5));
+    }
     /* per tap: flat pixel shift (TMA coordinate); halo mode: start of the tap's rows inside the stage, in 16-byte units */
     if (threadIdx.x < TC_MAX_TAPS) s_shift[threadIdx.x] = p.halo ? ((p.a_shift[threadIdx.x] - p.halo_min) * p.a_row_bytes) >> 4 : p.a_shift[threadIdx.x];
     if (GATHER) {
@@ -342,22 +383,27 @@ k_conv_tc(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUte
     if (p.dbg == 6) goto teardown; /* tuning aid: prologue + teardown only */
 
     if (warp < EPI) {
-        /* ===== epilogue: TMEM -> registers -> requant index -> word table -> stores =====
-         * A warp's work items are (tile, 16-column unit) pairs; the TMEM load of item k+1 is issued before item k
-         * is processed, so the load latency (and, at a tile boundary, the wait for the next accumulator) hides
-         * behind the arithmetic and the stores of the current item. */
+        /* ===== epilogue: TMEM -> registers -> requantised byte -> (word table) -> stores =====
+         * Work items of an accumulator group are (M tile g, 16-column unit u) pairs, g-major; the EPI / 4 warps of a TMEM
+         * lane quadrant take contiguous blocks of them, so the per-M-tile values (pixel coordinates, output pointers) are
+         * recomputed as rarely as possible.  The TMEM load of item k+1 is issued before item k is processed, so the load
+         * latency (and, at a group boundary, the wait for the next accumulator when it is already there) hides behind
+         * the arithmetic and the stores of the current item. */
         const int quad = warp & 3, part = warp >> 2, parts = EPI >> 2;
         const int r = quad * 32 + lane; /* accumulator row = pixel of the tile */
         const int n_units = p.n_tile >> 4;
         const long long plane = p.plane;
         const float cs = p.cs;
         const uint32_t acc_lane = tmem_d + ((uint32_t)(quad * 32) << 16);
-        const uint32_t sa_lut = smem_u32(s_lutw), sa_cm = smem_u32(s_cm);
+        const uint32_t sa_cm = smem_u32(s_cm);
+        const uint32_t tab_lane = smem_base + p.tab_off + 128u * 128u + 4u * (uint32_t)lane; /* entry r = 0 of this lane's copy */
         const uint32_t sa_full = smem_u32(&bar_tmem_full[0]), sa_empty = smem_u32(&bar_tmem_empty[0]);
         const bool flat = !GATHER && p.Wp == p.Wo && !NHWC; /* no pad columns: the tile row index IS the pixel index */
         uint8_t *const obase = p.out_base + r; /* + image * slot_stride + pixel + channel * plane + stream offset */
         const int G = p.grp, gcols = p.grp * p.n_tile;
-        if (part >= n_units || p.dbg == 7 || p.dbg == 9) { /* narrow N tile: nothing to read for this warp, it only releases the accumulators */
+        const int total_items = G * n_units, ipp = (total_items + parts - 1) / parts;
+        const int i_lo = part * ipp, i_hi = min(total_items, i_lo + ipp);
+        if (i_lo >= i_hi || p.dbg == 7 || p.dbg == 9) { /* narrow group: nothing to read for this warp, it only releases the accumulators */
             int ab = 0, aph = 0; /* accumulator ring position and phase */
             for (TileIter ti(blockIdx.x, gridDim.x, tiles_per_img); ti.img < p.n_img; ti.next()) {
                 mbar_wait_relaxed(sa_full + 8u * ab, aph);
@@ -366,46 +412,47 @@ k_conv_tc(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUte
                 if (++ab == p.acc_bufs) { ab = 0; aph ^= 1; }
             }
         } else {
-            /* current item: group ti (ring slot ab / phase aph), M tile g of the group, unit u */
+            const int g_first = i_lo / n_units, u_first = i_lo - g_first * n_units;
+            /* current item: group ti (ring slot ab / phase aph), item index idx = g * n_units + u */
             TileIter ti(blockIdx.x, gridDim.x, tiles_per_img);
-            int tl = 0, g = 0, u = part, ab = 0, aph = 0;
+            int idx = i_lo, g = g_first, u = u_first, ab = 0, aph = 0;
             /* per-M-tile values of the current item, recomputed when the M tile changes */
-            int cached_key = -1, n0 = 0, co_left = 0;
+            int cached_g = -1, n0 = 0, co_left = 0;
             uint8_t *b0 = nullptr, *b1 = nullptr, *b2 = nullptr, *nh = nullptr;
             uint32_t va[16], vb[16];
             bool have = ti.img < p.n_img;
             if (have) {
                 mbar_wait_relaxed(sa_full, 0);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                tmem_ld16_issue(acc_lane + (uint32_t)(u * 16), va);
+                tmem_ld16_issue(acc_lane + (uint32_t)(g * p.n_tile + u * 16), va);
             }
             auto step = [&](uint32_t (&vc)[16], uint32_t (&vn)[16]) {
                 /* the next item of this warp */
+                const bool last_of_group = idx + 1 == i_hi;
                 TileIter nti = ti;
-                int ntl = tl, ng = g, nu = u + parts, nab = ab, naph = aph;
-                if (nu >= n_units) {
-                    nu = part;
-                    if (++ng == G) {
-                        ng = 0; ntl++; nti.next();
-                        if (++nab == p.acc_bufs) { nab = 0; naph ^= 1; }
-                    }
-                }
+                int nidx = idx + 1, ng = g, nu = u + 1, nab = ab, naph = aph;
+                if (last_of_group) {
+                    nidx = i_lo; ng = g_first; nu = u_first; nti.next();
+                    if (++nab == p.acc_bufs) { nab = 0; naph ^= 1; }
+                } else if (nu == n_units) { nu = 0; ng++; }
                 const bool have_n = nti.img < p.n_img;
                 tmem_ld_wait(vc);
-                if (ntl != tl || !have_n) { /* last read of this accumulator group by this warp: hand it back */
+                bool issued = false;
+                if (last_of_group) { /* last read of this accumulator group by this warp: hand it back */
                     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
                     __syncwarp();
                     if (lane == 0) mbar_arrive(sa_empty + 8u * ab);
-                }
-                if (have_n) {
-                    if (ntl != tl) {
-                        mbar_wait_relaxed(sa_full + 8u * nab, naph);
+                    if (have_n && mbar_test(sa_full + 8u * nab, naph)) { /* next accumulator already there: start its first load now */
                         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                        tmem_ld16_issue(acc_lane + (uint32_t)(nab * gcols + ng * p.n_tile + nu * 16), vn);
+                        issued = true;
                     }
-                    tmem_ld16_issue(acc_lane + (uint32_t)(nab * gcols + ng * p.n_tile + nu * 16), vn);
+                } else {
+                    tmem_ld16_issue(acc_lane + (uint32_t)(ab * gcols + ng * p.n_tile + nu * 16), vn);
+                    issued = true;
                 }
-                if (cached_key != tl * 8 + g) {
-                    cached_key = tl * 8 + g;
+                if (cached_g != g) {
+                    cached_g = g;
                     const int mg = p.n_tiles == 1 ? ti.rem : ti.rem / p.n_tiles;
                     n0 = (ti.rem - mg * p.n_tiles) * p.n_tile;
                     const int mt = mg * G + g;
@@ -442,8 +489,14 @@ k_conv_tc(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUte
                 const int c0 = u * 16;
                 const long long coff = (long long)c0 * plane;
                 if (p.dbg >= 2) { if (vc[0] == 0x12345678u && vc[7] == 0x9abcdef0u) b0[0] = 1; }
-                else epilogue_unit<FAST, NST, NHWC, 16>(vc, sa_cm + 4u * (uint32_t)(n0 + c0), sa_lut, cs, b0 + coff, b1 + coff, b2 + coff, plane, co_left - c0, nh + c0);
-                ti = nti; tl = ntl; g = ng; u = nu; ab = nab; aph = naph; have = have_n;
+                else epilogue_unit<FAST, TAB, NST, NHWC>(vc, sa_cm + 4u * (uint32_t)(n0 + c0), tab_lane, cs, b0 + coff, b1 + coff, b2 + coff, plane, co_left - c0, nh + c0);
+                if (last_of_group) cached_g = -1; /* the next group is another tile */
+                if (have_n && !issued) { /* the next accumulator was not ready when this item started */
+                    mbar_wait_relaxed(sa_full + 8u * nab, naph);
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    tmem_ld16_issue(acc_lane + (uint32_t)(nab * gcols + ng * p.n_tile + nu * 16), vn);
+                }
+                ti = nti; idx = nidx; g = ng; u = nu; ab = nab; aph = naph; have = have_n;
             };
             while (have) {
                 step(va, vb);
@@ -774,7 +827,7 @@ struct TcPlanImpl {
     bool has_linked = false;
     TcParams p;
     int prepass = 0;
-    bool fast = false;
+    bool fast = false, tab = false; /* tab: the epilogue looks its byte up in the per-lane word table */
     int C = 0, Cp = 0, H = 0, W = 0, pt = 0, pl = 0, plane = 0, npix = 0; /* Cp: bytes per pixel of the channel-innermost copy */
     const uint8_t *src_slot0 = nullptr; /* input tensor in slot 0 */
     uint8_t *scratch = nullptr;
@@ -936,15 +989,14 @@ int tc_n_tiles(int oc) {
 bool tc_uses_copy(const Op &o) { return tc_geometry(o).prepass != 0; }
 bool tc_linkable(const Op &o) { const TcGeom g = tc_geometry(o); return g.ok && (g.prepass == 1 || g.prepass == 2) && !g.kpad; }
 
-/* the word table of the epilogue: index = sign << 8 | magnitude (0..128); byte k = value of output stream k.
- * Stream order: a fused conv stores [Z, S, Y] (Z = SiLU product, the stream almost every consumer reads, sits in the
- * low byte), a plain conv stores [Y]. */
+/* the word table of the epilogue: index = r + 128 (r = the clamped conv output); byte k = value of output stream k, byte 3 =
+ * the side-output stream.  Stream order: a fused conv stores [Z, S, Y] (Z = SiLU product, the stream almost every consumer
+ * reads, sits in the low byte), a plain conv stores [Y]. */
 static void build_lutw(const Op &o, const uint8_t *h_cpool, const int stream_byte[3], int nhwc_stream, uint32_t *t) {
     const int8_t *ls = o.lut_s >= 0 ? reinterpret_cast<const int8_t *>(h_cpool + o.lut_s) : nullptr;
     const int8_t *lz = o.lut_z >= 0 ? reinterpret_cast<const int8_t *>(h_cpool + o.lut_z) : nullptr;
-    for (int idx = 0; idx < 512; idx++) {
-        const int mag = idx & 0xFF;
-        int y = (idx & 0x100) ? -std::min(mag, 128) : std::min(mag, 127);
+    for (int idx = 0; idx < 256; idx++) {
+        int y = idx - 128;
         if (o.post_relu && y < 0) y = 0;
         /* stream values: fused conv = {Z, S, Y}, plain conv = {Y} */
         uint8_t val[3] = {(uint8_t)y, 0, 0};
@@ -957,7 +1009,7 @@ static void build_lutw(const Op &o, const uint8_t *h_cpool, const int stream_byt
     }
 }
 
-/* may the layer use the conversion-free requantisation?  max |acc| over all output channels, from the real weights */
+/* may the layer use the magic-number int -> float conversion (FAST)?  max |acc| over all output channels, from the real weights */
 static bool fast_requant_ok(const Op &o, const ArenaGeom &ag) {
     if (!(fabsf(o.f0) < 512.0f)) return false; /* also rejects NaN */
     const int8_t *w = reinterpret_cast<const int8_t *>(ag.h_weights + o.w);
@@ -972,25 +1024,34 @@ static bool fast_requant_ok(const Op &o, const ArenaGeom &ag) {
     return true;
 }
 
-/* kernel variants: FAST requant x GATHER producer x number of stored NCHW streams x NHWC side output */
+/* kernel variants: FAST requant x GATHER producer x word table x number of stored NCHW streams x NHWC side output.
+ * Without a table (plain conv, no byte-ReLU) there is one stream at most. */
 template <bool FAST, bool GATHER, int EPI>
-static TcKernel pick_kernel2(int nst, bool nhwc) {
+static TcKernel pick_kernel2(bool tab, int nst, bool nhwc) {
+    if (!tab) {
+        switch (nst * 2 + (nhwc ? 1 : 0)) {
+            case 0: return k_conv_tc<FAST, GATHER, false, 0, false, EPI>;
+            case 1: return k_conv_tc<FAST, GATHER, false, 0, true, EPI>;
+            case 2: return k_conv_tc<FAST, GATHER, false, 1, false, EPI>;
+            default: return k_conv_tc<FAST, GATHER, false, 1, true, EPI>;
+        }
+    }
     switch (nst * 2 + (nhwc ? 1 : 0)) {
-        case 0: return k_conv_tc<FAST, GATHER, 0, false, EPI>;
-        case 1: return k_conv_tc<FAST, GATHER, 0, true, EPI>;
-        case 2: return k_conv_tc<FAST, GATHER, 1, false, EPI>;
-        case 3: return k_conv_tc<FAST, GATHER, 1, true, EPI>;
-        case 4: return k_conv_tc<FAST, GATHER, 2, false, EPI>;
-        case 5: return k_conv_tc<FAST, GATHER, 2, true, EPI>;
-        case 6: return k_conv_tc<FAST, GATHER, 3, false, EPI>;
-        default: return k_conv_tc<FAST, GATHER, 3, true, EPI>;
+        case 0: return k_conv_tc<FAST, GATHER, true, 0, false, EPI>;
+        case 1: return k_conv_tc<FAST, GATHER, true, 0, true, EPI>;
+        case 2: return k_conv_tc<FAST, GATHER, true, 1, false, EPI>;
+        case 3: return k_conv_tc<FAST, GATHER, true, 1, true, EPI>;
+        case 4: return k_conv_tc<FAST, GATHER, true, 2, false, EPI>;
+        case 5: return k_conv_tc<FAST, GATHER, true, 2, true, EPI>;
+        case 6: return k_conv_tc<FAST, GATHER, true, 3, false, EPI>;
+        default: return k_conv_tc<FAST, GATHER, true, 3, true, EPI>;
     }
 }
 /* gather mode always runs two CTAs per SM (N tile <= 256 columns of TMEM in total), i.e. 8 epilogue warps */
-static TcKernel pick_kernel(bool fast, bool gather, int nst, bool nhwc, int epi) {
-    if (gather) return fast ? pick_kernel2<true, true, 8>(nst, nhwc) : pick_kernel2<false, true, 8>(nst, nhwc);
-    if (epi == 16) return fast ? pick_kernel2<true, false, 16>(nst, nhwc) : pick_kernel2<false, false, 16>(nst, nhwc);
-    return fast ? pick_kernel2<true, false, 8>(nst, nhwc) : pick_kernel2<false, false, 8>(nst, nhwc);
+static TcKernel pick_kernel(bool fast, bool gather, bool tab, int nst, bool nhwc, int epi) {
+    if (gather) return fast ? pick_kernel2<true, true, 8>(tab, nst, nhwc) : pick_kernel2<false, true, 8>(tab, nst, nhwc);
+    if (epi == 16) return fast ? pick_kernel2<true, false, 16>(tab, nst, nhwc) : pick_kernel2<false, false, 16>(tab, nst, nhwc);
+    return fast ? pick_kernel2<true, false, 8>(tab, nst, nhwc) : pick_kernel2<false, false, 8>(tab, nst, nhwc);
 }
 
 bool tc_plan(const Op &o, const ArenaGeom &ag, uint8_t *scratch, size_t scratch_stride, uint8_t *linked, size_t linked_stride,
@@ -1029,7 +1090,11 @@ bool tc_plan(const Op &o, const ArenaGeom &ag, uint8_t *scratch, size_t scratch_
     p.acc_bufs = std::max(2, std::min(4, p.tmem_cols / (p.grp * p.n_tile)));
     p.a_stage_bytes = p.grp * p.a_tile_bytes;
     p.tx_bytes = p.a_stage_bytes + (uint32_t)(p.n_tile * p.bk);
-    const int budget = t->ctas_per_sm == 1 ? 200 * 1024 : 100 * 1024;
+    /* the op needs the word table when it has fused followers or a byte-ReLU (plain conv: the byte is r itself) */
+    t->tab = o.fused_layers > 0 || o.post_relu;
+    const int tab_bytes = t->tab ? 256 * 32 * 4 : 0;
+    /* dynamic shared memory of a CTA: stages + weights + table (+ 1 KiB alignment slack); 227 KiB per SM, ~7 KiB static */
+    const int budget = (t->ctas_per_sm == 1 ? 200 * 1024 : 104 * 1024) - tab_bytes;
     const int nsteps = g.ntaps * p.ksteps_per_tap;
     if (gather) { /* + 3 x 4 KiB patch ring + 8 KiB patch-word tables */
         if (p.grp > 2) { p.grp = 2; p.a_stage_bytes = p.grp * p.a_tile_bytes; p.acc_bufs = std::max(2, std::min(4, p.tmem_cols / (p.grp * p.n_tile))); }
@@ -1066,6 +1131,10 @@ bool tc_plan(const Op &o, const ArenaGeom &ag, uint8_t *scratch, size_t scratch_
             p.stages = std::max(2, std::min(8, budget / stage_bytes));
             t->smem = 1024 + (size_t)p.stages * stage_bytes;
         }
+    }
+    if (t->tab) { /* the per-lane table copies sit behind everything else */
+        p.tab_off = (uint32_t)round_up((int)(t->smem - 1024), 128);
+        t->smem = 1024 + (size_t)p.tab_off + (size_t)tab_bytes;
     }
     /* keep residency at ctas_per_sm: a further CTA would fit the registers but stall in tcgen05.alloc */
     t->smem = std::max<size_t>(t->smem, t->ctas_per_sm == 1 ? 120 * 1024 : 80 * 1024);
@@ -1145,7 +1214,7 @@ bool tc_plan(const Op &o, const ArenaGeom &ag, uint8_t *scratch, size_t scratch_
 
     /* weights: [tap][co_pad][Ci] K-major, and the epilogue table */
     const size_t wr_bytes = (size_t)g.ntaps * co_pad * ci_eff;
-    uint32_t lutw[512];
+    uint32_t lutw[256];
     build_lutw(o, ag.h_cpool, t->stream_byte, t->nhwc_stream, lutw);
     if (cudaMalloc(&t->d_wr, wr_bytes) != cudaSuccess || cudaMalloc(&t->d_lutw, sizeof lutw) != cudaSuccess) {
         cudaFree(t->d_wr); delete t; return false;
@@ -1179,7 +1248,7 @@ bool tc_plan(const Op &o, const ArenaGeom &ag, uint8_t *scratch, size_t scratch_
     ok = ok && make_map3(&t->mapB, t->d_wr, (uint64_t)ci_eff, (uint64_t)co_pad, (uint64_t)g.ntaps, (uint64_t)ci_eff,
                          (uint64_t)co_pad * ci_eff, (uint32_t)p.bk, (uint32_t)p.n_tile, ksw);
     t->epi = (!gather && t->ctas_per_sm == 1) ? 16 : 8;
-    t->kernel = pick_kernel(t->fast, gather, t->nst, p.nhwc_sel >= 0, t->epi);
+    t->kernel = pick_kernel(t->fast, gather, t->tab, t->nst, p.nhwc_sel >= 0, t->epi);
     ok = ok && cudaFuncSetAttribute((const void *)t->kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 210 * 1024) == cudaSuccess;
     if (!ok) { cudaFree(t->d_wr); cudaFree(t->d_lutw); delete t; return false; }
     plan->impl = t;
