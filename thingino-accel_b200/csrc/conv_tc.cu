@@ -57,7 +57,7 @@ struct TcParams {
     const int32_t *bias;     /* device pointer or null */
     float cs;
     const uint32_t *lutw;    /* 256-entry word table: index = r + 128, byte k = value of output stream k, byte 3 = side-output stream */
-    uint32_t tab_off;        /* offset of the per-lane replicated copy ([256][32] words) in dynamic shared memory */
+    uint32_t tab_off, tab_rep; /* offset of the replicated table ([256][tab_rep] words) in dynamic shared memory; copies (8, 16 or 32) */
     uint8_t *out_base;       /* slot 0 of the launch */
     unsigned long long slot_stride;
     long long out_off[3];    /* slot-relative byte offset of output stream k (NCHW), -1 = not stored */
@@ -219,10 +219,18 @@ __device__ __forceinline__ int4 lds_v4(uint32_t addr) {
  * avoided the conversion with five integer-pipe instructions; the integer pipe (16 lanes per scheduler) is what limits
  * the epilogue.  The +-0.5 add stays a scalar FADD: ptxas contracts mul.rn.f32x2 + add.rn.f32x2 into FFMA2 (one
  * rounding), which is not the reference's arithmetic. */
-template <bool FAST>
+/* RQ = 0: general (I2F, x86 overflow rule); 1: FAST, sign-exact, F2I; 2: FAST, round-half-up without conversion instructions.
+ *
+ * RQ 2 (the common case).  ncu on the F2I variant showed the XU pipe (conversions, 16 lanes per SM) 87 % busy: one F2I per
+ * output element is what limited the epilogue.  floor(fl(sc + 0.5f)) needs none: a round-down add of 1.5 * 2^23 leaves
+ * floor(h) in the low mantissa bits, and one VIADDMNMX.RELU (DPX) subtracts the exponent pattern and clamps to [0, 255]
+ * = r + 128.  Round-half-up differs from the reference's round-half-away only when sc is a NEGATIVE exact tie -(n + 0.5)
+ * (or -pred(0.5), where fl(sc - 0.5f) rounds to -1): the host enumerates those few floats per layer and selects RQ 2 only
+ * when no accumulator value in the layer's range maps onto one of them (halfup_requant_ok). */
+template <int RQ>
 __device__ __forceinline__ void requant_pair(int32_t t0, int32_t t1, float cs, int &r0, int &r1) {
     float s0, s1;
-    if (FAST) {
+    if (RQ != 0) {
         unsigned long long a, b, c2;
         asm("mov.b64 %0, {%1, %2};" : "=l"(a) : "r"(t0), "r"(t1));
         asm("add.rn.f32x2 %0, %1, %2;" : "=l"(b) : "l"(a), "l"(0xCB400000CB400000ull)); /* - 12582912.0f, twice */
@@ -233,10 +241,16 @@ __device__ __forceinline__ void requant_pair(int32_t t0, int32_t t1, float cs, i
         s0 = __fmul_rn(__int2float_rn(t0), cs);
         s1 = __fmul_rn(__int2float_rn(t1), cs);
     }
+    if (RQ == 2) { /* returns r + 128 in [0, 255] */
+        const int i0 = __float_as_int(__fadd_rd(__fadd_rn(s0, 0.5f), 12582912.0f)), i1 = __float_as_int(__fadd_rd(__fadd_rn(s1, 0.5f), 12582912.0f));
+        r0 = __viaddmin_s32_relu(i0, -(0x4B400000 - 128), 255);
+        r1 = __viaddmin_s32_relu(i1, -(0x4B400000 - 128), 255);
+        return;
+    }
     const float h0 = __fadd_rn(s0, copysignf(0.5f, s0)), h1 = __fadd_rn(s1, copysignf(0.5f, s1)); /* +-0: both signs truncate to 0 */
     asm("cvt.rzi.s8.f32 %0, %1;" : "=r"(r0) : "f"(h0)); /* truncate + clamp to [-128, 127]; NaN -> 0 */
     asm("cvt.rzi.s8.f32 %0, %1;" : "=r"(r1) : "f"(h1));
-    if (!FAST) { /* x86: +overflow and NaN -> INT_MIN -> -128 */
+    if (RQ == 0) { /* x86: +overflow and NaN -> INT_MIN -> -128 */
         if (!(h0 < 2147483648.0f)) r0 = -128;
         if (!(h1 < 2147483648.0f)) r1 = -128;
     }
@@ -262,8 +276,8 @@ struct TileIter {
  * NST = number of NCHW output streams stored (table bytes 0..NST-1), NHWC = also pack the side byte of every 16 channels
  * into one 16-byte store of the consumer's channel-innermost copy.  o0..o2 point at channel c0 of this pixel; nch = how
  * many of the 16 channels exist (16 = all, <= 0 = none / pixel outside the image). */
-template <bool FAST, bool TAB, int NST, bool NHWC>
-__device__ __forceinline__ void epilogue_unit(const uint32_t (&v)[16], uint32_t cm, uint32_t tab_lane, float cs,
+template <int RQ, bool TAB, int NST, bool NHWC>
+__device__ __forceinline__ void epilogue_unit(const uint32_t (&v)[16], uint32_t cm, uint32_t tab_lane, uint32_t tab_stride, float cs,
                                               uint8_t *o0, uint8_t *o1, uint8_t *o2, long long plane, int nch, uint8_t *nh) {
     if (nch <= 0) return; /* cm: shared address of the unit's bias words; tab_lane: shared address of entry r = 0 of this lane's table */
     if (nch >= 16) {
@@ -276,9 +290,9 @@ __device__ __forceinline__ void epilogue_unit(const uint32_t (&v)[16], uint32_t 
 #pragma unroll
             for (int k = 0; k < 4; k += 2) {
                 int r0, r1;
-                requant_pair<FAST>((int32_t)(v[j4 * 4 + k] + (uint32_t)cc[k]), (int32_t)(v[j4 * 4 + k + 1] + (uint32_t)cc[k + 1]), cs, r0, r1);
-                w[k] = TAB ? lds_u32(tab_lane + (uint32_t)(r0 * 128)) : (uint32_t)r0;
-                w[k + 1] = TAB ? lds_u32(tab_lane + (uint32_t)(r1 * 128)) : (uint32_t)r1;
+                requant_pair<RQ>((int32_t)(v[j4 * 4 + k] + (uint32_t)cc[k]), (int32_t)(v[j4 * 4 + k + 1] + (uint32_t)cc[k + 1]), cs, r0, r1);
+                w[k] = TAB ? lds_u32(tab_lane + (uint32_t)r0 * tab_stride) : (RQ == 2 ? (uint32_t)r0 ^ 0x80u : (uint32_t)r0);
+                w[k + 1] = TAB ? lds_u32(tab_lane + (uint32_t)r1 * tab_stride) : (RQ == 2 ? (uint32_t)r1 ^ 0x80u : (uint32_t)r1);
             }
 #pragma unroll
             for (int k = 0; k < 4; k++) {
@@ -297,9 +311,9 @@ __device__ __forceinline__ void epilogue_unit(const uint32_t (&v)[16], uint32_t 
         for (int j = 0; j < 16; j += 2) {
             if (j < nch) {
                 int r0, r1;
-                requant_pair<FAST>((int32_t)(v[j] + lds_u32(cm + 4u * j)), (int32_t)(v[j + 1] + lds_u32(cm + 4u * j + 4u)), cs, r0, r1);
-                const uint32_t w0 = TAB ? lds_u32(tab_lane + (uint32_t)(r0 * 128)) : (uint32_t)r0;
-                const uint32_t w1 = TAB ? lds_u32(tab_lane + (uint32_t)(r1 * 128)) : (uint32_t)r1;
+                requant_pair<RQ>((int32_t)(v[j] + lds_u32(cm + 4u * j)), (int32_t)(v[j + 1] + lds_u32(cm + 4u * j + 4u)), cs, r0, r1);
+                const uint32_t w0 = TAB ? lds_u32(tab_lane + (uint32_t)r0 * tab_stride) : (RQ == 2 ? (uint32_t)r0 ^ 0x80u : (uint32_t)r0);
+                const uint32_t w1 = TAB ? lds_u32(tab_lane + (uint32_t)r1 * tab_stride) : (RQ == 2 ? (uint32_t)r1 ^ 0x80u : (uint32_t)r1);
                 if (NST > 0) o0[(long long)j * plane] = (uint8_t)w0;
                 if (NST > 1) o1[(long long)j * plane] = (uint8_t)(w0 >> 8);
                 if (NST > 2) o2[(long long)j * plane] = (uint8_t)(w0 >> 16);
@@ -321,7 +335,7 @@ __device__ __forceinline__ void epilogue_unit(const uint32_t (&v)[16], uint32_t 
  * GATHER (small Ci, e.g. the 6x6 stride-2 stem): M tiles are tw x th output pixels; four producer warps stage the
  * input patch of the tile in shared memory (next tile's patch is in flight in registers meanwhile) and build the
  * 128-byte K rows of the A operand from it, in the 128B-swizzled K-major layout TMA would have produced. */
-template <bool FAST, bool GATHER, bool TAB, int NST, bool NHWC, int EPI>
+template <int RQ, bool GATHER, bool TAB, int NST, bool NHWC, int EPI>
 __global__ void __launch_bounds__((EPI + (GATHER ? 5 : 2)) * 32, EPI == 8 ? 2 : 1)
 k_conv_tc(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, const TcParams p) {
     extern __shared__ uint8_t smem_raw[];
@@ -355,10 +369,11 @@ k_conv_tc(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUte
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     for (int i = threadIdx.x; i < TC_MAX_CO; i += blockDim.x)
-        s_cm[i] = (int32_t)((uint32_t)((p.bias && i < p.Co) ? p.bias[i] : 0) + (FAST ? 0x4B400000u : 0u));
-    if (TAB) { /* [256][32] words: every lane reads its own copy (bank = lane), so the data-dependent lookups never conflict */
+        s_cm[i] = (int32_t)((uint32_t)((p.bias && i < p.Co) ? p.bias[i] : 0) + (RQ != 0 ? 0x4B400000u : 0u));
+    if (TAB) { /* [256][rep] words: lane l reads copy l % rep; with rep = 32 (bank = lane) the data-dependent lookups never conflict */
         uint32_t *tab = reinterpret_cast<uint32_t *>(smem_al + p.tab_off);
-        for (int i = threadIdx.x; i < 256 * 32; i += blockDim.x) tab[i] = __ldg(p.lutw + (i >> 5));
+        const int sh = p.tab_rep == 32 ? 5 : (p.tab_rep == 16 ? 4 : 3);
+        for (int i = threadIdx.x; i < (256 << sh); i += blockDim.x) tab[i] = __ldg(p.lutw + (i >> sh));
     }
     /* per tap: flat pixel shift (TMA coordinate); halo mode: start of the tap's rows inside the stage, in 16-byte units */
     if (threadIdx.x < TC_MAX_TAPS) s_shift[threadIdx.x] = p.halo ? ((p.a_shift[threadIdx.x] - p.halo_min) * p.a_row_bytes) >> 4 : p.a_shift[threadIdx.x];
@@ -396,7 +411,8 @@ k_conv_tc(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUte
         const float cs = p.cs;
         const uint32_t acc_lane = tmem_d + ((uint32_t)(quad * 32) << 16);
         const uint32_t sa_cm = smem_u32(s_cm);
-        const uint32_t tab_lane = smem_base + p.tab_off + 128u * 128u + 4u * (uint32_t)lane; /* entry r = 0 of this lane's copy */
+        const uint32_t tab_stride = 4u * p.tab_rep; /* bytes between consecutive table entries */
+        const uint32_t tab_lane = smem_base + p.tab_off + (RQ == 2 ? 0u : 128u * tab_stride) + 4u * ((uint32_t)lane & (p.tab_rep - 1u)); /* this lane's copy: entry r = 0 (RQ 2: entry r = -128, the requantisation returns r + 128) */
         const uint32_t sa_full = smem_u32(&bar_tmem_full[0]), sa_empty = smem_u32(&bar_tmem_empty[0]);
         const bool flat = !GATHER && p.Wp == p.Wo && !NHWC; /* no pad columns: the tile row index IS the pixel index */
         uint8_t *const obase = p.out_base + r; /* + image * slot_stride + pixel + channel * plane + stream offset */
@@ -412,49 +428,22 @@ k_conv_tc(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUte
                 if (++ab == p.acc_bufs) { ab = 0; aph ^= 1; }
             }
         } else {
+            /* this warp's block of items, as (M tile, unit range) runs: [g_first, u_first) ... [g_last, u_last] */
             const int g_first = i_lo / n_units, u_first = i_lo - g_first * n_units;
-            /* current item: group ti (ring slot ab / phase aph), item index idx = g * n_units + u */
-            TileIter ti(blockIdx.x, gridDim.x, tiles_per_img);
-            int idx = i_lo, g = g_first, u = u_first, ab = 0, aph = 0;
-            /* per-M-tile values of the current item, recomputed when the M tile changes */
-            int cached_g = -1, n0 = 0, co_left = 0;
-            uint8_t *b0 = nullptr, *b1 = nullptr, *b2 = nullptr, *nh = nullptr;
+            const int g_last = (i_hi - 1) / n_units, u_last_end = i_hi - g_last * n_units; /* units [0, u_last_end) of the last M tile */
+            int ab = 0, aph = 0;
             uint32_t va[16], vb[16];
-            bool have = ti.img < p.n_img;
-            if (have) {
-                mbar_wait_relaxed(sa_full, 0);
+            for (TileIter ti(blockIdx.x, gridDim.x, tiles_per_img); ti.img < p.n_img; ti.next()) {
+                mbar_wait_relaxed(sa_full + 8u * ab, aph);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                tmem_ld16_issue(acc_lane + (uint32_t)(g * p.n_tile + u * 16), va);
-            }
-            auto step = [&](uint32_t (&vc)[16], uint32_t (&vn)[16]) {
-                /* the next item of this warp */
-                const bool last_of_group = idx + 1 == i_hi;
-                TileIter nti = ti;
-                int nidx = idx + 1, ng = g, nu = u + 1, nab = ab, naph = aph;
-                if (last_of_group) {
-                    nidx = i_lo; ng = g_first; nu = u_first; nti.next();
-                    if (++nab == p.acc_bufs) { nab = 0; naph ^= 1; }
-                } else if (nu == n_units) { nu = 0; ng++; }
-                const bool have_n = nti.img < p.n_img;
-                tmem_ld_wait(vc);
-                bool issued = false;
-                if (last_of_group) { /* last read of this accumulator group by this warp: hand it back */
-                    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(sa_empty + 8u * ab);
-                    if (have_n && mbar_test(sa_full + 8u * nab, naph)) { /* next accumulator already there: start its first load now */
-                        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                        tmem_ld16_issue(acc_lane + (uint32_t)(nab * gcols + ng * p.n_tile + nu * 16), vn);
-                        issued = true;
-                    }
-                } else {
-                    tmem_ld16_issue(acc_lane + (uint32_t)(ab * gcols + ng * p.n_tile + nu * 16), vn);
-                    issued = true;
-                }
-                if (cached_g != g) {
-                    cached_g = g;
-                    const int mg = p.n_tiles == 1 ? ti.rem : ti.rem / p.n_tiles;
-                    n0 = (ti.rem - mg * p.n_tiles) * p.n_tile;
+                const int mg = p.n_tiles == 1 ? ti.rem : ti.rem / p.n_tiles;
+                const int n0 = (ti.rem - mg * p.n_tiles) * p.n_tile;
+                const uint32_t acc_grp = acc_lane + (uint32_t)(ab * gcols);
+                uint8_t *const img_base = obase + ((unsigned long long)ti.img * p.slot_stride + (long long)n0 * plane);
+                const uint32_t cm0 = sa_cm + 4u * (uint32_t)n0;
+                for (int g = g_first; g <= g_last; g++) {
+                    const int u_lo = g == g_first ? u_first : 0, u_hi = g == g_last ? u_last_end : n_units;
+                    /* per-M-tile values: pixel of this lane, validity, output pointers */
                     const int mt = mg * G + g;
                     int oh = 0, ow = 0, pix;
                     bool valid;
@@ -474,9 +463,9 @@ k_conv_tc(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUte
                         }
                         pix = oh * p.Wo + ow - r;
                     }
-                    uint8_t *pix_base = obase + ((unsigned long long)ti.img * p.slot_stride + (long long)n0 * plane + pix);
-                    b0 = pix_base + p.out_off[0]; b1 = pix_base + p.out_off[1]; b2 = pix_base + p.out_off[2];
-                    co_left = valid ? p.Co - n0 : 0; /* channels of this N tile that exist for this pixel (<= 0: nothing to store) */
+                    const int co_left = valid ? p.Co - n0 : 0; /* channels of this N tile that exist for this pixel (<= 0: nothing to store) */
+                    uint8_t *pix_base = img_base + pix + (long long)(u_lo * 16) * plane; /* channel n0 + 16 u_lo of this pixel */
+                    uint8_t *nh = nullptr;
                     if (NHWC) {
                         long long dp;
                         if (p.nhwc_mode == 2) {
@@ -485,23 +474,40 @@ k_conv_tc(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUte
                         } else dp = (long long)oh * p.nhwc_Wp + ow + p.nhwc_pl;
                         nh = p.nhwc_base + (unsigned long long)ti.img * p.nhwc_stride + dp * p.nhwc_C + n0;
                     }
+                    const long long plane16 = plane * 16;
+                    const uint32_t acc_g = acc_grp + (uint32_t)(g * p.n_tile);
+                    const bool last_g = g == g_last;
+                    /* units u_lo .. u_hi-1 of this M tile, the TMEM load of the next one in flight while one is processed */
+                    int u = u_lo;
+                    tmem_ld16_issue(acc_g + (uint32_t)(u * 16), va);
+                    for (;;) {
+                        tmem_ld_wait(va);
+                        if (u + 1 < u_hi) tmem_ld16_issue(acc_g + (uint32_t)((u + 1) * 16), vb);
+                        else if (last_g) { /* last read of this accumulator group by this warp: hand it back */
+                            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                            __syncwarp();
+                            if (lane == 0) mbar_arrive(sa_empty + 8u * ab);
+                        }
+                        if (p.dbg >= 2) { if (va[0] == 0x12345678u && va[7] == 0x9abcdef0u) pix_base[p.out_off[0]] = 1; }
+                        else epilogue_unit<RQ, TAB, NST, NHWC>(va, cm0 + 64u * (uint32_t)u, tab_lane, tab_stride, cs, pix_base + p.out_off[0], pix_base + p.out_off[1],
+                                                               pix_base + p.out_off[2], plane, co_left - u * 16, nh + u * 16);
+                        pix_base += plane16;
+                        if (++u >= u_hi) break;
+                        tmem_ld_wait(vb);
+                        if (u + 1 < u_hi) tmem_ld16_issue(acc_g + (uint32_t)((u + 1) * 16), va);
+                        else if (last_g) {
+                            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                            __syncwarp();
+                            if (lane == 0) mbar_arrive(sa_empty + 8u * ab);
+                        }
+                        if (p.dbg >= 2) { if (vb[0] == 0x12345678u && vb[7] == 0x9abcdef0u) pix_base[p.out_off[0]] = 1; }
+                        else epilogue_unit<RQ, TAB, NST, NHWC>(vb, cm0 + 64u * (uint32_t)u, tab_lane, tab_stride, cs, pix_base + p.out_off[0], pix_base + p.out_off[1],
+                                                               pix_base + p.out_off[2], plane, co_left - u * 16, nh + u * 16);
+                        pix_base += plane16;
+                        if (++u >= u_hi) break;
+                    }
                 }
-                const int c0 = u * 16;
-                const long long coff = (long long)c0 * plane;
-                if (p.dbg >= 2) { if (vc[0] == 0x12345678u && vc[7] == 0x9abcdef0u) b0[0] = 1; }
-                else epilogue_unit<FAST, TAB, NST, NHWC>(vc, sa_cm + 4u * (uint32_t)(n0 + c0), tab_lane, cs, b0 + coff, b1 + coff, b2 + coff, plane, co_left - c0, nh + c0);
-                if (last_of_group) cached_g = -1; /* the next group is another tile */
-                if (have_n && !issued) { /* the next accumulator was not ready when this item started */
-                    mbar_wait_relaxed(sa_full + 8u * nab, naph);
-                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                    tmem_ld16_issue(acc_lane + (uint32_t)(nab * gcols + ng * p.n_tile + nu * 16), vn);
-                }
-                ti = nti; idx = nidx; g = ng; u = nu; ab = nab; aph = naph; have = have_n;
-            };
-            while (have) {
-                step(va, vb);
-                if (!have) break;
-                step(vb, va);
+                if (++ab == p.acc_bufs) { ab = 0; aph ^= 1; }
             }
         }
     } else if (warp == WARP_MMA) {
@@ -827,6 +833,7 @@ struct TcPlanImpl {
     bool has_linked = false;
     TcParams p;
     int prepass = 0;
+    int rq = 0;     /* requantisation variant of the epilogue (requant_pair) */
     bool fast = false, tab = false; /* tab: the epilogue looks its byte up in the per-lane word table */
     int C = 0, Cp = 0, H = 0, W = 0, pt = 0, pl = 0, plane = 0, npix = 0; /* Cp: bytes per pixel of the channel-innermost copy */
     const uint8_t *src_slot0 = nullptr; /* input tensor in slot 0 */
@@ -1009,49 +1016,84 @@ static void build_lutw(const Op &o, const uint8_t *h_cpool, const int stream_byt
     }
 }
 
-/* may the layer use the magic-number int -> float conversion (FAST)?  max |acc| over all output channels, from the real weights */
-static bool fast_requant_ok(const Op &o, const ArenaGeom &ag) {
-    if (!(fabsf(o.f0) < 512.0f)) return false; /* also rejects NaN */
+/* may the layer use the magic-number int -> float conversion (FAST)?  max |acc + bias| over all output channels, from the real
+ * weights; returns that bound, or -1 when it does not fit */
+static long long fast_requant_bound(const Op &o, const ArenaGeom &ag) {
+    if (!(fabsf(o.f0) < 512.0f)) return -1; /* also rejects NaN */
     const int8_t *w = reinterpret_cast<const int8_t *>(ag.h_weights + o.w);
     const long long K = (long long)o.ic * o.kh * o.kw;
+    long long bound = 0;
     for (int co = 0; co < o.oc; co++) {
         long long sum = 0;
         for (long long k = 0; k < K; k++) sum += std::abs((int)w[co * K + k]);
         long long b = 0;
         if (o.bias >= 0) { int32_t bv; memcpy(&bv, ag.h_weights + o.bias + 4 * (size_t)co, 4); b = std::llabs((long long)bv); }
-        if (sum * 128 + b >= (1ll << 22)) return false;
+        if (sum * 128 + b >= (1ll << 22)) return -1;
+        bound = std::max(bound, sum * 128 + b);
+    }
+    return bound;
+}
+
+/* Is floor(fl(sc + 0.5f)) the reference's (int32)(sc + (sc >= 0 ? 0.5f : -0.5f)) (src/mars/mxu_conv.c:663-666) for every
+ * t = acc + bias with |t| <= bound, sc = fl((float)t * cs)?  For sc >= 0 both are floor(fl(sc + 0.5f)).  For sc < 0 the sum
+ * sc + 0.5f is exact, and the two differ exactly when sc is a tie -(n + 0.5) (half-away gives -(n + 1), half-up -n; equal after
+ * the clamp for n >= 128) or sc = -pred(0.5), where the reference's fl(sc - 0.5f) rounds to -1.0.  Those 129 floats are
+ * enumerated and the integers t around c / cs tested. */
+static bool halfup_requant_ok(float cs, long long bound) {
+    if (!(fabsf(cs) > 0.0f)) return true; /* sc is always +-0 */
+    /* the round-down add of 1.5 * 2^23 must stay inside [2^23, 2^24): |sc| + 0.5 < 2^22 */
+    if (!((double)bound * fabs((double)cs) < 4194300.0)) return false;
+    for (int n = -1; n <= 127; n++) {
+        const float c = n < 0 ? -nextafterf(0.5f, 0.0f) : -((float)n + 0.5f);
+        const double t0 = (double)c / (double)cs;
+        if (fabs(t0) > (double)bound + 8.0) continue;
+        const double ulp = (double)(nextafterf(fabsf(c), 1e30f) - fabsf(c));
+        const double span = 2.0 * ulp / fabs((double)cs) + 3.0;
+        if (span > 4096.0) return false;
+        const long long tc = llround(t0), W = (long long)span;
+        for (long long t = tc - W; t <= tc + W; t++) {
+            if (std::llabs(t) > bound) continue;
+            volatile float sc = (float)t * cs;
+            if (sc == c) return false;
+        }
     }
     return true;
 }
 
 /* kernel variants: FAST requant x GATHER producer x word table x number of stored NCHW streams x NHWC side output.
  * Without a table (plain conv, no byte-ReLU) there is one stream at most. */
-template <bool FAST, bool GATHER, int EPI>
+template <int RQ, bool GATHER, int EPI>
 static TcKernel pick_kernel2(bool tab, int nst, bool nhwc) {
     if (!tab) {
         switch (nst * 2 + (nhwc ? 1 : 0)) {
-            case 0: return k_conv_tc<FAST, GATHER, false, 0, false, EPI>;
-            case 1: return k_conv_tc<FAST, GATHER, false, 0, true, EPI>;
-            case 2: return k_conv_tc<FAST, GATHER, false, 1, false, EPI>;
-            default: return k_conv_tc<FAST, GATHER, false, 1, true, EPI>;
+            case 0: return k_conv_tc<RQ, GATHER, false, 0, false, EPI>;
+            case 1: return k_conv_tc<RQ, GATHER, false, 0, true, EPI>;
+            case 2: return k_conv_tc<RQ, GATHER, false, 1, false, EPI>;
+            default: return k_conv_tc<RQ, GATHER, false, 1, true, EPI>;
         }
     }
     switch (nst * 2 + (nhwc ? 1 : 0)) {
-        case 0: return k_conv_tc<FAST, GATHER, true, 0, false, EPI>;
-        case 1: return k_conv_tc<FAST, GATHER, true, 0, true, EPI>;
-        case 2: return k_conv_tc<FAST, GATHER, true, 1, false, EPI>;
-        case 3: return k_conv_tc<FAST, GATHER, true, 1, true, EPI>;
-        case 4: return k_conv_tc<FAST, GATHER, true, 2, false, EPI>;
-        case 5: return k_conv_tc<FAST, GATHER, true, 2, true, EPI>;
-        case 6: return k_conv_tc<FAST, GATHER, true, 3, false, EPI>;
-        default: return k_conv_tc<FAST, GATHER, true, 3, true, EPI>;
+        case 0: return k_conv_tc<RQ, GATHER, true, 0, false, EPI>;
+        case 1: return k_conv_tc<RQ, GATHER, true, 0, true, EPI>;
+        case 2: return k_conv_tc<RQ, GATHER, true, 1, false, EPI>;
+        case 3: return k_conv_tc<RQ, GATHER, true, 1, true, EPI>;
+        case 4: return k_conv_tc<RQ, GATHER, true, 2, false, EPI>;
+        case 5: return k_conv_tc<RQ, GATHER, true, 2, true, EPI>;
+        case 6: return k_conv_tc<RQ, GATHER, true, 3, false, EPI>;
+        default: return k_conv_tc<RQ, GATHER, true, 3, true, EPI>;
     }
 }
 /* gather mode always runs two CTAs per SM (N tile <= 256 columns of TMEM in total), i.e. 8 epilogue warps */
-static TcKernel pick_kernel(bool fast, bool gather, bool tab, int nst, bool nhwc, int epi) {
-    if (gather) return fast ? pick_kernel2<true, true, 8>(tab, nst, nhwc) : pick_kernel2<false, true, 8>(tab, nst, nhwc);
-    if (epi == 16) return fast ? pick_kernel2<true, false, 16>(tab, nst, nhwc) : pick_kernel2<false, false, 16>(tab, nst, nhwc);
-    return fast ? pick_kernel2<true, false, 8>(tab, nst, nhwc) : pick_kernel2<false, false, 8>(tab, nst, nhwc);
+template <int RQ>
+static TcKernel pick_kernel1(bool gather, bool tab, int nst, bool nhwc, int epi) {
+    if (gather) return pick_kernel2<RQ, true, 8>(tab, nst, nhwc);
+    if (epi == 16) return pick_kernel2<RQ, false, 16>(tab, nst, nhwc);
+    return pick_kernel2<RQ, false, 8>(tab, nst, nhwc);
+}
+static TcKernel pick_kernel(int rq, bool gather, bool tab, int nst, bool nhwc, int epi) {
+    if (rq == 2) return pick_kernel1<2>(gather, tab, nst, nhwc, epi);
+    if (rq == 1) return pick_kernel1<1>(gather, tab, nst, nhwc, epi);
+    return pick_kernel1<0>(gather, tab, nst, nhwc, epi);
 }
 
 bool tc_plan(const Op &o, const ArenaGeom &ag, uint8_t *scratch, size_t scratch_stride, uint8_t *linked, size_t linked_stride,
@@ -1090,51 +1132,71 @@ bool tc_plan(const Op &o, const ArenaGeom &ag, uint8_t *scratch, size_t scratch_
     p.acc_bufs = std::max(2, std::min(4, p.tmem_cols / (p.grp * p.n_tile)));
     p.a_stage_bytes = p.grp * p.a_tile_bytes;
     p.tx_bytes = p.a_stage_bytes + (uint32_t)(p.n_tile * p.bk);
-    /* the op needs the word table when it has fused followers or a byte-ReLU (plain conv: the byte is r itself) */
+    /* the op needs the word table when it has fused followers or a byte-ReLU (plain conv: the byte is r itself).  The table is
+     * replicated per lane group in shared memory ([256][rep] words, lane l reads copy l % rep): rep = 32 makes the lookups
+     * conflict free; 16 or 8 (two / four lanes per bank) when the stages, the halo region or the resident weights need the room */
     t->tab = o.fused_layers > 0 || o.post_relu;
-    const int tab_bytes = t->tab ? 256 * 32 * 4 : 0;
-    /* dynamic shared memory of a CTA: stages + weights + table (+ 1 KiB alignment slack); 227 KiB per SM, ~7 KiB static */
-    const int budget = (t->ctas_per_sm == 1 ? 200 * 1024 : 104 * 1024) - tab_bytes;
     const int nsteps = g.ntaps * p.ksteps_per_tap;
-    if (gather) { /* + 3 x 4 KiB patch ring + 8 KiB patch-word tables */
-        if (p.grp > 2) { p.grp = 2; p.a_stage_bytes = p.grp * p.a_tile_bytes; p.acc_bufs = std::max(2, std::min(4, p.tmem_cols / (p.grp * p.n_tile))); }
-        p.stages = std::max(2, std::min(8, (budget - (int)p.b_stage_bytes - 20480 - 1024) / (int)p.a_stage_bytes));
-        t->smem = 1024 + (size_t)p.stages * p.a_stage_bytes + p.b_stage_bytes + 20480;
-    } else {
-        /* small weight matrices stay resident in shared memory for the whole (persistent) launch: one TMA per k-step */
-        const size_t b_all = (size_t)nsteps * p.b_stage_bytes;
-        p.b_resident = (p.n_tiles == 1 && b_all <= (size_t)budget / 2) ? 1 : 0;
-        /* kxk stride 1 over the padded channel-innermost copy: every tap is a row shift of the same pixel rows, so one
-         * load of the tile's rows plus its halo (128 + (kh-1)*Wp + kw-1 rows) serves all taps of a k block */
-        static const bool halo_enabled = !(getenv("MARS_TC_HALO") && atoi(getenv("MARS_TC_HALO")) == 0);
-        if (s2d && !p.b_resident) { delete t; return false; }
-        if ((halo_enabled && g.prepass == 1 && p.b_resident && g.ntaps > 1) || s2d) {
-            /* s2d: the copy has a one-pixel zero border, so tap (ky2, pair) of output pixel q = oh*Wp + ow starts at row
-             * q + (ky2 + 1 - pt/2)*Wp + (2*pair + 1 - pl/2) and reads two pixels; taps that leave the image hit the border, the
-             * next row's border column, or rows beyond the copy (zero-filled by TMA) */
-            const int s2d_min = (1 - o.pt / 2) * g.Wp + (1 - o.pl / 2);
-            const int smin = s2d ? s2d_min : -o.pt * g.Wp, smax = s2d ? s2d_min + 2 * g.Wp + 3 : (o.kh - 1 - o.pt) * g.Wp + o.kw - 1;
-            const int R = p.grp * TC_BM + smax - smin;
-            const int nb = (R + 255) / 256, rb = round_up((R + nb - 1) / nb, 8);
-            const uint32_t bytes = (uint32_t)round_up(nb * rb * p.a_row_bytes, 1024);
-            if (rb <= 256 && (size_t)2 * bytes + b_all <= (size_t)budget) {
-                p.halo = 1; p.halo_min = smin; p.halo_rb = rb; p.halo_nb = nb;
-                p.a_stage_bytes = bytes;
+    const int grp0 = p.grp, acc0 = p.acc_bufs;
+    const uint32_t a_stage0 = p.a_stage_bytes;
+    bool plan_ok = true;
+    /* dynamic shared memory of a CTA: stages + weights + table (+ 1 KiB alignment slack); 227 KiB per SM, ~7 KiB static */
+    auto plan_smem = [&](int tab_bytes) {
+        const int budget = (t->ctas_per_sm == 1 ? 200 * 1024 : 104 * 1024) - tab_bytes;
+        p.grp = grp0; p.acc_bufs = acc0; p.a_stage_bytes = a_stage0; p.halo = 0; p.b_resident = 0; plan_ok = true;
+        if (gather) { /* + 3 x 4 KiB patch ring + 8 KiB patch-word tables */
+            if (p.grp > 2) { p.grp = 2; p.a_stage_bytes = p.grp * p.a_tile_bytes; p.acc_bufs = std::max(2, std::min(4, p.tmem_cols / (p.grp * p.n_tile))); }
+            p.stages = std::max(2, std::min(8, (budget - (int)p.b_stage_bytes - 20480 - 1024) / (int)p.a_stage_bytes));
+            t->smem = 1024 + (size_t)p.stages * p.a_stage_bytes + p.b_stage_bytes + 20480;
+        } else {
+            /* small weight matrices stay resident in shared memory for the whole (persistent) launch: one TMA per k-step */
+            const size_t b_all = (size_t)nsteps * p.b_stage_bytes;
+            p.b_resident = (p.n_tiles == 1 && b_all <= (size_t)budget / 2) ? 1 : 0;
+            /* kxk stride 1 over the padded channel-innermost copy: every tap is a row shift of the same pixel rows, so one
+             * load of the tile's rows plus its halo (128 + (kh-1)*Wp + kw-1 rows) serves all taps of a k block */
+            static const bool halo_enabled = !(getenv("MARS_TC_HALO") && atoi(getenv("MARS_TC_HALO")) == 0);
+            if (s2d && !p.b_resident) { plan_ok = false; return; }
+            if ((halo_enabled && g.prepass == 1 && p.b_resident && g.ntaps > 1) || s2d) {
+                /* s2d: the copy has a one-pixel zero border, so tap (ky2, pair) of output pixel q = oh*Wp + ow starts at row
+                 * q + (ky2 + 1 - pt/2)*Wp + (2*pair + 1 - pl/2) and reads two pixels; taps that leave the image hit the border, the
+                 * next row's border column, or rows beyond the copy (zero-filled by TMA) */
+                const int s2d_min = (1 - o.pt / 2) * g.Wp + (1 - o.pl / 2);
+                const int smin = s2d ? s2d_min : -o.pt * g.Wp, smax = s2d ? s2d_min + 2 * g.Wp + 3 : (o.kh - 1 - o.pt) * g.Wp + o.kw - 1;
+                const int R = p.grp * TC_BM + smax - smin;
+                const int nb = (R + 255) / 256, rb = round_up((R + nb - 1) / nb, 8);
+                const uint32_t bytes = (uint32_t)round_up(nb * rb * p.a_row_bytes, 1024);
+                if (rb <= 256 && (size_t)2 * bytes + b_all <= (size_t)budget) {
+                    p.halo = 1; p.halo_min = smin; p.halo_rb = rb; p.halo_nb = nb;
+                    p.a_stage_bytes = bytes;
+                }
+            }
+            if (s2d && !p.halo) { plan_ok = false; return; }
+            if (p.b_resident) {
+                p.stages = std::max(2, std::min(8, (budget - (int)b_all) / (int)p.a_stage_bytes));
+                t->smem = 1024 + (size_t)p.stages * p.a_stage_bytes + b_all;
+            } else {
+                const int stage_bytes = (int)(p.a_stage_bytes + p.b_stage_bytes);
+                p.stages = std::max(2, std::min(8, budget / stage_bytes));
+                t->smem = 1024 + (size_t)p.stages * stage_bytes;
             }
         }
-        if (s2d && !p.halo) { delete t; return false; }
-        if (p.b_resident) {
-            p.stages = std::max(2, std::min(8, (budget - (int)b_all) / (int)p.a_stage_bytes));
-            t->smem = 1024 + (size_t)p.stages * p.a_stage_bytes + b_all;
-        } else {
-            const int stage_bytes = (int)(p.a_stage_bytes + p.b_stage_bytes);
-            p.stages = std::max(2, std::min(8, budget / stage_bytes));
-            t->smem = 1024 + (size_t)p.stages * stage_bytes;
+    };
+    int rep = t->tab ? 8 : 0;
+    plan_smem(rep * 1024);
+    if (!plan_ok) { delete t; return false; }
+    if (t->tab) { /* widen the replication while the pipeline keeps its shape (resident weights, halo loads, >= 3 stages) */
+        const int res8 = p.b_resident, halo8 = p.halo, st8 = p.stages;
+        static const int rep_max = getenv("MARS_TC_TABREP") ? atoi(getenv("MARS_TC_TABREP")) : 32;
+        for (int r2 = 32; r2 > 8; r2 >>= 1) {
+            if (r2 > rep_max) continue;
+            plan_smem(r2 * 1024);
+            static const int min_st = getenv("MARS_TC_MINST") ? atoi(getenv("MARS_TC_MINST")) : 3;
+            if (plan_ok && p.b_resident == res8 && p.halo == halo8 && p.stages >= std::min(st8, min_st)) { rep = r2; break; }
         }
-    }
-    if (t->tab) { /* the per-lane table copies sit behind everything else */
-        p.tab_off = (uint32_t)round_up((int)(t->smem - 1024), 128);
-        t->smem = 1024 + (size_t)p.tab_off + (size_t)tab_bytes;
+        if (rep == 8) plan_smem(8 * 1024);
+        p.tab_rep = (uint32_t)rep;
+        p.tab_off = (uint32_t)round_up((int)(t->smem - 1024), 128); /* the table copies sit behind everything else */
+        t->smem = 1024 + (size_t)p.tab_off + (size_t)rep * 1024;
     }
     /* keep residency at ctas_per_sm: a further CTA would fit the registers but stall in tcgen05.alloc */
     t->smem = std::max<size_t>(t->smem, t->ctas_per_sm == 1 ? 120 * 1024 : 80 * 1024);
@@ -1195,7 +1257,13 @@ bool tc_plan(const Op &o, const ArenaGeom &ag, uint8_t *scratch, size_t scratch_
         p.nhwc_base = linked + consumer->copy_off;
         p.nhwc_stride = linked_stride;
     }
-    t->fast = fast_requant_ok(o, ag);
+    {
+        const long long bound = fast_requant_bound(o, ag);
+        static const int rq_max = getenv("MARS_TC_RQ") ? atoi(getenv("MARS_TC_RQ")) : 2; /* tuning / test aid: cap the variant */
+        t->fast = bound >= 0;
+        t->rq = !t->fast ? 0 : ((rq_max >= 2 && halfup_requant_ok(o.f0, bound)) ? 2 : 1);
+        if (rq_max == 0) { t->rq = 0; t->fast = false; }
+    }
     t->prepass = g.prepass; t->C = o.ic; t->Cp = ci_eff; t->H = o.ih; t->W = o.iw; t->pt = o.pt; t->pl = o.pl;
     t->plane = g.plane; t->npix = g.npix;
     t->src_slot0 = ag.d_slots + (o.in0 - (int64_t)ag.W);
@@ -1248,9 +1316,13 @@ bool tc_plan(const Op &o, const ArenaGeom &ag, uint8_t *scratch, size_t scratch_
     ok = ok && make_map3(&t->mapB, t->d_wr, (uint64_t)ci_eff, (uint64_t)co_pad, (uint64_t)g.ntaps, (uint64_t)ci_eff,
                          (uint64_t)co_pad * ci_eff, (uint32_t)p.bk, (uint32_t)p.n_tile, ksw);
     t->epi = (!gather && t->ctas_per_sm == 1) ? 16 : 8;
-    t->kernel = pick_kernel(t->fast, gather, t->tab, t->nst, p.nhwc_sel >= 0, t->epi);
+    t->kernel = pick_kernel(t->rq, gather, t->tab, t->nst, p.nhwc_sel >= 0, t->epi);
     ok = ok && cudaFuncSetAttribute((const void *)t->kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 210 * 1024) == cudaSuccess;
     if (!ok) { cudaFree(t->d_wr); cudaFree(t->d_lutw); delete t; return false; }
+    if (getenv("MARS_TC_VERBOSE"))
+        fprintf(stderr, "tc_plan layer %d: %dx%d k%d s%d ci %d co %d | n_tile %d grp %d acc %d stages %d bk %d halo %d b_res %d ctas %d epi %d | rq %d tab %d rep %u nst %d side %d smem %zu\n",
+                o.layer, o.oh, o.ow, o.kh, o.sh, o.ic, o.oc, p.n_tile, p.grp, p.acc_bufs, p.stages, p.bk, p.halo, p.b_resident, t->ctas_per_sm, t->epi,
+                t->rq, (int)t->tab, p.tab_rep, t->nst, p.nhwc_sel >= 0, t->smem);
     plan->impl = t;
     plan->valid = true;
     return true;
