@@ -53,6 +53,10 @@ void mars_b200_set_opt_level(mars_model_t *m, int level);
 /* 0 = reference semantics (DEPTHWISE_CONV2D is a no-op, src/mars/mars_runtime.c:1168-1170),
  * 1 = restated depthwise convolution (parity unpinned) */
 void mars_b200_set_depthwise_mode(mars_model_t *m, int mode);
+/* strict mode (also MARS_STRICT=1): when a convolution cannot be planned on the tensor-core kernel the library normally
+ * recompiles the whole model on the exact direct kernels (correct, ~100x slower) and says so on stderr; in strict mode the
+ * call that compiles the model (mars_load_*, mars_b200_set_batch, ...) fails with MARS_ERR_LAYER_FAILED instead */
+void mars_b200_set_strict(int on);
 
 /* ---- image batch ---------------------------------------------------------- */
 /* allocate `capacity` image slots (each = one set of work buffers; weights shared) */

@@ -134,3 +134,92 @@ def test_anchor_grid_decode_matches_the_reference_python_formula(ob):
         assert np.allclose(d["confidence"], np.array(want["confidence"]), rtol=0, atol=1e-6)
         got = np.stack([d["x0"], d["y0"], d["x1"], d["y1"]], 1).astype(np.float64)
         assert np.abs(got - np.array(want["boxes"])).max() < 1e-3
+
+
+# ---- the restatement against the reference library on GENERATED models --------------------------------------
+# The GPU parity tests of the generated graphs (yolov5s-shaped headline model, NanoDet-shaped, f32, micro shapes) compare
+# CUDA with the restatement (oracle/mars_oracle.c).  These tests close that chain: restatement == libmars_ref.so, whole
+# arena, on the same generated files.
+def _nan_words(a):
+    """float32 NaN bit patterns among the 4-byte words of a byte array"""
+    w = a[: a.size // 4 * 4].view(np.uint32)
+    return ((w & 0x7F800000) == 0x7F800000) & ((w & 0x007FFFFF) != 0)
+
+
+def _same_arena(rb, ob, blob, arena, x, nan_payload_free=False):
+    """nan_payload_free (float32 models): words that are NaN on both sides may differ in sign / payload -- which operand's
+    payload an x86 mulss / addss returns depends on the operand order the C compiler picked, not on the source"""
+    r = rb.RefRuntime(blob, arena_bytes=arena)
+    m = ob.OracleModel(blob, arena_bytes=arena)
+    for run in range(2):
+        xr = x if run == 0 else np.roll(x, 7919)
+        r.set_input(xr)
+        r.run()
+        m.set_input(xr)
+        m.run()
+        a, b = r.arena()[: m.arena_bytes], m.arena()
+        if nan_payload_free:
+            W = m.weights_size // 4 * 4  # work buffers start at weights_size (4-byte aligned in generated files)
+            wa, wb = a[W:], b[W:]
+            both_nan = _nan_words(wa) & _nan_words(wb)
+            ne = wa[: wa.size // 4 * 4].view(np.uint32) != wb[: wb.size // 4 * 4].view(np.uint32)
+            d = np.nonzero(ne & ~both_nan)[0]
+            assert d.size == 0, "run %d: %d words differ beyond NaN payloads, first at byte %d" % (run + 1, d.size, W + 4 * int(d[0]))
+            continue
+        d = np.nonzero(a != b)[0]
+        assert d.size == 0, "run %d: %d arena bytes differ, first at %d" % (run + 1, d.size, int(d[0]))
+    out = m.output_bytes().copy()
+    r.close()
+    m.close()
+    return out
+
+
+def test_restatement_equals_reference_on_headline_model(pkg, ob, rb):
+    """BASELINE configs[2]: the yolov5s-shaped int8 graph at 640x640 (writer seed 5), image seed 1000"""
+    mf = pkg.marsfile
+    blob = mf.build_yolov5(width=0.5, size=640, seed=5).to_bytes()
+    x = np.random.default_rng(1000).integers(-128, 128, size=3 * 640 * 640, dtype=np.int8)
+    _same_arena(rb, ob, blob, mf.ARENA_YOLOV5S_INT8, x)
+
+
+def test_restatement_equals_reference_on_nhwc_model(pkg, ob, rb):
+    """the --nhwc convention of the compiler (conv2d_int8_nhwc_mxu, src/mars/mxu_conv.c:713-757) at yolov5s width, 320 px"""
+    mf = pkg.marsfile
+    blob = mf.build_yolov5(width=0.5, size=320, seed=5, nhwc=True).to_bytes()
+    x = np.random.default_rng(1001).integers(-128, 128, size=3 * 320 * 320, dtype=np.int8)
+    _same_arena(rb, ob, blob, mf.ARENA_YOLOV5S_INT8, x)
+
+
+def test_restatement_equals_reference_on_nanodet_like(pkg, ob, rb):
+    mf = pkg.marsfile
+    blob = mf.build_nanodet_like(size=320, seed=7).to_bytes()
+    x = np.random.default_rng(7).integers(-128, 128, size=3 * 320 * 320, dtype=np.int8)
+    _same_arena(rb, ob, blob, 16 << 20, x)
+
+
+def test_restatement_equals_reference_on_f32_model(pkg, ob, rb):
+    """BASELINE configs[3] shape: yolov5s width, float32 (320 px here: the CPU cost of 640 px is paid once, in the GPU test)"""
+    mf = pkg.marsfile
+    blob = mf.build_yolov5(width=0.5, size=320, seed=6, f32=True).to_bytes()
+    x = np.random.default_rng(6).random(3 * 320 * 320, dtype=np.float32)
+    _same_arena(rb, ob, blob, mf.ARENA_YOLOV5S_F32, x.view(np.int8), nan_payload_free=True)
+
+
+from util import MICRO  # noqa: E402
+
+
+@pytest.mark.parametrize("kind,kw", [(k, kw) for k, kw in MICRO if k != "depthwise"])
+def test_restatement_equals_reference_on_micro_models(pkg, ob, rb, kind, kw):
+    """(the depthwise micro-model is excluded: the reference's DEPTHWISE_CONV2D is a no-op, the restated kernel is unpinned)"""
+    blob = pkg.marsfile.build_single_layer(kind, **kw).to_bytes()
+    r = rb.RefRuntime(blob)
+    m = ob.OracleModel(blob)
+    rng = np.random.default_rng(1)
+    fill = rng.integers(0, 256, size=m.arena_bytes - m.weights_size, dtype=np.uint8)
+    m.arena()[m.weights_size:] = fill
+    r.arena()[m.weights_size: m.arena_bytes] = fill
+    r.run()
+    m.run()
+    assert np.array_equal(r.arena()[: m.arena_bytes], m.arena())
+    r.close()
+    m.close()

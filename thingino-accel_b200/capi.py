@@ -140,6 +140,7 @@ SIGNATURES = {
     "mars_b200_describe": (C.c_size_t, [PM, C.c_char_p, C.c_size_t]),
     "mars_b200_set_opt_level": (None, [PM, C.c_int]),
     "mars_b200_set_depthwise_mode": (None, [PM, C.c_int]),
+    "mars_b200_set_strict": (None, [C.c_int]),
     "mars_b200_set_batch": (C.c_int, [PM, C.c_int]),
     "mars_b200_get_batch": (C.c_int, [PM]),
     "mars_b200_input_bytes": (C.c_size_t, [PM]),

@@ -848,6 +848,7 @@ struct TcPlanImpl {
     size_t smem = 0;
     int ctas_per_sm = 2;
     int epi = 8; /* epilogue warps per CTA */
+    int sms = 0; /* multiprocessors of the device the plan was built on */
     bool gather_direct = false; /* gather mode reads the input tensor in the arena itself (no private copy needed) */
 };
 
@@ -1315,6 +1316,7 @@ bool tc_plan(const Op &o, const ArenaGeom &ag, uint8_t *scratch, size_t scratch_
     }
     ok = ok && make_map3(&t->mapB, t->d_wr, (uint64_t)ci_eff, (uint64_t)co_pad, (uint64_t)g.ntaps, (uint64_t)ci_eff,
                          (uint64_t)co_pad * ci_eff, (uint32_t)p.bk, (uint32_t)p.n_tile, ksw);
+    { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&t->sms, cudaDevAttrMultiProcessorCount, dev); }
     t->epi = (!gather && t->ctas_per_sm == 1) ? 16 : 8;
     t->kernel = pick_kernel(t->rq, gather, t->tab, t->nst, p.nhwc_sel >= 0, t->epi);
     ok = ok && cudaFuncSetAttribute((const void *)t->kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 210 * 1024) == cudaSuccess;
@@ -1356,8 +1358,8 @@ bool tc_launch(const TcPlan &plan, uint8_t *slots_base, int first, int n, bool u
     }
     if (p.nhwc_sel >= 0) p.nhwc_base += (size_t)first * p.nhwc_stride;
     const long long total_tiles = (long long)p.m_groups * p.n_tiles * n;
-    static int sms = 0;
-    if (!sms) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); if (sms <= 0) sms = 148; }
+    int sms = t->sms;
+    if (sms <= 0) sms = 148;
     const unsigned grid = (unsigned)std::min<long long>(total_tiles, (long long)sms * t->ctas_per_sm);
     t->kernel<<<grid, (t->epi + (t->prepass == 3 ? 5 : 2)) * 32, t->smem, s>>>((use_linked && t->has_linked) ? t->mapA_linked : t->mapA, t->mapB, p);
     (*launches)++;

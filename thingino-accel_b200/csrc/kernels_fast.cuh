@@ -162,12 +162,11 @@ static inline void launch_inplace_reg(const ArenaView &v, const KOp &o, int n_im
     const unsigned P = (unsigned)o.oh * o.ow;
     dim3 g((P + 127) / 128, n_img);
     const size_t smem = (size_t)o.oc * (o.ic / 4 + 1) * 4;
-    static bool attr = false;
-    if (!attr) {
+    static unsigned long long attr = 0; /* function attributes are per device */
+    if (first_time_on_device(&attr)) {
         cudaFuncSetAttribute(k_conv1x1_inplace_reg<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
         cudaFuncSetAttribute(k_conv1x1_inplace_reg<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
         cudaFuncSetAttribute(k_conv1x1_inplace_reg<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
-        attr = true;
     }
     if (o.ic == 32) k_conv1x1_inplace_reg<8><<<g, 128, smem, s>>>(v, o);
     else if (o.ic == 64) k_conv1x1_inplace_reg<16><<<g, 128, smem, s>>>(v, o);
@@ -390,8 +389,8 @@ static inline void launch_fast_spatial(const ArenaView &v, const KOp &o, int n_i
         int TH = 32;
         while (TH > 1 && (size_t)2 * (TH + o.kh - 1) * RW * 4 > 96 * 1024) TH >>= 1;
         if ((size_t)2 * (TH + o.kh - 1) * RW * 4 <= 96 * 1024) {
-            static bool attr = false;
-            if (!attr) { cudaFuncSetAttribute(k_maxpool_sep, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024); attr = true; }
+            static unsigned long long attr = 0;
+            if (first_time_on_device(&attr)) cudaFuncSetAttribute(k_maxpool_sep, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
             dim3 g((o.oh + TH - 1) / TH, n_img);
             k_maxpool_sep<<<g, 256, (size_t)2 * (TH + o.kh - 1) * RW * 4, s>>>(v, o, TH);
             return;

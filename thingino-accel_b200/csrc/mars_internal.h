@@ -103,6 +103,7 @@ struct Program {
     std::vector<uint8_t> const_pool; /* 256-byte tables, uploaded once */
     size_t scratch_bytes = 0;        /* per-image scratch for EXEC_OC_PASSES_SCRATCH */
     size_t linked_bytes = 0;         /* per-image bytes of producer-written conv input copies */
+    size_t max_extent = 0;           /* highest arena offset (exclusive) any op reads or writes: an image slot must reach that far */
 };
 
 /* device-side view of the arena; passed by value to kernels */
@@ -122,6 +123,9 @@ struct Model; /* defined in runtime.cu */
 size_t tensor_byte_size(const mars_tensor_t *t);
 int find_tensor(const mars_header_t &h, const mars_runtime_tensor_t *tensors, uint32_t id);
 void set_last_error(const char *fmt, ...);
+/* once per CUDA device: true the first time it is called with this mask on the current device (function attributes and
+ * SM counts are per device; the API supports several devices in one process) */
+bool first_time_on_device(unsigned long long *mask);
 
 /* compile the layer table into ops (program.cpp) */
 mars_error_t compile_program(const mars_header_t &h, const mars_runtime_tensor_t *tensors,

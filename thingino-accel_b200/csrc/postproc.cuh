@@ -650,12 +650,11 @@ __global__ void __launch_bounds__(NMS_SUP_THREADS, 8) k_nms_suppress(const mars_
 static inline cudaError_t launch_nms_center(const mars_det_t *dets_in, const int32_t *counts_in, mars_det_t *dets_out,
                                             int32_t *counts_out, int det_stride, float thresh, int n_img, unsigned *scratch /* NMS_SCRATCH_WORDS per image */,
                                             cudaStream_t s, int *launches = nullptr) {
-    static bool attr = false;
+    static unsigned long long attr = 0; /* function attributes are per device */
     static const bool block_sort = getenv("MARS_NMS_BLOCKSORT") && atoi(getenv("MARS_NMS_BLOCKSORT")) != 0;
-    if (!attr) {
+    if (first_time_on_device(&attr)) {
         cudaError_t e = cudaFuncSetAttribute(k_nms_center, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(NmsShared));
         if (e != cudaSuccess) return e;
-        attr = true;
     }
     if (!block_sort) {
         k_nms_sort_warp<<<n_img, 32, 0, s>>>(dets_in, counts_in, det_stride, scratch, NMS_SCRATCH_WORDS);

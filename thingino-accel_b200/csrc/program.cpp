@@ -112,6 +112,7 @@ static mars_error_t check_write(const Ctx &c, int layer, int64_t lo, int64_t hi)
                        layer, (long long)hi, (long long)c.A);
         return MARS_ERR_INVALID_LAYER;
     }
+    c.prog->max_extent = std::max(c.prog->max_extent, (size_t)hi); /* the image slot is sized to the furthest access */
     return MARS_OK;
 }
 static mars_error_t check_read(const Ctx &c, int layer, int64_t lo, int64_t hi) {
@@ -121,6 +122,7 @@ static mars_error_t check_read(const Ctx &c, int layer, int64_t lo, int64_t hi) 
                        (long long)hi, (long long)c.A);
         return MARS_ERR_INVALID_LAYER;
     }
+    c.prog->max_extent = std::max(c.prog->max_extent, (size_t)hi);
     return MARS_OK;
 }
 
@@ -729,6 +731,7 @@ mars_error_t compile_program(const mars_header_t &h, const mars_runtime_tensor_t
     out->const_pool.clear();
     out->scratch_bytes = 0;
     out->linked_bytes = 0;
+    out->max_extent = 0;
     Ctx c{h, tensors, toff, (int64_t)weights_size, (int64_t)arena_size, out};
     for (uint32_t i = 0; i < h.num_layers; i++) {
         const mars_layer_t &L = layers[i].desc;

@@ -57,7 +57,20 @@ void set_last_error(const char *fmt, ...) {
         }                                                                                      \
     } while (0)
 
+bool first_time_on_device(unsigned long long *mask) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev > 63) return true;
+    if ((*mask >> dev) & 1ull) return false;
+    *mask |= 1ull << dev;
+    return true;
+}
+
 /* ---- process-wide device state (reference: g_nna_dev, src/device.c:105-131) -- */
+static int g_strict = -1; /* -1: MARS_STRICT from the environment; 1: a failed tensor-core plan is an error, not a silent drop to the direct kernels */
+static bool strict_mode() {
+    if (g_strict < 0) { const char *e = getenv("MARS_STRICT"); g_strict = (e && atoi(e) != 0) ? 1 : 0; }
+    return g_strict != 0;
+}
 static int g_device = -1;
 static bool g_ready = false;
 static size_t g_arena_bytes = 0;
@@ -185,6 +198,7 @@ struct Model {
     /* tensor-core conv plans (conv_tc.cu) */
     std::vector<TcPlan> tc;
     bool compiled = false;
+    uint64_t weights_hash = 0; /* FNV-1a of the host weight blob the compiled plans were built from */
 };
 
 static Model *as_model(mars_model_t *p) {
@@ -195,6 +209,12 @@ static Model *as_model(mars_model_t *p) {
 
 static inline uint8_t *dev_addr(const Model *m, size_t off, int slot) {
     return off < m->weights_size ? m->d_weights + off : m->d_slots + (size_t)slot * m->slot_stride + (off - m->weights_size);
+}
+
+static uint64_t fnv1a(const uint8_t *p, size_t n) {
+    uint64_t h = 1469598103934665603ull;
+    for (size_t i = 0; i < n; i++) { h ^= p[i]; h *= 1099511628211ull; }
+    return h;
 }
 
 static void release_graphs(Model *m) {
@@ -324,7 +344,15 @@ static mars_error_t compile_model(Model *m) {
         if (o.impl != CONV_TC_NCHW) continue;
         const Op *consumer = o.nhwc_consumer >= 0 ? &m->prog.ops[o.nhwc_consumer] : nullptr;
         if (!tc_plan(o, g, m->d_tc_scratch, m->tc_scratch_stride, m->d_linked, m->linked_stride, consumer, &m->tc[i])) {
-            /* a fused op cannot simply fall back (its followers were folded): recompile exact */
+            /* a fused op cannot simply fall back (its followers were folded): recompile exact -- unless the caller asked
+             * to be told (mars_b200_set_strict / MARS_STRICT=1): the direct kernels are ~100x slower */
+            if (strict_mode()) {
+                char why[600];
+                snprintf(why, sizeof why, "%s", g_err);
+                set_last_error("strict mode: tensor-core plan failed for layer %d (%s)", o.layer, why);
+                tc_release(m->tc);
+                return MARS_ERR_LAYER_FAILED;
+            }
             fprintf(stderr, "mars_b200: tensor-core plan failed for layer %d (%s); using the direct CUDA kernels\n", o.layer, g_err);
             tc_release(m->tc);
             m->opt_level = 0;
@@ -333,6 +361,7 @@ static mars_error_t compile_model(Model *m) {
     }
     m->prof_ms.assign(m->prog.ops.size(), 0.0);
     m->prof_calls.assign(m->prog.ops.size(), 0);
+    m->weights_hash = fnv1a(m->h_arena, m->weights_size);
     /* tables, the zeroed link area and the repacked weights are complete before a (non-blocking) stream uses them */
     CU_OK(cudaDeviceSynchronize(), MARS_ERR_LAYER_FAILED);
     m->compiled = true;
@@ -376,7 +405,7 @@ static mars_error_t launch_op(Model *m, size_t op_index, int first, int n, bool 
     const bool xl = o.xlat;
     const int is_conv = o.kind == OP_CONV_I8_NCHW || o.kind == OP_CONV_I8_NHWC || o.kind == OP_CONV_F32_NCHW || o.kind == OP_DW_I8;
     if (o.mode == EXEC_SERIAL) {
-        if (xl) k_serial<true><<<n, 32, 0, s>>>(v, k); else k_serial<true><<<n, 32, 0, s>>>(v, k);
+        if (xl) k_serial<true><<<n, 32, 0, s>>>(v, k); else k_serial<false><<<n, 32, 0, s>>>(v, k);
         m->launches++;
     } else if (is_conv) {
         const uint64_t P = (uint64_t)o.oh * o.ow;
@@ -410,8 +439,8 @@ static mars_error_t launch_op(Model *m, size_t op_index, int first, int n, bool 
         } else if (o.mode == EXEC_PIXEL_SERIAL && o.kind == OP_CONV_I8_NCHW) {
             dim3 g(blocks_for(P, 128), n);
             const size_t smem = (size_t)o.ic * 128 + (size_t)o.oc * o.ic;
-            static bool attr_set = false;
-            if (!attr_set) { cudaFuncSetAttribute(k_conv1x1_nchw_inplace, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); attr_set = true; }
+            static unsigned long long attr_set = 0;
+            if (first_time_on_device(&attr_set)) cudaFuncSetAttribute(k_conv1x1_nchw_inplace, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
             k_conv1x1_nchw_inplace<<<g, 128, smem, s>>>(v, k);
             m->launches++;
         } else if (o.mode == EXEC_PIXEL_SERIAL) {
@@ -696,6 +725,19 @@ mars_error_t mars_load_memory(const void *data, size_t size, mars_model_t **out_
     m->pub.weights = m->h_arena;
     m->pub.weights_size = m->weights_size;
 
+    /* An image slot must reach as far as any layer reads or writes.  In the reference an access behind the last work buffer
+     * lands in unused arena (extents taken from another tensor or dtype, the reduced-buffer case); here it would land in the
+     * next image's slot, so the slot is sized to the furthest access of a dry compile (it stays private and zero-initialised). */
+    {
+        Program dry;
+        mars_error_t de = compile_program(m->pub.header, m->pub.tensors, m->pub.layers, m->toff, m->weights_size, m->arena_size, 0,
+                                          m->depthwise_mode, &dry);
+        if (de != MARS_OK) { model_release(m); return de; }
+        if (dry.max_extent > m->weights_size + m->slot_bytes) {
+            m->slot_bytes = dry.max_extent - m->weights_size;
+            m->slot_stride = (m->slot_bytes + 1023) & ~(size_t)1023;
+        }
+    }
     mars_error_t e = set_capacity(m, 1);
     if (e == MARS_OK) e = compile_model(m);
     if (e != MARS_OK) { model_release(m); return e; }
@@ -831,12 +873,15 @@ mars_error_t mars_b200_arena_upload(mars_model_t *model, int slot) {
     if (!m) return MARS_ERR_INVALID_FILE;
     CU_OK(cudaSetDevice(m->device), MARS_ERR_NNA_INIT_FAILED);
     if (!range_ok(m, slot, 1)) return MARS_ERR_INVALID_TENSOR;
+    /* the host mirror of the weights is writable (model->weights, tensor->vaddr, as in the reference): the tensor-core plans
+     * hold a repacked copy and requantisation bounds derived from the blob, so an edit invalidates the compiled program */
+    if (m->compiled && fnv1a(m->h_arena, m->weights_size) != m->weights_hash) { cudaStreamSynchronize(m->stream); m->compiled = false; }
     CU_OK(cudaMemcpyAsync(m->d_weights, m->h_arena, m->weights_size, cudaMemcpyHostToDevice, m->stream), MARS_ERR_LAYER_FAILED);
     size_t nbytes = std::min(m->slot_bytes, m->arena_size - m->weights_size);
     CU_OK(cudaMemcpyAsync(m->d_slots + (size_t)slot * m->slot_stride, m->h_arena + m->weights_size, nbytes,
                           cudaMemcpyHostToDevice, m->stream), MARS_ERR_LAYER_FAILED);
     CU_OK(cudaStreamSynchronize(m->stream), MARS_ERR_LAYER_FAILED);
-    return MARS_OK;
+    return compile_model(m);
 }
 
 mars_error_t mars_b200_arena_download(mars_model_t *model, int slot, void *host_dst, size_t bytes) {
@@ -900,6 +945,7 @@ void mars_b200_set_opt_level(mars_model_t *model, int level) {
     m->opt_level = level;
     m->compiled = false;
 }
+void mars_b200_set_strict(int on) { g_strict = on ? 1 : 0; }
 void mars_b200_set_depthwise_mode(mars_model_t *model, int mode) {
     Model *m = as_model(model);
     if (!m || m->depthwise_mode == mode) return;
@@ -1265,7 +1311,8 @@ mars_error_t mars_b200_submit_batch(mars_model_t *model, int pool, int n, const 
     const size_t in_bytes = io_bytes(&m->pub, 0);
     if (in_stride < in_bytes) in_stride = in_bytes;
     const int first = pool * half;
-    mars_error_t e = MARS_OK;
+    mars_error_t e = compile_model(m); /* also drops captured graphs of an older program (set_opt_level, set_depthwise_mode) */
+    if (e != MARS_OK) return e;
     if (n > 0) {
         /* the half is free: its previous batch was waited for (read-back complete) before this call */
         e = copy_io(m, first, n, const_cast<void *>(inputs), in_stride, 0, m->h2d_stream);
