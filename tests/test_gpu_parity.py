@@ -157,10 +157,12 @@ def test_unknown_layer_fails_like_the_reference(pkg):
 
 
 @pytest.mark.parametrize("opt", [2, 3])
-@pytest.mark.parametrize("width,size,arena", [(0.125, 160, 8 << 20), (0.25, 320, 16 << 20), (0.5, 128, 8 << 20), (0.5, 256, 8 << 20)])
-def test_generated_yolov5_batch(pkg, ob, width, size, arena, opt):
-    """batch sharded over image slots == oracle per image (run + decode + NMS)"""
-    blob = pkg.marsfile.build_yolov5(width=width, size=size, seed=9).to_bytes()
+@pytest.mark.parametrize("width,size,arena,nhwc", [(0.125, 160, 8 << 20, False), (0.25, 320, 16 << 20, False), (0.5, 128, 8 << 20, False),
+                                                   (0.5, 256, 8 << 20, False), (0.5, 256, 8 << 20, True), (0.25, 320, 16 << 20, True)])
+def test_generated_yolov5_batch(pkg, ob, width, size, arena, nhwc, opt):
+    """batch sharded over image slots == oracle per image (run + decode + NMS); nhwc = the compiler's --nhwc convention
+    (channel-innermost activations, OHWI weights: conv2d_int8_nhwc_mxu, reference src/mars/mxu_conv.c:713-757)"""
+    blob = pkg.marsfile.build_yolov5(width=width, size=size, seed=9, nhwc=nhwc).to_bytes()
     n = 5
     gm = pkg.MarsModel(blob, arena_bytes=arena, batch=n)
     gm.set_opt_level(opt)
@@ -195,12 +197,13 @@ def test_generated_yolov5_batch(pkg, ob, width, size, arena, opt):
     gm.close()
 
 
-def test_yolov5s_full_size(pkg, ob):
+@pytest.mark.parametrize("nhwc", [False, True])
+def test_yolov5s_full_size(pkg, ob, nhwc):
     """BASELINE config 3 shape: yolov5s-shaped 640x640 int8; two consecutive batches through the
     same image slots (default opt level), output tensor + detections bit-exact vs the oracle fed
-    the same image sequence per slot"""
+    the same image sequence per slot.  nhwc: the same graph in the compiler's --nhwc convention."""
     mf = pkg.marsfile
-    blob = mf.build_yolov5(width=0.5, size=640, seed=5).to_bytes()
+    blob = mf.build_yolov5(width=0.5, size=640, seed=5, nhwc=nhwc).to_bytes()
     n = 3
     gm = pkg.MarsModel(blob, arena_bytes=mf.ARENA_YOLOV5S_INT8, batch=n)
     oms = [ob.OracleModel(blob, arena_bytes=mf.ARENA_YOLOV5S_INT8) for _ in range(n)]

@@ -75,4 +75,14 @@ MICRO = [
     ("conv", dict(k=1, s=1, c=464, co=300, h=12, w=12)), ("conv", dict(k=3, s=1, c=48, co=32, h=20, w=20)),
     ("conv", dict(k=3, s=2, c=24, co=40, h=40, w=40)), ("conv", dict(k=3, s=1, c=116, co=58, h=20, w=20, padding=1)),
     ("conv", dict(k=5, s=1, c=40, co=272, h=12, w=14)),
+    # channel-innermost (--nhwc convention, conv2d_int8_nhwc_mxu) shapes on the tensor-core path: flat 1x1 tiles from the arena,
+    # rectangular tiles with one 4-d TMA box per tap (OOB zero fill, traversal stride 2), the stem, ragged channel counts
+    ("conv", dict(k=1, s=1, nhwc=True, c=32, co=64, h=20, w=20)), ("conv", dict(k=1, s=1, nhwc=True, c=128, co=512, h=8, w=8)),
+    ("conv", dict(k=1, s=1, nhwc=True, c=64, co=32, h=16, w=24)), ("conv", dict(k=1, s=1, nhwc=True, c=256, co=255, h=20, w=20)),
+    ("conv", dict(k=3, s=1, nhwc=True, c=32, co=32, h=20, w=20)), ("conv", dict(k=3, s=1, nhwc=True, c=64, co=255, h=13, w=11)),
+    ("conv", dict(k=3, s=1, nhwc=True, c=32, co=48, h=40, w=40, padding=1)), ("conv", dict(k=3, s=2, nhwc=True, c=64, co=128, h=40, w=40)),
+    ("conv", dict(k=3, s=2, nhwc=True, c=32, co=64, h=34, w=30, padding=1)), ("conv", dict(k=5, s=1, nhwc=True, c=32, co=32, h=20, w=20)),
+    ("conv", dict(k=3, s=1, nhwc=True, c=128, co=128, h=40, w=40)), ("conv", dict(k=3, s=1, nhwc=True, c=96, co=16, h=9, w=50, no_bias=True)),
+    ("conv", dict(k=6, s=2, nhwc=True, c=3, co=32, h=128, w=128, pad=2)), ("conv", dict(k=6, s=2, nhwc=True, c=4, co=48, h=128, w=160, pad=2, padding=1)),
+    ("conv", dict(k=3, s=1, nhwc=True, c=256, co=512, h=20, w=20)),
 ]

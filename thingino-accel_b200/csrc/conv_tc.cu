@@ -52,7 +52,7 @@ struct TcParams {
     uint32_t idesc;
     uint32_t b_layout;       /* UMMA LayoutType of the K-major operands: 2 = SW128, 4 = SW64, 6 = SW32 */
     int a_kmajor;            /* 0: A = NCHW planes (MN-major, SW128); 1: A = channel-innermost rows (K-major, swizzle = bk) */
-    uint32_t a_stage_bytes, b_stage_bytes, tx_bytes;
+    uint32_t a_stage_bytes, b_stage_bytes, tx_bytes, a_tx_bytes; /* a_tx_bytes: bytes the A loads of one pipeline step deliver */
     int a_shift[TC_MAX_TAPS];
     const int32_t *bias;     /* device pointer or null */
     float cs;
@@ -83,6 +83,12 @@ struct TcParams {
     int tw_shift, tiles_x;   /* M tile = (1 << tw_shift) x (128 >> tw_shift) output pixels */
     int gPH, gPWW, gdx;      /* patch rows per channel, 4-byte words per patch row, byte column of tap x = 0 */
     int g_align2;
+    /* rect mode (channel-innermost activations read straight from the arena, conv2d_int8_nhwc_mxu): an M tile is tw x th output
+     * pixels, a tap (kh, kw) is ONE 4-d TMA box {bk channels, tw pixels, th rows, 1 image} at input pixel (s*x0 + kw - pl,
+     * s*y0 + kh - pt) with traversal stride s; pixels outside the image arrive as zeros (the reference skips those taps) */
+    int rect, tw, th, rs, rpt, rpl;
+    unsigned tw_magic;       /* floor(2^32 / tw) + 1 */
+    int onhwc_vec;           /* OUT 2: 16-byte stores are legal (Co % 16 == 0, 16-byte aligned tensors) */
 };
 
 /* ---- PTX wrappers ------------------------------------------------------------- */
@@ -122,6 +128,10 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
 __device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap *map, uint32_t bar, int c0, int c1, int c2) {
     asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
                  ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap *map, uint32_t bar, int c0, int c1, int c2, int c3) {
+    asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+                 ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
 }
 /* D[tmem] (+)= A[smem] * B[smem]; the two 64-bit shared-memory matrix descriptors are given as 32-bit halves (the high
  * halves are loop invariants of the issuing thread) */
@@ -327,15 +337,57 @@ __device__ __forceinline__ void epilogue_unit(const uint32_t (&v)[16], uint32_t 
     }
 }
 
+/* OUT 2: the same 16 channels written channel-innermost -- one 16-byte store per stream (bytes of stream k = byte k of the
+ * table words); `vec` = the tensor allows 16-byte stores (Co % 16 == 0), otherwise (e.g. 255 head channels) bytes.
+ * o0..o2 point at channel c0 of this pixel in each stream's NHWC tensor. */
+template <int RQ, bool TAB, int NST>
+__device__ __forceinline__ void epilogue_unit_nhwc(const uint32_t (&v)[16], uint32_t cm, uint32_t tab_lane, uint32_t tab_stride, float cs,
+                                                   uint8_t *o0, uint8_t *o1, uint8_t *o2, int nch, bool vec) {
+    if (nch <= 0) return;
+    uint32_t pk[3][4];
+#pragma unroll
+    for (int j4 = 0; j4 < 4; j4++) {
+        const int4 c4 = lds_v4(cm + (uint32_t)j4 * 16u);
+        const int cc[4] = {c4.x, c4.y, c4.z, c4.w};
+        uint32_t w[4];
+#pragma unroll
+        for (int k = 0; k < 4; k += 2) {
+            int r0, r1;
+            requant_pair<RQ>((int32_t)(v[j4 * 4 + k] + (uint32_t)cc[k]), (int32_t)(v[j4 * 4 + k + 1] + (uint32_t)cc[k + 1]), cs, r0, r1);
+            w[k] = TAB ? lds_u32(tab_lane + (uint32_t)r0 * tab_stride) : (RQ == 2 ? (uint32_t)r0 ^ 0x80u : (uint32_t)r0);
+            w[k + 1] = TAB ? lds_u32(tab_lane + (uint32_t)r1 * tab_stride) : (RQ == 2 ? (uint32_t)r1 ^ 0x80u : (uint32_t)r1);
+        }
+        pk[0][j4] = __byte_perm(__byte_perm(w[0], w[1], 0x0040), __byte_perm(w[2], w[3], 0x0040), 0x5410);
+        if (NST > 1) pk[1][j4] = __byte_perm(__byte_perm(w[0], w[1], 0x0051), __byte_perm(w[2], w[3], 0x0051), 0x5410);
+        if (NST > 2) pk[2][j4] = __byte_perm(__byte_perm(w[0], w[1], 0x0062), __byte_perm(w[2], w[3], 0x0062), 0x5410);
+    }
+    if (vec && nch >= 16) {
+        *reinterpret_cast<uint4 *>(o0) = make_uint4(pk[0][0], pk[0][1], pk[0][2], pk[0][3]);
+        if (NST > 1) *reinterpret_cast<uint4 *>(o1) = make_uint4(pk[1][0], pk[1][1], pk[1][2], pk[1][3]);
+        if (NST > 2) *reinterpret_cast<uint4 *>(o2) = make_uint4(pk[2][0], pk[2][1], pk[2][2], pk[2][3]);
+    } else {
+#pragma unroll
+        for (int j = 0; j < 16; j++) {
+            if (j < nch) {
+                o0[j] = (uint8_t)(pk[0][j >> 2] >> (8 * (j & 3)));
+                if (NST > 1) o1[j] = (uint8_t)(pk[1][j >> 2] >> (8 * (j & 3)));
+                if (NST > 2) o2[j] = (uint8_t)(pk[2][j >> 2] >> (8 * (j & 3)));
+            }
+        }
+    }
+}
+
 /* ---- the kernel ----------------------------------------------------------------
  * Persistent: CTA b walks tiles b, b + gridDim.x, ... of the launch's (image, M tile, N tile) space; barriers, TMEM
  * and tables are set up once.  The accumulator is double buffered in TMEM, so the epilogue of tile t overlaps the
  * loads and MMAs of tile t+1.  Epilogue warps never synchronise with each other: thread = output pixel (TMEM lane),
  * registers = 16 output channels; per channel the 32 lanes of a warp store 32 consecutive pixels of one NCHW plane.
+ * OUT: 0 = NCHW planes, 1 = NCHW planes + the consumer's channel-innermost side copy, 2 = channel-innermost (NHWC) output
+ * tensors, 16 bytes per thread and unit.
  * GATHER (small Ci, e.g. the 6x6 stride-2 stem): M tiles are tw x th output pixels; four producer warps stage the
  * input patch of the tile in shared memory (next tile's patch is in flight in registers meanwhile) and build the
  * 128-byte K rows of the A operand from it, in the 128B-swizzled K-major layout TMA would have produced. */
-template <int RQ, bool GATHER, bool TAB, int NST, bool NHWC, int EPI>
+template <int RQ, bool GATHER, bool TAB, int NST, int OUT, int EPI>
 __global__ void __launch_bounds__((EPI + (GATHER ? 5 : 2)) * 32, EPI == 8 ? 2 : 1)
 k_conv_tc(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, const TcParams p) {
     extern __shared__ uint8_t smem_raw[];
@@ -414,7 +466,7 @@ k_conv_tc(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUte
         const uint32_t tab_stride = 4u * p.tab_rep; /* bytes between consecutive table entries */
         const uint32_t tab_lane = smem_base + p.tab_off + (RQ == 2 ? 0u : 128u * tab_stride) + 4u * ((uint32_t)lane & (p.tab_rep - 1u)); /* this lane's copy: entry r = 0 (RQ 2: entry r = -128, the requantisation returns r + 128) */
         const uint32_t sa_full = smem_u32(&bar_tmem_full[0]), sa_empty = smem_u32(&bar_tmem_empty[0]);
-        const bool flat = !GATHER && p.Wp == p.Wo && !NHWC; /* no pad columns: the tile row index IS the pixel index */
+        const bool flat = !GATHER && !p.rect && p.Wp == p.Wo && OUT != 1; /* no pad columns: the tile row index IS the pixel index */
         uint8_t *const obase = p.out_base + r; /* + image * slot_stride + pixel + channel * plane + stream offset */
         const int G = p.grp, gcols = p.grp * p.n_tile;
         const int total_items = G * n_units, ipp = (total_items + parts - 1) / parts;
@@ -456,6 +508,11 @@ k_conv_tc(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUte
                             oh = ty * (TC_BM >> p.tw_shift) + (r >> p.tw_shift);
                             ow = (tx << p.tw_shift) + (r & ((1 << p.tw_shift) - 1));
                             valid = oh < p.Ho && ow < p.Wo;
+                        } else if (p.rect) { /* tw x th output pixels, row-major inside the tile */
+                            const int ty = mt / p.tiles_x, tx = mt - ty * p.tiles_x;
+                            const int ry = (int)__umulhi((unsigned)r, p.tw_magic), rx = r - ry * p.tw;
+                            oh = ty * p.th + ry; ow = tx * p.tw + rx;
+                            valid = ry < p.th && oh < p.Ho && ow < p.Wo;
                         } else {
                             const int q = mt * TC_BM + r;
                             oh = (int)__umulhi((unsigned)q, p.wp_magic); ow = q - oh * p.Wp; /* q / Wp, exact for q * Wp < 2^32 (checked on the host) */
@@ -464,9 +521,11 @@ k_conv_tc(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUte
                         pix = oh * p.Wo + ow - r;
                     }
                     const int co_left = valid ? p.Co - n0 : 0; /* channels of this N tile that exist for this pixel (<= 0: nothing to store) */
-                    uint8_t *pix_base = img_base + pix + (long long)(u_lo * 16) * plane; /* channel n0 + 16 u_lo of this pixel */
+                    /* channel n0 + 16 u_lo of this pixel: NCHW planes, or (OUT 2) the pixel's channel vector */
+                    uint8_t *pix_base = OUT == 2 ? p.out_base + ((unsigned long long)ti.img * p.slot_stride + (long long)(pix + r) * p.Co + n0 + u_lo * 16)
+                                                 : img_base + pix + (long long)(u_lo * 16) * plane;
                     uint8_t *nh = nullptr;
-                    if (NHWC) {
+                    if (OUT == 1) {
                         long long dp;
                         if (p.nhwc_mode == 2) {
                             const int yy = oh + p.nhwc_pt, xx = ow + p.nhwc_pl;
@@ -474,7 +533,7 @@ k_conv_tc(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUte
                         } else dp = (long long)oh * p.nhwc_Wp + ow + p.nhwc_pl;
                         nh = p.nhwc_base + (unsigned long long)ti.img * p.nhwc_stride + dp * p.nhwc_C + n0;
                     }
-                    const long long plane16 = plane * 16;
+                    const long long plane16 = OUT == 2 ? 16 : plane * 16;
                     const uint32_t acc_g = acc_grp + (uint32_t)(g * p.n_tile);
                     const bool last_g = g == g_last;
                     /* units u_lo .. u_hi-1 of this M tile, the TMEM load of the next one in flight while one is processed */
@@ -489,8 +548,10 @@ k_conv_tc(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUte
                             if (lane == 0) mbar_arrive(sa_empty + 8u * ab);
                         }
                         if (p.dbg >= 2) { if (va[0] == 0x12345678u && va[7] == 0x9abcdef0u) pix_base[p.out_off[0]] = 1; }
-                        else epilogue_unit<RQ, TAB, NST, NHWC>(va, cm0 + 64u * (uint32_t)u, tab_lane, tab_stride, cs, pix_base + p.out_off[0], pix_base + p.out_off[1],
-                                                               pix_base + p.out_off[2], plane, co_left - u * 16, nh + u * 16);
+                        else if (OUT == 2) epilogue_unit_nhwc<RQ, TAB, NST>(va, cm0 + 64u * (uint32_t)u, tab_lane, tab_stride, cs, pix_base + p.out_off[0], pix_base + p.out_off[1],
+                                                                            pix_base + p.out_off[2], co_left - u * 16, p.onhwc_vec != 0);
+                        else epilogue_unit<RQ, TAB, NST, OUT == 1>(va, cm0 + 64u * (uint32_t)u, tab_lane, tab_stride, cs, pix_base + p.out_off[0], pix_base + p.out_off[1],
+                                                                   pix_base + p.out_off[2], plane, co_left - u * 16, nh + u * 16);
                         pix_base += plane16;
                         if (++u >= u_hi) break;
                         tmem_ld_wait(vb);
@@ -501,8 +562,10 @@ k_conv_tc(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUte
                             if (lane == 0) mbar_arrive(sa_empty + 8u * ab);
                         }
                         if (p.dbg >= 2) { if (vb[0] == 0x12345678u && vb[7] == 0x9abcdef0u) pix_base[p.out_off[0]] = 1; }
-                        else epilogue_unit<RQ, TAB, NST, NHWC>(vb, cm0 + 64u * (uint32_t)u, tab_lane, tab_stride, cs, pix_base + p.out_off[0], pix_base + p.out_off[1],
-                                                               pix_base + p.out_off[2], plane, co_left - u * 16, nh + u * 16);
+                        else if (OUT == 2) epilogue_unit_nhwc<RQ, TAB, NST>(vb, cm0 + 64u * (uint32_t)u, tab_lane, tab_stride, cs, pix_base + p.out_off[0], pix_base + p.out_off[1],
+                                                                            pix_base + p.out_off[2], co_left - u * 16, p.onhwc_vec != 0);
+                        else epilogue_unit<RQ, TAB, NST, OUT == 1>(vb, cm0 + 64u * (uint32_t)u, tab_lane, tab_stride, cs, pix_base + p.out_off[0], pix_base + p.out_off[1],
+                                                                   pix_base + p.out_off[2], plane, co_left - u * 16, nh + u * 16);
                         pix_base += plane16;
                         if (++u >= u_hi) break;
                     }
@@ -607,19 +670,24 @@ k_conv_tc(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUte
                     }
                 }
             } else {
-                const uint32_t tx = b_res ? a_stb : p.tx_bytes;
+                const uint32_t tx = p.a_tx_bytes + (b_res ? 0u : (uint32_t)(p.n_tile * bk));
+                const bool rect = p.rect != 0;
                 for (TileIter ti(blockIdx.x, gridDim.x, tiles_per_img); ti.img < n_img; ti.next()) {
                     const int mg = n_tiles == 1 ? ti.rem : ti.rem / n_tiles, n0 = (ti.rem - mg * n_tiles) * p.n_tile;
                     const int q0 = mg * G * TC_BM, zc = p.img0 + ti.img;
                     for (int tap = 0; tap < ntaps; tap++) {
-                        const int qa = q0 + s_shift[tap];
+                        const int sh = s_shift[tap], qa = q0 + sh; /* rect mode: sh = kh << 16 | kw */
                         for (int kb = 0; kb < ksteps; kb++) {
                             mbar_wait(sa_empty + 8u * s, ph);
                             const uint32_t full = sa_full + 8u * s;
                             if (p.dbg == 3 || p.dbg == 9) { mbar_arrive(full); if (++s == stages) { s = 0; ph ^= 1; } continue; }
                             mbar_expect_tx(full, tx);
                             for (int g = 0; g < G; g++) { /* rows beyond the tensor (last, partial group) are zero-filled */
-                                if (a_km) tma_load_3d(a_base + s * a_stb + g * a_tb, &mapA, full, kb * bk, qa + g * TC_BM, zc);
+                                if (rect) {
+                                    const int mt = mg * G + g, ty = mt / p.tiles_x, tx0 = mt - ty * p.tiles_x;
+                                    tma_load_4d(a_base + s * a_stb + g * a_tb, &mapA, full, kb * bk, tx0 * p.tw * p.rs + (sh & 0xFFFF) - p.rpl,
+                                                ty * p.th * p.rs + (sh >> 16) - p.rpt, zc);
+                                } else if (a_km) tma_load_3d(a_base + s * a_stb + g * a_tb, &mapA, full, kb * bk, qa + g * TC_BM, zc);
                                 else tma_load_3d(a_base + s * a_stb + g * a_tb, &mapA, full, q0 + g * TC_BM, kb * bk, zc);
                             }
                             if (!b_res) tma_load_3d(b_base + s * b_stb, &mapB, full, kb * bk, n0, tap);
@@ -765,7 +833,7 @@ __global__ void __launch_bounds__(256) k_to_nhwc(const uint8_t *src_base, unsign
  * image): P[(y+1)*Wp + (x+1)][16] = the 2x2 input block (2y+py, 2x+px) of every channel, byte c' = ci*4 + py*2 + px,
  * zero border and zero beyond 4*C bytes.  One thread per P pixel. */
 __global__ void __launch_bounds__(256) k_s2d16(const uint8_t *__restrict__ src_base, unsigned long long src_stride, uint8_t *__restrict__ dst_base,
-                                               unsigned long long dst_stride, int C, int H, int W, int Wp, int npix) {
+                                               unsigned long long dst_stride, int C, int H, int W, int Wp, int npix, int src_nhwc) {
     const uint8_t *src = src_base + (unsigned long long)blockIdx.y * src_stride;
     uint4 *dst = reinterpret_cast<uint4 *>(dst_base + (unsigned long long)blockIdx.y * dst_stride);
     /* four pixels per thread, 256 apart: all their loads are issued before the first store (the kernel is pure latency) */
@@ -783,8 +851,13 @@ __global__ void __launch_bounds__(256) k_s2d16(const uint8_t *__restrict__ src_b
 #pragma unroll
                 for (int ci = 0; ci < 4; ci++) { /* the mode requires C <= 4 */
                     if (ci < C) {
-                        const uint8_t *r0 = src + ((long long)ci * H + 2 * y) * W + 2 * x;
-                        w[k][ci] = (uint32_t)*reinterpret_cast<const uint16_t *>(r0) | ((uint32_t)*reinterpret_cast<const uint16_t *>(r0 + W) << 16);
+                        if (src_nhwc) { /* channel-innermost source: pixel (yy, xx) channel ci at (yy * W + xx) * C + ci */
+                            const uint8_t *r0 = src + ((long long)(2 * y) * W + 2 * x) * C + ci;
+                            w[k][ci] = (uint32_t)r0[0] | ((uint32_t)r0[C] << 8) | ((uint32_t)r0[(long long)W * C] << 16) | ((uint32_t)r0[(long long)W * C + C] << 24);
+                        } else {
+                            const uint8_t *r0 = src + ((long long)ci * H + 2 * y) * W + 2 * x;
+                            w[k][ci] = (uint32_t)*reinterpret_cast<const uint16_t *>(r0) | ((uint32_t)*reinterpret_cast<const uint16_t *>(r0 + W) << 16);
+                        }
                     }
                 }
             }
@@ -797,13 +870,14 @@ __global__ void __launch_bounds__(256) k_s2d16(const uint8_t *__restrict__ src_b
     }
 }
 /* OIHW 6x6 weights -> [t = ky2*2 + pair][Co_pad][32]: K byte k = (pixel kx2 = 2*pair + k/16, channel byte c' = k%16) */
-__global__ void k_repack_s2d(const int8_t *w, int8_t *dst, int Co, int Co_pad, int Ci) {
+__global__ void k_repack_s2d(const int8_t *w, int8_t *dst, int Co, int Co_pad, int Ci, int ohwi) {
     const long long total = 6ll * Co_pad * 32;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
         const int k = (int)(i % 32), co = (int)((i / 32) % Co_pad), t = (int)(i / (32ll * Co_pad));
         const int ky2 = t >> 1, kx2 = 2 * (t & 1) + (k >> 4), cp = k & 15, ci = cp >> 2, py = (cp >> 1) & 1, px = cp & 1;
         int8_t v = 0;
-        if (co < Co && ci < Ci && kx2 < 3) v = w[(((long long)co * Ci + ci) * 6 + (2 * ky2 + py)) * 6 + (2 * kx2 + px)];
+        if (co < Co && ci < Ci && kx2 < 3) v = ohwi ? w[(((long long)co * 6 + (2 * ky2 + py)) * 6 + (2 * kx2 + px)) * Ci + ci]
+                                                    : w[(((long long)co * Ci + ci) * 6 + (2 * ky2 + py)) * 6 + (2 * kx2 + px)];
         dst[i] = v;
     }
 }
@@ -816,13 +890,13 @@ __global__ void k_repack_rows(const int8_t *w, int8_t *dst, int Co, int Co_pad, 
     }
 }
 /* OIHW -> [tap][Co_pad][Cip], rows beyond Co and columns beyond Ci zero */
-__global__ void k_repack_weights(const int8_t *w, int8_t *dst, int Co, int Co_pad, int Ci, int Cip, int ntaps) {
+__global__ void k_repack_weights(const int8_t *w, int8_t *dst, int Co, int Co_pad, int Ci, int Cip, int ntaps, int ohwi) {
     long long total = (long long)ntaps * Co_pad * Cip; /* Cip >= Ci: K extent per tap, columns beyond Ci zero */
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
         int ci = (int)(i % Cip);
         long long r = i / Cip;
         int co = (int)(r % Co_pad), tap = (int)(r / Co_pad);
-        dst[i] = (co < Co && ci < Ci) ? w[((long long)co * Ci + ci) * ntaps + tap] : (int8_t)0;
+        dst[i] = (co < Co && ci < Ci) ? (ohwi ? w[((long long)co * ntaps + tap) * Ci + ci] : w[((long long)co * Ci + ci) * ntaps + tap]) : (int8_t)0;
     }
 }
 
@@ -849,6 +923,7 @@ struct TcPlanImpl {
     int ctas_per_sm = 2;
     int epi = 8; /* epilogue warps per CTA */
     int sms = 0; /* multiprocessors of the device the plan was built on */
+    int nhwc_in = 0;  /* channel-innermost activations / OHWI weights (OP_CONV_I8_NHWC) */
     bool gather_direct = false; /* gather mode reads the input tensor in the arena itself (no private copy needed) */
 };
 
@@ -888,20 +963,78 @@ static bool make_map3(CUtensorMap *m, void *base, uint64_t d0, uint64_t d1, uint
     return true;
 }
 
+/* 4-d map over channel-innermost activations: dims (C, W, H, images), box {bc channels, bw, bh, 1} traversed with stride es in W
+ * and H (the box covers bw / es x bh / es pixels); coordinates outside the tensor read as zeros */
+static bool make_map4(CUtensorMap *m, void *base, uint64_t C, uint64_t W, uint64_t H, uint64_t N, uint64_t img_stride, uint32_t bc,
+                      uint32_t bw, uint32_t bh, uint32_t es, CUtensorMapSwizzle sw) {
+    EncodeTiledFn enc = encode_tiled();
+    if (!enc) return false;
+    cuuint64_t dims[4] = {C, W, H, N};
+    cuuint64_t strides[3] = {C, W * C, img_stride};
+    cuuint32_t box[4] = {bc, bw, bh, 1};
+    cuuint32_t estr[4] = {1, es, es, 1};
+    CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_UINT8, 4, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
+                     CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        set_last_error("cuTensorMapEncodeTiled (4-d) failed: %d (dims %llu %llu %llu %llu box %u %u %u stride %u)", (int)r, (unsigned long long)C,
+                       (unsigned long long)W, (unsigned long long)H, (unsigned long long)N, bc, bw, bh, es);
+        return false;
+    }
+    return true;
+}
+
 static int round_up(int x, int a) { return (x + a - 1) / a * a; }
 
 /* geometry shared by tc_scratch_need and tc_plan */
 struct TcGeom {
     bool ok = false;
     int prepass = 0; /* 4: space-to-depth copy with 16-byte pixels (stem); 0: A from the arena (1x1); 1: NHWC copy, rows padded (stride 1); 2: NHWC 2x2 phase split (stride 2);
-                        3: gather -- A rows built in shared memory from a private NCHW copy of the input (small Ci) */
+                        3: gather -- A rows built in shared memory from a private NCHW copy of the input (small Ci);
+                        5: NHWC 1x1 -- flat tiles, A rows = the arena tensor's pixels; 6: NHWC kxk -- rect tiles, one 4-d TMA box per tap */
     int Wp = 0, plane = 0, npix = 0, ntaps = 0, Kp = 0;
     int kpad = 0; /* prepass 0 with Ci not a multiple of 32: K extent padded with zeros (TMA fills the missing channel rows, the repacked weights hold zeros) */
     int tw_shift = 0, PH = 0, PWW = 0, dx = 0; /* gather: M tile shape and input patch geometry */
+    int rtw = 0, rth = 0; /* rect mode (prepass 6): output pixels per tile row / tile rows, rtw * rth <= 128 */
     size_t scratch_bytes = 0;
 };
 static TcGeom tc_geometry(const Op &o) {
     TcGeom g;
+    if (o.kind == OP_CONV_I8_NHWC) { /* channel-innermost activations and OHWI weights (reference src/mars/mxu_conv.c:713-757) */
+        if (o.mode != EXEC_PARALLEL || o.xlat) return g;
+        if (o.oc < 16 || o.sh != o.sw || o.sh < 1 || o.sh > 2 || o.kh < 1 || o.kh != o.kw) return g;
+        if (o.oh <= 0 || o.ow <= 0 || o.ih <= 0 || o.iw <= 0 || o.ic <= 0 || round_up(o.oc, 16) > TC_MAX_CO) return g;
+        if (o.pt < 0 || o.pl < 0 || o.pt >= o.kh || o.pl >= o.kw) return g;
+        g.ntaps = o.kh * o.kw;
+        if (g.ntaps > TC_MAX_TAPS) return g;
+        static const bool s2d_enabled = !(getenv("MARS_TC_S2D") && atoi(getenv("MARS_TC_S2D")) == 0);
+        if (s2d_enabled && o.sh == 2 && o.kh == 6 && (o.pt == 0 || o.pt == 2) && (o.pl == 0 || o.pl == 2) && o.ic <= 4 && o.ih % 2 == 0 &&
+            o.iw % 2 == 0 && o.oh <= o.ih / 2 && o.ow <= o.iw / 2 && round_up(o.oc, 16) <= 128 && (long long)o.oh * o.ow >= 4096) {
+            /* the stem: the same space-to-depth copy as the NCHW stem, gathered from interleaved pixels */
+            g.prepass = 4; g.Wp = o.iw / 2 + 2; g.plane = (o.ih / 2 + 2) * g.Wp; g.npix = g.plane; g.ntaps = 6; g.Kp = 32;
+            g.scratch_bytes = (size_t)g.npix * 16;
+            g.ok = true;
+            return g;
+        }
+        if (o.ic < 32 || o.ic % 32) return g; /* K rows are the pixels' channel vectors: whole 32-byte k-steps only */
+        if (o.kh == 1 && o.sh == 1 && o.pt == 0 && o.pl == 0 && o.oh <= o.ih && o.ow == o.iw) {
+            g.prepass = 5; g.Wp = o.iw; /* 1x1: flat 128-pixel tiles, A rows straight from the arena tensor (or a private copy) */
+            g.scratch_bytes = (size_t)o.ic * o.ih * o.iw;
+        } else {
+            /* kxk / strided: an M tile is tw x th output pixels; a tap is one 4-d TMA box with OOB zero fill.  Least waste wins */
+            long long best = -1;
+            for (int tw = 2; tw <= 128 && tw <= o.ow + 15; tw++) {
+                const int th = 128 / tw;
+                if (tw * o.sh > 256 || th * o.sh > 256 || th < 1) continue;
+                const long long tiles = (long long)((o.ow + tw - 1) / tw) * ((o.oh + th - 1) / th);
+                if (best < 0 || tiles < best) { best = tiles; g.rtw = tw; g.rth = th; }
+            }
+            if (best < 0) return g;
+            g.prepass = 6; g.Wp = o.ow;
+            g.scratch_bytes = (size_t)o.ic * o.ih * o.iw; /* private copy of the input when a fused output overwrites it */
+        }
+        g.ok = true;
+        return g;
+    }
     if (o.kind != OP_CONV_I8_NCHW || o.mode != EXEC_PARALLEL || o.xlat) return g;
     if (o.oc < 16 || o.sh != o.sw || o.sh < 1 || o.kh < 1 || o.kw < 1) return g;
     if (o.oh <= 0 || o.ow <= 0 || o.ih <= 0 || o.iw <= 0 || o.ic <= 0) return g;
@@ -994,7 +1127,7 @@ int tc_n_tiles(int oc) {
     const int nt = co_pad <= 256 ? co_pad : (co_pad % 256 == 0 ? 256 : 128);
     return (co_pad + nt - 1) / nt;
 }
-bool tc_uses_copy(const Op &o) { return tc_geometry(o).prepass != 0; }
+bool tc_uses_copy(const Op &o) { return tc_geometry(o).prepass != 0; } /* (NHWC layers: a private copy on demand, see tc_plan) */
 bool tc_linkable(const Op &o) { const TcGeom g = tc_geometry(o); return g.ok && (g.prepass == 1 || g.prepass == 2) && !g.kpad; }
 
 /* the word table of the epilogue: index = r + 128 (r = the clamped conv output); byte k = value of output stream k, byte 3 =
@@ -1061,40 +1194,50 @@ static bool halfup_requant_ok(float cs, long long bound) {
     return true;
 }
 
-/* kernel variants: FAST requant x GATHER producer x word table x number of stored NCHW streams x NHWC side output.
- * Without a table (plain conv, no byte-ReLU) there is one stream at most. */
+/* kernel variants: requantisation x GATHER producer x word table x number of stored streams x output mode (0 NCHW planes,
+ * 1 + side copy, 2 channel-innermost tensors).  Without a table (plain conv, no byte-ReLU) there is one stream at most. */
 template <int RQ, bool GATHER, int EPI>
-static TcKernel pick_kernel2(bool tab, int nst, bool nhwc) {
-    if (!tab) {
-        switch (nst * 2 + (nhwc ? 1 : 0)) {
-            case 0: return k_conv_tc<RQ, GATHER, false, 0, false, EPI>;
-            case 1: return k_conv_tc<RQ, GATHER, false, 0, true, EPI>;
-            case 2: return k_conv_tc<RQ, GATHER, false, 1, false, EPI>;
-            default: return k_conv_tc<RQ, GATHER, false, 1, true, EPI>;
+static TcKernel pick_kernel2(bool tab, int nst, int out) {
+    if (out == 2) {
+        if (GATHER) return nullptr;
+        if (!tab) return nst == 1 ? k_conv_tc<RQ, false, false, 1, 2, EPI> : nullptr;
+        switch (nst) {
+            case 1: return k_conv_tc<RQ, false, true, 1, 2, EPI>;
+            case 2: return k_conv_tc<RQ, false, true, 2, 2, EPI>;
+            case 3: return k_conv_tc<RQ, false, true, 3, 2, EPI>;
+            default: return nullptr;
         }
     }
-    switch (nst * 2 + (nhwc ? 1 : 0)) {
-        case 0: return k_conv_tc<RQ, GATHER, true, 0, false, EPI>;
-        case 1: return k_conv_tc<RQ, GATHER, true, 0, true, EPI>;
-        case 2: return k_conv_tc<RQ, GATHER, true, 1, false, EPI>;
-        case 3: return k_conv_tc<RQ, GATHER, true, 1, true, EPI>;
-        case 4: return k_conv_tc<RQ, GATHER, true, 2, false, EPI>;
-        case 5: return k_conv_tc<RQ, GATHER, true, 2, true, EPI>;
-        case 6: return k_conv_tc<RQ, GATHER, true, 3, false, EPI>;
-        default: return k_conv_tc<RQ, GATHER, true, 3, true, EPI>;
+    if (!tab) {
+        switch (nst * 2 + out) {
+            case 0: return k_conv_tc<RQ, GATHER, false, 0, 0, EPI>;
+            case 1: return k_conv_tc<RQ, GATHER, false, 0, 1, EPI>;
+            case 2: return k_conv_tc<RQ, GATHER, false, 1, 0, EPI>;
+            default: return k_conv_tc<RQ, GATHER, false, 1, 1, EPI>;
+        }
+    }
+    switch (nst * 2 + out) {
+        case 0: return k_conv_tc<RQ, GATHER, true, 0, 0, EPI>;
+        case 1: return k_conv_tc<RQ, GATHER, true, 0, 1, EPI>;
+        case 2: return k_conv_tc<RQ, GATHER, true, 1, 0, EPI>;
+        case 3: return k_conv_tc<RQ, GATHER, true, 1, 1, EPI>;
+        case 4: return k_conv_tc<RQ, GATHER, true, 2, 0, EPI>;
+        case 5: return k_conv_tc<RQ, GATHER, true, 2, 1, EPI>;
+        case 6: return k_conv_tc<RQ, GATHER, true, 3, 0, EPI>;
+        default: return k_conv_tc<RQ, GATHER, true, 3, 1, EPI>;
     }
 }
 /* gather mode always runs two CTAs per SM (N tile <= 256 columns of TMEM in total), i.e. 8 epilogue warps */
 template <int RQ>
-static TcKernel pick_kernel1(bool gather, bool tab, int nst, bool nhwc, int epi) {
-    if (gather) return pick_kernel2<RQ, true, 8>(tab, nst, nhwc);
-    if (epi == 16) return pick_kernel2<RQ, false, 16>(tab, nst, nhwc);
-    return pick_kernel2<RQ, false, 8>(tab, nst, nhwc);
+static TcKernel pick_kernel1(bool gather, bool tab, int nst, int out, int epi) {
+    if (gather) return pick_kernel2<RQ, true, 8>(tab, nst, out);
+    if (epi == 16) return pick_kernel2<RQ, false, 16>(tab, nst, out);
+    return pick_kernel2<RQ, false, 8>(tab, nst, out);
 }
-static TcKernel pick_kernel(int rq, bool gather, bool tab, int nst, bool nhwc, int epi) {
-    if (rq == 2) return pick_kernel1<2>(gather, tab, nst, nhwc, epi);
-    if (rq == 1) return pick_kernel1<1>(gather, tab, nst, nhwc, epi);
-    return pick_kernel1<0>(gather, tab, nst, nhwc, epi);
+static TcKernel pick_kernel(int rq, bool gather, bool tab, int nst, int out, int epi) {
+    if (rq == 2) return pick_kernel1<2>(gather, tab, nst, out, epi);
+    if (rq == 1) return pick_kernel1<1>(gather, tab, nst, out, epi);
+    return pick_kernel1<0>(gather, tab, nst, out, epi);
 }
 
 bool tc_plan(const Op &o, const ArenaGeom &ag, uint8_t *scratch, size_t scratch_stride, uint8_t *linked, size_t linked_stride,
@@ -1106,7 +1249,9 @@ bool tc_plan(const Op &o, const ArenaGeom &ag, uint8_t *scratch, size_t scratch_
     TcPlanImpl *t = new TcPlanImpl();
     TcParams &p = t->p;
     memset(&p, 0, sizeof p);
-    const bool gather = g.prepass == 3, s2d = g.prepass == 4;
+    const bool gather = g.prepass == 3, s2d = g.prepass == 4, rect = g.prepass == 6;
+    const int nhwc_in = o.kind == OP_CONV_I8_NHWC ? 1 : 0;
+    t->nhwc_in = nhwc_in;
     const int ci_eff = (gather || s2d) ? g.Kp : (g.kpad ? g.kpad : o.ic); /* K extent of one tap */
     p.Co = o.oc; p.Ho = o.oh; p.Wo = o.ow; p.Wp = g.Wp; p.mflat = o.oh * g.Wp; p.plane = o.oh * o.ow;
     const int co_pad = round_up(o.oc, 16);
@@ -1210,7 +1355,8 @@ bool tc_plan(const Op &o, const ArenaGeom &ag, uint8_t *scratch, size_t scratch_
     for (int kh = 0; kh < ((gather || s2d) ? (s2d ? 0 : 1) : o.kh); kh++)
         for (int kw = 0; kw < (gather ? 1 : o.kw); kw++) {
             const int tap = kh * o.kw + kw;
-            if (g.prepass == 0 || gather) p.a_shift[tap] = 0;
+            if (g.prepass == 0 || g.prepass == 5 || gather) p.a_shift[tap] = 0;
+            else if (rect) p.a_shift[tap] = (kh << 16) | kw;
             else if (g.prepass == 1) p.a_shift[tap] = (kh - o.pt) * g.Wp + kw;
             else p.a_shift[tap] = ((kh & 1) * 2 + (kw & 1)) * g.plane + (kh / 2) * g.Wp + kw / 2;
         }
@@ -1223,6 +1369,16 @@ bool tc_plan(const Op &o, const ArenaGeom &ag, uint8_t *scratch, size_t scratch_
     p.wp_magic = (unsigned)((1ull << 32) / (unsigned)g.Wp) + 1u;
     /* (+ 2 rows: the s2d pre-pass divides pixel indices of the bordered image by Wp with the same multiply-high trick) */
     if ((unsigned long long)(p.mflat + 2 * g.Wp) * (unsigned)g.Wp >= (1ull << 32) || (long long)p.m_tiles * p.n_tiles * ag.capacity >= (1ll << 31)) { delete t; return false; }
+    p.a_tx_bytes = p.a_stage_bytes;
+    if (rect) {
+        p.rect = 1; p.tw = g.rtw; p.th = g.rth; p.rs = o.sh; p.rpt = o.pt; p.rpl = o.pl;
+        p.tw_magic = (unsigned)((1ull << 32) / (unsigned)g.rtw) + 1u;
+        p.tiles_x = (o.ow + g.rtw - 1) / g.rtw;
+        p.m_tiles = p.tiles_x * ((o.oh + g.rth - 1) / g.rth);
+        p.m_groups = (p.m_tiles + p.grp - 1) / p.grp;
+        p.a_tx_bytes = (uint32_t)(p.grp * p.bk * g.rtw * g.rth);
+    }
+    if (nhwc_in) p.onhwc_vec = (o.oc % 16 == 0) ? 1 : 0;
     if (gather) {
         const int tw = 1 << g.tw_shift, th = TC_BM >> g.tw_shift;
         p.tw_shift = g.tw_shift;
@@ -1281,6 +1437,20 @@ bool tc_plan(const Op &o, const ArenaGeom &ag, uint8_t *scratch, size_t scratch_
         p.gKt = o.ic * o.kh * o.kw;
     }
 
+    if (rect || g.prepass == 5) {
+        /* read the arena tensor itself unless a stored stream overwrites it while other tiles still need it (round-robin work
+         * buffers).  A 1x1 layer with Ci == Co and one N tile may write onto its own input: every CTA has read the
+         * pixels it overwrites (same bytes) before its epilogue starts. */
+        const int64_t in_lo = o.in0 - (int64_t)ag.W, in_hi = in_lo + (int64_t)o.ic * o.ih * o.iw;
+        t->gather_direct = true;
+        for (int k = 0; k < t->nst; k++) {
+            if (!(p.out_off[k] < in_hi && in_lo < p.out_off[k] + (int64_t)o.oc * o.oh * o.ow)) continue;
+            const bool own_pixels = g.prepass == 5 && p.out_off[k] == in_lo && o.ic == o.oc && p.n_tiles == 1;
+            if (!own_pixels) t->gather_direct = false;
+        }
+    }
+    if (nhwc_in && t->nst == 0) { delete t; return false; } /* nothing to store: not a case the planner produces */
+
     /* weights: [tap][co_pad][Ci] K-major, and the epilogue table */
     const size_t wr_bytes = (size_t)g.ntaps * co_pad * ci_eff;
     uint32_t lutw[256];
@@ -1291,11 +1461,11 @@ bool tc_plan(const Op &o, const ArenaGeom &ag, uint8_t *scratch, size_t scratch_
     cudaMemcpy(t->d_lutw, lutw, sizeof lutw, cudaMemcpyHostToDevice);
     p.lutw = t->d_lutw;
     if (s2d)
-        k_repack_s2d<<<64, 256>>>(reinterpret_cast<const int8_t *>(ag.d_weights + o.w), t->d_wr, o.oc, co_pad, o.ic);
+        k_repack_s2d<<<64, 256>>>(reinterpret_cast<const int8_t *>(ag.d_weights + o.w), t->d_wr, o.oc, co_pad, o.ic, nhwc_in);
     else if (gather)
         k_repack_rows<<<256, 256>>>(reinterpret_cast<const int8_t *>(ag.d_weights + o.w), t->d_wr, o.oc, co_pad, o.ic * o.kh * o.kw, g.Kp);
     else
-        k_repack_weights<<<256, 256>>>(reinterpret_cast<const int8_t *>(ag.d_weights + o.w), t->d_wr, o.oc, co_pad, o.ic, ci_eff, g.ntaps);
+        k_repack_weights<<<256, 256>>>(reinterpret_cast<const int8_t *>(ag.d_weights + o.w), t->d_wr, o.oc, co_pad, o.ic, ci_eff, g.ntaps, nhwc_in);
     bool ok = cudaDeviceSynchronize() == cudaSuccess;
 
     const CUtensorMapSwizzle ksw = p.bk == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : (p.bk == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
@@ -1305,6 +1475,13 @@ bool tc_plan(const Op &o, const ArenaGeom &ag, uint8_t *scratch, size_t scratch_
     else if (ok && s2d) /* 16-byte pixels, linear rows (no swizzle): the MMA reads them as overlapping 32-byte K rows */
         ok = make_map3(&t->mapA, scratch, 16, (uint64_t)g.npix, (uint64_t)ag.capacity, 16, scratch_stride, 16, (uint32_t)p.halo_rb,
                        CU_TENSOR_MAP_SWIZZLE_NONE);
+    else if (ok && g.prepass == 5) /* the arena tensor's pixels are the K rows: dims (C, pixels, images), K-major box {bk, 128} */
+        ok = make_map3(&t->mapA, t->gather_direct ? (void *)t->src_slot0 : (void *)scratch, (uint64_t)o.ic, (uint64_t)o.ih * o.iw, (uint64_t)ag.capacity,
+                       (uint64_t)o.ic, t->gather_direct ? ag.slot_stride : scratch_stride, (uint32_t)p.bk, TC_BM, ksw);
+    else if (ok && rect)
+        ok = make_map4(&t->mapA, t->gather_direct ? (void *)t->src_slot0 : (void *)scratch, (uint64_t)o.ic, (uint64_t)o.iw, (uint64_t)o.ih,
+                       (uint64_t)ag.capacity, t->gather_direct ? ag.slot_stride : scratch_stride, (uint32_t)p.bk, (uint32_t)(g.rtw * o.sh),
+                       (uint32_t)(g.rth * o.sh), (uint32_t)o.sh, ksw);
     else if (ok && !gather) /* NHWC copy: dims (C, pixels, images), K-major box {bk, 128} */
         ok = make_map3(&t->mapA, scratch, (uint64_t)ci_eff, (uint64_t)g.npix, (uint64_t)ag.capacity, (uint64_t)ci_eff,
                        scratch_stride, (uint32_t)p.bk, p.halo ? (uint32_t)p.halo_rb : TC_BM, ksw);
@@ -1318,7 +1495,8 @@ bool tc_plan(const Op &o, const ArenaGeom &ag, uint8_t *scratch, size_t scratch_
                          (uint64_t)co_pad * ci_eff, (uint32_t)p.bk, (uint32_t)p.n_tile, ksw);
     { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&t->sms, cudaDevAttrMultiProcessorCount, dev); }
     t->epi = (!gather && t->ctas_per_sm == 1) ? 16 : 8;
-    t->kernel = pick_kernel(t->rq, gather, t->tab, t->nst, p.nhwc_sel >= 0, t->epi);
+    t->kernel = pick_kernel(t->rq, gather, t->tab, t->nst, nhwc_in ? 2 : (p.nhwc_sel >= 0 ? 1 : 0), t->epi);
+    ok = ok && t->kernel != nullptr;
     ok = ok && cudaFuncSetAttribute((const void *)t->kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 210 * 1024) == cudaSuccess;
     if (!ok) { cudaFree(t->d_wr); cudaFree(t->d_lutw); delete t; return false; }
     if (getenv("MARS_TC_VERBOSE"))
@@ -1340,8 +1518,11 @@ bool tc_launch(const TcPlan &plan, uint8_t *slots_base, int first, int n, bool u
         if (cudaMemcpy2DAsync(scr, t->scratch_stride, src, t->slot_stride, (size_t)t->C * t->H * t->W, (size_t)n,
                               cudaMemcpyDeviceToDevice, s) != cudaSuccess) return false;
     } else if (t->prepass == 4) {
-        k_s2d16<<<dim3((t->npix + 1023) / 1024, n), 256, 0, s>>>(src, t->slot_stride, scr, t->scratch_stride, t->C, t->H, t->W, t->p.Wp, t->npix);
+        k_s2d16<<<dim3((t->npix + 1023) / 1024, n), 256, 0, s>>>(src, t->slot_stride, scr, t->scratch_stride, t->C, t->H, t->W, t->p.Wp, t->npix, t->nhwc_in);
         (*launches)++;
+    } else if (t->prepass == 6 || t->prepass == 5) {
+        if (!t->gather_direct && cudaMemcpy2DAsync(scr, t->scratch_stride, src, t->slot_stride, (size_t)t->C * t->H * t->W, (size_t)n,
+                                                  cudaMemcpyDeviceToDevice, s) != cudaSuccess) return false;
     } else if (t->prepass && t->prepass != 3 && !(use_linked && t->has_linked)) {
         dim3 g((t->npix + 31) / 32, (t->Cp + 31) / 32, n);
         k_to_nhwc<<<g, 256, 0, s>>>(src, t->slot_stride, scr, t->scratch_stride, t->C, t->Cp, t->H, t->W, t->p.Wp, t->plane, t->npix,

@@ -369,8 +369,27 @@ __global__ void __launch_bounds__(256) k_upsample_rep(ArenaView v, KOp o) {
     }
 }
 
+/* concat input with fewer channels than the output (a real channel concat: NHWC-convention models, reference
+ * src/mars/mars_runtime.c:963-1000): pixel p copies its ic bytes to out[p * oc + coff]; 16 bytes per thread, consecutive
+ * threads walk the channel chunks of a pixel and then the next pixel (coalesced on both sides) */
+__global__ void __launch_bounds__(256) k_concat_strided16(ArenaView v, KOp o) {
+    const Img im = make_img(v, blockIdx.y);
+    const uint4 *in = reinterpret_cast<const uint4 *>(im.s_minus_W + o.in0);
+    uint8_t *out = im.s_minus_W + o.out + o.coff;
+    const int cpp = o.ic >> 4; /* 16-byte chunks per pixel */
+    const unsigned m_cpp = 0xFFFFFFFFu / (unsigned)cpp + 1u;
+    const int64_t total = (int64_t)(o.n >> 4);
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const unsigned px = cpp == 1 ? (unsigned)i : __umulhi((unsigned)i, m_cpp), c = (unsigned)i - px * (unsigned)cpp;
+        *reinterpret_cast<uint4 *>(out + (int64_t)px * o.oc + 16 * c) = in[i];
+    }
+}
+
 static inline bool fast_spatial_ok(const ArenaView &v, const KOp &o) {
     if (o.mode != EXEC_PARALLEL || o.out < (int64_t)v.W) return false;
+    if (o.kind == OP_CONCAT && o.ic != o.oc) /* strided: 16-byte chunks on both sides, 32-bit chunk index */
+        return o.in0 >= (int64_t)v.W && o.ic > 0 && o.ic % 16 == 0 && o.oc % 16 == 0 && o.coff % 16 == 0 && o.n >= 64 && o.n < (1ull << 35) &&
+               (o.n >> 4) < 0x7FFFFFFFull && ((o.in0 - (int64_t)v.W) & 15) == 0 && ((o.out - (int64_t)v.W) & 15) == 0;
     if (o.kind == OP_CONCAT) return o.in0 >= (int64_t)v.W && o.ic == o.oc && o.n >= 64;
     if (o.kind == OP_CONCAT_PERIODIC) return o.coff > 0 && o.n >= 64;
     if (o.kind == OP_MAXPOOL || o.kind == OP_UPSAMPLE)
@@ -404,6 +423,10 @@ static inline void launch_fast_spatial(const ArenaView &v, const KOp &o, int n_i
         /* one output word per thread: the loads of a thread are dependent, so parallelism comes from the number of warps */
         dim3 g((unsigned)(((uint64_t)o.oh * o.ow * (o.ic >> 2) + 255) / 256), n_img);
         k_spatial_vec4<<<g, 256, 0, s>>>(v, o);
+        return;
+    }
+    if (o.kind == OP_CONCAT && o.ic != o.oc) {
+        k_concat_strided16<<<dim3(fast_grid(o.n >> 4), n_img), 256, 0, s>>>(v, o);
         return;
     }
     const int periodic = o.kind == OP_CONCAT_PERIODIC;

@@ -54,7 +54,7 @@ enum ExecMode : int {
 
 enum ConvImpl : int {
     CONV_DIRECT = 0,    /* exact direct kernel (any shape) */
-    CONV_TC_NCHW        /* tcgen05 implicit GEMM over NCHW activations (conv_tc.cu) */
+    CONV_TC_NCHW        /* tcgen05 implicit GEMM (conv_tc.cu): NCHW / OIHW layers and, despite the name, NHWC / OHWI ones */
 };
 
 /* epilogue applied to an int8 value produced by an op (fused following layers) */

@@ -512,7 +512,7 @@ static mars_error_t compile_concat(Ctx &c, int li, const mars_layer_t &L) {
 /* ---- opt_level >= 1: route hazard-free GEMM-shaped convs to the tcgen05 kernel ---------- */
 static void select_tensor_core_convs(Program *p) {
     for (auto &o : p->ops)
-        if (o.kind == OP_CONV_I8_NCHW && o.mode == EXEC_PARALLEL && !o.xlat && tc_supported(o)) o.impl = CONV_TC_NCHW;
+        if ((o.kind == OP_CONV_I8_NCHW || o.kind == OP_CONV_I8_NHWC) && o.mode == EXEC_PARALLEL && !o.xlat && tc_supported(o)) o.impl = CONV_TC_NCHW;
 }
 
 /* reference src/mars/mars_runtime.c:818-835 for one (a, b) byte pair */
@@ -537,7 +537,7 @@ static void fuse_silu(Program *p, int64_t W) {
     std::vector<Op> &ops = p->ops;
     for (size_t i = 0; i + 2 < ops.size(); i++) {
         Op &c = ops[i];
-        if (c.impl != CONV_TC_NCHW || c.kind != OP_CONV_I8_NCHW || c.post_relu) continue;
+        if (c.impl != CONV_TC_NCHW || (c.kind != OP_CONV_I8_NCHW && c.kind != OP_CONV_I8_NHWC) || c.post_relu) continue;
         Op &s = ops[i + 1], &m = ops[i + 2];
         if (s.kind != OP_SIGMOID_I8 || s.mode != EXEC_PARALLEL || s.xlat) continue;
         if (m.kind != OP_MUL_I8 || m.mode != EXEC_PARALLEL || m.xlat) continue;
@@ -706,7 +706,7 @@ static void elide_dead_stores(Program *p, const IvSet &observed, const IvSet &ho
         for (auto &iv : live_in.v) live.add(iv.first, iv.second);
         for (size_t k = p->ops.size(); k-- > 0;) {
             Op &o = p->ops[k];
-            if (o.fused_layers > 0 && o.kind == OP_CONV_I8_NCHW) {
+            if (o.fused_layers > 0 && (o.kind == OP_CONV_I8_NCHW || o.kind == OP_CONV_I8_NHWC)) {
                 const int64_t numel = (int64_t)o.oc * o.oh * o.ow;
                 /* later stages of the chain overwrite equal ranges, so test each against what is live AFTER the op */
                 if (o.store_y && !live.hits(o.out, o.out + numel)) { o.store_y = false; o.note += " -Y"; }

@@ -17,7 +17,7 @@ import os
 if os.environ.get("PROFILE_MODEL") == "nanodet":  # BASELINE config 5 shape
     blob, arena, side = mf.build_nanodet_like(size=320, seed=7).to_bytes(), 16 << 20, 320
 else:
-    blob, arena, side = mf.build_yolov5(width=0.5, size=640, seed=5).to_bytes(), mf.ARENA_YOLOV5S_INT8, 640
+    blob, arena, side = mf.build_yolov5(width=0.5, size=640, seed=5, nhwc=os.environ.get("PROFILE_MODEL") == "nhwc").to_bytes(), mf.ARENA_YOLOV5S_INT8, 640
 gm = pkg.MarsModel(blob, arena_bytes=arena, batch=B)
 x = np.random.default_rng(1000).integers(-128, 128, size=(1, 3 * side * side), dtype=np.int8)
 for i in range(B):
