@@ -57,6 +57,11 @@ void mars_b200_set_depthwise_mode(mars_model_t *m, int mode);
  * recompiles the whole model on the exact direct kernels (correct, ~100x slower) and says so on stderr; in strict mode the
  * call that compiles the model (mars_load_*, mars_b200_set_batch, ...) fails with MARS_ERR_LAYER_FAILED instead */
 void mars_b200_set_strict(int on);
+/* float32 convolutions (reference conv2d_float32_mxu, src/mars/mxu_conv.c:673-710): 2 (default; also MARS_F32_MODE) = tcgen05
+ * kind::tf32 with a hi/lo operand split, three MMAs per k-step (fp32-grade products, results within ~1e-6 relative of the
+ * reference's sequential fp32 sum); 1 = plain tf32 (operands rounded to 10 mantissa bits, ~5e-4 per product); 0 = the
+ * exact-order fp32 kernel, bit-identical to the reference (the control) */
+void mars_b200_set_f32_mode(mars_model_t *m, int mode);
 
 /* ---- image batch ---------------------------------------------------------- */
 /* allocate `capacity` image slots (each = one set of work buffers; weights shared) */

@@ -141,6 +141,7 @@ SIGNATURES = {
     "mars_b200_set_opt_level": (None, [PM, C.c_int]),
     "mars_b200_set_depthwise_mode": (None, [PM, C.c_int]),
     "mars_b200_set_strict": (None, [C.c_int]),
+    "mars_b200_set_f32_mode": (None, [PM, C.c_int]),
     "mars_b200_set_batch": (C.c_int, [PM, C.c_int]),
     "mars_b200_get_batch": (C.c_int, [PM]),
     "mars_b200_input_bytes": (C.c_size_t, [PM]),
@@ -285,6 +286,9 @@ class MarsModel:
 
     def set_opt_level(self, lvl):
         lib().mars_b200_set_opt_level(self.m, lvl)
+
+    def set_f32_mode(self, mode):
+        lib().mars_b200_set_f32_mode(self.m, mode)
 
     def set_depthwise_mode(self, mode):
         lib().mars_b200_set_depthwise_mode(self.m, mode)

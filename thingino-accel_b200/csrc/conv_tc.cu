@@ -35,6 +35,7 @@
 #include <string.h>
 
 #include "conv_tc.h"
+#include "conv_tf32.h"
 
 namespace marsb200 {
 
@@ -1549,6 +1550,7 @@ bool tc_launch(const TcPlan &plan, uint8_t *slots_base, int first, int n, bool u
 
 void tc_release(std::vector<TcPlan> &plans) {
     for (auto &pl : plans) {
+        if (pl.f32) { tf32_release_one(pl); continue; }
         TcPlanImpl *t = static_cast<TcPlanImpl *>(pl.impl);
         if (t) { cudaFree(t->d_wr); cudaFree(t->d_lutw); delete t; }
         pl.impl = nullptr;

@@ -25,7 +25,8 @@ struct ArenaGeom {
 
 struct TcPlan {
     bool valid = false;
-    void *impl = nullptr; /* TcPlanImpl*, owned */
+    void *impl = nullptr; /* TcPlanImpl* (conv_tc.cu) or F32PlanImpl* (conv_tf32.cu, f32 == true), owned */
+    bool f32 = false;
 };
 
 /* can this op run on the tensor-core kernel at all (shape / hazard rules)? */

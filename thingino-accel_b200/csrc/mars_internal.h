@@ -54,7 +54,8 @@ enum ExecMode : int {
 
 enum ConvImpl : int {
     CONV_DIRECT = 0,    /* exact direct kernel (any shape) */
-    CONV_TC_NCHW        /* tcgen05 implicit GEMM (conv_tc.cu): NCHW / OIHW layers and, despite the name, NHWC / OHWI ones */
+    CONV_TC_NCHW,       /* tcgen05 implicit GEMM (conv_tc.cu): NCHW / OIHW layers and, despite the name, NHWC / OHWI ones */
+    CONV_TC_F32         /* tcgen05 kind::tf32 implicit GEMM for float32 layers (conv_tf32.cu) */
 };
 
 /* epilogue applied to an int8 value produced by an op (fused following layers) */
@@ -131,7 +132,7 @@ bool first_time_on_device(unsigned long long *mask);
 mars_error_t compile_program(const mars_header_t &h, const mars_runtime_tensor_t *tensors,
                              const mars_runtime_layer_t *layers, const std::vector<size_t> &toff,
                              size_t weights_size, size_t arena_size, int opt_level, int depthwise_mode,
-                             Program *out);
+                             Program *out, int f32_mode = 0);
 std::string describe_program(const Program &p);
 
 } // namespace marsb200

@@ -20,6 +20,7 @@
 #include <algorithm>
 
 #include "conv_tc.h"
+#include "conv_tf32.h"
 #include "mars_internal.h"
 
 namespace marsb200 {
@@ -510,7 +511,9 @@ static mars_error_t compile_concat(Ctx &c, int li, const mars_layer_t &L) {
 
 
 /* ---- opt_level >= 1: route hazard-free GEMM-shaped convs to the tcgen05 kernel ---------- */
-static void select_tensor_core_convs(Program *p) {
+static void select_tensor_core_convs(Program *p, int f32_mode) {
+    for (auto &o : p->ops)
+        if (o.kind == OP_CONV_F32_NCHW && tf32_supported(o, f32_mode)) o.impl = CONV_TC_F32;
     for (auto &o : p->ops)
         if ((o.kind == OP_CONV_I8_NCHW || o.kind == OP_CONV_I8_NHWC) && o.mode == EXEC_PARALLEL && !o.xlat && tc_supported(o)) o.impl = CONV_TC_NCHW;
 }
@@ -726,7 +729,7 @@ static void elide_dead_stores(Program *p, const IvSet &observed, const IvSet &ho
 mars_error_t compile_program(const mars_header_t &h, const mars_runtime_tensor_t *tensors,
                              const mars_runtime_layer_t *layers, const std::vector<size_t> &toff,
                              size_t weights_size, size_t arena_size, int opt_level, int depthwise_mode,
-                             Program *out) {
+                             Program *out, int f32_mode) {
     out->ops.clear();
     out->const_pool.clear();
     out->scratch_bytes = 0;
@@ -756,7 +759,7 @@ mars_error_t compile_program(const mars_header_t &h, const mars_runtime_tensor_t
         }
         if (e != MARS_OK) return e;
     }
-    if (opt_level >= 1) select_tensor_core_convs(out);
+    if (opt_level >= 1) select_tensor_core_convs(out, f32_mode);
     if (opt_level >= 2) fuse_silu(out, (int64_t)weights_size);
     if (opt_level >= 2) link_nhwc_copies(out);
     if (opt_level >= 3) {

@@ -30,6 +30,7 @@
 #include "../../include/nna.h"
 #include "../../include/nna_memory.h"
 #include "conv_tc.h"
+#include "conv_tf32.h"
 #include "kernels_exact.cuh"
 #include "kernels_fast.cuh"
 #include "mars_internal.h"
@@ -165,6 +166,7 @@ struct Model {
     size_t linked_stride = 0;
     Program prog;
     int opt_level = 3, depthwise_mode = 0;
+    int f32_mode = 2; /* float32 convolutions: 0 = exact-order fp32 (bit-exact control), 1 = tf32, 2 = tf32x3 (conv_tf32.cu) */
     cudaStream_t stream = nullptr, h2d_stream = nullptr, d2h_stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     cudaEvent_t ev_in[2] = {nullptr, nullptr}, ev_done[2] = {nullptr, nullptr}, ev_out[2] = {nullptr, nullptr};
@@ -304,7 +306,7 @@ static mars_error_t compile_model(Model *m) {
     release_graphs(m); /* kernel parameters (slot addresses, tensor maps, tables) are about to change */
     Program p;
     mars_error_t e = compile_program(m->pub.header, m->pub.tensors, m->pub.layers, m->toff, m->weights_size,
-                                     m->arena_size, m->opt_level, m->depthwise_mode, &p);
+                                     m->arena_size, m->opt_level, m->depthwise_mode, &p, m->f32_mode);
     if (e != MARS_OK) return e;
     m->prog = std::move(p);
     cudaFree(m->d_cpool);
@@ -321,8 +323,10 @@ static mars_error_t compile_model(Model *m) {
     tc_release(m->tc);
     m->tc.assign(m->prog.ops.size(), TcPlan());
     size_t need = 0;
-    for (const Op &o : m->prog.ops)
+    for (const Op &o : m->prog.ops) {
         if (o.impl == CONV_TC_NCHW) need = std::max(need, tc_scratch_need(o));
+        if (o.impl == CONV_TC_F32) need = std::max(need, tf32_scratch_need(o, m->f32_mode));
+    }
     need = (need + 1023) & ~(size_t)1023;
     if (need > m->tc_scratch_stride || (need && !m->d_tc_scratch)) {
         cudaFree(m->d_tc_scratch);
@@ -341,6 +345,19 @@ static mars_error_t compile_model(Model *m) {
     ArenaGeom g{m->d_weights, m->d_slots, m->weights_size, m->slot_stride, m->capacity, m->h_arena, m->prog.const_pool.data()};
     for (size_t i = 0; i < m->prog.ops.size(); i++) {
         Op &o = m->prog.ops[i];
+        if (o.impl == CONV_TC_F32) { /* float32 layer on the tf32 tensor path; a failed plan simply stays on the exact kernel */
+            if (!tf32_plan(o, g, m->f32_mode, m->d_tc_scratch, m->tc_scratch_stride, &m->tc[i])) {
+                if (strict_mode()) {
+                    char why[600];
+                    snprintf(why, sizeof why, "%s", g_err);
+                    set_last_error("strict mode: tf32 plan failed for layer %d (%s)", o.layer, why);
+                    tc_release(m->tc);
+                    return MARS_ERR_LAYER_FAILED;
+                }
+                o.impl = CONV_DIRECT;
+            }
+            continue;
+        }
         if (o.impl != CONV_TC_NCHW) continue;
         const Op *consumer = o.nhwc_consumer >= 0 ? &m->prog.ops[o.nhwc_consumer] : nullptr;
         if (!tc_plan(o, g, m->d_tc_scratch, m->tc_scratch_stride, m->d_linked, m->linked_stride, consumer, &m->tc[i])) {
@@ -410,7 +427,9 @@ static mars_error_t launch_op(Model *m, size_t op_index, int first, int n, bool 
     } else if (is_conv) {
         const uint64_t P = (uint64_t)o.oh * o.ow;
         const int es = o.kind == OP_CONV_F32_NCHW ? 4 : 1;
-        if (o.impl == CONV_TC_NCHW && m->tc[op_index].valid) {
+        if (o.impl == CONV_TC_F32 && m->tc[op_index].valid) {
+            if (!tf32_launch(m->tc[op_index], m->d_slots, first, n, s, &m->launches)) return MARS_ERR_LAYER_FAILED;
+        } else if (o.impl == CONV_TC_NCHW && m->tc[op_index].valid) {
             if (!tc_launch(m->tc[op_index], m->d_slots, first, n, full_pass, s, &m->launches)) return MARS_ERR_LAYER_FAILED;
         } else if (o.mode == EXEC_PARALLEL) {
             if (o.kind == OP_CONV_I8_NCHW && !xl && fast_conv_nchw_ok(k)) {
@@ -631,6 +650,7 @@ mars_error_t mars_load_memory(const void *data, size_t size, mars_model_t **out_
     if (!m) return MARS_ERR_ALLOC_FAILED;
     memset(&m->pub, 0, sizeof m->pub);
     m->device = g_device;
+    { const char *e = getenv("MARS_F32_MODE"); if (e && *e) m->f32_mode = std::max(0, std::min(2, atoi(e))); }
     m->pub.header = h;
     m->pub.tensors = (mars_runtime_tensor_t *)calloc(h.num_tensors ? h.num_tensors : 1, sizeof(mars_runtime_tensor_t));
     m->pub.layers = (mars_runtime_layer_t *)calloc(h.num_layers ? h.num_layers : 1, sizeof(mars_runtime_layer_t));
@@ -946,6 +966,14 @@ void mars_b200_set_opt_level(mars_model_t *model, int level) {
     m->compiled = false;
 }
 void mars_b200_set_strict(int on) { g_strict = on ? 1 : 0; }
+void mars_b200_set_f32_mode(mars_model_t *model, int mode) {
+    Model *m = as_model(model);
+    if (!m || m->f32_mode == mode) return;
+    cudaSetDevice(m->device);
+    cudaStreamSynchronize(m->stream);
+    m->f32_mode = mode < 0 ? 0 : (mode > 2 ? 2 : mode);
+    m->compiled = false;
+}
 void mars_b200_set_depthwise_mode(mars_model_t *model, int mode) {
     Model *m = as_model(model);
     if (!m || m->depthwise_mode == mode) return;
