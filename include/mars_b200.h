@@ -96,6 +96,9 @@ mars_error_t mars_b200_detect_batch(mars_model_t *m, int n, const void *inputs, 
 mars_error_t mars_b200_submit_batch(mars_model_t *m, int pool, int n, const void *inputs, size_t in_stride,
                                     mars_det_t *dets, int32_t *counts, int maxd, float nms_thresh);
 mars_error_t mars_b200_wait_batch(mars_model_t *m, int pool);
+/* the same without the YOLO post-process: output tensor 0 of every image is read back (out_stride bytes apart); waited for
+ * with mars_b200_wait_batch like a detection batch */
+mars_error_t mars_b200_submit_run_batch(mars_model_t *m, int pool, int n, const void *inputs, size_t in_stride, void *outputs, size_t out_stride);
 /* end to end from host buffers returning raw output tensor 0 per image */
 mars_error_t mars_b200_run_batch(mars_model_t *m, int n, const void *inputs, size_t in_stride,
                                  void *outputs, size_t out_stride);
@@ -104,6 +107,19 @@ mars_error_t mars_b200_step_resident(mars_model_t *m, int first, int n, float nm
 /* device addresses of the resident detection records, for a device-side gather (NCCL):
  * dets = mars_det_t[capacity][*stride_dets], counts = int32[capacity] */
 void mars_b200_detections_device(mars_model_t *m, void **dets, void **counts, int *stride_dets);
+
+/* ---- several GPUs of one box behind one call (batch sharded over the devices, no inter-GPU traffic on the path) ---------- */
+typedef struct mars_b200_group mars_b200_group_t;
+/* one replica of the model per device (devices = NULL: ordinals 0 .. n_devices-1), `per_gpu_batch` image slots each */
+mars_error_t mars_b200_group_load(const void *data, size_t size, const int *devices, int n_devices, int per_gpu_batch, mars_b200_group_t **out);
+void mars_b200_group_free(mars_b200_group_t *g);
+int mars_b200_group_size(mars_b200_group_t *g);
+/* the replica on the i-th device of the group (for per-device settings: opt level, f32 mode, ...) */
+mars_model_t *mars_b200_group_model(mars_b200_group_t *g, int i);
+/* mars_b200_detect_batch over the whole group: image b runs on GPU b / ceil(n / G), one host thread per GPU; dets[n][maxd] and
+ * counts[n] are filled directly by every GPU's read-back (the single-process form of the detection gather) */
+mars_error_t mars_b200_group_detect_batch(mars_b200_group_t *g, int n, const void *inputs, size_t in_stride, mars_det_t *dets, int32_t *counts,
+                                          int maxd, float nms_thresh);
 
 /* ---- introspection (tests, bench) ----------------------------------------- */
 /* record CUDA events around every device op of full passes; read back with mars_b200_op_info */

@@ -141,6 +141,12 @@ SIGNATURES = {
     "mars_b200_set_opt_level": (None, [PM, C.c_int]),
     "mars_b200_set_depthwise_mode": (None, [PM, C.c_int]),
     "mars_b200_set_strict": (None, [C.c_int]),
+    "mars_b200_submit_run_batch": (C.c_int, [PM, C.c_int, C.c_int, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t]),
+    "mars_b200_group_load": (C.c_int, [C.c_void_p, C.c_size_t, C.POINTER(C.c_int), C.c_int, C.c_int, C.POINTER(C.c_void_p)]),
+    "mars_b200_group_free": (None, [C.c_void_p]),
+    "mars_b200_group_size": (C.c_int, [C.c_void_p]),
+    "mars_b200_group_model": (PM, [C.c_void_p, C.c_int]),
+    "mars_b200_group_detect_batch": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_int, C.c_float]),
     "mars_b200_set_f32_mode": (None, [PM, C.c_int]),
     "mars_b200_set_batch": (C.c_int, [PM, C.c_int]),
     "mars_b200_get_batch": (C.c_int, [PM]),
@@ -371,6 +377,10 @@ class MarsModel:
         """queue a batch on half `pool` of the slot pool; buffers must stay alive until wait_batch(pool)"""
         self._check(lib().mars_b200_submit_batch(self.m, pool, n, _addr(inputs), in_stride, _addr(dets), _addr(counts), maxd, thresh),
                     "submit_batch")
+
+    def submit_run_batch(self, pool, n, inputs, in_stride, outputs, out_stride):
+        """queue a batch without the YOLO post-process (raw output tensors read back); wait with wait_batch(pool)"""
+        self._check(lib().mars_b200_submit_run_batch(self.m, pool, n, _addr(inputs), in_stride, _addr(outputs), out_stride), "submit_run_batch")
 
     def wait_batch(self, pool):
         self._check(lib().mars_b200_wait_batch(self.m, pool), "wait_batch")

@@ -23,6 +23,8 @@
 
 #include <algorithm>
 #include <new>
+#include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/mxu_ops.h"
@@ -1360,6 +1362,45 @@ mars_error_t mars_b200_submit_batch(mars_model_t *model, int pool, int n, const 
     return MARS_OK;
 }
 
+/* mars_b200_submit_batch without the YOLO post-process: the raw output tensor 0 of every image is read back instead
+ * (models whose output is not a [1, N, 85] head: NanoDet-style heads, float32 models).  Same pools, same wait. */
+mars_error_t mars_b200_submit_run_batch(mars_model_t *model, int pool, int n, const void *inputs, size_t in_stride, void *outputs, size_t out_stride) {
+    Model *m = as_model(model);
+    if (!m || !inputs || !outputs || pool < 0 || pool > 1) return MARS_ERR_INVALID_FILE;
+    CU_OK(cudaSetDevice(m->device), MARS_ERR_NNA_INIT_FAILED);
+    const int half = m->capacity / 2;
+    if (half < 1 || n < 0 || n > half) {
+        set_last_error("submit_run_batch: %d images do not fit half of the slot pool (capacity %d; mars_b200_set_batch)", n, m->capacity);
+        return MARS_ERR_INVALID_TENSOR;
+    }
+    if (m->pending[pool].active) {
+        set_last_error("submit_run_batch: pool %d still has a batch in flight (mars_b200_wait_batch first)", pool);
+        return MARS_ERR_LAYER_FAILED;
+    }
+    const size_t in_bytes = io_bytes(&m->pub, 0), out_bytes = io_bytes(&m->pub, 1);
+    if (in_stride < in_bytes) in_stride = in_bytes;
+    if (out_stride < out_bytes) out_stride = out_bytes;
+    const int first = pool * half;
+    mars_error_t e = compile_model(m);
+    if (e != MARS_OK) return e;
+    if (n > 0) {
+        e = copy_io(m, first, n, const_cast<void *>(inputs), in_stride, 0, m->h2d_stream);
+        if (e != MARS_OK) return e;
+        cudaEventRecord(m->ev_in[pool], m->h2d_stream);
+        cudaStreamWaitEvent(m->stream, m->ev_in[pool], 0);
+        e = enqueue_step_graphed(m, first, n, 0.0f, 0);
+        if (e != MARS_OK) { cudaStreamSynchronize(m->stream); return e; }
+        cudaEventRecord(m->ev_done[pool], m->stream);
+        cudaStreamWaitEvent(m->d2h_stream, m->ev_done[pool], 0);
+        e = copy_io(m, first, n, outputs, out_stride, 1, m->d2h_stream);
+        if (e != MARS_OK) return e;
+    }
+    cudaEventRecord(m->ev_out[pool], m->d2h_stream);
+    m->pending[pool].active = true;
+    m->pending[pool].n = 0; m->pending[pool].maxd = 0; m->pending[pool].counts = nullptr;
+    return MARS_OK;
+}
+
 mars_error_t mars_b200_wait_batch(mars_model_t *model, int pool) {
     Model *m = as_model(model);
     if (!m || pool < 0 || pool > 1) return MARS_ERR_INVALID_FILE;
@@ -1440,6 +1481,85 @@ size_t mars_b200_tensor_offset(mars_model_t *model, uint32_t index) {
     Model *m = as_model(model);
     if (!m || index >= model->header.num_tensors) return (size_t)-1;
     return m->toff[index];
+}
+
+/* ---- several GPUs behind one C call (north_star: "work is partitioned across the GPUs of one box by sharding the
+ * image batch, with no inter-GPU traffic on the hot path") --------------------------------------------------------------
+ * A group holds one replica of the model per device.  mars_b200_group_detect_batch shards the n images into contiguous
+ * blocks of ceil(n / G), runs every block on its GPU from its own host thread (H2D, all layers, decode, NMS, D2H, pipelined
+ * in chunks exactly like mars_b200_detect_batch) and returns when all are done; the detection records land directly in the
+ * caller's arrays, which is the "gather" of a single-process caller (bench.py, one process per GPU, gathers over NCCL). */
+struct mars_b200_group {
+    std::vector<mars_model_t *> models;
+    std::vector<int> devices;
+};
+
+mars_error_t mars_b200_group_load(const void *data, size_t size, const int *devices, int n_devices, int per_gpu_batch, mars_b200_group_t **out) {
+    if (!data || !out || n_devices < 1 || per_gpu_batch < 1) return MARS_ERR_INVALID_FILE;
+    int visible = 0;
+    if (cudaGetDeviceCount(&visible) != cudaSuccess || visible < 1) {
+        set_last_error("no CUDA device (this library has no CPU fallback)");
+        return MARS_ERR_NNA_INIT_FAILED;
+    }
+    mars_b200_group *g = new (std::nothrow) mars_b200_group();
+    if (!g) return MARS_ERR_ALLOC_FAILED;
+    const int saved = g_device;
+    mars_error_t e = MARS_OK;
+    for (int i = 0; i < n_devices && e == MARS_OK; i++) {
+        const int d = devices ? devices[i] : i;
+        if (d < 0 || d >= visible) { set_last_error("group: device ordinal %d out of range (%d visible)", d, visible); e = MARS_ERR_NNA_INIT_FAILED; break; }
+        if (mars_b200_set_device(d) != 0) { e = MARS_ERR_NNA_INIT_FAILED; break; }
+        mars_model_t *m = nullptr;
+        e = mars_load_memory(data, size, &m);
+        if (e == MARS_OK) e = mars_b200_set_batch(m, per_gpu_batch);
+        if (e != MARS_OK) { if (m) mars_free(m); break; }
+        g->models.push_back(m);
+        g->devices.push_back(d);
+    }
+    if (saved >= 0) mars_b200_set_device(saved);
+    if (e != MARS_OK) {
+        for (auto *m : g->models) mars_free(m);
+        delete g;
+        return e;
+    }
+    *out = g;
+    return MARS_OK;
+}
+
+void mars_b200_group_free(mars_b200_group_t *g) {
+    if (!g) return;
+    for (auto *m : g->models) mars_free(m);
+    delete g;
+}
+
+int mars_b200_group_size(mars_b200_group_t *g) { return g ? (int)g->models.size() : 0; }
+mars_model_t *mars_b200_group_model(mars_b200_group_t *g, int i) { return (g && i >= 0 && (size_t)i < g->models.size()) ? g->models[i] : nullptr; }
+
+mars_error_t mars_b200_group_detect_batch(mars_b200_group_t *g, int n, const void *inputs, size_t in_stride, mars_det_t *dets, int32_t *counts,
+                                          int maxd, float nms_thresh) {
+    if (!g || g->models.empty() || !inputs || !dets || !counts || n < 0) return MARS_ERR_INVALID_FILE;
+    const int G = (int)g->models.size();
+    const size_t in_bytes = mars_b200_input_bytes(g->models[0]);
+    if (in_stride < in_bytes) in_stride = in_bytes;
+    if (maxd > 1000) maxd = 1000;
+    if (maxd < 0) maxd = 0;
+    const int per = (n + G - 1) / G;
+    std::vector<mars_error_t> err((size_t)G, MARS_OK);
+    std::vector<std::string> why((size_t)G);
+    std::vector<std::thread> th;
+    for (int r = 0; r < G; r++) {
+        const int first = std::min(r * per, n), cnt = std::max(0, std::min(per, n - first));
+        if (cnt == 0) continue;
+        th.emplace_back([=, &err, &why]() {
+            err[r] = mars_b200_detect_batch(g->models[r], cnt, (const uint8_t *)inputs + (size_t)first * in_stride, in_stride,
+                                            dets + (size_t)first * maxd, counts + first, maxd, nms_thresh);
+            if (err[r] != MARS_OK) why[r] = g_err; /* the diagnostic is thread-local: carry it to the caller's thread */
+        });
+    }
+    for (auto &t : th) t.join();
+    for (int r = 0; r < G; r++)
+        if (err[r] != MARS_OK) { set_last_error("group: GPU %d: %s", g->devices[r], why[r].c_str()); return err[r]; }
+    return MARS_OK;
 }
 
 } /* extern "C" */
