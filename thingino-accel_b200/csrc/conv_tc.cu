@@ -398,6 +398,7 @@ k_conv_tc(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUte
     __shared__ __align__(16) int s_koff[GATHER ? 128 : 4]; /* gather: patch-relative byte offset of tap k */
     __shared__ int s_shift[TC_MAX_TAPS];
 
+    pdl_release_dependents(); /* the next kernel of the step may be scheduled as CTAs of this one retire (mars_internal.h) */
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     uint8_t *smem_al = smem_raw + (smem_base - smem_u32(smem_raw));
@@ -448,6 +449,9 @@ k_conv_tc(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUte
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem_d = tmem_base_slot;
+    /* everything above read only weights, biases and tables (written at load time); the activations this kernel reads, and the
+     * buffers it overwrites, belong to the previous kernel of the step until it has completed */
+    pdl_wait_prior_grid();
     if (p.dbg == 6) goto teardown; /* tuning aid: prologue + teardown only */
 
     if (warp < EPI) {
@@ -800,6 +804,7 @@ teardown:
 __global__ void __launch_bounds__(256) k_to_nhwc(const uint8_t *src_base, unsigned long long src_stride, uint8_t *dst_base,
                                                  unsigned long long dst_stride, int C, int Cp, int H, int W, int Wp, int plane, int npix,
                                                  int stride2, int pt, int pl) { /* Cp >= C: bytes per pixel of the copy */
+    pdl_begin();
     __shared__ uint8_t tile[32][33];
     const uint8_t *src = src_base + (unsigned long long)blockIdx.z * src_stride;
     uint8_t *dst = dst_base + (unsigned long long)blockIdx.z * dst_stride;
@@ -835,6 +840,7 @@ __global__ void __launch_bounds__(256) k_to_nhwc(const uint8_t *src_base, unsign
  * zero border and zero beyond 4*C bytes.  One thread per P pixel. */
 __global__ void __launch_bounds__(256) k_s2d16(const uint8_t *__restrict__ src_base, unsigned long long src_stride, uint8_t *__restrict__ dst_base,
                                                unsigned long long dst_stride, int C, int H, int W, int Wp, int npix, int src_nhwc) {
+    pdl_begin();
     const uint8_t *src = src_base + (unsigned long long)blockIdx.y * src_stride;
     uint4 *dst = reinterpret_cast<uint4 *>(dst_base + (unsigned long long)blockIdx.y * dst_stride);
     /* four pixels per thread, 256 apart: all their loads are issued before the first store (the kernel is pure latency) */
@@ -1519,15 +1525,15 @@ bool tc_launch(const TcPlan &plan, uint8_t *slots_base, int first, int n, bool u
         if (cudaMemcpy2DAsync(scr, t->scratch_stride, src, t->slot_stride, (size_t)t->C * t->H * t->W, (size_t)n,
                               cudaMemcpyDeviceToDevice, s) != cudaSuccess) return false;
     } else if (t->prepass == 4) {
-        k_s2d16<<<dim3((t->npix + 1023) / 1024, n), 256, 0, s>>>(src, t->slot_stride, scr, t->scratch_stride, t->C, t->H, t->W, t->p.Wp, t->npix, t->nhwc_in);
+        launch_pdl(k_s2d16, dim3((t->npix + 1023) / 1024, n), dim3(256), 0, s, src, (unsigned long long)t->slot_stride, scr, (unsigned long long)t->scratch_stride, t->C, t->H, t->W, t->p.Wp, t->npix, t->nhwc_in);
         (*launches)++;
     } else if (t->prepass == 6 || t->prepass == 5) {
         if (!t->gather_direct && cudaMemcpy2DAsync(scr, t->scratch_stride, src, t->slot_stride, (size_t)t->C * t->H * t->W, (size_t)n,
                                                   cudaMemcpyDeviceToDevice, s) != cudaSuccess) return false;
     } else if (t->prepass && t->prepass != 3 && !(use_linked && t->has_linked)) {
         dim3 g((t->npix + 31) / 32, (t->Cp + 31) / 32, n);
-        k_to_nhwc<<<g, 256, 0, s>>>(src, t->slot_stride, scr, t->scratch_stride, t->C, t->Cp, t->H, t->W, t->p.Wp, t->plane, t->npix,
-                                    t->prepass == 2, t->pt, t->pl);
+        launch_pdl(k_to_nhwc, g, dim3(256), 0, s, src, (unsigned long long)t->slot_stride, scr, (unsigned long long)t->scratch_stride, t->C, t->Cp, t->H, t->W,
+                   t->p.Wp, t->plane, t->npix, (int)(t->prepass == 2), t->pt, t->pl);
         (*launches)++;
     }
     TcParams p = t->p;
@@ -1543,7 +1549,7 @@ bool tc_launch(const TcPlan &plan, uint8_t *slots_base, int first, int n, bool u
     int sms = t->sms;
     if (sms <= 0) sms = 148;
     const unsigned grid = (unsigned)std::min<long long>(total_tiles, (long long)sms * t->ctas_per_sm);
-    t->kernel<<<grid, (t->epi + (t->prepass == 3 ? 5 : 2)) * 32, t->smem, s>>>((use_linked && t->has_linked) ? t->mapA_linked : t->mapA, t->mapB, p);
+    launch_pdl(t->kernel, dim3(grid), dim3((t->epi + (t->prepass == 3 ? 5 : 2)) * 32), t->smem, s, (use_linked && t->has_linked) ? t->mapA_linked : t->mapA, t->mapB, p);
     (*launches)++;
     return cudaGetLastError() == cudaSuccess;
 }

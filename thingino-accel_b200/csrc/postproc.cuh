@@ -63,6 +63,7 @@ __device__ __forceinline__ int block_excl_scan(int v, int *total, int *warp_sums
 __global__ void __launch_bounds__(256) k_parse_output(const int8_t *data, size_t img_stride, int npred, float scale,
                                                       const DecodeTables *tab, mars_det_t *dets, int32_t *counts,
                                                       int maxd, int det_stride) {
+    pdl_begin();
     __shared__ int warp_sums[32];
     const int8_t *rows = data + (size_t)blockIdx.x * img_stride;
     mars_det_t *out = dets + (size_t)blockIdx.x * det_stride;
@@ -367,6 +368,7 @@ __device__ __forceinline__ void nms_sort_image(const mars_det_t *in, int n, uint
 
 __global__ void __launch_bounds__(32) k_nms_sort_warp(const mars_det_t *dets_in, const int32_t *counts_in, int det_stride,
                                                       unsigned *scratch, size_t scratch_stride_words) {
+    pdl_begin();
     const int img = blockIdx.x, lane = threadIdx.x;
     const mars_det_t *in = dets_in + (size_t)img * det_stride;
     uint16_t *order = reinterpret_cast<uint16_t *>(scratch + (size_t)img * scratch_stride_words + (size_t)MARS_MAX_DETS * 32);
@@ -415,6 +417,7 @@ __device__ __forceinline__ float iou_pre(float ax0, float ay0, float ax1, float 
 __global__ void __launch_bounds__(NMS_THREADS, 2) k_nms_center(const mars_det_t *dets_in, const int32_t *counts_in,
                                                                mars_det_t *dets_out, int32_t *counts_out, int det_stride,
                                                                float thresh, unsigned *mask_scratch, int presorted) {
+    pdl_begin();
     extern __shared__ __align__(16) uint8_t nms_smem[];
     NmsShared &sh = *reinterpret_cast<NmsShared *>(nms_smem);
     const mars_det_t *in = dets_in + (size_t)blockIdx.x * det_stride;
@@ -531,6 +534,7 @@ struct NmsSupShared {
 __global__ void __launch_bounds__(NMS_SUP_THREADS, 8) k_nms_suppress(const mars_det_t *dets_in, const int32_t *counts_in,
                                                                      mars_det_t *dets_out, int32_t *counts_out, int det_stride,
                                                                      float thresh, unsigned *scratch) {
+    pdl_begin();
     __shared__ NmsSupShared sh;
     const mars_det_t *in = dets_in + (size_t)blockIdx.x * det_stride;
     mars_det_t *out = dets_out + (size_t)blockIdx.x * det_stride;
@@ -657,13 +661,13 @@ static inline cudaError_t launch_nms_center(const mars_det_t *dets_in, const int
         if (e != cudaSuccess) return e;
     }
     if (!block_sort) {
-        k_nms_sort_warp<<<n_img, 32, 0, s>>>(dets_in, counts_in, det_stride, scratch, NMS_SCRATCH_WORDS);
+        launch_pdl(k_nms_sort_warp, dim3(n_img), dim3(32), 0, s, dets_in, counts_in, det_stride, scratch, NMS_SCRATCH_WORDS);
         /* many images: eight 256-thread blocks per SM keep the whole batch resident (throughput); few images: 1024 threads
          * per image finish each one sooner (latency) */
         static const int force = getenv("MARS_NMS_SUPPRESS") ? atoi(getenv("MARS_NMS_SUPPRESS")) : -1; /* 1 / 0: always / never (tests) */
-        if (force == 1 || (force != 0 && n_img > 2 * 296)) k_nms_suppress<<<n_img, NMS_SUP_THREADS, 0, s>>>(dets_in, counts_in, dets_out, counts_out, det_stride, thresh, scratch);
-        else k_nms_center<<<n_img, NMS_THREADS, sizeof(NmsShared), s>>>(dets_in, counts_in, dets_out, counts_out, det_stride, thresh, scratch, 1);
-    } else k_nms_center<<<n_img, NMS_THREADS, sizeof(NmsShared), s>>>(dets_in, counts_in, dets_out, counts_out, det_stride, thresh, scratch, 0);
+        if (force == 1 || (force != 0 && n_img > 2 * 296)) launch_pdl(k_nms_suppress, dim3(n_img), dim3(NMS_SUP_THREADS), 0, s, dets_in, counts_in, dets_out, counts_out, det_stride, thresh, scratch);
+        else launch_pdl(k_nms_center, dim3(n_img), dim3(NMS_THREADS), sizeof(NmsShared), s, dets_in, counts_in, dets_out, counts_out, det_stride, thresh, scratch, 1);
+    } else launch_pdl(k_nms_center, dim3(n_img), dim3(NMS_THREADS), sizeof(NmsShared), s, dets_in, counts_in, dets_out, counts_out, det_stride, thresh, scratch, 0);
     if (launches) *launches = block_sort ? 1 : 2;
     return cudaGetLastError();
 }
