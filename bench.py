@@ -465,8 +465,9 @@ def run_cuda_arm(args):
     # The user-facing call pair mars_b200_submit_batch / mars_b200_wait_batch: every step copies its B images from
     # pinned host memory to HBM and reads its detection records back; batch k+1 is submitted before batch k is
     # waited for, so the copies overlap the kernels (two halves of a 2B-slot pool).  K steps are timed, pipeline
-    # fill and drain included.  At least four submits per step, so that the copies of a step overlap its own kernels.
-    SUB = min(B, int(os.environ.get("MARS_BENCH_SUB", "512")), max(16, B // 4))
+    # fill and drain included.  Two submits per step (measured at 8 GPUs, 128 images per GPU: 132k images/s with one or two
+    # submits per step against 101k with four -- smaller launches lose more than the extra overlap gains).
+    SUB = min(B, int(os.environ.get("MARS_BENCH_SUB", "512")), max(16, B // int(os.environ.get("MARS_BENCH_SUBMITS", "2"))))
     gm.set_batch(2 * SUB)
     outs = []
     for _ in range(2):
