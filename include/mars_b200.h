@@ -152,6 +152,15 @@ int mars_b200_letterbox_rgba(const uint8_t *rgb, int w, int h, int tw, int th, u
  * axis sums, in the order stbir_resize_uint8 adds them.  start[out_size + 1]; returns the tap count (> cap: nothing copied). */
 int mars_b200_resize_taps(int in_size, int out_size, int32_t *start, int32_t *src, float *w, int cap);
 
+/* ---- conv requantisation in integers (host half, no GPU needed) ----------- */
+/* The tcgen05 conv epilogue replaces the float requantisation of reference src/mars/mxu_conv.c:663-666,
+ * r = clamp((int32)(fl((float)t * scale) +- 0.5f)), by clamp(floor((t * m + c) / 2^(32 + s))) when integers (m, s, c) exist that
+ * reproduce it for EVERY |t| <= tmax (t = accumulator + bias).  Returns 1 and fills m / s / c, or 0 when no such triple exists
+ * (the layer then keeps a float variant).  Exposed so that the CPU test suite can check the fit by brute force. */
+int mars_b200_requant_fit(float scale, long long tmax, int *m, int *s, long long *c);
+/* the reference's requantisation of one value, restated (what the fit is checked against) */
+int mars_b200_requant_ref(int t, float scale);
+
 /* ---- YOLO post-process on host buffers ----------------------------------- */
 /* parse_output of reference src/mars/mars_yolo_test.c:80-104 (conf threshold 0.25) */
 int mars_yolo_parse_output(const int8_t *data, int npred, float scale, mars_det_t *dets, int maxd);

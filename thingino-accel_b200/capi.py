@@ -177,6 +177,8 @@ SIGNATURES = {
     "mars_b200_letterbox": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
     "mars_b200_letterbox_rgba": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
     "mars_b200_resize_taps": (C.c_int, [C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]),
+    "mars_b200_requant_fit": (C.c_int, [C.c_float, C.c_longlong, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_longlong)]),
+    "mars_b200_requant_ref": (C.c_int, [C.c_int, C.c_float]),
     "mars_yolo_nms_boxes": (C.c_int, [C.c_void_p, C.c_int, C.c_float]),
     "mars_yolo_scale_detections": (None, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]),
     "mars_yolo_decode_anchor_grid": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_float, C.c_int, C.c_float, C.c_void_p, C.c_int, C.c_int]),

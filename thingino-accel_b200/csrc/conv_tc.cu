@@ -57,6 +57,9 @@ struct TcParams {
     int a_shift[TC_MAX_TAPS];
     const int32_t *bias;     /* device pointer or null */
     float cs;
+    int q_m, q_s;            /* RQ 3 (integer requantisation): multiplier m = cs * 2^(32 + q_s), shift */
+    long long q_c;           /* RQ 3: rounding addend c; the kernel forms c64[ch] = bias[ch] * m + c */
+    uint32_t cm_off;         /* RQ 3: offset of the int64 per-channel addends in dynamic shared memory */
     const uint32_t *lutw;    /* 256-entry word table: index = r + 128, byte k = value of output stream k, byte 3 = side-output stream */
     uint32_t tab_off, tab_rep; /* offset of the replicated table ([256][tab_rep] words) in dynamic shared memory; copies (8, 16 or 32) */
     uint8_t *out_base;       /* slot 0 of the launch */
@@ -280,40 +283,91 @@ struct TileIter {
     }
 };
 
-/* ---- epilogue of one unit: 16 accumulator columns (output channels) of this thread's pixel -----------------
+/* ---- requantisation, integer form (RQ 3) ----------------------------------------
+ * The reference's r(t) = clamp((int32)(fl(t * cs) + copysign(0.5f, .))) (src/mars/mxu_conv.c:663-666) is a monotone step function
+ * of the integer t = acc + bias with 255 steps.  So is g(t) = clamp(floor((t * m + c) / 2^(32 + s))) for integers m, c, s, and two
+ * monotone step functions are equal exactly when their 255 thresholds are: the host finds the reference's thresholds by bisection
+ * over the layer's accumulator range and looks for a c that reproduces all of them (int_requant_fit; m = cs * 2^(32 + s) exactly,
+ * s as large as keeps m below 2^31).  When one exists -- almost always: it fails for scales with short mantissas, whose exact ties
+ * the float arithmetic rounds away from zero on both sides -- the epilogue needs one IMAD.HI, one shift and one clamp per element
+ * instead of the magic-number int -> float conversion, two packed float operations, two float adds and the clamp; the bias is
+ * folded into the 64-bit addend (c64[ch] = bias[ch] * m + c), and there is no accumulator-range restriction (RQ 1 / 2 need
+ * |t| < 2^22).  Returns r + 128 in [0, 255] like RQ 2. */
+__device__ __forceinline__ int requant_int(uint32_t acc, int c_lo, int c_hi, int m, int sh) {
+    const long long c = (long long)(((unsigned long long)(uint32_t)c_hi << 32) | (uint32_t)c_lo);
+    const long long x = (long long)(int32_t)acc * (long long)m + c;
+    return __viaddmin_s32_relu((int)(x >> 32) >> sh, 128, 255);
+}
+
+/* the 16 table words (or plain bytes) of one unit: 16 accumulator columns (output channels) of this thread's pixel.
+ * cm: shared address of the unit's per-channel constants -- int32 bias (+ the int->float magic when RQ 1 / 2), or the int64
+ * addends of RQ 3; cs: the conv scale, for RQ 3 the bits of the multiplier m; qs: the shift s of RQ 3.
  * TAB = the op has fused followers: r indexes this lane's copy of the 256-entry word table (byte k = value of output
  * stream k, byte 3 = the side-output stream); the table is replicated per lane ([256][32] words), so the data-dependent
- * lookups of a warp never meet in a bank (the shared 512-entry table of round 1 cost ~3 wavefronts per lookup).
- * NST = number of NCHW output streams stored (table bytes 0..NST-1), NHWC = also pack the side byte of every 16 channels
- * into one 16-byte store of the consumer's channel-innermost copy.  o0..o2 point at channel c0 of this pixel; nch = how
- * many of the 16 channels exist (16 = all, <= 0 = none / pixel outside the image). */
-template <int RQ, bool TAB, int NST, bool NHWC>
-__device__ __forceinline__ void epilogue_unit(const uint32_t (&v)[16], uint32_t cm, uint32_t tab_lane, uint32_t tab_stride, float cs,
-                                              uint8_t *o0, uint8_t *o1, uint8_t *o2, long long plane, int nch, uint8_t *nh) {
-    if (nch <= 0) return; /* cm: shared address of the unit's bias words; tab_lane: shared address of entry r = 0 of this lane's table */
-    if (nch >= 16) {
-        uint32_t pk[4];
+ * lookups of a warp never meet in a bank (the shared 512-entry table of round 1 cost ~3 wavefronts per lookup). */
+template <int RQ, bool TAB>
+__device__ __forceinline__ void unit_words(const uint32_t (&v)[16], uint32_t cm, uint32_t tab_lane, uint32_t tab_stride, float cs, int qs, uint32_t (&w)[16]) {
+    constexpr bool R128 = RQ >= 2; /* the requantisation returns r + 128 */
+    if (RQ == 3) {
+        const int m = __float_as_int(cs);
+#pragma unroll
+        for (int j2 = 0; j2 < 8; j2++) {
+            const int4 c4 = lds_v4(cm + (uint32_t)j2 * 16u);
+            const int r0 = requant_int(v[2 * j2], c4.x, c4.y, m, qs), r1 = requant_int(v[2 * j2 + 1], c4.z, c4.w, m, qs);
+            w[2 * j2] = TAB ? lds_u32(tab_lane + (uint32_t)r0 * tab_stride) : (uint32_t)r0 ^ 0x80u;
+            w[2 * j2 + 1] = TAB ? lds_u32(tab_lane + (uint32_t)r1 * tab_stride) : (uint32_t)r1 ^ 0x80u;
+        }
+    } else {
 #pragma unroll
         for (int j4 = 0; j4 < 4; j4++) {
             const int4 c4 = lds_v4(cm + (uint32_t)j4 * 16u);
             const int cc[4] = {c4.x, c4.y, c4.z, c4.w};
-            uint32_t w[4];
 #pragma unroll
             for (int k = 0; k < 4; k += 2) {
                 int r0, r1;
                 requant_pair<RQ>((int32_t)(v[j4 * 4 + k] + (uint32_t)cc[k]), (int32_t)(v[j4 * 4 + k + 1] + (uint32_t)cc[k + 1]), cs, r0, r1);
-                w[k] = TAB ? lds_u32(tab_lane + (uint32_t)r0 * tab_stride) : (RQ == 2 ? (uint32_t)r0 ^ 0x80u : (uint32_t)r0);
-                w[k + 1] = TAB ? lds_u32(tab_lane + (uint32_t)r1 * tab_stride) : (RQ == 2 ? (uint32_t)r1 ^ 0x80u : (uint32_t)r1);
+                w[j4 * 4 + k] = TAB ? lds_u32(tab_lane + (uint32_t)r0 * tab_stride) : (R128 ? (uint32_t)r0 ^ 0x80u : (uint32_t)r0);
+                w[j4 * 4 + k + 1] = TAB ? lds_u32(tab_lane + (uint32_t)r1 * tab_stride) : (R128 ? (uint32_t)r1 ^ 0x80u : (uint32_t)r1);
             }
+        }
+    }
+}
+/* one channel pair (j, j+1) of a ragged unit */
+template <int RQ, bool TAB>
+__device__ __forceinline__ void pair_words(uint32_t v0, uint32_t v1, uint32_t cm, int j, uint32_t tab_lane, uint32_t tab_stride, float cs, int qs,
+                                           uint32_t &w0, uint32_t &w1) {
+    constexpr bool R128 = RQ >= 2;
+    int r0, r1;
+    if (RQ == 3) {
+        const int4 c4 = lds_v4(cm + 8u * (uint32_t)j);
+        r0 = requant_int(v0, c4.x, c4.y, __float_as_int(cs), qs); r1 = requant_int(v1, c4.z, c4.w, __float_as_int(cs), qs);
+    } else requant_pair<RQ>((int32_t)(v0 + lds_u32(cm + 4u * j)), (int32_t)(v1 + lds_u32(cm + 4u * j + 4u)), cs, r0, r1);
+    w0 = TAB ? lds_u32(tab_lane + (uint32_t)r0 * tab_stride) : (R128 ? (uint32_t)r0 ^ 0x80u : (uint32_t)r0);
+    w1 = TAB ? lds_u32(tab_lane + (uint32_t)r1 * tab_stride) : (R128 ? (uint32_t)r1 ^ 0x80u : (uint32_t)r1);
+}
+
+/* ---- epilogue of one unit: 16 accumulator columns (output channels) of this thread's pixel -----------------
+ * NST = number of NCHW output streams stored (table bytes 0..NST-1), NHWC = also pack the side byte of every 16 channels
+ * into one 16-byte store of the consumer's channel-innermost copy.  o0..o2 point at channel c0 of this pixel; nch = how
+ * many of the 16 channels exist (16 = all, <= 0 = none / pixel outside the image). */
+template <int RQ, bool TAB, int NST, bool NHWC>
+__device__ __forceinline__ void epilogue_unit(const uint32_t (&v)[16], uint32_t cm, uint32_t tab_lane, uint32_t tab_stride, float cs, int qs,
+                                              uint8_t *o0, uint8_t *o1, uint8_t *o2, long long plane, int nch, uint8_t *nh) {
+    if (nch <= 0) return; /* cm: shared address of the unit's per-channel constants; tab_lane: shared address of entry r = 0 of this lane's table */
+    if (nch >= 16) {
+        uint32_t w[16], pk[4];
+        unit_words<RQ, TAB>(v, cm, tab_lane, tab_stride, cs, qs, w);
+#pragma unroll
+        for (int j4 = 0; j4 < 4; j4++) {
 #pragma unroll
             for (int k = 0; k < 4; k++) {
-                if (NST > 0) { *o0 = (uint8_t)w[k]; o0 += plane; }
-                if (NST > 1) { *o1 = (uint8_t)(w[k] >> 8); o1 += plane; }
-                if (NST > 2) { *o2 = (uint8_t)(w[k] >> 16); o2 += plane; }
+                if (NST > 0) { *o0 = (uint8_t)w[4 * j4 + k]; o0 += plane; }
+                if (NST > 1) { *o1 = (uint8_t)(w[4 * j4 + k] >> 8); o1 += plane; }
+                if (NST > 2) { *o2 = (uint8_t)(w[4 * j4 + k] >> 16); o2 += plane; }
             }
             if (NHWC) { /* the side-output stream sits in the top byte of the table word (plain conv: the value itself) */
                 const uint32_t sel = TAB ? 0x0073u : 0x0040u;
-                pk[j4] = __byte_perm(__byte_perm(w[0], w[1], sel), __byte_perm(w[2], w[3], sel), 0x5410);
+                pk[j4] = __byte_perm(__byte_perm(w[4 * j4], w[4 * j4 + 1], sel), __byte_perm(w[4 * j4 + 2], w[4 * j4 + 3], sel), 0x5410);
             }
         }
         if (NHWC) *reinterpret_cast<uint4 *>(nh) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
@@ -321,10 +375,8 @@ __device__ __forceinline__ void epilogue_unit(const uint32_t (&v)[16], uint32_t 
 #pragma unroll
         for (int j = 0; j < 16; j += 2) {
             if (j < nch) {
-                int r0, r1;
-                requant_pair<RQ>((int32_t)(v[j] + lds_u32(cm + 4u * j)), (int32_t)(v[j + 1] + lds_u32(cm + 4u * j + 4u)), cs, r0, r1);
-                const uint32_t w0 = TAB ? lds_u32(tab_lane + (uint32_t)r0 * tab_stride) : (RQ == 2 ? (uint32_t)r0 ^ 0x80u : (uint32_t)r0);
-                const uint32_t w1 = TAB ? lds_u32(tab_lane + (uint32_t)r1 * tab_stride) : (RQ == 2 ? (uint32_t)r1 ^ 0x80u : (uint32_t)r1);
+                uint32_t w0, w1;
+                pair_words<RQ, TAB>(v[j], v[j + 1], cm, j, tab_lane, tab_stride, cs, qs, w0, w1);
                 if (NST > 0) o0[(long long)j * plane] = (uint8_t)w0;
                 if (NST > 1) o1[(long long)j * plane] = (uint8_t)(w0 >> 8);
                 if (NST > 2) o2[(long long)j * plane] = (uint8_t)(w0 >> 16);
@@ -342,25 +394,16 @@ __device__ __forceinline__ void epilogue_unit(const uint32_t (&v)[16], uint32_t 
  * table words); `vec` = the tensor allows 16-byte stores (Co % 16 == 0), otherwise (e.g. 255 head channels) bytes.
  * o0..o2 point at channel c0 of this pixel in each stream's NHWC tensor. */
 template <int RQ, bool TAB, int NST>
-__device__ __forceinline__ void epilogue_unit_nhwc(const uint32_t (&v)[16], uint32_t cm, uint32_t tab_lane, uint32_t tab_stride, float cs,
+__device__ __forceinline__ void epilogue_unit_nhwc(const uint32_t (&v)[16], uint32_t cm, uint32_t tab_lane, uint32_t tab_stride, float cs, int qs,
                                                    uint8_t *o0, uint8_t *o1, uint8_t *o2, int nch, bool vec) {
     if (nch <= 0) return;
-    uint32_t pk[3][4];
+    uint32_t w[16], pk[3][4];
+    unit_words<RQ, TAB>(v, cm, tab_lane, tab_stride, cs, qs, w);
 #pragma unroll
     for (int j4 = 0; j4 < 4; j4++) {
-        const int4 c4 = lds_v4(cm + (uint32_t)j4 * 16u);
-        const int cc[4] = {c4.x, c4.y, c4.z, c4.w};
-        uint32_t w[4];
-#pragma unroll
-        for (int k = 0; k < 4; k += 2) {
-            int r0, r1;
-            requant_pair<RQ>((int32_t)(v[j4 * 4 + k] + (uint32_t)cc[k]), (int32_t)(v[j4 * 4 + k + 1] + (uint32_t)cc[k + 1]), cs, r0, r1);
-            w[k] = TAB ? lds_u32(tab_lane + (uint32_t)r0 * tab_stride) : (RQ == 2 ? (uint32_t)r0 ^ 0x80u : (uint32_t)r0);
-            w[k + 1] = TAB ? lds_u32(tab_lane + (uint32_t)r1 * tab_stride) : (RQ == 2 ? (uint32_t)r1 ^ 0x80u : (uint32_t)r1);
-        }
-        pk[0][j4] = __byte_perm(__byte_perm(w[0], w[1], 0x0040), __byte_perm(w[2], w[3], 0x0040), 0x5410);
-        if (NST > 1) pk[1][j4] = __byte_perm(__byte_perm(w[0], w[1], 0x0051), __byte_perm(w[2], w[3], 0x0051), 0x5410);
-        if (NST > 2) pk[2][j4] = __byte_perm(__byte_perm(w[0], w[1], 0x0062), __byte_perm(w[2], w[3], 0x0062), 0x5410);
+        pk[0][j4] = __byte_perm(__byte_perm(w[4 * j4], w[4 * j4 + 1], 0x0040), __byte_perm(w[4 * j4 + 2], w[4 * j4 + 3], 0x0040), 0x5410);
+        if (NST > 1) pk[1][j4] = __byte_perm(__byte_perm(w[4 * j4], w[4 * j4 + 1], 0x0051), __byte_perm(w[4 * j4 + 2], w[4 * j4 + 3], 0x0051), 0x5410);
+        if (NST > 2) pk[2][j4] = __byte_perm(__byte_perm(w[4 * j4], w[4 * j4 + 1], 0x0062), __byte_perm(w[4 * j4 + 2], w[4 * j4 + 3], 0x0062), 0x5410);
     }
     if (vec && nch >= 16) {
         *reinterpret_cast<uint4 *>(o0) = make_uint4(pk[0][0], pk[0][1], pk[0][2], pk[0][3]);
@@ -422,8 +465,14 @@ k_conv_tc(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUte
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_slot)), "r"((uint32_t)p.tmem_cols) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
-    for (int i = threadIdx.x; i < TC_MAX_CO; i += blockDim.x)
-        s_cm[i] = (int32_t)((uint32_t)((p.bias && i < p.Co) ? p.bias[i] : 0) + (RQ != 0 ? 0x4B400000u : 0u));
+    if (RQ == 3) { /* int64 addends c64[ch] = bias[ch] * m + c in dynamic shared memory (p.cm_off), all N tiles */
+        long long *cm64 = reinterpret_cast<long long *>(smem_al + p.cm_off);
+        for (int i = threadIdx.x; i < p.n_tiles * p.n_tile; i += blockDim.x)
+            cm64[i] = (long long)((p.bias && i < p.Co) ? p.bias[i] : 0) * (long long)p.q_m + p.q_c;
+    } else {
+        for (int i = threadIdx.x; i < TC_MAX_CO; i += blockDim.x)
+            s_cm[i] = (int32_t)((uint32_t)((p.bias && i < p.Co) ? p.bias[i] : 0) + (RQ != 0 ? 0x4B400000u : 0u));
+    }
     if (TAB) { /* [256][rep] words: lane l reads copy l % rep; with rep = 32 (bank = lane) the data-dependent lookups never conflict */
         uint32_t *tab = reinterpret_cast<uint32_t *>(smem_al + p.tab_off);
         const int sh = p.tab_rep == 32 ? 5 : (p.tab_rep == 16 ? 4 : 3);
@@ -465,11 +514,13 @@ k_conv_tc(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUte
         const int r = quad * 32 + lane; /* accumulator row = pixel of the tile */
         const int n_units = p.n_tile >> 4;
         const long long plane = p.plane;
-        const float cs = p.cs;
+        const float cs = RQ == 3 ? __int_as_float(p.q_m) : p.cs; /* RQ 3: the multiplier travels in the scale's place */
+        const int qs = p.q_s;
         const uint32_t acc_lane = tmem_d + ((uint32_t)(quad * 32) << 16);
-        const uint32_t sa_cm = smem_u32(s_cm);
+        const uint32_t sa_cm = RQ == 3 ? smem_base + p.cm_off : smem_u32(s_cm);
+        constexpr uint32_t CMB = RQ == 3 ? 8u : 4u; /* bytes per channel constant */
         const uint32_t tab_stride = 4u * p.tab_rep; /* bytes between consecutive table entries */
-        const uint32_t tab_lane = smem_base + p.tab_off + (RQ == 2 ? 0u : 128u * tab_stride) + 4u * ((uint32_t)lane & (p.tab_rep - 1u)); /* this lane's copy: entry r = 0 (RQ 2: entry r = -128, the requantisation returns r + 128) */
+        const uint32_t tab_lane = smem_base + p.tab_off + (RQ >= 2 ? 0u : 128u * tab_stride) + 4u * ((uint32_t)lane & (p.tab_rep - 1u)); /* this lane's copy: entry r = 0 (RQ 2 / 3: entry r = -128, the requantisation returns r + 128) */
         const uint32_t sa_full = smem_u32(&bar_tmem_full[0]), sa_empty = smem_u32(&bar_tmem_empty[0]);
         const bool flat = !GATHER && !p.rect && p.Wp == p.Wo && OUT != 1; /* no pad columns: the tile row index IS the pixel index */
         uint8_t *const obase = p.out_base + r; /* + image * slot_stride + pixel + channel * plane + stream offset */
@@ -497,7 +548,7 @@ k_conv_tc(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUte
                 const int n0 = (ti.rem - mg * p.n_tiles) * p.n_tile;
                 const uint32_t acc_grp = acc_lane + (uint32_t)(ab * gcols);
                 uint8_t *const img_base = obase + ((unsigned long long)ti.img * p.slot_stride + (long long)n0 * plane);
-                const uint32_t cm0 = sa_cm + 4u * (uint32_t)n0;
+                const uint32_t cm0 = sa_cm + CMB * (uint32_t)n0;
                 for (int g = g_first; g <= g_last; g++) {
                     const int u_lo = g == g_first ? u_first : 0, u_hi = g == g_last ? u_last_end : n_units;
                     /* per-M-tile values: pixel of this lane, validity, output pointers */
@@ -553,9 +604,9 @@ k_conv_tc(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUte
                             if (lane == 0) mbar_arrive(sa_empty + 8u * ab);
                         }
                         if (p.dbg >= 2) { if (va[0] == 0x12345678u && va[7] == 0x9abcdef0u) pix_base[p.out_off[0]] = 1; }
-                        else if (OUT == 2) epilogue_unit_nhwc<RQ, TAB, NST>(va, cm0 + 64u * (uint32_t)u, tab_lane, tab_stride, cs, pix_base + p.out_off[0], pix_base + p.out_off[1],
+                        else if (OUT == 2) epilogue_unit_nhwc<RQ, TAB, NST>(va, cm0 + 16u * CMB * (uint32_t)u, tab_lane, tab_stride, cs, qs, pix_base + p.out_off[0], pix_base + p.out_off[1],
                                                                             pix_base + p.out_off[2], co_left - u * 16, p.onhwc_vec != 0);
-                        else epilogue_unit<RQ, TAB, NST, OUT == 1>(va, cm0 + 64u * (uint32_t)u, tab_lane, tab_stride, cs, pix_base + p.out_off[0], pix_base + p.out_off[1],
+                        else epilogue_unit<RQ, TAB, NST, OUT == 1>(va, cm0 + 16u * CMB * (uint32_t)u, tab_lane, tab_stride, cs, qs, pix_base + p.out_off[0], pix_base + p.out_off[1],
                                                                    pix_base + p.out_off[2], plane, co_left - u * 16, nh + u * 16);
                         pix_base += plane16;
                         if (++u >= u_hi) break;
@@ -567,9 +618,9 @@ k_conv_tc(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUte
                             if (lane == 0) mbar_arrive(sa_empty + 8u * ab);
                         }
                         if (p.dbg >= 2) { if (vb[0] == 0x12345678u && vb[7] == 0x9abcdef0u) pix_base[p.out_off[0]] = 1; }
-                        else if (OUT == 2) epilogue_unit_nhwc<RQ, TAB, NST>(vb, cm0 + 64u * (uint32_t)u, tab_lane, tab_stride, cs, pix_base + p.out_off[0], pix_base + p.out_off[1],
+                        else if (OUT == 2) epilogue_unit_nhwc<RQ, TAB, NST>(vb, cm0 + 16u * CMB * (uint32_t)u, tab_lane, tab_stride, cs, qs, pix_base + p.out_off[0], pix_base + p.out_off[1],
                                                                             pix_base + p.out_off[2], co_left - u * 16, p.onhwc_vec != 0);
-                        else epilogue_unit<RQ, TAB, NST, OUT == 1>(vb, cm0 + 64u * (uint32_t)u, tab_lane, tab_stride, cs, pix_base + p.out_off[0], pix_base + p.out_off[1],
+                        else epilogue_unit<RQ, TAB, NST, OUT == 1>(vb, cm0 + 16u * CMB * (uint32_t)u, tab_lane, tab_stride, cs, qs, pix_base + p.out_off[0], pix_base + p.out_off[1],
                                                                    pix_base + p.out_off[2], plane, co_left - u * 16, nh + u * 16);
                         pix_base += plane16;
                         if (++u >= u_hi) break;
@@ -1201,6 +1252,93 @@ static bool halfup_requant_ok(float cs, long long bound) {
     return true;
 }
 
+/* max |acc + bias| over all output channels, from the real weights (int32 accumulation: K * 127 * 128 stays far below 2^31) */
+static long long acc_bound(const Op &o, const ArenaGeom &ag) {
+    const int8_t *w = reinterpret_cast<const int8_t *>(ag.h_weights + o.w);
+    const long long K = (long long)o.ic * o.kh * o.kw;
+    long long bound = 0;
+    for (int co = 0; co < o.oc; co++) {
+        long long sum = 0;
+        for (long long k = 0; k < K; k++) sum += std::abs((int)w[co * K + k]);
+        long long b = 0;
+        if (o.bias >= 0) { int32_t bv; memcpy(&bv, ag.h_weights + o.bias + 4 * (size_t)co, 4); b = std::llabs((long long)bv); }
+        bound = std::max(bound, sum * 128 + b);
+    }
+    return bound;
+}
+
+/* the reference's requantisation of t = acc + bias (src/mars/mxu_conv.c:663-666), x86 float -> int rule included */
+static int ref_requant(int32_t t, float cs) {
+    volatile float sc = (float)t * cs;
+    volatile float h = sc + (sc >= 0 ? 0.5f : -0.5f);
+    const float hv = h;
+    const int32_t r = !(hv > -2147483904.0f && hv < 2147483648.0f) ? INT32_MIN : (int32_t)hv;
+    return r > 127 ? 127 : (r < -128 ? -128 : r);
+}
+
+/* RQ 3: integers (m, s, c) with clamp(floor((t * m + c) / 2^(32 + s))) == ref_requant(t, cs) for EVERY |t| <= tmax, or false.
+ * Both sides are monotone step functions of t (cs > 0), so they agree everywhere iff they agree on the two points either side of
+ * each of the reference's steps: with theta_k the first t whose reference value is >= k (bisection),
+ *     theta_k * m + c >= k * 2^(32+s)      and      (theta_k - 1) * m + c <= k * 2^(32+s) - 1        for k = -127 .. 127
+ * (plus the two range ends).  For a given m the valid c form the interval [lo(m), hi(m)]; hi - lo is concave in m, so the best m
+ * is found by ternary search around cs * 2^(32+s).  The second degree of freedom matters: the float product fl(t * cs) rounds
+ * values just below a tie n + 0.5 up to it on BOTH sides of zero (the reference then rounds away from zero), which a slightly
+ * larger multiplier reproduces and a rounding addend alone cannot.  What remains unfittable are scales where that rounding,
+ * constant per binade, and the linear tilt disagree on some integer t -- the caller then keeps a float variant. */
+static bool int_requant_fit(float cs, long long tmax, int *m_out, int *s_out, long long *c_out) {
+    if (!(cs > 0.0f) || !(cs < 0.49f) || tmax < 1 || tmax > 2147483647ll) return false;
+    int sh = 0;
+    while (sh < 24 && ldexp((double)cs, 32 + sh + 1) < 2147483647.0) sh++;
+    const long long m0 = llround(ldexp((double)cs, 32 + sh));
+    const int lo_r = ref_requant((int32_t)-tmax, cs), hi_r = ref_requant((int32_t)tmax, cs);
+    if (lo_r > hi_r || m0 < 1) return false;
+    typedef __int128 i128;
+    const i128 S = (i128)1 << (32 + sh);
+    struct Con { long long t; int k; };
+    std::vector<Con> ge, le; /* ge: t * m + c >= k * S;  le: t * m + c <= k * S - 1 */
+    for (int k = -127; k <= 127; k++) {
+        if (k <= lo_r) ge.push_back({-tmax, k});      /* the reference is >= k on the whole range */
+        else if (k > hi_r) le.push_back({tmax, k});   /* ... < k on the whole range */
+        else {
+            long long a = -tmax, b = tmax; /* ref(a) < k <= ref(b) */
+            while (b - a > 1) {
+                const long long mid = a + (b - a) / 2;
+                if (ref_requant((int32_t)mid, cs) >= k) b = mid; else a = mid;
+            }
+            ge.push_back({b, k});
+            le.push_back({b - 1, k});
+        }
+    }
+    auto slack = [&](long long m, i128 *lo, i128 *hi) -> i128 {
+        i128 l = -((i128)1 << 120), h = (i128)1 << 120;
+        for (const Con &c : ge) l = std::max(l, (i128)c.k * S - (i128)c.t * m);
+        for (const Con &c : le) h = std::min(h, (i128)c.k * S - 1 - (i128)c.t * m);
+        if (lo) *lo = l;
+        if (hi) *hi = h;
+        return h - l;
+    };
+    long long a = std::max(1ll, m0 - (1ll << 20)), b = std::min(2147483647ll, m0 + (1ll << 20));
+    while (b - a > 2) {
+        const long long m1 = a + (b - a) / 3, m2 = b - (b - a) / 3;
+        if (slack(m1, nullptr, nullptr) < slack(m2, nullptr, nullptr)) a = m1; else b = m2;
+    }
+    long long m = a;
+    for (long long q = a + 1; q <= b; q++) if (slack(q, nullptr, nullptr) > slack(m, nullptr, nullptr)) m = q;
+    i128 cl, ch;
+    if (slack(m, &cl, &ch) < 0) return false;
+    const i128 c = cl + (ch - cl) / 2;
+    /* the sum t * m + c64 (c64 = bias * m + c, |t - bias| + |bias| <= 2 tmax) must stay inside int64 */
+    const i128 cabs = c < 0 ? -c : c;
+    if (cabs > ((i128)1 << 61) || (i128)2 * tmax * m + cabs >= ((i128)1 << 62)) return false;
+    /* belt and braces: both sides evaluated around every step and at the range ends */
+    auto g = [&](long long t) { i128 x = ((i128)t * m + c) >> (32 + sh); return (int)(x > 127 ? 127 : (x < -128 ? -128 : x)); };
+    for (const Con &cn : ge) for (long long t = cn.t - 2; t <= cn.t + 2; t++)
+        if (t >= -tmax && t <= tmax && g(t) != ref_requant((int32_t)t, cs)) return false;
+    if (g(-tmax) != lo_r || g(tmax) != hi_r) return false;
+    *m_out = (int)m; *s_out = sh; *c_out = (long long)c;
+    return true;
+}
+
 /* kernel variants: requantisation x GATHER producer x word table x number of stored streams x output mode (0 NCHW planes,
  * 1 + side copy, 2 channel-innermost tensors).  Without a table (plain conv, no byte-ReLU) there is one stream at most. */
 template <int RQ, bool GATHER, int EPI>
@@ -1242,6 +1380,7 @@ static TcKernel pick_kernel1(bool gather, bool tab, int nst, int out, int epi) {
     return pick_kernel2<RQ, false, 8>(tab, nst, out);
 }
 static TcKernel pick_kernel(int rq, bool gather, bool tab, int nst, int out, int epi) {
+    if (rq == 3) return pick_kernel1<3>(gather, tab, nst, out, epi);
     if (rq == 2) return pick_kernel1<2>(gather, tab, nst, out, epi);
     if (rq == 1) return pick_kernel1<1>(gather, tab, nst, out, epi);
     return pick_kernel1<0>(gather, tab, nst, out, epi);
@@ -1289,6 +1428,15 @@ bool tc_plan(const Op &o, const ArenaGeom &ag, uint8_t *scratch, size_t scratch_
      * replicated per lane group in shared memory ([256][rep] words, lane l reads copy l % rep): rep = 32 makes the lookups
      * conflict free; 16 or 8 (two / four lanes per bank) when the stages, the halo region or the resident weights need the room */
     t->tab = o.fused_layers > 0 || o.post_relu;
+    { /* requantisation variant of the epilogue (requant_pair / requant_int) */
+        static const int rq_max = getenv("MARS_TC_RQ") ? atoi(getenv("MARS_TC_RQ")) : 3; /* tuning / test aid: cap the variant */
+        const long long bound = fast_requant_bound(o, ag);
+        t->fast = bound >= 0;
+        t->rq = !t->fast ? 0 : ((rq_max >= 2 && halfup_requant_ok(o.f0, bound)) ? 2 : 1);
+        if (rq_max == 0) { t->rq = 0; t->fast = false; }
+        if (rq_max >= 3 && int_requant_fit(o.f0, std::max(1ll, acc_bound(o, ag)), &p.q_m, &p.q_s, &p.q_c)) t->rq = 3;
+    }
+    const int cm64_bytes = t->rq == 3 ? 8 * p.n_tiles * p.n_tile : 0; /* RQ 3: per-channel int64 addends behind the table */
     const int nsteps = g.ntaps * p.ksteps_per_tap;
     const int grp0 = p.grp, acc0 = p.acc_bufs;
     const uint32_t a_stage0 = p.a_stage_bytes;
@@ -1335,21 +1483,25 @@ bool tc_plan(const Op &o, const ArenaGeom &ag, uint8_t *scratch, size_t scratch_
         }
     };
     int rep = t->tab ? 8 : 0;
-    plan_smem(rep * 1024);
+    plan_smem(rep * 1024 + cm64_bytes);
     if (!plan_ok) { delete t; return false; }
     if (t->tab) { /* widen the replication while the pipeline keeps its shape (resident weights, halo loads, >= 3 stages) */
         const int res8 = p.b_resident, halo8 = p.halo, st8 = p.stages;
         static const int rep_max = getenv("MARS_TC_TABREP") ? atoi(getenv("MARS_TC_TABREP")) : 32;
         for (int r2 = 32; r2 > 8; r2 >>= 1) {
             if (r2 > rep_max) continue;
-            plan_smem(r2 * 1024);
+            plan_smem(r2 * 1024 + cm64_bytes);
             static const int min_st = getenv("MARS_TC_MINST") ? atoi(getenv("MARS_TC_MINST")) : 3;
             if (plan_ok && p.b_resident == res8 && p.halo == halo8 && p.stages >= std::min(st8, min_st)) { rep = r2; break; }
         }
-        if (rep == 8) plan_smem(8 * 1024);
+        if (rep == 8) plan_smem(8 * 1024 + cm64_bytes);
         p.tab_rep = (uint32_t)rep;
         p.tab_off = (uint32_t)round_up((int)(t->smem - 1024), 128); /* the table copies sit behind everything else */
         t->smem = 1024 + (size_t)p.tab_off + (size_t)rep * 1024;
+    }
+    if (cm64_bytes) {
+        p.cm_off = (uint32_t)round_up((int)(t->smem - 1024), 128);
+        t->smem = 1024 + (size_t)p.cm_off + (size_t)cm64_bytes;
     }
     /* keep residency at ctas_per_sm: a further CTA would fit the registers but stall in tcgen05.alloc */
     t->smem = std::max<size_t>(t->smem, t->ctas_per_sm == 1 ? 120 * 1024 : 80 * 1024);
@@ -1420,13 +1572,6 @@ bool tc_plan(const Op &o, const ArenaGeom &ag, uint8_t *scratch, size_t scratch_
         p.nhwc_C = consumer->ic;
         p.nhwc_base = linked + consumer->copy_off;
         p.nhwc_stride = linked_stride;
-    }
-    {
-        const long long bound = fast_requant_bound(o, ag);
-        static const int rq_max = getenv("MARS_TC_RQ") ? atoi(getenv("MARS_TC_RQ")) : 2; /* tuning / test aid: cap the variant */
-        t->fast = bound >= 0;
-        t->rq = !t->fast ? 0 : ((rq_max >= 2 && halfup_requant_ok(o.f0, bound)) ? 2 : 1);
-        if (rq_max == 0) { t->rq = 0; t->fast = false; }
     }
     t->prepass = g.prepass; t->C = o.ic; t->Cp = ci_eff; t->H = o.ih; t->W = o.iw; t->pt = o.pt; t->pl = o.pl;
     t->plane = g.plane; t->npix = g.npix;
@@ -1566,3 +1711,15 @@ void tc_release(std::vector<TcPlan> &plans) {
 }
 
 } // namespace marsb200
+
+extern "C" {
+int mars_b200_requant_fit(float scale, long long tmax, int *m, int *s, long long *c) {
+    int mm = 0, ss = 0; long long cc = 0;
+    if (!marsb200::int_requant_fit(scale, tmax, &mm, &ss, &cc)) return 0;
+    if (m) *m = mm;
+    if (s) *s = ss;
+    if (c) *c = cc;
+    return 1;
+}
+int mars_b200_requant_ref(int t, float scale) { return marsb200::ref_requant((int32_t)t, scale); }
+}

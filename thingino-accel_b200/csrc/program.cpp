@@ -711,6 +711,11 @@ static void elide_dead_stores(Program *p, const IvSet &observed, const IvSet &ho
             Op &o = p->ops[k];
             if (o.fused_layers > 0 && (o.kind == OP_CONV_I8_NCHW || o.kind == OP_CONV_I8_NHWC)) {
                 const int64_t numel = (int64_t)o.oc * o.oh * o.ow;
+                if (getenv("MARS_LIVE_DEBUG") && iter == 0) { /* how many output planes of every stream are live after the op */
+                    const int64_t P = (int64_t)o.oh * o.ow;
+                    auto cnt = [&](int64_t base) { int n = 0; if (base < 0) return -1; for (int c = 0; c < o.oc; c++) n += live.hits(base + c * P, base + (c + 1) * P) ? 1 : 0; return n; };
+                    fprintf(stderr, "live op %zu layer %d oc %d: Y %d%s S %d Z %d%s\n", k, o.layer, o.oc, cnt(o.out), o.store_y ? "" : "(off)", cnt(o.out_s), cnt(o.out_z), o.store_z ? "" : "(off)");
+                }
                 /* later stages of the chain overwrite equal ranges, so test each against what is live AFTER the op */
                 if (o.store_y && !live.hits(o.out, o.out + numel)) { o.store_y = false; o.note += " -Y"; }
                 if (o.out_s >= 0 && !live.hits(o.out_s, o.out_s + numel)) { o.out_s = -1; o.note += " -S"; }

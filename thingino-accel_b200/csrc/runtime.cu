@@ -507,11 +507,18 @@ static mars_error_t launch_op(Model *m, size_t op_index, int first, int n, bool 
     return MARS_OK;
 }
 
-/* all ops (or the ops of one layer) over slots [first, first+n) on m->stream */
-static mars_error_t enqueue_ops(Model *m, int first, int n, int only_layer) {
+/* all ops (or the ops of one layer, or the ops [op_lo, op_hi)) over slots [first, first+n) on m->stream */
+static mars_error_t enqueue_ops(Model *m, int first, int n, int only_layer, size_t op_lo = 0, size_t op_hi = (size_t)-1) {
     mars_error_t e = compile_model(m);
     if (e != MARS_OK) return e;
     const size_t nops = m->prog.ops.size();
+    if (op_lo != 0 || op_hi < nops) { /* a slice of the op list (micro-batched head / full-batch tail): no per-op events */
+        for (size_t i = op_lo; i < std::min(op_hi, nops); i++) {
+            e = launch_op(m, i, first, n, true);
+            if (e != MARS_OK) return e;
+        }
+        return MARS_OK;
+    }
     if (m->profile && m->prof_ev.size() < nops + 1) {
         while (m->prof_ev.size() < nops + 1) {
             cudaEvent_t ev;
@@ -1111,25 +1118,44 @@ mars_error_t mars_b200_preprocess_batch(mars_model_t *model, int first, int n, c
     return MARS_OK;
 }
 
-/* micro-batch so that the slots being worked on stay L2-resident between layers */
-static int micro_batch(Model *m) {
+/* Layer-group micro-batching (replaces the reference's one-image-at-a-time schedule, src/mars/mars_runtime.c:439-459): the
+ * head of the op list -- the layers at the large resolutions, whose activations dominate the traffic -- runs over
+ * MARS_MICRO_BATCH images at a time, all its layers back to back, so that a layer finds its producer's output in L2 instead
+ * of HBM; the tail (small planes, where a micro-batch would not fill the 296 persistent CTAs) runs over the whole batch.
+ * MARS_MICRO_OPS = number of head ops (default: everything in front of the first conv whose output plane is <= 80 x 80;
+ * 0 = the whole list per micro-batch).  Images are independent, so any order across images is the same computation.
+ * Off by default (MARS_MICRO_BATCH unset): profiles/r02h_micro_batch_sweep.txt has the measurement. */
+static int micro_batch() {
     static int mb = -1;
     if (mb < 0) {
         const char *e = getenv("MARS_MICRO_BATCH");
         mb = (e && *e) ? atoi(e) : 0;
     }
-    (void)m;
     return mb;
+}
+static size_t micro_split(Model *m) {
+    const char *e = getenv("MARS_MICRO_OPS");
+    if (e && *e) return (size_t)std::max(0, atoi(e));
+    for (size_t i = 0; i < m->prog.ops.size(); i++) {
+        const Op &o = m->prog.ops[i];
+        if ((o.kind == OP_CONV_I8_NCHW || o.kind == OP_CONV_I8_NHWC) && (long long)o.oh * o.ow <= 6400) return i;
+    }
+    return 0;
 }
 
 static mars_error_t enqueue_run(Model *m, int first, int n) {
-    int mb = micro_batch(m);
-    if (mb <= 0 || mb >= n) return enqueue_ops(m, first, n, -1);
+    const int mb = micro_batch();
+    if (mb <= 0 || mb >= n || m->profile) return enqueue_ops(m, first, n, -1);
+    mars_error_t e = compile_model(m);
+    if (e != MARS_OK) return e;
+    const size_t nops = m->prog.ops.size(), split = micro_split(m);
+    const size_t head = (split == 0 || split > nops) ? nops : split;
     for (int i = 0; i < n; i += mb) {
-        mars_error_t e = enqueue_ops(m, first + i, std::min(mb, n - i), -1);
+        e = enqueue_ops(m, first + i, std::min(mb, n - i), -1, 0, head);
         if (e != MARS_OK) return e;
     }
-    return MARS_OK;
+    if (head < nops) e = enqueue_ops(m, first, n, -1, head, nops);
+    return e;
 }
 
 mars_error_t mars_b200_run_resident(mars_model_t *model, int first, int n) {
