@@ -60,6 +60,14 @@ struct TcParams {
     int q_m, q_s;            /* RQ 3 (integer requantisation): multiplier m = cs * 2^(32 + q_s), shift */
     long long q_c;           /* RQ 3: rounding addend c; the kernel forms c64[ch] = bias[ch] * m + c */
     uint32_t cm_off;         /* RQ 3: offset of the int64 per-channel addends in dynamic shared memory */
+    /* TST (plane stores through shared memory + TMA): staging area [team][2][NST][16 channels][128 pixels] in dynamic shared
+     * memory; st_wp = row pitch of the tile's pixel index in the store tensor's (x, y) space (the padded width of kxk layers;
+     * "one long row" for flat 1x1 tiles), st_magic = floor(2^32 / st_wp) + 1 */
+    int side_pair;           /* OUT 1: units (2k, 2k+1) of a pixel go out as one 32-byte store (consumer channels % 32 == 0, 32-byte aligned copy) */
+    uint32_t stg_off;
+    int st_manual;           /* TST: the staged block is written by the team's threads, 16 pixels of one channel each (padded tiles: TMA stores cannot clip on the left) */
+    int st_wp;
+    unsigned st_magic;
     const uint32_t *lutw;    /* 256-entry word table: index = r + 128, byte k = value of output stream k, byte 3 = side-output stream */
     uint32_t tab_off, tab_rep; /* offset of the replicated table ([256][tab_rep] words) in dynamic shared memory; copies (8, 16 or 32) */
     uint8_t *out_base;       /* slot 0 of the launch */
@@ -137,6 +145,12 @@ __device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap *map
     asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
                  ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
 }
+/* shared -> global tile store (bulk async group of the issuing thread); coordinates beyond the tensor are clipped */
+__device__ __forceinline__ void tma_store_4d(const CUtensorMap *map, uint32_t src, int c0, int c1, int c2, int c3) {
+    asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
+                 ::"l"(map), "r"(src), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
+__device__ __forceinline__ void sts_u8(uint32_t addr, uint32_t v) { asm volatile("st.shared.u8 [%0], %1;" ::"r"(addr), "r"(v) : "memory"); }
 /* D[tmem] (+)= A[smem] * B[smem]; the two 64-bit shared-memory matrix descriptors are given as 32-bit halves (the high
  * halves are loop invariants of the issuing thread) */
 __device__ __forceinline__ void umma_i8_parts(uint32_t tmem_d, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi, uint32_t idesc,
@@ -352,7 +366,8 @@ __device__ __forceinline__ void pair_words(uint32_t v0, uint32_t v1, uint32_t cm
  * many of the 16 channels exist (16 = all, <= 0 = none / pixel outside the image). */
 template <int RQ, bool TAB, int NST, bool NHWC>
 __device__ __forceinline__ void epilogue_unit(const uint32_t (&v)[16], uint32_t cm, uint32_t tab_lane, uint32_t tab_stride, float cs, int qs,
-                                              uint8_t *o0, uint8_t *o1, uint8_t *o2, long long plane, int nch, uint8_t *nh) {
+                                              uint8_t *o0, uint8_t *o1, uint8_t *o2, long long plane, int nch, uint8_t *nh, int skip,
+                                              int pair, uint32_t (&keep)[4]) {
     if (nch <= 0) return; /* cm: shared address of the unit's per-channel constants; tab_lane: shared address of entry r = 0 of this lane's table */
     if (nch >= 16) {
         uint32_t w[16], pk[4];
@@ -361,16 +376,25 @@ __device__ __forceinline__ void epilogue_unit(const uint32_t (&v)[16], uint32_t 
         for (int j4 = 0; j4 < 4; j4++) {
 #pragma unroll
             for (int k = 0; k < 4; k++) {
-                if (NST > 0) { *o0 = (uint8_t)w[4 * j4 + k]; o0 += plane; }
-                if (NST > 1) { *o1 = (uint8_t)(w[4 * j4 + k] >> 8); o1 += plane; }
-                if (NST > 2) { *o2 = (uint8_t)(w[4 * j4 + k] >> 16); o2 += plane; }
+                if (NST > 0) { if (!(skip & 1)) *o0 = (uint8_t)w[4 * j4 + k]; o0 += plane; } /* skip: tuning aid (MARS_TC_DEBUG 12-14), 0 otherwise */
+                if (NST > 1) { if (!(skip & 1)) *o1 = (uint8_t)(w[4 * j4 + k] >> 8); o1 += plane; }
+                if (NST > 2) { if (!(skip & 1)) *o2 = (uint8_t)(w[4 * j4 + k] >> 16); o2 += plane; }
             }
             if (NHWC) { /* the side-output stream sits in the top byte of the table word (plain conv: the value itself) */
                 const uint32_t sel = TAB ? 0x0073u : 0x0040u;
                 pk[j4] = __byte_perm(__byte_perm(w[4 * j4], w[4 * j4 + 1], sel), __byte_perm(w[4 * j4 + 2], w[4 * j4 + 3], sel), 0x5410);
             }
         }
-        if (NHWC) *reinterpret_cast<uint4 *>(nh) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+        /* side output: one 16-byte store per unit, or -- units (2k, 2k+1) of a pixel handled back to back by this thread -- one
+         * 32-byte store (STG.256) per pair: half as many partially written lines on their way to L2 (pair: 1 = first unit of
+         * a pair, the packed bytes stay in `keep`; 2 = second unit) */
+        if (NHWC && !(skip & 2)) {
+            if (pair == 1) { keep[0] = pk[0]; keep[1] = pk[1]; keep[2] = pk[2]; keep[3] = pk[3]; }
+            else if (pair == 2)
+                asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(nh - 16), "r"(keep[0]), "r"(keep[1]), "r"(keep[2]), "r"(keep[3]),
+                             "r"(pk[0]), "r"(pk[1]), "r"(pk[2]), "r"(pk[3]) : "memory");
+            else *reinterpret_cast<uint4 *>(nh) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+        }
     } else { /* ragged last unit (e.g. 255 head channels); a side-output consumer always has Ci = Co, a multiple of 32 */
 #pragma unroll
         for (int j = 0; j < 16; j += 2) {
@@ -387,6 +411,29 @@ __device__ __forceinline__ void epilogue_unit(const uint32_t (&v)[16], uint32_t 
                 }
             }
         }
+    }
+}
+
+/* TST: the NCHW streams of the unit go into the team's staging block [stream][16 channels][128 pixels] (this thread's pixel =
+ * byte r of every row; immediate offsets, no pointer arithmetic); a TMA store writes the block afterwards.  The side output
+ * (NHWC) is stored directly as before. */
+template <int RQ, bool TAB, int NST, bool NHWC>
+__device__ __forceinline__ void epilogue_unit_staged(const uint32_t (&v)[16], uint32_t cm, uint32_t tab_lane, uint32_t tab_stride, float cs, int qs,
+                                                     uint32_t stg_r, bool side_ok, uint8_t *nh) {
+    uint32_t w[16], pk[4];
+    unit_words<RQ, TAB>(v, cm, tab_lane, tab_stride, cs, qs, w);
+#pragma unroll
+    for (int j = 0; j < 16; j++) {
+        if (NST > 0) sts_u8(stg_r + (uint32_t)j * 128u, w[j]);
+        if (NST > 1) sts_u8(stg_r + 2048u + (uint32_t)j * 128u, w[j] >> 8);
+        if (NST > 2) sts_u8(stg_r + 4096u + (uint32_t)j * 128u, w[j] >> 16);
+    }
+    if (NHWC) {
+        const uint32_t sel = TAB ? 0x0073u : 0x0040u;
+#pragma unroll
+        for (int j4 = 0; j4 < 4; j4++)
+            pk[j4] = __byte_perm(__byte_perm(w[4 * j4], w[4 * j4 + 1], sel), __byte_perm(w[4 * j4 + 2], w[4 * j4 + 3], sel), 0x5410);
+        if (side_ok) *reinterpret_cast<uint4 *>(nh) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
     }
 }
 
@@ -431,9 +478,10 @@ __device__ __forceinline__ void epilogue_unit_nhwc(const uint32_t (&v)[16], uint
  * GATHER (small Ci, e.g. the 6x6 stride-2 stem): M tiles are tw x th output pixels; four producer warps stage the
  * input patch of the tile in shared memory (next tile's patch is in flight in registers meanwhile) and build the
  * 128-byte K rows of the A operand from it, in the 128B-swizzled K-major layout TMA would have produced. */
-template <int RQ, bool GATHER, bool TAB, int NST, int OUT, int EPI>
+template <int RQ, bool GATHER, bool TAB, int NST, int OUT, int EPI, bool TST = false>
 __global__ void __launch_bounds__((EPI + (GATHER ? 5 : 2)) * 32, EPI == 8 ? 2 : 1)
-k_conv_tc(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, const TcParams p) {
+k_conv_tc(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, const __grid_constant__ CUtensorMap mapO0,
+          const __grid_constant__ CUtensorMap mapO1, const __grid_constant__ CUtensorMap mapO2, const TcParams p) {
     extern __shared__ uint8_t smem_raw[];
     __shared__ __align__(8) uint64_t bar_full[8], bar_empty[8], bar_tmem_full[8], bar_tmem_empty[8], bar_b;
     __shared__ uint32_t tmem_base_slot;
@@ -516,6 +564,7 @@ k_conv_tc(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUte
         const long long plane = p.plane;
         const float cs = RQ == 3 ? __int_as_float(p.q_m) : p.cs; /* RQ 3: the multiplier travels in the scale's place */
         const int qs = p.q_s;
+        const int skip = p.dbg == 12 ? 5 : (p.dbg == 13 ? 6 : (p.dbg == 14 ? 7 : 0)); /* tuning aid: 12 = no plane stores, 13 = no side stores, 14 = neither */
         const uint32_t acc_lane = tmem_d + ((uint32_t)(quad * 32) << 16);
         const uint32_t sa_cm = RQ == 3 ? smem_base + p.cm_off : smem_u32(s_cm);
         constexpr uint32_t CMB = RQ == 3 ? 8u : 4u; /* bytes per channel constant */
@@ -541,6 +590,12 @@ k_conv_tc(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUte
             const int g_last = (i_hi - 1) / n_units, u_last_end = i_hi - g_last * n_units; /* units [0, u_last_end) of the last M tile */
             int ab = 0, aph = 0;
             uint32_t va[16], vb[16];
+            /* TST: the four warps of a part (one per TMEM lane quadrant) form a team that fills one staging block per unit;
+             * the team's leader thread issues the block's TMA stores and, before the next barrier, waits until the previous
+             * block has been read (its buffer is the one the unit after this one fills) */
+            const uint32_t stg_team = smem_base + p.stg_off + (uint32_t)part * (2u * NST * 2048u) + (uint32_t)r;
+            const bool leader = quad == 0 && lane == 0;
+            uint32_t cnt = 0;
             for (TileIter ti(blockIdx.x, gridDim.x, tiles_per_img); ti.img < p.n_img; ti.next()) {
                 mbar_wait_relaxed(sa_full + 8u * ab, aph);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -592,8 +647,50 @@ k_conv_tc(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUte
                     const long long plane16 = OUT == 2 ? 16 : plane * 16;
                     const uint32_t acc_g = acc_grp + (uint32_t)(g * p.n_tile);
                     const bool last_g = g == g_last;
+                    /* TST: where the tile's pixel 0 sits in the store tensor: (x0, y0) = (q0 % st_wp, q0 / st_wp); flat tiles: one long row */
+                    const int q0 = mt * TC_BM, ty0 = (int)__umulhi((unsigned)q0, p.st_magic), tx0 = q0 - ty0 * p.st_wp;
+                    const int nseg = (int)__umulhi((unsigned)(tx0 + TC_BM - 1), p.st_magic) + 1; /* rows the 128 pixels touch */
+                    /* manual copy-out: thread r of the team owns the 16-pixel chunk (r & 7) of channel (r >> 3) of every unit */
+                    const int cq = q0 + (r & 7) * 16, cy = (int)__umulhi((unsigned)cq, p.st_magic), cx = cq - cy * p.st_wp;
+                    const bool c_ok = p.st_magic ? (cx < p.Wo && cy < p.Ho) : (cq < p.plane);
+                    const long long c_off = (long long)(unsigned long long)ti.img * (long long)p.slot_stride + (long long)cy * p.Wo + cx;
+                    auto staged = [&](const uint32_t (&v)[16], int uu) {
+                        const uint32_t sb = stg_team + (cnt & 1u) * (NST * 2048u);
+                        epilogue_unit_staged<RQ, TAB, NST, OUT == 1>(v, cm0 + 16u * CMB * (uint32_t)uu, tab_lane, tab_stride, cs, qs, sb, valid, nh + uu * 16);
+                        asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); /* generic-proxy writes -> visible to the TMA store */
+                        if (leader && !p.st_manual) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); /* the previous block has left shared memory */
+                        asm volatile("bar.sync %0, 128;" ::"r"(1 + part) : "memory");
+                        if (p.st_manual) {
+                            const int c = n0 + uu * 16 + (r >> 3);
+                            const uint32_t src = sb - (uint32_t)r + (uint32_t)(r >> 3) * 128u + (uint32_t)(r & 7) * 16u;
+                            if (c_ok && c < p.Co) {
+                                uint8_t *dst = p.out_base + (c_off + (long long)c * plane);
+                                const int4 d0 = lds_v4(src);
+                                *reinterpret_cast<int4 *>(dst + p.out_off[0]) = d0;
+                                if (NST > 1) { const int4 d1 = lds_v4(src + 2048u); *reinterpret_cast<int4 *>(dst + p.out_off[1]) = d1; }
+                                if (NST > 2) { const int4 d2 = lds_v4(src + 4096u); *reinterpret_cast<int4 *>(dst + p.out_off[2]) = d2; }
+                            }
+                        } else if (leader) {
+                            const uint32_t src = sb - (uint32_t)r;
+                            const int c = n0 + uu * 16, zi = p.img0 + ti.img;
+                            for (int sg = 0; sg < nseg; sg++) { /* one store per image row the tile touches; pad columns and rows beyond the image are clipped */
+                                int xs = tx0 - sg * p.st_wp;
+                                if (p.dbg == 20 && sg > 0) break;
+                                if ((p.dbg == 21 || p.dbg == 23) && ty0 + sg >= p.Ho) break;
+                                if (p.dbg == 21 && xs < 0) continue;
+                                if (p.dbg == 22 && xs < 0) xs = 0;
+                                tma_store_4d(&mapO0, src, xs, ty0 + sg, c, zi);
+                                if (NST > 1) tma_store_4d(&mapO1, src + 2048u, xs, ty0 + sg, c, zi);
+                                if (NST > 2) tma_store_4d(&mapO2, src + 4096u, xs, ty0 + sg, c, zi);
+                            }
+                            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                        }
+                        cnt++;
+                    };
                     /* units u_lo .. u_hi-1 of this M tile, the TMEM load of the next one in flight while one is processed */
                     int u = u_lo;
+                    uint32_t keep[4] = {0u, 0u, 0u, 0u};
+                    const bool pair_ok = valid && p.side_pair != 0; /* a pair is stored by its second unit: both exist for a valid pixel (Co % 32 == 0) */
                     tmem_ld16_issue(acc_g + (uint32_t)(u * 16), va);
                     for (;;) {
                         tmem_ld_wait(va);
@@ -603,11 +700,13 @@ k_conv_tc(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUte
                             __syncwarp();
                             if (lane == 0) mbar_arrive(sa_empty + 8u * ab);
                         }
-                        if (p.dbg >= 2) { if (va[0] == 0x12345678u && va[7] == 0x9abcdef0u) pix_base[p.out_off[0]] = 1; }
+                        if (p.dbg >= 2 && p.dbg < 12) { if (va[0] == 0x12345678u && va[7] == 0x9abcdef0u) pix_base[p.out_off[0]] = 1; }
+                        else if (TST) staged(va, u);
                         else if (OUT == 2) epilogue_unit_nhwc<RQ, TAB, NST>(va, cm0 + 16u * CMB * (uint32_t)u, tab_lane, tab_stride, cs, qs, pix_base + p.out_off[0], pix_base + p.out_off[1],
                                                                             pix_base + p.out_off[2], co_left - u * 16, p.onhwc_vec != 0);
                         else epilogue_unit<RQ, TAB, NST, OUT == 1>(va, cm0 + 16u * CMB * (uint32_t)u, tab_lane, tab_stride, cs, qs, pix_base + p.out_off[0], pix_base + p.out_off[1],
-                                                                   pix_base + p.out_off[2], plane, co_left - u * 16, nh + u * 16);
+                                                                   pix_base + p.out_off[2], plane, co_left - u * 16, nh + u * 16, skip,
+                                                                   OUT == 1 && pair_ok ? ((u & 1) ? (u > u_lo ? 2 : 0) : (u + 1 < u_hi ? 1 : 0)) : 0, keep);
                         pix_base += plane16;
                         if (++u >= u_hi) break;
                         tmem_ld_wait(vb);
@@ -617,17 +716,20 @@ k_conv_tc(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUte
                             __syncwarp();
                             if (lane == 0) mbar_arrive(sa_empty + 8u * ab);
                         }
-                        if (p.dbg >= 2) { if (vb[0] == 0x12345678u && vb[7] == 0x9abcdef0u) pix_base[p.out_off[0]] = 1; }
+                        if (p.dbg >= 2 && p.dbg < 12) { if (vb[0] == 0x12345678u && vb[7] == 0x9abcdef0u) pix_base[p.out_off[0]] = 1; }
+                        else if (TST) staged(vb, u);
                         else if (OUT == 2) epilogue_unit_nhwc<RQ, TAB, NST>(vb, cm0 + 16u * CMB * (uint32_t)u, tab_lane, tab_stride, cs, qs, pix_base + p.out_off[0], pix_base + p.out_off[1],
                                                                             pix_base + p.out_off[2], co_left - u * 16, p.onhwc_vec != 0);
                         else epilogue_unit<RQ, TAB, NST, OUT == 1>(vb, cm0 + 16u * CMB * (uint32_t)u, tab_lane, tab_stride, cs, qs, pix_base + p.out_off[0], pix_base + p.out_off[1],
-                                                                   pix_base + p.out_off[2], plane, co_left - u * 16, nh + u * 16);
+                                                                   pix_base + p.out_off[2], plane, co_left - u * 16, nh + u * 16, skip,
+                                                                   OUT == 1 && pair_ok ? ((u & 1) ? (u > u_lo ? 2 : 0) : (u + 1 < u_hi ? 1 : 0)) : 0, keep);
                         pix_base += plane16;
                         if (++u >= u_hi) break;
                     }
                 }
                 if (++ab == p.acc_bufs) { ab = 0; aph ^= 1; }
             }
+            if (TST && leader) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); /* every store of this team has completed */
         }
     } else if (warp == WARP_MMA) {
         if (lane < p.grp) { /* ===== MMA issuers: lane g issues the MMAs of M tile g of every group =====
@@ -959,9 +1061,11 @@ __global__ void k_repack_weights(const int8_t *w, int8_t *dst, int Co, int Co_pa
 }
 
 /* ---- host side ------------------------------------------------------------------ */
-typedef void (*TcKernel)(const CUtensorMap, const CUtensorMap, const TcParams);
+typedef void (*TcKernel)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const CUtensorMap, const CUtensorMap, const TcParams);
 struct TcPlanImpl {
     CUtensorMap mapA, mapB, mapA_linked;
+    CUtensorMap mapO[3];   /* TST: store tensors of the NCHW output streams (x, y, channel, image) */
+    bool tst = false;      /* plane stores through shared memory + TMA */
     bool has_linked = false;
     TcParams p;
     int prepass = 0;
@@ -1041,7 +1145,41 @@ static bool make_map4(CUtensorMap *m, void *base, uint64_t C, uint64_t W, uint64
     return true;
 }
 
+/* store tensor of one NCHW output stream: dims (X, Y, C, images) = (row, rows, channels, slots), box {128 pixels, 1 row, 16 channels,
+ * 1 image}, no swizzle: the shared-memory source is a dense [16][128] byte block */
+static bool make_map_store(CUtensorMap *m, void *base, uint64_t X, uint64_t Y, uint64_t C, uint64_t N, uint64_t plane, uint64_t img_stride) {
+    EncodeTiledFn enc = encode_tiled();
+    if (!enc) return false;
+    cuuint64_t dims[4] = {X, Y, C, N};
+    cuuint64_t strides[3] = {X, plane, img_stride};
+    cuuint32_t box[4] = {128, 1, 16, 1};
+    cuuint32_t estr[4] = {1, 1, 1, 1};
+    CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_UINT8, 4, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                     CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { cudaGetLastError(); return false; }
+    return true;
+}
+
 static int round_up(int x, int a) { return (x + a - 1) / a * a; }
+
+/* MARS_TC_TST: which layers send their NCHW streams through the shared-memory staging block -- bit 0: tiles without pad columns,
+ * TMA stores; bit 1: padded tiles (kxk layers), written out by the team's threads in 16-byte pieces; bit 2: tiles without pad
+ * columns, written out by the threads */
+static int tst_modes() {
+    static const int m = getenv("MARS_TC_TST") ? atoi(getenv("MARS_TC_TST")) : 0;
+    return m;
+}
+
+/* Row pitch of the padded / phase-split pixel index.  TMA stores need a 16-byte aligned innermost coordinate (byte elements:
+ * anything else faults, measured), so when the output rows are a multiple of 16 pixels the pitch is rounded up to one as well:
+ * every 128-pixel tile then starts on a 16-pixel boundary of its row.  The extra pad columns are computed and discarded; the
+ * rounding is skipped when they would add more than MARS_TC_WPWASTE percent (default 20) to the layer. */
+static int store_pitch(int wp_min, int ow) {
+    static const int max_waste = getenv("MARS_TC_WPWASTE") ? atoi(getenv("MARS_TC_WPWASTE")) : 20;
+    if (!(tst_modes() & 2) || ow % 16 || wp_min % 16 == 0) return wp_min;
+    const int wp = (wp_min + 15) / 16 * 16;
+    return (wp - wp_min) * 100 <= max_waste * wp_min ? wp : wp_min;
+}
 
 /* geometry shared by tc_scratch_need and tc_plan */
 struct TcGeom {
@@ -1068,7 +1206,7 @@ static TcGeom tc_geometry(const Op &o) {
         if (s2d_enabled && o.sh == 2 && o.kh == 6 && (o.pt == 0 || o.pt == 2) && (o.pl == 0 || o.pl == 2) && o.ic <= 4 && o.ih % 2 == 0 &&
             o.iw % 2 == 0 && o.oh <= o.ih / 2 && o.ow <= o.iw / 2 && round_up(o.oc, 16) <= 128 && (long long)o.oh * o.ow >= 4096) {
             /* the stem: the same space-to-depth copy as the NCHW stem, gathered from interleaved pixels */
-            g.prepass = 4; g.Wp = o.iw / 2 + 2; g.plane = (o.ih / 2 + 2) * g.Wp; g.npix = g.plane; g.ntaps = 6; g.Kp = 32;
+            g.prepass = 4; g.Wp = store_pitch(o.iw / 2 + 2, o.ow); g.plane = (o.ih / 2 + 2) * g.Wp; g.npix = g.plane; g.ntaps = 6; g.Kp = 32;
             g.scratch_bytes = (size_t)g.npix * 16;
             g.ok = true;
             return g;
@@ -1117,7 +1255,7 @@ static TcGeom tc_geometry(const Op &o) {
         if (s2d_enabled && o.sh == 2 && o.sw == 2 && o.kh == 6 && o.kw == 6 && (o.pt == 0 || o.pt == 2) && (o.pl == 0 || o.pl == 2) &&
             o.ic <= 4 && o.ih % 2 == 0 && o.iw % 2 == 0 && o.oh <= o.ih / 2 && o.ow <= o.iw / 2 && round_up(o.oc, 16) <= 128 &&
             (long long)o.oh * o.ow >= 4096) {
-            g.prepass = 4; g.Wp = o.iw / 2 + 2; g.plane = (o.ih / 2 + 2) * g.Wp; g.npix = g.plane; g.ntaps = 6; g.Kp = 32;
+            g.prepass = 4; g.Wp = store_pitch(o.iw / 2 + 2, o.ow); g.plane = (o.ih / 2 + 2) * g.Wp; g.npix = g.plane; g.ntaps = 6; g.Kp = 32;
             g.scratch_bytes = (size_t)g.npix * 16;
             g.ok = true;
             return true;
@@ -1156,12 +1294,12 @@ static TcGeom tc_geometry(const Op &o) {
         g.prepass = 0; g.Wp = o.iw;
     } else if (o.sh == 1) {
         if (o.pl >= o.kw || o.pt >= o.kh) return g;
-        g.prepass = 1; g.Wp = o.iw + o.kw - 1; g.plane = o.ih * g.Wp; g.npix = g.plane;
+        g.prepass = 1; g.Wp = store_pitch(o.iw + o.kw - 1, o.ow); g.plane = o.ih * g.Wp; g.npix = g.plane;
     } else if (o.sh == 2) {
         if (o.pl >= o.kw || o.pt >= o.kh) return g;
         /* phase plane: rows a = 0 .. , pitch Wp >= ow + (k-1)/2; enough zero rows below that the
          * deepest tap of the last output row stays inside its own plane */
-        g.prepass = 2; g.Wp = o.ow + (o.kw - 1) / 2;
+        g.prepass = 2; g.Wp = store_pitch(o.ow + (o.kw - 1) / 2, o.ow);
         const int rows = std::max((o.ih - 1 + o.pt) / 2 + 1, o.oh + (o.kh - 1) / 2);
         g.plane = rows * g.Wp; g.npix = 4 * g.plane;
     } else return g;
@@ -1341,10 +1479,10 @@ static bool int_requant_fit(float cs, long long tmax, int *m_out, int *s_out, lo
 
 /* kernel variants: requantisation x GATHER producer x word table x number of stored streams x output mode (0 NCHW planes,
  * 1 + side copy, 2 channel-innermost tensors).  Without a table (plain conv, no byte-ReLU) there is one stream at most. */
-template <int RQ, bool GATHER, int EPI>
+template <int RQ, bool GATHER, int EPI, bool TST>
 static TcKernel pick_kernel2(bool tab, int nst, int out) {
     if (out == 2) {
-        if (GATHER) return nullptr;
+        if (GATHER || TST) return nullptr;
         if (!tab) return nst == 1 ? k_conv_tc<RQ, false, false, 1, 2, EPI> : nullptr;
         switch (nst) {
             case 1: return k_conv_tc<RQ, false, true, 1, 2, EPI>;
@@ -1353,37 +1491,38 @@ static TcKernel pick_kernel2(bool tab, int nst, int out) {
             default: return nullptr;
         }
     }
+    if (TST && nst == 0) return nullptr;
     if (!tab) {
         switch (nst * 2 + out) {
-            case 0: return k_conv_tc<RQ, GATHER, false, 0, 0, EPI>;
-            case 1: return k_conv_tc<RQ, GATHER, false, 0, 1, EPI>;
-            case 2: return k_conv_tc<RQ, GATHER, false, 1, 0, EPI>;
-            default: return k_conv_tc<RQ, GATHER, false, 1, 1, EPI>;
+            case 0: return k_conv_tc<RQ, GATHER, false, 0, 0, EPI, false>;
+            case 1: return k_conv_tc<RQ, GATHER, false, 0, 1, EPI, false>;
+            case 2: return k_conv_tc<RQ, GATHER, false, 1, 0, EPI, TST>;
+            default: return k_conv_tc<RQ, GATHER, false, 1, 1, EPI, TST>;
         }
     }
     switch (nst * 2 + out) {
-        case 0: return k_conv_tc<RQ, GATHER, true, 0, 0, EPI>;
-        case 1: return k_conv_tc<RQ, GATHER, true, 0, 1, EPI>;
-        case 2: return k_conv_tc<RQ, GATHER, true, 1, 0, EPI>;
-        case 3: return k_conv_tc<RQ, GATHER, true, 1, 1, EPI>;
-        case 4: return k_conv_tc<RQ, GATHER, true, 2, 0, EPI>;
-        case 5: return k_conv_tc<RQ, GATHER, true, 2, 1, EPI>;
-        case 6: return k_conv_tc<RQ, GATHER, true, 3, 0, EPI>;
-        default: return k_conv_tc<RQ, GATHER, true, 3, 1, EPI>;
+        case 0: return k_conv_tc<RQ, GATHER, true, 0, 0, EPI, false>;
+        case 1: return k_conv_tc<RQ, GATHER, true, 0, 1, EPI, false>;
+        case 2: return k_conv_tc<RQ, GATHER, true, 1, 0, EPI, TST>;
+        case 3: return k_conv_tc<RQ, GATHER, true, 1, 1, EPI, TST>;
+        case 4: return k_conv_tc<RQ, GATHER, true, 2, 0, EPI, TST>;
+        case 5: return k_conv_tc<RQ, GATHER, true, 2, 1, EPI, TST>;
+        case 6: return k_conv_tc<RQ, GATHER, true, 3, 0, EPI, TST>;
+        default: return k_conv_tc<RQ, GATHER, true, 3, 1, EPI, TST>;
     }
 }
 /* gather mode always runs two CTAs per SM (N tile <= 256 columns of TMEM in total), i.e. 8 epilogue warps */
 template <int RQ>
-static TcKernel pick_kernel1(bool gather, bool tab, int nst, int out, int epi) {
-    if (gather) return pick_kernel2<RQ, true, 8>(tab, nst, out);
-    if (epi == 16) return pick_kernel2<RQ, false, 16>(tab, nst, out);
-    return pick_kernel2<RQ, false, 8>(tab, nst, out);
+static TcKernel pick_kernel1(bool gather, bool tab, int nst, int out, int epi, bool tst) {
+    if (gather) return pick_kernel2<RQ, true, 8, false>(tab, nst, out);
+    if (epi == 16) return tst ? pick_kernel2<RQ, false, 16, true>(tab, nst, out) : pick_kernel2<RQ, false, 16, false>(tab, nst, out);
+    return tst ? pick_kernel2<RQ, false, 8, true>(tab, nst, out) : pick_kernel2<RQ, false, 8, false>(tab, nst, out);
 }
-static TcKernel pick_kernel(int rq, bool gather, bool tab, int nst, int out, int epi) {
-    if (rq == 3) return pick_kernel1<3>(gather, tab, nst, out, epi);
-    if (rq == 2) return pick_kernel1<2>(gather, tab, nst, out, epi);
-    if (rq == 1) return pick_kernel1<1>(gather, tab, nst, out, epi);
-    return pick_kernel1<0>(gather, tab, nst, out, epi);
+static TcKernel pick_kernel(int rq, bool gather, bool tab, int nst, int out, int epi, bool tst) {
+    if (rq == 3) return pick_kernel1<3>(gather, tab, nst, out, epi, tst);
+    if (rq == 2) return pick_kernel1<2>(gather, tab, nst, out, epi, tst);
+    if (rq == 1) return pick_kernel1<1>(gather, tab, nst, out, epi, tst);
+    return pick_kernel1<0>(gather, tab, nst, out, epi, tst);
 }
 
 bool tc_plan(const Op &o, const ArenaGeom &ag, uint8_t *scratch, size_t scratch_stride, uint8_t *linked, size_t linked_stride,
@@ -1428,6 +1567,33 @@ bool tc_plan(const Op &o, const ArenaGeom &ag, uint8_t *scratch, size_t scratch_
      * replicated per lane group in shared memory ([256][rep] words, lane l reads copy l % rep): rep = 32 makes the lookups
      * conflict free; 16 or 8 (two / four lanes per bank) when the stages, the halo region or the resident weights need the room */
     t->tab = o.fused_layers > 0 || o.post_relu;
+    /* output streams: the values the op produces per element, in table-byte order (see build_lutw); the ones the
+     * planner keeps are compacted to table bytes 0..nst-1 */
+    int64_t stream_off[3] = {-1, -1, -1};
+    if (o.fused_layers > 0) {
+        stream_off[0] = o.store_z ? o.out_z : -1; stream_off[1] = o.out_s; stream_off[2] = o.store_y ? o.out : -1;
+    } else stream_off[0] = o.store_y ? o.out : -1;
+    t->nst = 0;
+    for (int k = 0; k < 3; k++) {
+        t->stream_byte[k] = -1;
+        p.out_off[k] = 0;
+    }
+    for (int k = 0; k < 3; k++)
+        if (stream_off[k] >= 0) { t->stream_byte[k] = t->nst; p.out_off[t->nst++] = stream_off[k] - (int64_t)ag.W; }
+    /* TST: the NCHW streams leave through a shared-memory staging block and TMA stores (full 128-byte rows) instead of one byte per
+     * lane and channel.  Needs the tile's pixel index to be row-major over (oh, ow) with pitch Wp (every copy-based and plane-based
+     * mode; not the gather / rect tiles), 16-byte aligned stream bases, and a store tensor TMA can address: the planes as one long
+     * row when the tile has no pad columns, else rows of Wo bytes (Wo a multiple of 16). */
+
+    const bool st_flat = g.Wp == o.ow && ((long long)o.oh * o.ow) % 16 == 0;
+    /* TMA stores fault on negative coordinates (measured), which clipping the left end of a row segment would need: padded tiles
+     * are copied out by the threads instead */
+    const bool st_padded = !st_flat && g.Wp != o.ow && o.ow % 16 == 0 && g.Wp % 16 == 0;
+    t->tst = !gather && !rect && !nhwc_in && t->nst >= 1 && ((st_flat && (tst_modes() & 5)) || (st_padded && (tst_modes() & 2)));
+    p.st_manual = (t->tst && (st_padded || (tst_modes() & 4))) ? 1 : 0;
+    for (int k = 0; k < t->nst; k++) if (p.out_off[k] % 16) t->tst = false;
+    const int epi_warps = (!gather && t->ctas_per_sm == 1) ? 16 : 8;
+    const int stg_bytes = t->tst ? (epi_warps / 4) * 2 * t->nst * 2048 : 0;
     { /* requantisation variant of the epilogue (requant_pair / requant_int) */
         static const int rq_max = getenv("MARS_TC_RQ") ? atoi(getenv("MARS_TC_RQ")) : 3; /* tuning / test aid: cap the variant */
         const long long bound = fast_requant_bound(o, ag);
@@ -1438,9 +1604,9 @@ bool tc_plan(const Op &o, const ArenaGeom &ag, uint8_t *scratch, size_t scratch_
     }
     const int cm64_bytes = t->rq == 3 ? 8 * p.n_tiles * p.n_tile : 0; /* RQ 3: per-channel int64 addends behind the table */
     const int nsteps = g.ntaps * p.ksteps_per_tap;
-    const int grp0 = p.grp, acc0 = p.acc_bufs;
-    const uint32_t a_stage0 = p.a_stage_bytes;
-    bool plan_ok = true;
+    int grp0 = p.grp, acc0 = p.acc_bufs;
+    uint32_t a_stage0 = p.a_stage_bytes;
+    bool plan_ok = true, over = false; /* over: even the two-stage minimum does not fit the budget (a second CTA would not be resident) */
     /* dynamic shared memory of a CTA: stages + weights + table (+ 1 KiB alignment slack); 227 KiB per SM, ~7 KiB static */
     auto plan_smem = [&](int tab_bytes) {
         const int budget = (t->ctas_per_sm == 1 ? 200 * 1024 : 104 * 1024) - tab_bytes;
@@ -1481,20 +1647,25 @@ bool tc_plan(const Op &o, const ArenaGeom &ag, uint8_t *scratch, size_t scratch_
                 t->smem = 1024 + (size_t)p.stages * stage_bytes;
             }
         }
+        over = (long long)t->smem - 1024 > (long long)budget;
     };
     int rep = t->tab ? 8 : 0;
-    plan_smem(rep * 1024 + cm64_bytes);
+    plan_smem(rep * 1024 + cm64_bytes + stg_bytes);
+    while (plan_ok && over && grp0 > 1 && !gather) { /* fewer M tiles per pipeline step rather than one CTA per SM */
+        grp0 /= 2; a_stage0 = grp0 * p.a_tile_bytes; acc0 = std::max(2, std::min(4, p.tmem_cols / (grp0 * p.n_tile)));
+        plan_smem(rep * 1024 + cm64_bytes + stg_bytes);
+    }
     if (!plan_ok) { delete t; return false; }
     if (t->tab) { /* widen the replication while the pipeline keeps its shape (resident weights, halo loads, >= 3 stages) */
         const int res8 = p.b_resident, halo8 = p.halo, st8 = p.stages;
         static const int rep_max = getenv("MARS_TC_TABREP") ? atoi(getenv("MARS_TC_TABREP")) : 32;
         for (int r2 = 32; r2 > 8; r2 >>= 1) {
             if (r2 > rep_max) continue;
-            plan_smem(r2 * 1024 + cm64_bytes);
+            plan_smem(r2 * 1024 + cm64_bytes + stg_bytes);
             static const int min_st = getenv("MARS_TC_MINST") ? atoi(getenv("MARS_TC_MINST")) : 3;
-            if (plan_ok && p.b_resident == res8 && p.halo == halo8 && p.stages >= std::min(st8, min_st)) { rep = r2; break; }
+            if (plan_ok && !over && p.b_resident == res8 && p.halo == halo8 && p.stages >= std::min(st8, min_st)) { rep = r2; break; }
         }
-        if (rep == 8) plan_smem(8 * 1024 + cm64_bytes);
+        if (rep == 8) plan_smem(8 * 1024 + cm64_bytes + stg_bytes);
         p.tab_rep = (uint32_t)rep;
         p.tab_off = (uint32_t)round_up((int)(t->smem - 1024), 128); /* the table copies sit behind everything else */
         t->smem = 1024 + (size_t)p.tab_off + (size_t)rep * 1024;
@@ -1502,6 +1673,12 @@ bool tc_plan(const Op &o, const ArenaGeom &ag, uint8_t *scratch, size_t scratch_
     if (cm64_bytes) {
         p.cm_off = (uint32_t)round_up((int)(t->smem - 1024), 128);
         t->smem = 1024 + (size_t)p.cm_off + (size_t)cm64_bytes;
+    }
+    if (stg_bytes) {
+        p.stg_off = (uint32_t)round_up((int)(t->smem - 1024), 128);
+        t->smem = 1024 + (size_t)p.stg_off + (size_t)stg_bytes;
+        p.st_wp = st_flat ? (1 << 30) : g.Wp;
+        p.st_magic = st_flat ? 0u : (unsigned)((1ull << 32) / (unsigned)g.Wp) + 1u;
     }
     /* keep residency at ctas_per_sm: a further CTA would fit the registers but stall in tcgen05.alloc */
     t->smem = std::max<size_t>(t->smem, t->ctas_per_sm == 1 ? 120 * 1024 : 80 * 1024);
@@ -1547,19 +1724,6 @@ bool tc_plan(const Op &o, const ArenaGeom &ag, uint8_t *scratch, size_t scratch_
         p.gPH = g.PH; p.gPWW = g.PWW; p.gdx = g.dx;
         p.g_align2 = (o.sh % 2 == 0 && o.kw % 2 == 0 && g.dx % 2 == 0) ? 1 : 0;
     }
-    /* output streams: the values the op produces per element, in table-byte order (see build_lutw); the ones the
-     * planner keeps are compacted to table bytes 0..nst-1 */
-    int64_t stream_off[3] = {-1, -1, -1};
-    if (o.fused_layers > 0) {
-        stream_off[0] = o.store_z ? o.out_z : -1; stream_off[1] = o.out_s; stream_off[2] = o.store_y ? o.out : -1;
-    } else stream_off[0] = o.store_y ? o.out : -1;
-    t->nst = 0;
-    for (int k = 0; k < 3; k++) {
-        t->stream_byte[k] = -1;
-        p.out_off[k] = 0;
-    }
-    for (int k = 0; k < 3; k++)
-        if (stream_off[k] >= 0) { t->stream_byte[k] = t->nst; p.out_off[t->nst++] = stream_off[k] - (int64_t)ag.W; }
     p.dbg = getenv("MARS_TC_DEBUG") ? atoi(getenv("MARS_TC_DEBUG")) : 0;
     p.nhwc_sel = -1;
     if (consumer && linked) { /* this op's epilogue also writes the consumer's channel-innermost input copy */
@@ -1572,6 +1736,9 @@ bool tc_plan(const Op &o, const ArenaGeom &ag, uint8_t *scratch, size_t scratch_
         p.nhwc_C = consumer->ic;
         p.nhwc_base = linked + consumer->copy_off;
         p.nhwc_stride = linked_stride;
+        static const bool pair_enabled = !(getenv("MARS_TC_SIDEPAIR") && atoi(getenv("MARS_TC_SIDEPAIR")) == 0);
+        p.side_pair = (pair_enabled && consumer->ic % 32 == 0 && p.n_tile % 32 == 0 && consumer->copy_off % 32 == 0 && linked_stride % 32 == 0 &&
+                       ((uintptr_t)linked % 32) == 0) ? 1 : 0;
     }
     t->prepass = g.prepass; t->C = o.ic; t->Cp = ci_eff; t->H = o.ih; t->W = o.iw; t->pt = o.pt; t->pl = o.pl;
     t->plane = g.plane; t->npix = g.npix;
@@ -1646,15 +1813,23 @@ bool tc_plan(const Op &o, const ArenaGeom &ag, uint8_t *scratch, size_t scratch_
     ok = ok && make_map3(&t->mapB, t->d_wr, (uint64_t)ci_eff, (uint64_t)co_pad, (uint64_t)g.ntaps, (uint64_t)ci_eff,
                          (uint64_t)co_pad * ci_eff, (uint32_t)p.bk, (uint32_t)p.n_tile, ksw);
     { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&t->sms, cudaDevAttrMultiProcessorCount, dev); }
-    t->epi = (!gather && t->ctas_per_sm == 1) ? 16 : 8;
-    t->kernel = pick_kernel(t->rq, gather, t->tab, t->nst, nhwc_in ? 2 : (p.nhwc_sel >= 0 ? 1 : 0), t->epi);
+    t->epi = epi_warps;
+    for (int k = 0; ok && t->tst && k < t->nst; k++) {
+        uint8_t *base = ag.d_slots + p.out_off[k];
+        const uint64_t plane_b = (uint64_t)o.oh * o.ow;
+        if (!(st_flat ? make_map_store(&t->mapO[k], base, plane_b, 1, (uint64_t)o.oc, (uint64_t)ag.capacity, plane_b, ag.slot_stride)
+                      : make_map_store(&t->mapO[k], base, (uint64_t)o.ow, (uint64_t)o.oh, (uint64_t)o.oc, (uint64_t)ag.capacity, plane_b, ag.slot_stride)))
+            ok = false;
+    }
+    for (int k = t->tst ? t->nst : 0; k < 3; k++) t->mapO[k] = t->mapB; /* unused slots: any valid map */
+    t->kernel = pick_kernel(t->rq, gather, t->tab, t->nst, nhwc_in ? 2 : (p.nhwc_sel >= 0 ? 1 : 0), t->epi, t->tst);
     ok = ok && t->kernel != nullptr;
     ok = ok && cudaFuncSetAttribute((const void *)t->kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 210 * 1024) == cudaSuccess;
     if (!ok) { cudaFree(t->d_wr); cudaFree(t->d_lutw); delete t; return false; }
     if (getenv("MARS_TC_VERBOSE"))
-        fprintf(stderr, "tc_plan layer %d: %dx%d k%d s%d ci %d co %d | n_tile %d grp %d acc %d stages %d bk %d halo %d b_res %d ctas %d epi %d | rq %d tab %d rep %u nst %d side %d smem %zu\n",
+        fprintf(stderr, "tc_plan layer %d: %dx%d k%d s%d ci %d co %d | n_tile %d grp %d acc %d stages %d bk %d halo %d b_res %d ctas %d epi %d | rq %d tab %d rep %u nst %d side %d tst %d smem %zu\n",
                 o.layer, o.oh, o.ow, o.kh, o.sh, o.ic, o.oc, p.n_tile, p.grp, p.acc_bufs, p.stages, p.bk, p.halo, p.b_resident, t->ctas_per_sm, t->epi,
-                t->rq, (int)t->tab, p.tab_rep, t->nst, p.nhwc_sel >= 0, t->smem);
+                t->rq, (int)t->tab, p.tab_rep, t->nst, p.nhwc_sel >= 0, (int)t->tst, t->smem);
     plan->impl = t;
     plan->valid = true;
     return true;
@@ -1694,7 +1869,7 @@ bool tc_launch(const TcPlan &plan, uint8_t *slots_base, int first, int n, bool u
     int sms = t->sms;
     if (sms <= 0) sms = 148;
     const unsigned grid = (unsigned)std::min<long long>(total_tiles, (long long)sms * t->ctas_per_sm);
-    launch_pdl(t->kernel, dim3(grid), dim3((t->epi + (t->prepass == 3 ? 5 : 2)) * 32), t->smem, s, (use_linked && t->has_linked) ? t->mapA_linked : t->mapA, t->mapB, p);
+    launch_pdl(t->kernel, dim3(grid), dim3((t->epi + (t->prepass == 3 ? 5 : 2)) * 32), t->smem, s, (use_linked && t->has_linked) ? t->mapA_linked : t->mapA, t->mapB, t->mapO[0], t->mapO[1], t->mapO[2], p);
     (*launches)++;
     return cudaGetLastError() == cudaSuccess;
 }
