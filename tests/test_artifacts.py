@@ -37,6 +37,8 @@ def test_committed_bench_lines_follow_the_contract():
 
 
 def test_committed_reference_line():
-    d = last_json_line(os.path.join(ROOT, "profiles", latest_prefix() + "_bench_reference_n1.json"))
+    names = sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_bench_reference_n1.json")))  # the most recent reference-arm line
+    assert names
+    d = last_json_line(names[-1])
     assert d["impl"] == "reference" and d["value"] > 0 and d["cpu_baseline"]["kind"] in ("reference", "port")
     assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0

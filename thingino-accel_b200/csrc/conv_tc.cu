@@ -1087,6 +1087,7 @@ struct TcPlanImpl {
     int sms = 0; /* multiprocessors of the device the plan was built on */
     int nhwc_in = 0;  /* channel-innermost activations / OHWI weights (OP_CONV_I8_NHWC) */
     bool gather_direct = false; /* gather mode reads the input tensor in the arena itself (no private copy needed) */
+    bool private_in = false;    /* 1x1 from NCHW planes: the planes are copied to the scratch area before every launch */
 };
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
@@ -1240,7 +1241,7 @@ static TcGeom tc_geometry(const Op &o) {
     if (o.ic >= 16 && o.ic % 32 && o.kh == 1 && o.kw == 1 && o.sh == 1 && o.pt == 0 && o.pl == 0 && o.oh <= o.ih && o.ow == o.iw) {
         g.ntaps = 1; g.Wp = o.iw;
         g.kpad = o.ic > 64 ? round_up(o.ic, 128) : round_up(o.ic, 32);
-        if (((long long)o.ih * o.iw) % 16 == 0) { g.prepass = 0; g.scratch_bytes = 0; }
+        if (((long long)o.ih * o.iw) % 16 == 0) { g.prepass = 0; g.scratch_bytes = o.private_in ? (size_t)o.ic * o.ih * o.iw : 0; }
         else { /* planes that TMA cannot address (stride not a multiple of 16 bytes, e.g. 10 x 10): channel-innermost copy, kpad bytes per pixel */
             g.prepass = 1; g.plane = o.ih * g.Wp; g.npix = g.plane;
             g.scratch_bytes = (size_t)g.npix * g.kpad;
@@ -1304,7 +1305,7 @@ static TcGeom tc_geometry(const Op &o) {
         g.plane = rows * g.Wp; g.npix = 4 * g.plane;
     } else return g;
     if (o.ow > g.Wp) return g;
-    g.scratch_bytes = g.prepass ? (size_t)g.npix * (g.kpad ? g.kpad : o.ic) : 0;
+    g.scratch_bytes = g.prepass ? (size_t)g.npix * (g.kpad ? g.kpad : o.ic) : (o.private_in ? (size_t)o.ic * o.ih * o.iw : 0);
     g.ok = true;
     return g;
 }
@@ -1323,6 +1324,7 @@ int tc_n_tiles(int oc) {
     const int nt = co_pad <= 256 ? co_pad : (co_pad % 256 == 0 ? 256 : 128);
     return (co_pad + nt - 1) / nt;
 }
+bool tc_private_input_ok(const Op &o) { const TcGeom g = tc_geometry(o); return g.ok && g.prepass == 0; }
 bool tc_uses_copy(const Op &o) { return tc_geometry(o).prepass != 0; } /* (NHWC layers: a private copy on demand, see tc_plan) */
 bool tc_linkable(const Op &o) { const TcGeom g = tc_geometry(o); return g.ok && (g.prepass == 1 || g.prepass == 2) && !g.kpad; }
 
@@ -1788,9 +1790,10 @@ bool tc_plan(const Op &o, const ArenaGeom &ag, uint8_t *scratch, size_t scratch_
     bool ok = cudaDeviceSynchronize() == cudaSuccess;
 
     const CUtensorMapSwizzle ksw = p.bk == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : (p.bk == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
-    if (ok && g.prepass == 0)
-        ok = make_map3(&t->mapA, (void *)t->src_slot0, (uint64_t)o.ih * o.iw, (uint64_t)o.ic, (uint64_t)ag.capacity,
-                       (uint64_t)o.ih * o.iw, ag.slot_stride, TC_BM, (uint32_t)p.bk, CU_TENSOR_MAP_SWIZZLE_128B);
+    t->private_in = g.prepass == 0 && o.private_in;
+    if (ok && g.prepass == 0) /* the NCHW planes in the arena, or their private copy (Op::private_in) */
+        ok = make_map3(&t->mapA, t->private_in ? (void *)scratch : (void *)t->src_slot0, (uint64_t)o.ih * o.iw, (uint64_t)o.ic, (uint64_t)ag.capacity,
+                       (uint64_t)o.ih * o.iw, t->private_in ? scratch_stride : ag.slot_stride, TC_BM, (uint32_t)p.bk, CU_TENSOR_MAP_SWIZZLE_128B);
     else if (ok && s2d) /* 16-byte pixels, linear rows (no swizzle): the MMA reads them as overlapping 32-byte K rows */
         ok = make_map3(&t->mapA, scratch, 16, (uint64_t)g.npix, (uint64_t)ag.capacity, 16, scratch_stride, 16, (uint32_t)p.halo_rb,
                        CU_TENSOR_MAP_SWIZZLE_NONE);
@@ -1844,6 +1847,9 @@ bool tc_launch(const TcPlan &plan, uint8_t *slots_base, int first, int n, bool u
         /* private copy of the input tensor: the fused outputs may overwrite the input's work buffer */
         if (cudaMemcpy2DAsync(scr, t->scratch_stride, src, t->slot_stride, (size_t)t->C * t->H * t->W, (size_t)n,
                               cudaMemcpyDeviceToDevice, s) != cudaSuccess) return false;
+    } else if (t->prepass == 0 && t->private_in) {
+        if (cudaMemcpy2DAsync(scr, t->scratch_stride, src, t->slot_stride, (size_t)t->C * t->H * t->W, (size_t)n, cudaMemcpyDeviceToDevice, s) != cudaSuccess) return false;
+        (*launches)++;
     } else if (t->prepass == 4) {
         launch_pdl(k_s2d16, dim3((t->npix + 1023) / 1024, n), dim3(256), 0, s, src, (unsigned long long)t->slot_stride, scr, (unsigned long long)t->scratch_stride, t->C, t->H, t->W, t->p.Wp, t->npix, t->nhwc_in);
         (*launches)++;

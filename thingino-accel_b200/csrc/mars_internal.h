@@ -94,6 +94,9 @@ struct Op {
      * own layout pre-pass (copy_from = producer op, copy_off = byte offset of its region in the per-image link area) */
     int copy_from = -1, nhwc_consumer = -1, nhwc_stream = -1;
     int64_t copy_off = 0;
+    /* 1x1 tensor-core conv whose fused outputs overwrite its own input buffer while other CTAs (a second N tile) still read it:
+     * the kernel reads a private device copy of the input made just before the launch (round-robin work buffers) */
+    bool private_in = false;
     /* write/read extents for hazard analysis and bounds checks */
     int64_t wlo = 0, whi = 0;
     std::string note;

@@ -496,9 +496,11 @@ static mars_error_t compile_concat(Ctx &c, int li, const mars_layer_t &L) {
     int64_t later_lo = -1, later_hi = -1;
     for (size_t k = c.prog->ops.size(); k-- > first_op;) {
         Op &o = c.prog->ops[k];
-        if (o.kind != OP_CONCAT || o.mode != EXEC_PARALLEL || o.ic != o.oc || o.xlat) break;
+        if ((o.kind != OP_CONCAT && o.kind != OP_CONCAT_PERIODIC) || o.mode != EXEC_PARALLEL || o.ic != o.oc || o.xlat) break;
         const int64_t lo = o.wlo, hi = o.wlo + (int64_t)o.n;
-        if (later_lo >= 0 && later_lo > lo && later_lo < hi && later_hi >= hi) {
+        /* an in-place (periodic) input reads only out[0, coff) -- bytes in front of its own writes, which the trimmed copies
+         * below keep -- and overwrites [out + coff, out + coff + n) like any other input; it is not trimmed itself */
+        if (o.kind == OP_CONCAT && later_lo >= 0 && later_lo > lo && later_lo < hi && later_hi >= hi) {
             o.n = (uint64_t)(later_lo - lo);
             o.whi = later_lo;
             o.note = "concat input trimmed to the bytes later inputs do not overwrite";
@@ -556,7 +558,13 @@ static void fuse_silu(Program *p, int64_t W) {
             const bool same_tile = c.kh == 1 && c.kw == 1 && tc_n_tiles(c.oc) == 1 && c.oh == c.ih && c.ow == c.iw &&
                                    (s.out == c.in0 || !overlap(s.out, s.out + numel, x0, x1)) &&
                                    (m.out == c.in0 || !overlap(m.out, m.out + numel, x0, x1));
-            if (!tc_uses_copy(c) && !same_tile) continue;
+            if (!tc_uses_copy(c) && !same_tile) {
+                /* several N tiles (Co > 256): a CTA's outputs would overwrite input pixels the other N tile's CTAs still read.
+                 * A private copy of the input (one device-to-device copy per launch, a fraction of the two element-wise passes
+                 * it saves) makes the fusion legal */
+                if (c.kind == OP_CONV_I8_NCHW && c.kh == 1 && c.kw == 1 && !c.xlat && tc_private_input_ok(c)) c.private_in = true;
+                else continue;
+            }
         }
         /* neither follower may clobber the weights or the bias the kernel is still reading: both live below W */
         int8_t lut[256];
