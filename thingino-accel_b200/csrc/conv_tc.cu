@@ -1078,7 +1078,7 @@ struct TcPlanImpl {
     int8_t *d_wr = nullptr;     /* repacked weights */
     uint32_t *d_lutw = nullptr; /* epilogue word table */
     int nst = 0;                /* NCHW streams stored */
-    int stream_byte[3] = {-1, -1, -1}; /* table byte of stream Z / S / Y (plain conv: Y is stream 0), -1 = not in the table */
+    int stream_byte[4] = {-1, -1, -1, -1}; /* table byte of stream Z / S / Y (plain conv: Y is stream 0) / the forwarded copy, -1 = not in the table */
     int nhwc_stream = -1;              /* stream whose value also fills table byte 3 (side output), -1 = none */
     TcKernel kernel = nullptr;
     size_t smem = 0;
@@ -1331,7 +1331,7 @@ bool tc_linkable(const Op &o) { const TcGeom g = tc_geometry(o); return g.ok && 
 /* the word table of the epilogue: index = r + 128 (r = the clamped conv output); byte k = value of output stream k, byte 3 =
  * the side-output stream.  Stream order: a fused conv stores [Z, S, Y] (Z = SiLU product, the stream almost every consumer
  * reads, sits in the low byte), a plain conv stores [Y]. */
-static void build_lutw(const Op &o, const uint8_t *h_cpool, const int stream_byte[3], int nhwc_stream, uint32_t *t) {
+static void build_lutw(const Op &o, const uint8_t *h_cpool, const int stream_byte[4], int nhwc_stream, uint32_t *t) {
     const int8_t *ls = o.lut_s >= 0 ? reinterpret_cast<const int8_t *>(h_cpool + o.lut_s) : nullptr;
     const int8_t *lz = o.lut_z >= 0 ? reinterpret_cast<const int8_t *>(h_cpool + o.lut_z) : nullptr;
     for (int idx = 0; idx < 256; idx++) {
@@ -1343,6 +1343,7 @@ static void build_lutw(const Op &o, const uint8_t *h_cpool, const int stream_byt
         uint32_t w = 0;
         for (int k = 0; k < 3; k++)
             if (stream_byte[k] >= 0) w |= (uint32_t)val[k] << (8 * stream_byte[k]);
+        if (stream_byte[3] >= 0) w |= (uint32_t)val[o.fused_layers > 0 ? o.fwd_stream : 0] << (8 * stream_byte[3]); /* Op::fwd_out: a second copy of one stream */
         if (nhwc_stream >= 0) w |= (uint32_t)val[nhwc_stream] << 24; /* at most 3 stored streams use bytes 0..2 */
         t[idx] = w;
     }
@@ -1571,17 +1572,20 @@ bool tc_plan(const Op &o, const ArenaGeom &ag, uint8_t *scratch, size_t scratch_
     t->tab = o.fused_layers > 0 || o.post_relu;
     /* output streams: the values the op produces per element, in table-byte order (see build_lutw); the ones the
      * planner keeps are compacted to table bytes 0..nst-1 */
-    int64_t stream_off[3] = {-1, -1, -1};
+    int64_t stream_off[4] = {-1, -1, -1, -1};
     if (o.fused_layers > 0) {
         stream_off[0] = o.store_z ? o.out_z : -1; stream_off[1] = o.out_s; stream_off[2] = o.store_y ? o.out : -1;
     } else stream_off[0] = o.store_y ? o.out : -1;
+    if (o.fwd_out >= 0 && o.fwd_stream >= 0 && o.fwd_stream <= 2) stream_off[3] = o.fwd_out;
     t->nst = 0;
-    for (int k = 0; k < 3; k++) {
-        t->stream_byte[k] = -1;
-        p.out_off[k] = 0;
-    }
-    for (int k = 0; k < 3; k++)
-        if (stream_off[k] >= 0) { t->stream_byte[k] = t->nst; p.out_off[t->nst++] = stream_off[k] - (int64_t)ag.W; }
+    for (int k = 0; k < 4; k++) t->stream_byte[k] = -1;
+    for (int k = 0; k < 3; k++) p.out_off[k] = 0;
+    for (int k = 0; k < 4; k++)
+        if (stream_off[k] >= 0) {
+            if (t->nst == 3) { delete t; return false; } /* the planner forwards only when a table byte is free */
+            t->stream_byte[k] = t->nst; p.out_off[t->nst++] = stream_off[k] - (int64_t)ag.W;
+        }
+    if (t->nst > 1) t->tab = true; /* a plain conv with a forwarded second copy: the bytes of the streams come from the (identity) table */
     /* TST: the NCHW streams leave through a shared-memory staging block and TMA stores (full 128-byte rows) instead of one byte per
      * lane and channel.  Needs the tile's pixel index to be row-major over (oh, ow) with pitch Wp (every copy-based and plane-based
      * mode; not the gather / rect tiles), 16-byte aligned stream bases, and a store tensor TMA can address: the planes as one long

@@ -28,6 +28,10 @@ struct KOp {
     float f0, f1, f2;
     unsigned long long n;
     int lut, post_relu, post_lut;
+    /* in-place 1x1 conv with the following SIGMOID and MUL folded in (k_conv1x1_inplace_reg): S = table lut_s[y] stored at out_s,
+     * Z = table lut_z[y] at out_z (-1 = not stored), store_y = 0: the pre-activation plane itself is dead */
+    int64_t out_s, out_z;
+    int lut_s, lut_z, store_y;
     int pass_oc;     /* EXEC_OC_PASSES: the output channel of this launch */
     int use_scratch; /* write the pass to scratch instead of the output plane */
 };

@@ -123,6 +123,10 @@ __global__ void __launch_bounds__(128) k_conv1x1_inplace_reg(ArenaView v, KOp o)
     __syncthreads();
     if (p >= P) return;
     uint8_t *out = wr_ptr(im, o.out) + p;
+    /* fused followers (planner: fuse_silu): S and Z are tables of the output byte (reference src/mars/mars_runtime.c:724-838) */
+    uint8_t *out_s = o.out_s >= 0 ? wr_ptr(im, o.out_s) + p : nullptr, *out_z = o.out_z >= 0 ? wr_ptr(im, o.out_z) + p : nullptr;
+    const uint8_t *ts = o.lut_s >= 0 ? v.cpool + o.lut_s + 128 : nullptr, *tz = o.lut_z >= 0 ? v.cpool + o.lut_z + 128 : nullptr;
+    const bool store_y = o.store_y != 0;
     const float cs = o.f0;
 #pragma unroll
     for (int g = 0; g < CI4; g++) { /* output channels 4g .. 4g+3 feed back into word g */
@@ -140,7 +144,9 @@ __global__ void __launch_bounds__(128) k_conv1x1_inplace_reg(ArenaView v, KOp o)
                     acc = __dp4a((int)x[4 * k4 + 2], (int)w4.z, acc); acc = __dp4a((int)x[4 * k4 + 3], (int)w4.w, acc);
                 }
                 const int8_t y = requant_conv(acc, cs);
-                out[(int64_t)oc * P] = (uint8_t)y;
+                if (store_y) out[(int64_t)oc * P] = (uint8_t)y;
+                if (out_s) out_s[(int64_t)oc * P] = __ldg(ts + y);
+                if (out_z) out_z[(int64_t)oc * P] = __ldg(tz + y);
                 x[g] = (x[g] & ~(0xFFu << (8 * r))) | ((uint32_t)(uint8_t)y << (8 * r));
             }
         }
@@ -154,7 +160,10 @@ __global__ void __launch_bounds__(128) k_conv1x1_inplace_reg(ArenaView v, KOp o)
             acc = __dp4a((int)x[4 * k4], (int)w4.x, acc); acc = __dp4a((int)x[4 * k4 + 1], (int)w4.y, acc);
             acc = __dp4a((int)x[4 * k4 + 2], (int)w4.z, acc); acc = __dp4a((int)x[4 * k4 + 3], (int)w4.w, acc);
         }
-        out[(int64_t)oc * P] = (uint8_t)requant_conv(acc, cs);
+        const int8_t y = requant_conv(acc, cs);
+        if (store_y) out[(int64_t)oc * P] = (uint8_t)y;
+        if (out_s) out_s[(int64_t)oc * P] = __ldg(ts + y);
+        if (out_z) out_z[(int64_t)oc * P] = __ldg(tz + y);
     }
 }
 

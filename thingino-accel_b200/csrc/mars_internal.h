@@ -97,6 +97,10 @@ struct Op {
     /* 1x1 tensor-core conv whose fused outputs overwrite its own input buffer while other CTAs (a second N tile) still read it:
      * the kernel reads a private device copy of the input made just before the launch (round-robin work buffers) */
     bool private_in = false;
+    /* concat forwarding (opt level 3): the op's stream fwd_stream (0 = Z, 1 = S, 2 = Y) is ALSO written at arena offset fwd_out --
+     * its place in the output of the concat that would copy it there later (program.cpp forward_concat_inputs) */
+    int64_t fwd_out = -1;
+    int fwd_stream = -1;
     /* write/read extents for hazard analysis and bounds checks */
     int64_t wlo = 0, whi = 0;
     std::string note;

@@ -542,6 +542,34 @@ static void fuse_silu(Program *p, int64_t W) {
     std::vector<Op> &ops = p->ops;
     for (size_t i = 0; i + 2 < ops.size(); i++) {
         Op &c = ops[i];
+        /* the in-place 1x1 conv on its own planes (register kernel, kernels_fast.cuh): same fusion, the kernel keeps the pixel's
+         * channel vector in registers, so S and Z may go anywhere outside the conv's planes, weights and bias */
+        const bool inplace_reg = c.kind == OP_CONV_I8_NCHW && c.impl == CONV_DIRECT && c.mode == EXEC_PIXEL_SERIAL && !c.post_relu && !c.xlat &&
+                                 (c.ic == 32 || c.ic == 64 || c.ic == 128) && c.w >= 0 && (c.w & 3) == 0 && c.w + (int64_t)c.oc * c.ic <= W &&
+                                 (size_t)c.oc * (c.ic / 4 + 1) * 4 <= 160 * 1024; /* = inplace_reg_ok (kernels_fast.cuh) */
+        if (inplace_reg) {
+            Op &s = ops[i + 1], &m = ops[i + 2];
+            const int64_t numel = (int64_t)c.oc * c.oh * c.ow;
+            if (s.kind != OP_SIGMOID_I8 || s.mode != EXEC_PARALLEL || s.xlat || m.kind != OP_MUL_I8 || m.mode != EXEC_PARALLEL || m.xlat) continue;
+            if (s.in0 != c.out || (int64_t)s.n != numel || (int64_t)m.n != numel) continue;
+            const bool y_first = m.in0 == c.out && m.in1 == s.out, s_first = m.in0 == s.out && m.in1 == c.out;
+            if (!y_first && !s_first) continue;
+            const int64_t x0 = c.in0, x1 = c.in0 + (int64_t)c.ic * c.ih * c.iw;
+            if (s.out < W || m.out < W || s.out == m.out || overlap(s.out, s.out + numel, x0, x1) || overlap(m.out, m.out + numel, x0, x1) ||
+                overlap(s.out, s.out + numel, m.out, m.out + numel)) continue;
+            int8_t lut[256];
+            const int8_t *sig = reinterpret_cast<const int8_t *>(&p->const_pool[s.lut]);
+            for (int y = -128; y < 128; y++) {
+                int sv = sig[y + 128];
+                lut[y + 128] = y_first ? mul_point(y, sv, m.f0, m.f1, m.f2) : mul_point(sv, y, m.f0, m.f1, m.f2);
+            }
+            c.lut_s = s.lut; c.lut_z = pool_add(p, lut);
+            c.out_s = s.out; c.out_z = m.out; c.store_y = true; c.fused_layers = 2;
+            c.whi = std::max(c.whi, std::max(s.whi, m.whi));
+            c.note += " +sigmoid+mul fused";
+            s.kind = OP_NOP; s.note = "folded into the in-place conv"; m.kind = OP_NOP; m.note = "folded into the in-place conv";
+            continue;
+        }
         if (c.impl != CONV_TC_NCHW || (c.kind != OP_CONV_I8_NCHW && c.kind != OP_CONV_I8_NHWC) || c.post_relu) continue;
         Op &s = ops[i + 1], &m = ops[i + 2];
         if (s.kind != OP_SIGMOID_I8 || s.mode != EXEC_PARALLEL || s.xlat) continue;
@@ -592,8 +620,8 @@ static bool op_writes(const Op &o, int64_t lo, int64_t hi) {
     if (o.kind == OP_NOP || o.mode >= 1000) return false;
     if (o.kind == OP_CONV_I8_NCHW || o.kind == OP_CONV_I8_NHWC || o.kind == OP_CONV_F32_NCHW || o.kind == OP_DW_I8) {
         const int64_t numel = (int64_t)o.oc * o.oh * o.ow, es = o.kind == OP_CONV_F32_NCHW ? 4 : 1;
-        return overlap(o.out, o.out + numel * es, lo, hi) || (o.out_s >= 0 && overlap(o.out_s, o.out_s + numel, lo, hi)) ||
-               (o.out_z >= 0 && overlap(o.out_z, o.out_z + numel, lo, hi));
+        return (o.store_y && overlap(o.out, o.out + numel * es, lo, hi)) || (o.out_s >= 0 && overlap(o.out_s, o.out_s + numel, lo, hi)) ||
+               (o.out_z >= 0 && o.store_z && overlap(o.out_z, o.out_z + numel, lo, hi)) || (o.fwd_out >= 0 && overlap(o.fwd_out, o.fwd_out + numel, lo, hi));
     }
     return overlap(o.wlo, o.whi, lo, hi);
 }
@@ -629,6 +657,17 @@ static void link_nhwc_copies(Program *p) {
     }
     p->linked_bytes = total;
 }
+
+/* ---- opt_level >= 3: concat forwarding ---------------------------------------------------------------
+ * With NCHW-shaped descriptors a concat input is a flat copy: out[coff + t] = in[t].  When the head of that source
+ * range is exactly one output stream of the tensor-core conv that wrote it last, and nothing between that conv and the concat
+ * touches the destination bytes, the conv's epilogue writes the stream to its destination as well (Op::fwd_out) and the concat
+ * copies only what follows the stream.  Dead-store elision afterwards drops the conv's original store when nothing else reads it,
+ * so the forwarded bytes cost no extra store and save one read and one write.  Model outputs are unchanged; the intermediate
+ * arena differs from the reference's only in dead bytes (opt level 3 promises outputs, levels 0-2 the whole arena). */
+struct Access;
+static void op_access(const Op &o, Access *a);
+static void forward_concat_inputs(Program *p);
 
 /* ---- opt_level >= 3: dead-store elision in fused epilogues ------------------
  * Backward liveness over byte intervals of the image slot.  A byte is live after op i when some
@@ -689,6 +728,7 @@ static void op_access(const Op &o, Access *a) {
             if (o.store_y) K(o.out, numel * es);
             if (o.out_s >= 0) K(o.out_s, numel);
             if (o.out_z >= 0 && o.store_z) K(o.out_z, numel);
+            if (o.fwd_out >= 0) K(o.fwd_out, numel);
             break;
         }
         case OP_BYTE_RELU: R(o.out, (int64_t)o.n); break;
@@ -709,6 +749,63 @@ static void op_access(const Op &o, Access *a) {
     }
 }
 
+static void forward_concat_inputs(Program *p) {
+    std::vector<Op> &ops = p->ops;
+    Access a;
+    for (size_t j = 0; j < ops.size(); j++) {
+        Op &c = ops[j];
+        if (c.kind != OP_CONCAT || c.mode != EXEC_PARALLEL || c.ic != c.oc || c.xlat || c.n < 4096) continue;
+        const int64_t src = c.in0, n = (int64_t)c.n, dst = c.out + c.coff;
+        for (size_t i = j; i-- > 0;) {
+            Op &o = ops[i];
+            if (!op_writes(o, src, src + n)) continue;
+            /* o = the last op that writes any byte the concat reads */
+            if (o.impl != CONV_TC_NCHW || o.kind != OP_CONV_I8_NCHW || o.mode != EXEC_PARALLEL || o.fwd_out >= 0) break;
+            const int64_t numel = (int64_t)o.oc * o.oh * o.ow;
+            if (numel > n || numel < 4096) break;
+            const bool zs = o.fused_layers > 0 && o.out_z >= 0 && o.store_z, ss = o.fused_layers > 0 && o.out_s >= 0, ys = o.store_y;
+            int stream = -1;
+            if (zs && o.out_z == src) stream = 0;
+            else if (ss && o.out_s == src) stream = 1;
+            else if (ys && o.out == src) stream = 2;
+            if (stream < 0) break;
+            /* the op's other stored streams must leave the stream's bytes alone (the epilogue's store order is unspecified) */
+            if ((stream != 0 && zs && overlap(o.out_z, o.out_z + numel, src, src + numel)) || (stream != 1 && ss && overlap(o.out_s, o.out_s + numel, src, src + numel)) ||
+                (stream != 2 && ys && overlap(o.out, o.out + numel, src, src + numel))) break;
+            if ((int)zs + (int)ss + (int)ys >= 3) break; /* no table byte left for a fourth stream */
+            /* the destination: not read or written by the conv itself nor by anything up to the concat */
+            bool clash = false;
+            for (size_t k = i; k < j && !clash; k++) {
+                const Op &q = ops[k];
+                if (q.kind == OP_NOP) continue;
+                if (op_writes(q, dst, dst + numel)) clash = true;
+                op_access(q, &a);
+                for (auto &iv : a.reads) if (overlap(iv.first, iv.second, dst, dst + numel)) clash = true;
+                if (k == i && q.copy_from >= 0 && overlap(q.in0, q.in0 + (int64_t)q.ic * q.ih * q.iw, dst, dst + numel)) clash = true; /* (reads a copy, but keep it simple) */
+            }
+            if (clash) break;
+            /* earlier inputs of the same concat (the slivers that survive it) may read the stream too -- with the planner's buffer
+             * rotation the "first" input often IS this tensor.  They run after the conv, when the forwarded copy is
+             * already in place and nothing has modified it: read that copy instead, so that the original store can die */
+            for (size_t k = i + 1; k < j; k++) {
+                Op &q = ops[k];
+                if (q.kind != OP_CONCAT || q.mode != EXEC_PARALLEL || q.xlat || q.ic != q.oc) continue;
+                const int64_t qn = (int64_t)q.n, qdst = q.out + q.coff;
+                if (q.in0 < src || q.in0 + qn > src + numel) continue;
+                const int64_t nin = q.in0 + (dst - src);
+                if (overlap(nin, nin + qn, qdst, qdst + qn)) continue;
+                q.in0 = nin; q.note += " (reads the forwarded copy)";
+            }
+            o.fwd_out = dst; o.fwd_stream = stream;
+            o.whi = std::max(o.whi, dst + numel);
+            o.note += " +fwd";
+            if (numel == n) { c.kind = OP_NOP; c.note = "written by the producing conv (concat forwarding)"; }
+            else { c.in0 += numel; c.coff += (int)numel; c.wlo += numel; c.n -= (uint64_t)numel; c.note += " (head written by the producing conv)"; }
+            break;
+        }
+    }
+}
+
 static void elide_dead_stores(Program *p, const IvSet &observed, const IvSet &host_written) {
     IvSet live_in; /* live at the start of a run */
     Access a;
@@ -717,6 +814,8 @@ static void elide_dead_stores(Program *p, const IvSet &observed, const IvSet &ho
         for (auto &iv : live_in.v) live.add(iv.first, iv.second);
         for (size_t k = p->ops.size(); k-- > 0;) {
             Op &o = p->ops[k];
+            if (o.fused_layers == 0 && o.fwd_out >= 0 && o.kind == OP_CONV_I8_NCHW && o.store_y &&
+                !live.hits(o.out, o.out + (int64_t)o.oc * o.oh * o.ow)) { o.store_y = false; o.note += " -Y"; } /* only the forwarded copy is read */
             if (o.fused_layers > 0 && (o.kind == OP_CONV_I8_NCHW || o.kind == OP_CONV_I8_NHWC)) {
                 const int64_t numel = (int64_t)o.oc * o.oh * o.ow;
                 if (getenv("MARS_LIVE_DEBUG") && iter == 0) { /* how many output planes of every stream are live after the op */
@@ -727,7 +826,7 @@ static void elide_dead_stores(Program *p, const IvSet &observed, const IvSet &ho
                 /* later stages of the chain overwrite equal ranges, so test each against what is live AFTER the op */
                 if (o.store_y && !live.hits(o.out, o.out + numel)) { o.store_y = false; o.note += " -Y"; }
                 if (o.out_s >= 0 && !live.hits(o.out_s, o.out_s + numel)) { o.out_s = -1; o.note += " -S"; }
-                if (o.out_z >= 0 && o.store_z && o.nhwc_consumer >= 0 && !live.hits(o.out_z, o.out_z + numel)) { o.store_z = false; o.note += " -Z"; }
+                if (o.out_z >= 0 && o.store_z && (o.nhwc_consumer >= 0 || o.fwd_out >= 0) && !live.hits(o.out_z, o.out_z + numel)) { o.store_z = false; o.note += " -Z"; }
             }
             op_access(o, &a);
             for (auto &iv : a.kills) live.sub(iv.first, iv.second);
@@ -788,7 +887,12 @@ mars_error_t compile_program(const mars_header_t &h, const mars_runtime_tensor_t
             int64_t es = (d.dtype == MARS_DTYPE_FLOAT32 || d.dtype == MARS_DTYPE_INT32) ? 4 : (d.dtype == MARS_DTYPE_INT16 ? 2 : 1);
             host_written.add((int64_t)toff[ti], (int64_t)toff[ti] + (int64_t)numel_of(d) * es);
         }
-        elide_dead_stores(out, observed, host_written);
+        static const bool fwd_enabled = !(getenv("MARS_CONCAT_FWD") && atoi(getenv("MARS_CONCAT_FWD")) == 0);
+        elide_dead_stores(out, observed, host_written); /* first: which streams of a conv are stored at all */
+        if (fwd_enabled) {
+            forward_concat_inputs(out);
+            elide_dead_stores(out, observed, host_written); /* again: the original of a forwarded stream is usually dead now */
+        }
     }
     /* tables are addressed in 256-byte units; keep the pool non-empty so the upload is uniform */
     if (out->const_pool.empty()) out->const_pool.resize(256, 0);

@@ -407,6 +407,9 @@ static KOp to_kop(const Op &o) {
     k.n = o.n;
     k.lut = o.lut; k.post_relu = o.post_relu; k.post_lut = o.post_lut;
     k.pass_oc = 0; k.use_scratch = 0;
+    k.out_s = o.fused_layers > 0 ? o.out_s : -1;
+    k.out_z = (o.fused_layers > 0 && o.store_z) ? o.out_z : -1;
+    k.lut_s = o.lut_s; k.lut_z = o.lut_z; k.store_y = o.store_y ? 1 : 0;
     return k;
 }
 
@@ -465,6 +468,9 @@ static mars_error_t launch_op(Model *m, size_t op_index, int first, int n, bool 
         } else if (o.mode == EXEC_PIXEL_SERIAL && o.kind == OP_CONV_I8_NCHW && m->opt_level >= 1 && inplace_reg_ok(v, k)) {
             launch_inplace_reg(v, k, n, s);
             m->launches++;
+        } else if (o.mode == EXEC_PIXEL_SERIAL && o.kind == OP_CONV_I8_NCHW && o.fused_layers > 0) {
+            set_last_error("layer %d: fused in-place conv needs the register kernel", o.layer); /* the planner fuses only what inplace_reg_ok accepts */
+            return MARS_ERR_LAYER_FAILED;
         } else if (o.mode == EXEC_PIXEL_SERIAL && o.kind == OP_CONV_I8_NCHW) {
             dim3 g(blocks_for(P, 128), n);
             const size_t smem = (size_t)o.ic * 128 + (size_t)o.oc * o.ic;
