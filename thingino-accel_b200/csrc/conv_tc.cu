@@ -63,7 +63,6 @@ struct TcParams {
     /* TST (plane stores through shared memory + TMA): staging area [team][2][NST][16 channels][128 pixels] in dynamic shared
      * memory; st_wp = row pitch of the tile's pixel index in the store tensor's (x, y) space (the padded width of kxk layers;
      * "one long row" for flat 1x1 tiles), st_magic = floor(2^32 / st_wp) + 1 */
-    int side_pair;           /* OUT 1: units (2k, 2k+1) of a pixel go out as one 32-byte store (consumer channels % 32 == 0, 32-byte aligned copy) */
     uint32_t stg_off;
     int st_manual;           /* TST: the staged block is written by the team's threads, 16 pixels of one channel each (padded tiles: TMA stores cannot clip on the left) */
     int st_wp;
@@ -364,10 +363,9 @@ __device__ __forceinline__ void pair_words(uint32_t v0, uint32_t v1, uint32_t cm
  * NST = number of NCHW output streams stored (table bytes 0..NST-1), NHWC = also pack the side byte of every 16 channels
  * into one 16-byte store of the consumer's channel-innermost copy.  o0..o2 point at channel c0 of this pixel; nch = how
  * many of the 16 channels exist (16 = all, <= 0 = none / pixel outside the image). */
-template <int RQ, bool TAB, int NST, bool NHWC>
+template <int RQ, bool TAB, int NST, bool NHWC, int PAIR>
 __device__ __forceinline__ void epilogue_unit(const uint32_t (&v)[16], uint32_t cm, uint32_t tab_lane, uint32_t tab_stride, float cs, int qs,
-                                              uint8_t *o0, uint8_t *o1, uint8_t *o2, long long plane, int nch, uint8_t *nh, int skip,
-                                              int pair, uint32_t (&keep)[4]) {
+                                              uint8_t *o0, uint8_t *o1, uint8_t *o2, long long plane, int nch, uint8_t *nh, uint32_t (&keep)[4]) {
     if (nch <= 0) return; /* cm: shared address of the unit's per-channel constants; tab_lane: shared address of entry r = 0 of this lane's table */
     if (nch >= 16) {
         uint32_t w[16], pk[4];
@@ -376,21 +374,22 @@ __device__ __forceinline__ void epilogue_unit(const uint32_t (&v)[16], uint32_t 
         for (int j4 = 0; j4 < 4; j4++) {
 #pragma unroll
             for (int k = 0; k < 4; k++) {
-                if (NST > 0) { if (!(skip & 1)) *o0 = (uint8_t)w[4 * j4 + k]; o0 += plane; } /* skip: tuning aid (MARS_TC_DEBUG 12-14), 0 otherwise */
-                if (NST > 1) { if (!(skip & 1)) *o1 = (uint8_t)(w[4 * j4 + k] >> 8); o1 += plane; }
-                if (NST > 2) { if (!(skip & 1)) *o2 = (uint8_t)(w[4 * j4 + k] >> 16); o2 += plane; }
+                if (NST > 0) { *o0 = (uint8_t)w[4 * j4 + k]; o0 += plane; }
+                if (NST > 1) { *o1 = (uint8_t)(w[4 * j4 + k] >> 8); o1 += plane; }
+                if (NST > 2) { *o2 = (uint8_t)(w[4 * j4 + k] >> 16); o2 += plane; }
             }
             if (NHWC) { /* the side-output stream sits in the top byte of the table word (plain conv: the value itself) */
                 const uint32_t sel = TAB ? 0x0073u : 0x0040u;
                 pk[j4] = __byte_perm(__byte_perm(w[4 * j4], w[4 * j4 + 1], sel), __byte_perm(w[4 * j4 + 2], w[4 * j4 + 3], sel), 0x5410);
             }
         }
-        /* side output: one 16-byte store per unit, or -- units (2k, 2k+1) of a pixel handled back to back by this thread -- one
-         * 32-byte store (STG.256) per pair: half as many partially written lines on their way to L2 (pair: 1 = first unit of
-         * a pair, the packed bytes stay in `keep`; 2 = second unit) */
-        if (NHWC && !(skip & 2)) {
-            if (pair == 1) { keep[0] = pk[0]; keep[1] = pk[1]; keep[2] = pk[2]; keep[3] = pk[3]; }
-            else if (pair == 2)
+        /* side output: units (2k, 2k+1) of a pixel are handled back to back by this thread (the work split is in pairs) and go
+         * out as ONE 32-byte store (STG.256): half as many partially written 128-byte lines on their way to L2 as two 16-byte
+         * stores -- the L1 -> L2 request path is what saturates in the layers with a side output (profiles/r02i).  PAIR 1 = first
+         * unit of a pair: the packed bytes wait in `keep`; PAIR 2 = second unit: store both */
+        if (NHWC) {
+            if (PAIR == 1) { keep[0] = pk[0]; keep[1] = pk[1]; keep[2] = pk[2]; keep[3] = pk[3]; }
+            else if (PAIR == 2)
                 asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(nh - 16), "r"(keep[0]), "r"(keep[1]), "r"(keep[2]), "r"(keep[3]),
                              "r"(pk[0]), "r"(pk[1]), "r"(pk[2]), "r"(pk[3]) : "memory");
             else *reinterpret_cast<uint4 *>(nh) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
@@ -564,7 +563,6 @@ k_conv_tc(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUte
         const long long plane = p.plane;
         const float cs = RQ == 3 ? __int_as_float(p.q_m) : p.cs; /* RQ 3: the multiplier travels in the scale's place */
         const int qs = p.q_s;
-        const int skip = p.dbg == 12 ? 5 : (p.dbg == 13 ? 6 : (p.dbg == 14 ? 7 : 0)); /* tuning aid: 12 = no plane stores, 13 = no side stores, 14 = neither */
         const uint32_t acc_lane = tmem_d + ((uint32_t)(quad * 32) << 16);
         const uint32_t sa_cm = RQ == 3 ? smem_base + p.cm_off : smem_u32(s_cm);
         constexpr uint32_t CMB = RQ == 3 ? 8u : 4u; /* bytes per channel constant */
@@ -574,7 +572,8 @@ k_conv_tc(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUte
         const bool flat = !GATHER && !p.rect && p.Wp == p.Wo && OUT != 1; /* no pad columns: the tile row index IS the pixel index */
         uint8_t *const obase = p.out_base + r; /* + image * slot_stride + pixel + channel * plane + stream offset */
         const int G = p.grp, gcols = p.grp * p.n_tile;
-        const int total_items = G * n_units, ipp = (total_items + parts - 1) / parts;
+        /* OUT 1: items are handed out in pairs of units (the side output is stored per pair) */
+        const int total_items = G * n_units, ipp = OUT == 1 ? 2 * ((total_items / 2 + parts - 1) / parts) : (total_items + parts - 1) / parts;
         const int i_lo = part * ipp, i_hi = min(total_items, i_lo + ipp);
         if (i_lo >= i_hi || p.dbg == 7 || p.dbg == 9) { /* narrow group: nothing to read for this warp, it only releases the accumulators */
             int ab = 0, aph = 0; /* accumulator ring position and phase */
@@ -689,8 +688,7 @@ k_conv_tc(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUte
                     };
                     /* units u_lo .. u_hi-1 of this M tile, the TMEM load of the next one in flight while one is processed */
                     int u = u_lo;
-                    uint32_t keep[4] = {0u, 0u, 0u, 0u};
-                    const bool pair_ok = valid && p.side_pair != 0; /* a pair is stored by its second unit: both exist for a valid pixel (Co % 32 == 0) */
+                    uint32_t keep[4] = {0u, 0u, 0u, 0u}; /* OUT 1: the first unit's side bytes of a pair (runs start at even units and have even length) */
                     tmem_ld16_issue(acc_g + (uint32_t)(u * 16), va);
                     for (;;) {
                         tmem_ld_wait(va);
@@ -700,13 +698,12 @@ k_conv_tc(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUte
                             __syncwarp();
                             if (lane == 0) mbar_arrive(sa_empty + 8u * ab);
                         }
-                        if (p.dbg >= 2 && p.dbg < 12) { if (va[0] == 0x12345678u && va[7] == 0x9abcdef0u) pix_base[p.out_off[0]] = 1; }
+                        if (p.dbg >= 2) { if (va[0] == 0x12345678u && va[7] == 0x9abcdef0u) pix_base[p.out_off[0]] = 1; }
                         else if (TST) staged(va, u);
                         else if (OUT == 2) epilogue_unit_nhwc<RQ, TAB, NST>(va, cm0 + 16u * CMB * (uint32_t)u, tab_lane, tab_stride, cs, qs, pix_base + p.out_off[0], pix_base + p.out_off[1],
                                                                             pix_base + p.out_off[2], co_left - u * 16, p.onhwc_vec != 0);
-                        else epilogue_unit<RQ, TAB, NST, OUT == 1>(va, cm0 + 16u * CMB * (uint32_t)u, tab_lane, tab_stride, cs, qs, pix_base + p.out_off[0], pix_base + p.out_off[1],
-                                                                   pix_base + p.out_off[2], plane, co_left - u * 16, nh + u * 16, skip,
-                                                                   OUT == 1 && pair_ok ? ((u & 1) ? (u > u_lo ? 2 : 0) : (u + 1 < u_hi ? 1 : 0)) : 0, keep);
+                        else epilogue_unit<RQ, TAB, NST, OUT == 1, OUT == 1 ? 1 : 0>(va, cm0 + 16u * CMB * (uint32_t)u, tab_lane, tab_stride, cs, qs, pix_base + p.out_off[0], pix_base + p.out_off[1],
+                                                                   pix_base + p.out_off[2], plane, co_left - u * 16, nh + u * 16, keep);
                         pix_base += plane16;
                         if (++u >= u_hi) break;
                         tmem_ld_wait(vb);
@@ -716,13 +713,12 @@ k_conv_tc(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUte
                             __syncwarp();
                             if (lane == 0) mbar_arrive(sa_empty + 8u * ab);
                         }
-                        if (p.dbg >= 2 && p.dbg < 12) { if (vb[0] == 0x12345678u && vb[7] == 0x9abcdef0u) pix_base[p.out_off[0]] = 1; }
+                        if (p.dbg >= 2) { if (vb[0] == 0x12345678u && vb[7] == 0x9abcdef0u) pix_base[p.out_off[0]] = 1; }
                         else if (TST) staged(vb, u);
                         else if (OUT == 2) epilogue_unit_nhwc<RQ, TAB, NST>(vb, cm0 + 16u * CMB * (uint32_t)u, tab_lane, tab_stride, cs, qs, pix_base + p.out_off[0], pix_base + p.out_off[1],
                                                                             pix_base + p.out_off[2], co_left - u * 16, p.onhwc_vec != 0);
-                        else epilogue_unit<RQ, TAB, NST, OUT == 1>(vb, cm0 + 16u * CMB * (uint32_t)u, tab_lane, tab_stride, cs, qs, pix_base + p.out_off[0], pix_base + p.out_off[1],
-                                                                   pix_base + p.out_off[2], plane, co_left - u * 16, nh + u * 16, skip,
-                                                                   OUT == 1 && pair_ok ? ((u & 1) ? (u > u_lo ? 2 : 0) : (u + 1 < u_hi ? 1 : 0)) : 0, keep);
+                        else epilogue_unit<RQ, TAB, NST, OUT == 1, OUT == 1 ? 2 : 0>(vb, cm0 + 16u * CMB * (uint32_t)u, tab_lane, tab_stride, cs, qs, pix_base + p.out_off[0], pix_base + p.out_off[1],
+                                                                   pix_base + p.out_off[2], plane, co_left - u * 16, nh + u * 16, keep);
                         pix_base += plane16;
                         if (++u >= u_hi) break;
                     }
@@ -1742,9 +1738,8 @@ bool tc_plan(const Op &o, const ArenaGeom &ag, uint8_t *scratch, size_t scratch_
         p.nhwc_C = consumer->ic;
         p.nhwc_base = linked + consumer->copy_off;
         p.nhwc_stride = linked_stride;
-        static const bool pair_enabled = !(getenv("MARS_TC_SIDEPAIR") && atoi(getenv("MARS_TC_SIDEPAIR")) == 0);
-        p.side_pair = (pair_enabled && consumer->ic % 32 == 0 && p.n_tile % 32 == 0 && consumer->copy_off % 32 == 0 && linked_stride % 32 == 0 &&
-                       ((uintptr_t)linked % 32) == 0) ? 1 : 0;
+        /* the side output leaves in 32-byte pieces (two 16-channel units of a pixel per store) */
+        if (consumer->ic % 32 || p.n_tile % 32 || consumer->copy_off % 32 || linked_stride % 32 || ((uintptr_t)linked % 32)) { delete t; return false; }
     }
     t->prepass = g.prepass; t->C = o.ic; t->Cp = ci_eff; t->H = o.ih; t->W = o.iw; t->pt = o.pt; t->pl = o.pl;
     t->plane = g.plane; t->npix = g.npix;
