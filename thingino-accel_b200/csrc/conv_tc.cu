@@ -39,6 +39,14 @@
 
 namespace marsb200 {
 
+/* tuning aids (MARS_TC_DEBUG: 2 = epilogue only drains TMEM, 3 = 2 + no per-step TMA loads, 4 = 2 + no MMAs, 6 = prologue and
+ * teardown only, 7 / 9 = epilogue warps only hand the accumulators back): compiled in with -DMARS_TC_TUNING, otherwise the tests
+ * on them vanish from the kernels (they sat in the epilogue's inner loop) */
+#ifdef MARS_TC_TUNING
+#define TC_DBG(p) ((p).dbg)
+#else
+#define TC_DBG(p) 0
+#endif
 #define TC_MAX_TAPS 36
 #define TC_BM 128
 /* warp roles: warps 0..EPI-1 epilogue (EPI = 8, or 16 when one CTA owns the SM; quadrant = warp & 3), warp EPI = TMEM
@@ -548,7 +556,7 @@ k_conv_tc(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUte
     /* everything above read only weights, biases and tables (written at load time); the activations this kernel reads, and the
      * buffers it overwrites, belong to the previous kernel of the step until it has completed */
     pdl_wait_prior_grid();
-    if (p.dbg == 6) goto teardown; /* tuning aid: prologue + teardown only */
+    if (TC_DBG(p) == 6) goto teardown; /* tuning aid: prologue + teardown only */
 
     if (warp < EPI) {
         /* ===== epilogue: TMEM -> registers -> requantised byte -> (word table) -> stores =====
@@ -575,7 +583,7 @@ k_conv_tc(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUte
         /* OUT 1: items are handed out in pairs of units (the side output is stored per pair) */
         const int total_items = G * n_units, ipp = OUT == 1 ? 2 * ((total_items / 2 + parts - 1) / parts) : (total_items + parts - 1) / parts;
         const int i_lo = part * ipp, i_hi = min(total_items, i_lo + ipp);
-        if (i_lo >= i_hi || p.dbg == 7 || p.dbg == 9) { /* narrow group: nothing to read for this warp, it only releases the accumulators */
+        if (i_lo >= i_hi || TC_DBG(p) == 7 || TC_DBG(p) == 9) { /* narrow group: nothing to read for this warp, it only releases the accumulators */
             int ab = 0, aph = 0; /* accumulator ring position and phase */
             for (TileIter ti(blockIdx.x, gridDim.x, tiles_per_img); ti.img < p.n_img; ti.next()) {
                 mbar_wait_relaxed(sa_full + 8u * ab, aph);
@@ -673,11 +681,7 @@ k_conv_tc(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUte
                             const uint32_t src = sb - (uint32_t)r;
                             const int c = n0 + uu * 16, zi = p.img0 + ti.img;
                             for (int sg = 0; sg < nseg; sg++) { /* one store per image row the tile touches; pad columns and rows beyond the image are clipped */
-                                int xs = tx0 - sg * p.st_wp;
-                                if (p.dbg == 20 && sg > 0) break;
-                                if ((p.dbg == 21 || p.dbg == 23) && ty0 + sg >= p.Ho) break;
-                                if (p.dbg == 21 && xs < 0) continue;
-                                if (p.dbg == 22 && xs < 0) xs = 0;
+                                const int xs = tx0 - sg * p.st_wp;
                                 tma_store_4d(&mapO0, src, xs, ty0 + sg, c, zi);
                                 if (NST > 1) tma_store_4d(&mapO1, src + 2048u, xs, ty0 + sg, c, zi);
                                 if (NST > 2) tma_store_4d(&mapO2, src + 4096u, xs, ty0 + sg, c, zi);
@@ -698,7 +702,7 @@ k_conv_tc(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUte
                             __syncwarp();
                             if (lane == 0) mbar_arrive(sa_empty + 8u * ab);
                         }
-                        if (p.dbg >= 2) { if (va[0] == 0x12345678u && va[7] == 0x9abcdef0u) pix_base[p.out_off[0]] = 1; }
+                        if (TC_DBG(p) >= 2) { if (va[0] == 0x12345678u && va[7] == 0x9abcdef0u) pix_base[p.out_off[0]] = 1; }
                         else if (TST) staged(va, u);
                         else if (OUT == 2) epilogue_unit_nhwc<RQ, TAB, NST>(va, cm0 + 16u * CMB * (uint32_t)u, tab_lane, tab_stride, cs, qs, pix_base + p.out_off[0], pix_base + p.out_off[1],
                                                                             pix_base + p.out_off[2], co_left - u * 16, p.onhwc_vec != 0);
@@ -713,7 +717,7 @@ k_conv_tc(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUte
                             __syncwarp();
                             if (lane == 0) mbar_arrive(sa_empty + 8u * ab);
                         }
-                        if (p.dbg >= 2) { if (vb[0] == 0x12345678u && vb[7] == 0x9abcdef0u) pix_base[p.out_off[0]] = 1; }
+                        if (TC_DBG(p) >= 2) { if (vb[0] == 0x12345678u && vb[7] == 0x9abcdef0u) pix_base[p.out_off[0]] = 1; }
                         else if (TST) staged(vb, u);
                         else if (OUT == 2) epilogue_unit_nhwc<RQ, TAB, NST>(vb, cm0 + 16u * CMB * (uint32_t)u, tab_lane, tab_stride, cs, qs, pix_base + p.out_off[0], pix_base + p.out_off[1],
                                                                             pix_base + p.out_off[2], co_left - u * 16, p.onhwc_vec != 0);
@@ -784,7 +788,7 @@ k_conv_tc(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUte
                         mbar_wait(sa_full + 8u * s, ph);
                         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                         const uint32_t a_st = a_lo0 + s * a_st16, b_lo = b_lo0 + (b_res ? i : s) * b_st16;
-                        if (p.dbg != 4 && p.dbg != 9)
+                        if (TC_DBG(p) != 4 && TC_DBG(p) != 9)
                             for (int j = 0; j < nj; j++)
                                     umma_i8_parts(acc + (uint32_t)(lane * n_tile), a_st + lane * a_tile16 + a_j16 * j, hi_a, b_lo + 2u * j, hi_k, idesc, (uint32_t)((i | j) != 0));
                         umma_commit(sa_empty + 8u * s); /* frees the stage when these MMAs retire */
@@ -817,7 +821,7 @@ k_conv_tc(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUte
                     for (int kb = 0; kb < ksteps; kb++) {
                         mbar_wait(sa_empty + 8u * s, ph);
                         const uint32_t full = sa_full + 8u * s, dst = a_base + s * a_stb;
-                        if (p.dbg == 3 || p.dbg == 9) { mbar_arrive(full); if (++s == stages) { s = 0; ph ^= 1; } continue; }
+                        if (TC_DBG(p) == 3 || TC_DBG(p) == 9) { mbar_arrive(full); if (++s == stages) { s = 0; ph ^= 1; } continue; }
                         mbar_expect_tx(full, tx);
                         for (int b = 0; b < nb; b++) tma_load_3d(dst + b * box_b, &mapA, full, kb * bk, q0 + b * rb, zc);
                         if (++s == stages) { s = 0; ph ^= 1; }
@@ -834,7 +838,7 @@ k_conv_tc(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUte
                         for (int kb = 0; kb < ksteps; kb++) {
                             mbar_wait(sa_empty + 8u * s, ph);
                             const uint32_t full = sa_full + 8u * s;
-                            if (p.dbg == 3 || p.dbg == 9) { mbar_arrive(full); if (++s == stages) { s = 0; ph ^= 1; } continue; }
+                            if (TC_DBG(p) == 3 || TC_DBG(p) == 9) { mbar_arrive(full); if (++s == stages) { s = 0; ph ^= 1; } continue; }
                             mbar_expect_tx(full, tx);
                             for (int g = 0; g < G; g++) { /* rows beyond the tensor (last, partial group) are zero-filled */
                                 if (rect) {
@@ -1726,7 +1730,7 @@ bool tc_plan(const Op &o, const ArenaGeom &ag, uint8_t *scratch, size_t scratch_
         p.gPH = g.PH; p.gPWW = g.PWW; p.gdx = g.dx;
         p.g_align2 = (o.sh % 2 == 0 && o.kw % 2 == 0 && g.dx % 2 == 0) ? 1 : 0;
     }
-    p.dbg = getenv("MARS_TC_DEBUG") ? atoi(getenv("MARS_TC_DEBUG")) : 0;
+    p.dbg = getenv("MARS_TC_DEBUG") ? atoi(getenv("MARS_TC_DEBUG")) : 0; /* read by the kernels only in a -DMARS_TC_TUNING build */
     p.nhwc_sel = -1;
     if (consumer && linked) { /* this op's epilogue also writes the consumer's channel-innermost input copy */
         const TcGeom cg = tc_geometry(*consumer);

@@ -32,6 +32,7 @@ struct KOp {
      * Z = table lut_z[y] at out_z (-1 = not stored), store_y = 0: the pre-activation plane itself is dead */
     int64_t out_s, out_z;
     int lut_s, lut_z, store_y;
+    int fast_bin;    /* int8 mul / add: the host proved |result| < 2^31 and finite scales, the conversion-light sequence is exact */
     int pass_oc;     /* EXEC_OC_PASSES: the output channel of this launch */
     int use_scratch; /* write the pass to scratch instead of the output plane */
 };

@@ -38,6 +38,30 @@ __global__ void __launch_bounds__(256) k_lut16(ArenaView v, KOp o) {
     }
 }
 
+/* the same four elements without the int -> float conversions (the XU pipe, 16 lanes per SM, bounded the kernel at three
+ * conversions per element): (float)(int8) = as_float(0x4B400000 + sign-extended byte) - 1.5 * 2^23, exact; the final truncation is
+ * one saturating cvt.rzi.s8 -- equal to the reference's (int32) cast + clamp whenever the value is finite and below 2^31, which the
+ * host checks from the scales (KOp::fast_bin) */
+__device__ __forceinline__ uint32_t bin4_fast(uint32_t a, uint32_t b, int is_mul, float sa, float sb, float inv) {
+    uint32_t r[4];
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        const uint32_t sel = (uint32_t)k | ((uint32_t)(k | 8) << 4) | ((uint32_t)(k | 8) << 8) | ((uint32_t)(k | 8) << 12); /* byte k, then its sign three times */
+        uint32_t xa, xb; /* prmt in its default mode: selector values 8..15 replicate the sign bit of byte (value & 7) */
+        asm("prmt.b32 %0, %1, %2, %3;" : "=r"(xa) : "r"(a), "r"(0u), "r"(sel));
+        asm("prmt.b32 %0, %1, %2, %3;" : "=r"(xb) : "r"(b), "r"(0u), "r"(sel));
+        const float fa = __fadd_rn(__int_as_float((int)(xa + 0x4B400000u)), -12582912.0f);
+        const float fb = __fadd_rn(__int_as_float((int)(xb + 0x4B400000u)), -12582912.0f);
+        const float va = __fmul_rn(fa, sa), vb = __fmul_rn(fb, sb);
+        const float y = is_mul ? __fmul_rn(va, vb) : __fadd_rn(va, vb);
+        const float u = __fadd_rn(__fmul_rn(y, inv), 0.5f);
+        int q;
+        asm("cvt.rzi.s8.f32 %0, %1;" : "=r"(q) : "f"(u));
+        r[k] = (uint32_t)q;
+    }
+    return __byte_perm(__byte_perm(r[0], r[1], 0x0040), __byte_perm(r[2], r[3], 0x0040), 0x5410);
+}
+
 __device__ __forceinline__ uint32_t bin4(uint32_t a, uint32_t b, int is_mul, float sa, float sb, float inv) {
     uint32_t r = 0;
 #pragma unroll
@@ -60,8 +84,13 @@ __global__ void __launch_bounds__(256) k_bin16(ArenaView v, KOp o) {
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nv; i += (int64_t)gridDim.x * blockDim.x) {
         const uint4 x = reinterpret_cast<const uint4 *>(a)[i], y = reinterpret_cast<const uint4 *>(b)[i];
         uint4 r;
-        r.x = bin4(x.x, y.x, is_mul, o.f0, o.f1, o.f2); r.y = bin4(x.y, y.y, is_mul, o.f0, o.f1, o.f2);
-        r.z = bin4(x.z, y.z, is_mul, o.f0, o.f1, o.f2); r.w = bin4(x.w, y.w, is_mul, o.f0, o.f1, o.f2);
+        if (o.fast_bin) {
+            r.x = bin4_fast(x.x, y.x, is_mul, o.f0, o.f1, o.f2); r.y = bin4_fast(x.y, y.y, is_mul, o.f0, o.f1, o.f2);
+            r.z = bin4_fast(x.z, y.z, is_mul, o.f0, o.f1, o.f2); r.w = bin4_fast(x.w, y.w, is_mul, o.f0, o.f1, o.f2);
+        } else {
+            r.x = bin4(x.x, y.x, is_mul, o.f0, o.f1, o.f2); r.y = bin4(x.y, y.y, is_mul, o.f0, o.f1, o.f2);
+            r.z = bin4(x.z, y.z, is_mul, o.f0, o.f1, o.f2); r.w = bin4(x.w, y.w, is_mul, o.f0, o.f1, o.f2);
+        }
         reinterpret_cast<uint4 *>(out)[i] = r;
     }
     if (blockIdx.x == 0 && threadIdx.x < (int)(o.n & 15)) {

@@ -410,6 +410,14 @@ static KOp to_kop(const Op &o) {
     k.out_s = o.fused_layers > 0 ? o.out_s : -1;
     k.out_z = (o.fused_layers > 0 && o.store_z) ? o.out_z : -1;
     k.lut_s = o.lut_s; k.lut_z = o.lut_z; k.store_y = o.store_y ? 1 : 0;
+    /* int8 mul / add: |a * sa| <= 128 |sa| etc.; with everything finite and the scaled result below 2^30 neither the x86
+     * overflow rule nor NaN handling of the reference's float -> int conversion can trigger */
+    k.fast_bin = 0;
+    if (o.kind == OP_MUL_I8 || o.kind == OP_ADD_I8) {
+        const double a = 128.0 * fabs((double)o.f0), b = 128.0 * fabs((double)o.f1), inv = fabs((double)o.f2);
+        const double top = (o.kind == OP_MUL_I8 ? a * b : a + b) * inv + 1.0;
+        k.fast_bin = (std::isfinite(o.f0) && std::isfinite(o.f1) && std::isfinite(o.f2) && top < 1073741824.0 && a < 1e30 && b < 1e30) ? 1 : 0;
+    }
     return k;
 }
 
