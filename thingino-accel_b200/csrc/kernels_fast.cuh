@@ -110,8 +110,9 @@ __global__ void __launch_bounds__(256) k_shift_copy(ArenaView v, KOp o, int peri
     const uint8_t *in = periodic ? (const uint8_t *)(im.s_minus_W + o.out) : (const uint8_t *)(im.s_minus_W + o.in0);
     const int64_t nv = (int64_t)o.n / VEC;
     const int64_t per = o.coff / VEC; /* periodic: source index wraps every coff bytes */
+    const bool small = nv < (int64_t)0x7FFFFFFF; /* 32-bit remainder: the 64-bit one (a ~100-instruction sequence) bounded the periodic fill */
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nv; i += (int64_t)gridDim.x * blockDim.x) {
-        const int64_t si = periodic ? i % per : i;
+        const int64_t si = periodic ? (small ? (int64_t)((uint32_t)i % (uint32_t)per) : i % per) : i;
         if (VEC == 16) reinterpret_cast<uint4 *>(out)[i] = reinterpret_cast<const uint4 *>(in)[si];
         else if (VEC == 4) reinterpret_cast<uint32_t *>(out)[i] = reinterpret_cast<const uint32_t *>(in)[si];
         else out[i] = in[si];
