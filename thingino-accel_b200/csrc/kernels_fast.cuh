@@ -100,6 +100,51 @@ __global__ void __launch_bounds__(256) k_bin16(ArenaView v, KOp o) {
     }
 }
 
+/* Restated depthwise convolution (parity unpinned: the reference's DEPTHWISE_CONV2D is a no-op, src/mars/mars_runtime.c:1168-1170;
+ * convention of mars-compiler/src/main.rs:877-881), NCHW, four adjacent output pixels of one channel per thread: the input window of
+ * a kernel row is shared by the four (L1), every tap weight is loaded once for all of them, one 4-byte store.  Same arithmetic as dw_i8_point (int32 wrap-around accumulation in tap order, requant_conv);
+ * selected for hazard-free layers with ow % 4 == 0 and kernels up to 7 wide. */
+__global__ void __launch_bounds__(256) k_dw_nchw4(ArenaView v, KOp o) {
+    pdl_begin();
+    const Img im = make_img(v, blockIdx.y);
+    const int ow4 = o.ow >> 2;
+    const int64_t total = (int64_t)o.oc * o.oh * ow4;
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= total) return;
+    const int x4 = (int)(t % ow4), oh = (int)((t / ow4) % o.oh), c = (int)(t / ((int64_t)ow4 * o.oh));
+    const int8_t *in = reinterpret_cast<const int8_t *>(im.s_minus_W + o.in0) + (int64_t)c * o.ih * o.iw;
+    const int8_t *w = reinterpret_cast<const int8_t *>(im.w + o.w) + (int64_t)c * o.kh * o.kw;
+    const uint32_t b = (uint32_t)bias_i32<false>(im, o, c);
+    uint32_t acc[4] = {b, b, b, b};
+    const int iw0 = x4 * 4 * o.sw - o.pl; /* input column of output 0, tap 0 */
+    for (int y = 0; y < o.kh; y++) {
+        const int ih = oh * o.sh - o.pt + y;
+        if (ih < 0 || ih >= o.ih) continue;
+        const int8_t *row = in + (int64_t)ih * o.iw;
+        for (int x = 0; x < o.kw; x++) {
+            const int wv = (int)w[y * o.kw + x];
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                const int iw = iw0 + j * o.sw + x;
+                if (iw >= 0 && iw < o.iw) acc[j] += (uint32_t)((int)row[iw] * wv); /* taps outside the plane are skipped, like dw_i8_point */
+            }
+        }
+    }
+    uint32_t r = 0;
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+        int8_t q = requant_conv((int32_t)acc[j], o.f0);
+        if (o.post_relu && q < 0) q = 0;
+        if (o.post_lut >= 0) q = (int8_t)v.cpool[o.post_lut + (int)q + 128];
+        r |= (uint32_t)(uint8_t)q << (8 * j);
+    }
+    *reinterpret_cast<uint32_t *>(wr_ptr(im, o.out) + ((int64_t)c * o.oh + oh) * o.ow + x4 * 4) = r;
+}
+static inline bool dw_nchw4_ok(const ArenaView &v, const KOp &o) {
+    return o.kind == OP_DW_I8 && o.coff == 0 && o.mode == EXEC_PARALLEL && o.ow > 0 && o.ow % 4 == 0 && o.sw >= 1 && o.kw >= 1 && o.in0 >= (int64_t)v.W && o.out >= (int64_t)v.W && ((o.out - (int64_t)v.W) & 3) == 0 && o.w >= 0 &&
+           o.w + (int64_t)o.oc * o.kh * o.kw <= (int64_t)v.W && (o.bias < 0 || o.bias + 4 * (int64_t)o.oc <= (int64_t)v.W);
+}
+
 /* concat input whose channel count equals the output's (every concat of the shipped YOLO files,
  * SURVEY C.4): out[t + coff] = in[t], a shifted flat copy.  VEC = bytes per access. */
 template <int VEC>

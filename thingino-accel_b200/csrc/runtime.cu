@@ -455,6 +455,8 @@ static mars_error_t launch_op(Model *m, size_t op_index, int first, int n, bool 
         } else if (o.mode == EXEC_PARALLEL) {
             if (o.kind == OP_CONV_I8_NCHW && !xl && fast_conv_nchw_ok(k)) {
                 launch_fast_conv_nchw(v, k, n, s);
+            } else if (o.kind == OP_DW_I8 && !xl && m->opt_level >= 1 && dw_nchw4_ok(v, k)) {
+                launch_pdl(k_dw_nchw4, dim3(blocks_for((uint64_t)o.oc * o.oh * (o.ow >> 2), 256), n), dim3(256), (size_t)0, s, v, k);
             } else {
                 dim3 g(blocks_for(P * o.oc, 256), n);
                 if (xl) k_conv_point<true><<<g, 256, 0, s>>>(v, k); else k_conv_point<false><<<g, 256, 0, s>>>(v, k);
