@@ -152,6 +152,12 @@ int mars_b200_letterbox_rgba(const uint8_t *rgb, int w, int h, int tw, int th, u
  * axis sums, in the order stbir_resize_uint8 adds them.  start[out_size + 1]; returns the tap count (> cap: nothing copied). */
 int mars_b200_resize_taps(int in_size, int out_size, int32_t *start, int32_t *src, float *w, int cap);
 
+/* ---- planner (host half, no GPU needed) ----------------------------------- */
+/* What the library would do with a .mars blob: the compiled op list at `opt_level` (0 exact kernels ... 3 default), one line per
+ * device op with its kernel choice and the fused / linked / forwarded / elided output streams, written to dst (NUL terminated,
+ * truncated to cap).  arena_bytes = 0: the reference's 8 MiB (src/mars/mars_runtime.c:209).  Returns the full length, 0 on error. */
+size_t mars_b200_plan_describe(const void *data, size_t size, size_t arena_bytes, int opt_level, char *dst, size_t cap);
+
 /* ---- conv requantisation in integers (host half, no GPU needed) ----------- */
 /* The tcgen05 conv epilogue replaces the float requantisation of reference src/mars/mxu_conv.c:663-666,
  * r = clamp((int32)(fl((float)t * scale) +- 0.5f)), by clamp(floor((t * m + c) / 2^(32 + s))) when integers (m, s, c) exist that

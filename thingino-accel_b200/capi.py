@@ -177,6 +177,7 @@ SIGNATURES = {
     "mars_b200_letterbox": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
     "mars_b200_letterbox_rgba": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
     "mars_b200_resize_taps": (C.c_int, [C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]),
+    "mars_b200_plan_describe": (C.c_size_t, [C.c_void_p, C.c_size_t, C.c_size_t, C.c_int, C.c_char_p, C.c_size_t]),
     "mars_b200_requant_fit": (C.c_int, [C.c_float, C.c_longlong, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_longlong)]),
     "mars_b200_requant_ref": (C.c_int, [C.c_int, C.c_float]),
     "mars_yolo_nms_boxes": (C.c_int, [C.c_void_p, C.c_int, C.c_float]),

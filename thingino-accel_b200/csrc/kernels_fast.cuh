@@ -449,17 +449,21 @@ __global__ void __launch_bounds__(128) k_maxpool5_col(ArenaView v, KOp o, int ro
 /* nearest upsample (reference src/mars/mars_runtime.c:1027-1040: ih = min(oh / sh, ih - 1), same for columns): one block
  * per (output row, image); a thread produces consecutive output words (fully coalesced stores), reading the input row
  * through L1.  Divisions by multiplication. */
+#define UPS_ROWS 8
 __global__ void __launch_bounds__(256) k_upsample_rep(ArenaView v, KOp o) {
     pdl_begin(); /* dependents may be scheduled; wait for the previous kernel of the step before touching the arena */
     const Img im = make_img(v, blockIdx.y);
     const int c4 = o.ic >> 2, orw = o.ow * c4;
-    const uint32_t *in = reinterpret_cast<const uint32_t *>(im.s_minus_W + o.in0) + (int64_t)min((int)blockIdx.x / o.sh, o.ih - 1) * o.iw * c4;
-    uint32_t *out = reinterpret_cast<uint32_t *>(im.s_minus_W + o.out) + (int64_t)blockIdx.x * orw;
     const unsigned m_c4 = 0xFFFFFFFFu / (unsigned)c4 + 1u, m_sw = 0xFFFFFFFFu / (unsigned)o.sw + 1u; /* floor(a / d) = umulhi(a, m) */
-    for (int w = threadIdx.x; w < orw; w += blockDim.x) {
-        const int xo = (int)__umulhi((unsigned)w, m_c4), c = w - xo * c4;
-        const int xi = min(o.sw == 1 ? xo : (int)__umulhi((unsigned)xo, m_sw), o.iw - 1);
-        out[w] = in[xi * c4 + c];
+    /* UPS_ROWS output rows per block: the rows of the small planes are a few hundred bytes, one block per row was all launch overhead */
+    for (int row = blockIdx.x * UPS_ROWS; row < min((int)(blockIdx.x + 1) * UPS_ROWS, o.oh); row++) {
+        const uint32_t *in = reinterpret_cast<const uint32_t *>(im.s_minus_W + o.in0) + (int64_t)min(row / o.sh, o.ih - 1) * o.iw * c4;
+        uint32_t *out = reinterpret_cast<uint32_t *>(im.s_minus_W + o.out) + (int64_t)row * orw;
+        for (int w = threadIdx.x; w < orw; w += blockDim.x) {
+            const int xo = (int)__umulhi((unsigned)w, m_c4), c = w - xo * c4;
+            const int xi = min(o.sw == 1 ? xo : (int)__umulhi((unsigned)xo, m_sw), o.iw - 1);
+            out[w] = in[xi * c4 + c];
+        }
     }
 }
 
@@ -511,7 +515,7 @@ static inline void launch_fast_spatial(const ArenaView &v, const KOp &o, int n_i
         }
     }
     if (o.kind == OP_UPSAMPLE && o.oh <= 65535 && (long long)o.ow * (o.ic >> 2) < 65536) {
-        launch_pdl(k_upsample_rep, dim3(dim3(o.oh, n_img)), dim3(256), (size_t)(0), s, v, o);
+        launch_pdl(k_upsample_rep, dim3(dim3((o.oh + UPS_ROWS - 1) / UPS_ROWS, n_img)), dim3(256), (size_t)(0), s, v, o);
         return;
     }
     if (o.kind == OP_MAXPOOL || o.kind == OP_UPSAMPLE) {

@@ -608,7 +608,7 @@ static void fuse_silu(Program *p, int64_t W) {
         c.store_y = c.out != m.out;
         c.fused_layers = 2;
         c.whi = std::max(c.whi, std::max(s.whi, m.whi));
-        c.note = "conv+sigmoid+mul fused";
+        c.note = c.private_in ? "conv+sigmoid+mul fused (reads a private copy of its input)" : "conv+sigmoid+mul fused";
         s.kind = OP_NOP; s.note = "folded into the conv epilogue";
         m.kind = OP_NOP; m.note = "folded into the conv epilogue";
     }

@@ -658,6 +658,49 @@ const char *mars_get_error_string(mars_error_t err) {
 }
 
 /* reference src/mars/mars_runtime.c:126-349 */
+/* The planner's decisions for a .mars blob without touching a device: parses the tables, lays the tensors out as mars_load_memory
+ * does (reference src/mars/mars_runtime.c:248-337), compiles the layer table at `opt_level` and writes the op list (one line per
+ * op: kind, mode, kernel choice, fused / linked / forwarded / elided streams) to dst.  Returns the length of the description
+ * (0 on error).  Host logic only -- the CPU test suite checks fusion, concat trimming and forwarding through it. */
+size_t mars_b200_plan_describe(const void *data, size_t size, size_t arena_bytes, int opt_level, char *dst, size_t cap) {
+    if (!data || size < sizeof(mars_header_t)) return 0;
+    mars_header_t h;
+    memcpy(&h, data, sizeof h);
+    if (h.magic != MARS_MAGIC || h.version_major != MARS_VERSION_MAJOR) return 0;
+    const size_t tables = sizeof h + (size_t)h.num_tensors * sizeof(mars_tensor_t) + (size_t)h.num_layers * sizeof(mars_layer_t);
+    if (size < tables || h.weights_offset > size || h.weights_size > size - h.weights_offset) return 0;
+    std::vector<mars_runtime_tensor_t> tensors(h.num_tensors ? h.num_tensors : 1);
+    std::vector<mars_runtime_layer_t> layers(h.num_layers ? h.num_layers : 1);
+    memset(tensors.data(), 0, tensors.size() * sizeof(mars_runtime_tensor_t));
+    memset(layers.data(), 0, layers.size() * sizeof(mars_runtime_layer_t));
+    const uint8_t *p = (const uint8_t *)data + sizeof h;
+    for (uint32_t i = 0; i < h.num_tensors; i++, p += sizeof(mars_tensor_t)) memcpy(&tensors[i].desc, p, sizeof(mars_tensor_t));
+    for (uint32_t i = 0; i < h.num_layers; i++, p += sizeof(mars_layer_t)) memcpy(&layers[i].desc, p, sizeof(mars_layer_t));
+    const size_t arena = arena_bytes ? arena_bytes : (size_t)8 << 20, W = (size_t)h.weights_size;
+    if (W > arena) return 0;
+    size_t remaining = arena - W, maxsz = 0;
+    for (uint32_t i = 0; i < h.num_tensors; i++)
+        if (tensors[i].desc.data_size == 0) maxsz = std::max(maxsz, (tensor_byte_size(&tensors[i].desc) + 63) & ~(size_t)63);
+    size_t nb = 3, bs = maxsz;
+    if (bs * nb > remaining) nb = 2;
+    if (bs * nb > remaining) { bs = (remaining / 2) & ~(size_t)63; if (bs < 65536) return 0; }
+    std::vector<size_t> toff(h.num_tensors ? h.num_tensors : 1);
+    uint32_t k = 0;
+    for (uint32_t i = 0; i < h.num_tensors; i++) {
+        if (tensors[i].desc.data_size > 0) { toff[i] = (size_t)tensors[i].desc.data_offset; tensors[i].alloc_size = (size_t)tensors[i].desc.data_size; }
+        else { toff[i] = W + (size_t)(k % nb) * bs; tensors[i].alloc_size = bs; k++; }
+    }
+    Program prog;
+    if (compile_program(h, tensors.data(), layers.data(), toff, W, arena, opt_level, 0, &prog, 2 /* the library's default float32 mode: tf32x3 */) != MARS_OK) return 0;
+    const std::string s = describe_program(prog);
+    if (dst && cap) {
+        const size_t n = std::min(cap - 1, s.size());
+        memcpy(dst, s.data(), n);
+        dst[n] = 0;
+    }
+    return s.size();
+}
+
 mars_error_t mars_load_memory(const void *data, size_t size, mars_model_t **out_model) {
     if (!data || !out_model || size < sizeof(mars_header_t)) return MARS_ERR_INVALID_FILE;
     mars_header_t h;
