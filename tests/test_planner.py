@@ -44,9 +44,9 @@ def test_level2_fuses_but_never_drops_or_moves_a_store(headline):
     ops = plan(headline, mf.ARENA_YOLOV5S_INT8, 2)
     convs = [o for o in ops if o["kind"] == "conv_i8_nchw"]
     assert sum(o["impl"] == 1 for o in convs) == len(convs) - 1  # all but the in-place 1x1 layer run on the tensor pipe
-    assert sum(o["fused"] == 2 for o in convs) == 57             # every conv + sigmoid + mul chain of the graph, the in-place one included
+    assert sum(o["fused"] == 2 for o in convs) == 54             # every conv + sigmoid + mul chain but three (below), the in-place conv included
     assert not any(re.search(r" -[YSZ]\b|\+fwd|forwarded", o["note"]) for o in ops)  # whole-arena parity holds at levels 0-2
-    assert not any(o["kind"] in ("sigmoid_i8", "mul_i8") for o in ops)
+    assert sum(o["kind"] == "sigmoid_i8" for o in ops) == sum(o["kind"] == "mul_i8" for o in ops) == 3  # two-N-tile layers whose outputs overwrite their input: fusing needs a private input copy (opt-in, no gain)
 
 
 def test_level3_elides_forwards_and_trims(headline):
@@ -60,7 +60,6 @@ def test_level3_elides_forwards_and_trims(headline):
     # an input copied in front of a periodic (in-place) input survives only in the bytes that input reads: 80 of 1 638 400
     per = [i for i, o in enumerate(ops) if o["kind"] == "concat_periodic"]
     assert per and all(ops[i - 1]["kind"] == "concat" and ops[i - 1]["n"] <= 160 for i in per if ops[i - 1]["layer"] == ops[i]["layer"])
-    assert sum("private copy" in o["note"] for o in ops) == 3  # the Co = 512 layers whose fused outputs overwrite their input
     assert any(o["mode"] == "pixel-serial" and "+sigmoid+mul fused" in o["note"] for o in ops)
     assert not any("FAIL" in o["mode"] for o in ops)
 

@@ -1165,9 +1165,10 @@ static int round_up(int x, int a) { return (x + a - 1) / a * a; }
 
 /* MARS_TC_TST: which layers send their NCHW streams through the shared-memory staging block -- bit 0: tiles without pad columns,
  * TMA stores; bit 1: padded tiles (kxk layers), written out by the team's threads in 16-byte pieces; bit 2: tiles without pad
- * columns, written out by the threads */
+ * columns, written out by the threads; bit 3: only the space-to-depth stem, by the threads (the default: the stem writes the largest
+ * planes next to a side output and is the one layer class where staging pays, -7 %; profiles/r02l_staged_stores.txt) */
 static int tst_modes() {
-    static const int m = getenv("MARS_TC_TST") ? atoi(getenv("MARS_TC_TST")) : 0;
+    static const int m = getenv("MARS_TC_TST") ? atoi(getenv("MARS_TC_TST")) : 8; /* default: only the space-to-depth stem (bit 3), the one layer class where it pays (-7 %) */
     return m;
 }
 
@@ -1175,9 +1176,9 @@ static int tst_modes() {
  * anything else faults, measured), so when the output rows are a multiple of 16 pixels the pitch is rounded up to one as well:
  * every 128-pixel tile then starts on a 16-pixel boundary of its row.  The extra pad columns are computed and discarded; the
  * rounding is skipped when they would add more than MARS_TC_WPWASTE percent (default 20) to the layer. */
-static int store_pitch(int wp_min, int ow) {
+static int store_pitch(int wp_min, int ow, bool stem = false) {
     static const int max_waste = getenv("MARS_TC_WPWASTE") ? atoi(getenv("MARS_TC_WPWASTE")) : 20;
-    if (!(tst_modes() & 2) || ow % 16 || wp_min % 16 == 0) return wp_min;
+    if (!(tst_modes() & (stem ? 10 : 2)) || ow % 16 || wp_min % 16 == 0) return wp_min;
     const int wp = (wp_min + 15) / 16 * 16;
     return (wp - wp_min) * 100 <= max_waste * wp_min ? wp : wp_min;
 }
@@ -1207,7 +1208,7 @@ static TcGeom tc_geometry(const Op &o) {
         if (s2d_enabled && o.sh == 2 && o.kh == 6 && (o.pt == 0 || o.pt == 2) && (o.pl == 0 || o.pl == 2) && o.ic <= 4 && o.ih % 2 == 0 &&
             o.iw % 2 == 0 && o.oh <= o.ih / 2 && o.ow <= o.iw / 2 && round_up(o.oc, 16) <= 128 && (long long)o.oh * o.ow >= 4096) {
             /* the stem: the same space-to-depth copy as the NCHW stem, gathered from interleaved pixels */
-            g.prepass = 4; g.Wp = store_pitch(o.iw / 2 + 2, o.ow); g.plane = (o.ih / 2 + 2) * g.Wp; g.npix = g.plane; g.ntaps = 6; g.Kp = 32;
+            g.prepass = 4; g.Wp = store_pitch(o.iw / 2 + 2, o.ow, true); g.plane = (o.ih / 2 + 2) * g.Wp; g.npix = g.plane; g.ntaps = 6; g.Kp = 32;
             g.scratch_bytes = (size_t)g.npix * 16;
             g.ok = true;
             return g;
@@ -1256,7 +1257,7 @@ static TcGeom tc_geometry(const Op &o) {
         if (s2d_enabled && o.sh == 2 && o.sw == 2 && o.kh == 6 && o.kw == 6 && (o.pt == 0 || o.pt == 2) && (o.pl == 0 || o.pl == 2) &&
             o.ic <= 4 && o.ih % 2 == 0 && o.iw % 2 == 0 && o.oh <= o.ih / 2 && o.ow <= o.iw / 2 && round_up(o.oc, 16) <= 128 &&
             (long long)o.oh * o.ow >= 4096) {
-            g.prepass = 4; g.Wp = store_pitch(o.iw / 2 + 2, o.ow); g.plane = (o.ih / 2 + 2) * g.Wp; g.npix = g.plane; g.ntaps = 6; g.Kp = 32;
+            g.prepass = 4; g.Wp = store_pitch(o.iw / 2 + 2, o.ow, true); g.plane = (o.ih / 2 + 2) * g.Wp; g.npix = g.plane; g.ntaps = 6; g.Kp = 32;
             g.scratch_bytes = (size_t)g.npix * 16;
             g.ok = true;
             return true;
@@ -1595,7 +1596,7 @@ bool tc_plan(const Op &o, const ArenaGeom &ag, uint8_t *scratch, size_t scratch_
     /* TMA stores fault on negative coordinates (measured), which clipping the left end of a row segment would need: padded tiles
      * are copied out by the threads instead */
     const bool st_padded = !st_flat && g.Wp != o.ow && o.ow % 16 == 0 && g.Wp % 16 == 0;
-    t->tst = !gather && !rect && !nhwc_in && t->nst >= 1 && ((st_flat && (tst_modes() & 5)) || (st_padded && (tst_modes() & 2)));
+    t->tst = !gather && !rect && !nhwc_in && t->nst >= 1 && ((st_flat && (tst_modes() & 5)) || (st_padded && (tst_modes() & (s2d ? 10 : 2))));
     p.st_manual = (t->tst && (st_padded || (tst_modes() & 4))) ? 1 : 0;
     for (int k = 0; k < t->nst; k++) if (p.out_off[k] % 16) t->tst = false;
     const int epi_warps = (!gather && t->ctas_per_sm == 1) ? 16 : 8;

@@ -590,7 +590,10 @@ static void fuse_silu(Program *p, int64_t W) {
                 /* several N tiles (Co > 256): a CTA's outputs would overwrite input pixels the other N tile's CTAs still read.
                  * A private copy of the input (one device-to-device copy per launch, a fraction of the two element-wise passes
                  * it saves) makes the fusion legal */
-                if (c.kind == OP_CONV_I8_NCHW && c.kh == 1 && c.kw == 1 && !c.xlat && tc_private_input_ok(c)) c.private_in = true;
+                /* opt-in (MARS_FUSE_PRIVATE=1): measured a wash on the 20 x 20 layers it applies to in the headline model -- the copy
+                 * and the slower table epilogue cost what the two element-wise passes did (profiles/r02r) */
+                static const bool fuse_private = getenv("MARS_FUSE_PRIVATE") && atoi(getenv("MARS_FUSE_PRIVATE")) != 0;
+                if (fuse_private && c.kind == OP_CONV_I8_NCHW && c.kh == 1 && c.kw == 1 && !c.xlat && tc_private_input_ok(c)) c.private_in = true;
                 else continue;
             }
         }
