@@ -533,7 +533,10 @@ def run_cuda_arm(args):
     if roof:
         roof["ms_per_step_with_op_events"] = prof_ms_per_step
         direct = shares.get("conv_direct_i8", 0.0) + shares.get("conv_direct_f32", 0.0)
-        if direct > (0.05 if CFG is CONFIGS["int8"] else 1.0):  # (the --nhwc and float32 graphs each have one in-place convolution on an order-preserving kernel)
+        # the headline graph has ONE convolution off the tensor pipe -- the in-place 1x1 layer 43, whose output planes alias its input planes (order-preserving
+        # register kernel, with its SIGMOID + MUL folded in: 1.6 ms of a ~31 ms step = 5 %); a silent fall-back of the whole model to the exact kernels would
+        # put this share near 100 % (strict mode already turns that into an error at load)
+        if direct > (0.10 if CFG is CONFIGS["int8"] else 1.0):  # (the --nhwc and float32 graphs each have in-place convolutions on order-preserving kernels)
             raise SystemExit("bench.py: %.1f%% of the step runs on the direct (non tensor-core) convolution kernels" % (100 * direct))
         if roof["kernel"] == "conv_tcgen05_i8":
             ceil_by_n = load_i8_ceiling()
