@@ -167,6 +167,27 @@ int mars_b200_requant_fit(float scale, long long tmax, int *m, int *s, long long
 /* the reference's requantisation of one value, restated (what the fit is checked against) */
 int mars_b200_requant_ref(int t, float scale);
 
+/* ---- NNA-native tensor layouts -------------------------------- */
+/* The layouts behind the format tags MARS_FORMAT_NMHWSOIB2 / MARS_FORMAT_NDHWC32 (reference include/mars.h:46-56), which the
+ * reference's compiler can emit and its runtime only sizes (src/mars/mars_runtime.c:93-110):
+ *   NMHWSOIB2 weights  [ceil(Co/32)][ceil(Ci/32)][KH][KW][32 out][32 in], 1024-byte blocks, absent channels zero
+ *                      (packer: mars-compiler/src/mars_format.rs:436-470; unpackers: mgk-decompiler/mgk_decompiler.py:530-540,
+ *                      mgk-decompiler/scripts/extract_weights_nmhwsoib2.py:52-80)
+ *   NDHWC32 features   [N][ceil(C/32)][H][W][32], absent channels zero (mars-compiler/src/mars_format.rs:490-531)
+ * Byte permutations on the device; host-buffer forms (copy in, convert, copy out) and device-resident forms (`stream` is a
+ * cudaStream_t or NULL; the NDHWC32 buffer must be 16-byte aligned).  All return 0 on success, -1 on error
+ * (mars_b200_last_error); the size helpers return 0 for non-positive dimensions. */
+size_t mars_b200_nmhwsoib2_size(int out_ch, int in_ch, int kh, int kw);            /* mars_format.rs:472-476 */
+size_t mars_b200_ndhwc32_size(int batch, int channels, int height, int width);     /* mars_format.rs:485-488 */
+int mars_b200_pack_weights_nmhwsoib2(const int8_t *oihw, int out_ch, int in_ch, int kh, int kw, uint8_t *packed);
+int mars_b200_unpack_weights_nmhwsoib2(const uint8_t *packed, int out_ch, int in_ch, int kh, int kw, int8_t *oihw);
+int mars_b200_nchw_to_ndhwc32(const uint8_t *nchw, int batch, int channels, int height, int width, uint8_t *out);
+int mars_b200_ndhwc32_to_nchw(const uint8_t *native, int batch, int channels, int height, int width, uint8_t *nchw);
+int mars_b200_pack_weights_nmhwsoib2_device(const int8_t *d_oihw, int out_ch, int in_ch, int kh, int kw, uint8_t *d_packed, void *stream);
+int mars_b200_unpack_weights_nmhwsoib2_device(const uint8_t *d_packed, int out_ch, int in_ch, int kh, int kw, int8_t *d_oihw, void *stream);
+int mars_b200_nchw_to_ndhwc32_device(const uint8_t *d_nchw, int batch, int channels, int height, int width, uint8_t *d_out, void *stream);
+int mars_b200_ndhwc32_to_nchw_device(const uint8_t *d_native, int batch, int channels, int height, int width, uint8_t *d_nchw, void *stream);
+
 /* ---- YOLO post-process on host buffers ----------------------------------- */
 /* parse_output of reference src/mars/mars_yolo_test.c:80-104 (conf threshold 0.25) */
 int mars_yolo_parse_output(const int8_t *data, int npred, float scale, mars_det_t *dets, int maxd);

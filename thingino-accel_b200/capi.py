@@ -11,7 +11,7 @@ import os
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "lib", "libmars_b200.so")
+LIB_PATH = os.environ.get("MARS_B200_LIB") or os.path.join(HERE, "lib", "libmars_b200.so")  # (override: tuning builds, -DMARS_TC_TUNING)
 
 
 class MarsLibraryMissing(RuntimeError):
@@ -180,6 +180,16 @@ SIGNATURES = {
     "mars_b200_plan_describe": (C.c_size_t, [C.c_void_p, C.c_size_t, C.c_size_t, C.c_int, C.c_char_p, C.c_size_t]),
     "mars_b200_requant_fit": (C.c_int, [C.c_float, C.c_longlong, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_longlong)]),
     "mars_b200_requant_ref": (C.c_int, [C.c_int, C.c_float]),
+    "mars_b200_nmhwsoib2_size": (C.c_size_t, [C.c_int] * 4),
+    "mars_b200_ndhwc32_size": (C.c_size_t, [C.c_int] * 4),
+    "mars_b200_pack_weights_nmhwsoib2": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
+    "mars_b200_unpack_weights_nmhwsoib2": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
+    "mars_b200_nchw_to_ndhwc32": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
+    "mars_b200_ndhwc32_to_nchw": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
+    "mars_b200_pack_weights_nmhwsoib2_device": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
+    "mars_b200_unpack_weights_nmhwsoib2_device": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
+    "mars_b200_nchw_to_ndhwc32_device": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
+    "mars_b200_ndhwc32_to_nchw_device": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
     "mars_yolo_nms_boxes": (C.c_int, [C.c_void_p, C.c_int, C.c_float]),
     "mars_yolo_scale_detections": (None, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]),
     "mars_yolo_decode_anchor_grid": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_float, C.c_int, C.c_float, C.c_void_p, C.c_int, C.c_int]),

@@ -89,6 +89,11 @@ struct TcParams {
     int a_row_bytes;         /* bytes of one A row in a halo stage: bk, or 16 in s2d mode */
     int toep;                /* s2d mode: A rows are 16-byte pixels read as overlapping 32-byte K rows (no swizzle) */
     int halo, halo_min, halo_rb, halo_nb; /* kxk stride 1: one A load per (tile, k block) covers all taps: rows q0+halo_min .., halo_nb boxes of halo_rb rows */
+    /* halo regions: region r = halo_reg_nb[r] boxes of halo_rb rows starting at flat row q0 + halo_reg_row[r], stored back to back in
+     * the stage.  Stride 1 / s2d: one region.  halo == 2 (stride 2 over the phase-split copy): one region per 2x2 phase that has
+     * taps, and a_shift[tap] already is the tap's offset inside the stage in 16-byte units */
+    int halo_nreg, halo_reg_row[4], halo_reg_nb[4];
+    int halo_wide;           /* s2d: the halo region travels as 256-byte rows (16 pixels): halo_rb counts those rows, halo_min is a multiple of 16 */
     int acc_bufs;            /* TMEM accumulator ring depth */
     int grp, m_groups;       /* M tiles (128 rows each) per pipeline step and accumulator hand-over; groups per image */
     uint32_t a_tile_bytes;   /* bytes of one M tile's A block per k-step (a_stage_bytes = grp of them, or the halo region) */
@@ -534,7 +539,7 @@ k_conv_tc(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUte
         for (int i = threadIdx.x; i < (256 << sh); i += blockDim.x) tab[i] = __ldg(p.lutw + (i >> sh));
     }
     /* per tap: flat pixel shift (TMA coordinate); halo mode: start of the tap's rows inside the stage, in 16-byte units */
-    if (threadIdx.x < TC_MAX_TAPS) s_shift[threadIdx.x] = p.halo ? ((p.a_shift[threadIdx.x] - p.halo_min) * p.a_row_bytes) >> 4 : p.a_shift[threadIdx.x];
+    if (threadIdx.x < TC_MAX_TAPS) s_shift[threadIdx.x] = p.halo == 1 ? ((p.a_shift[threadIdx.x] - p.halo_min) * p.a_row_bytes) >> 4 : p.a_shift[threadIdx.x];
     if (GATHER) {
         const int PP = p.gPWW * 4;
         for (int k = threadIdx.x; k < 128; k += blockDim.x) {
@@ -814,16 +819,21 @@ k_conv_tc(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUte
             }
             int s = 0, ph = 1; /* waits on the empty barriers start with the opposite parity */
             if (p.halo) {
-                const int nb = p.halo_nb, rb = p.halo_rb, hmin = p.halo_min;
-                const uint32_t tx = (uint32_t)(nb * rb * p.a_row_bytes), box_b = (uint32_t)(rb * p.a_row_bytes);
+                const int nb = p.halo_nb, rb = p.halo_rb, nreg = p.halo_nreg;
+                /* wide mode: the same bytes as 256-byte rows of 16 pixels (TMA's cost is per row: measured ~2 cycles per 16-byte row) */
+                const int wide = p.halo_wide ? 16 : 1;
+                const uint32_t tx = (uint32_t)(nb * rb * p.a_row_bytes * wide), box_b = (uint32_t)(rb * p.a_row_bytes * wide);
                 for (TileIter ti(blockIdx.x, gridDim.x, tiles_per_img); ti.img < n_img; ti.next()) {
-                    const int q0 = ti.rem * G * TC_BM + hmin, zc = p.img0 + ti.img; /* n_tiles == 1 with resident weights */
+                    const int q0 = ti.rem * G * TC_BM, zc = p.img0 + ti.img; /* n_tiles == 1 with resident weights; q0 and the region rows are multiples of 16 in wide mode */
                     for (int kb = 0; kb < ksteps; kb++) {
                         mbar_wait(sa_empty + 8u * s, ph);
                         const uint32_t full = sa_full + 8u * s, dst = a_base + s * a_stb;
                         if (TC_DBG(p) == 3 || TC_DBG(p) == 9) { mbar_arrive(full); if (++s == stages) { s = 0; ph ^= 1; } continue; }
                         mbar_expect_tx(full, tx);
-                        for (int b = 0; b < nb; b++) tma_load_3d(dst + b * box_b, &mapA, full, kb * bk, q0 + b * rb, zc);
+                        for (int r = 0, bi = 0; r < nreg; r++) {
+                            const int qr = (q0 + p.halo_reg_row[r]) / wide, nbr = p.halo_reg_nb[r];
+                            for (int b = 0; b < nbr; b++, bi++) tma_load_3d(dst + bi * box_b, &mapA, full, kb * bk, qr + b * rb, zc);
+                        }
                         if (++s == stages) { s = 0; ph ^= 1; }
                     }
                 }
@@ -1617,7 +1627,7 @@ bool tc_plan(const Op &o, const ArenaGeom &ag, uint8_t *scratch, size_t scratch_
     /* dynamic shared memory of a CTA: stages + weights + table (+ 1 KiB alignment slack); 227 KiB per SM, ~7 KiB static */
     auto plan_smem = [&](int tab_bytes) {
         const int budget = (t->ctas_per_sm == 1 ? 200 * 1024 : 104 * 1024) - tab_bytes;
-        p.grp = grp0; p.acc_bufs = acc0; p.a_stage_bytes = a_stage0; p.halo = 0; p.b_resident = 0; plan_ok = true;
+        p.grp = grp0; p.acc_bufs = acc0; p.a_stage_bytes = a_stage0; p.halo = 0; p.halo_wide = 0; p.halo_nreg = 0; p.b_resident = 0; plan_ok = true;
         if (gather) { /* + 3 x 4 KiB patch ring + 8 KiB patch-word tables */
             if (p.grp > 2) { p.grp = 2; p.a_stage_bytes = p.grp * p.a_tile_bytes; p.acc_bufs = std::max(2, std::min(4, p.tmem_cols / (p.grp * p.n_tile))); }
             p.stages = std::max(2, std::min(8, (budget - (int)p.b_stage_bytes - 20480 - 1024) / (int)p.a_stage_bytes));
@@ -1636,13 +1646,62 @@ bool tc_plan(const Op &o, const ArenaGeom &ag, uint8_t *scratch, size_t scratch_
                  * next row's border column, or rows beyond the copy (zero-filled by TMA) */
                 const int s2d_min = (1 - o.pt / 2) * g.Wp + (1 - o.pl / 2);
                 const int smin = s2d ? s2d_min : -o.pt * g.Wp, smax = s2d ? s2d_min + 2 * g.Wp + 3 : (o.kh - 1 - o.pt) * g.Wp + o.kw - 1;
+                static const bool wide_enabled = !(getenv("MARS_TC_WIDE") && atoi(getenv("MARS_TC_WIDE")) == 0);
+                if (s2d && wide_enabled && g.npix % 16 == 0 && (p.grp * TC_BM) % 16 == 0) {
+                    /* the region starts on a 16-pixel boundary and travels as 256-byte rows: same shared-memory image, 1/16 of the rows */
+                    const int smin_al = (smin >= 0 ? smin / 16 : -((-smin + 15) / 16)) * 16;
+                    const int R16 = (p.grp * TC_BM + smax - smin_al + 15) / 16;
+                    const int nb = (R16 + 255) / 256, rb = (R16 + nb - 1) / nb;
+                    const uint32_t bytes = (uint32_t)round_up(nb * rb * 256, 1024);
+                    if ((size_t)2 * bytes + b_all <= (size_t)budget) {
+                        p.halo = 1; p.halo_min = smin_al; p.halo_rb = rb; p.halo_nb = nb; p.halo_wide = 1;
+                        p.halo_nreg = 1; p.halo_reg_row[0] = smin_al; p.halo_reg_nb[0] = nb;
+                        p.a_stage_bytes = bytes;
+                    }
+                }
                 const int R = p.grp * TC_BM + smax - smin;
                 const int nb = (R + 255) / 256, rb = round_up((R + nb - 1) / nb, 8);
                 const uint32_t bytes = (uint32_t)round_up(nb * rb * p.a_row_bytes, 1024);
-                if (rb <= 256 && (size_t)2 * bytes + b_all <= (size_t)budget) {
+                if (!p.halo && rb <= 256 && (size_t)2 * bytes + b_all <= (size_t)budget) {
                     p.halo = 1; p.halo_min = smin; p.halo_rb = rb; p.halo_nb = nb;
+                    p.halo_nreg = 1; p.halo_reg_row[0] = smin; p.halo_reg_nb[0] = nb;
                     p.a_stage_bytes = bytes;
                 }
+            }
+            /* kxk stride 2 over the 2x2 phase-split copy: the taps of one phase are row shifts of the same rows (0, 1, Wp, Wp + 1 for a
+             * 3x3 kernel), so one region per phase -- tile rows plus that phase's halo -- serves all taps in ONE pipeline step instead of
+             * one step per tap.  Fewer M tiles per step are accepted to make the regions fit */
+            static const bool halo2_enabled = getenv("MARS_TC_HALO2") && atoi(getenv("MARS_TC_HALO2")) != 0; /* opt-in: measured slower (32->64 s2 at 160^2: 2.65 ms against 2.15 ms with one step per tap -- the halo of a flat 128-pixel tile is a whole image row per phase, and only two such stages fit) */
+            if (halo_enabled && halo2_enabled && g.prepass == 2 && p.b_resident && g.ntaps > 1 && p.ksteps_per_tap >= 1) {
+                int rmin[4], rmax[4], used = 0;
+                for (int ph = 0; ph < 4; ph++) { rmin[ph] = 1 << 30; rmax[ph] = -(1 << 30); }
+                for (int kh = 0; kh < o.kh; kh++)
+                    for (int kw = 0; kw < o.kw; kw++) {
+                        const int ph = (kh & 1) * 2 + (kw & 1), loc = (kh / 2) * g.Wp + kw / 2;
+                        rmin[ph] = std::min(rmin[ph], loc); rmax[ph] = std::max(rmax[ph], loc);
+                    }
+                for (int ph = 0; ph < 4; ph++) used += rmax[ph] >= rmin[ph];
+                for (int gtry = p.grp; gtry >= 1 && !p.halo; gtry /= 2) {
+                    int best_rb = 0, best_boxes = 0; long long best_rows = -1;
+                    for (int rb = 8; rb <= 256; rb += 8) {
+                        int boxes = 0;
+                        for (int ph = 0; ph < 4; ph++) if (rmax[ph] >= rmin[ph]) boxes += (gtry * TC_BM + rmax[ph] - rmin[ph] + rb - 1) / rb;
+                        if (boxes > 12) continue;
+                        if (best_rows < 0 || (long long)boxes * rb < best_rows) { best_rows = (long long)boxes * rb; best_rb = rb; best_boxes = boxes; }
+                    }
+                    if (best_rows < 0) continue;
+                    const uint32_t bytes = (uint32_t)round_up((int)best_rows * p.a_row_bytes, 1024);
+                    if ((size_t)2 * bytes + b_all > (size_t)budget) continue;
+                    p.halo = 2; p.halo_min = 0; p.halo_rb = best_rb; p.halo_nb = best_boxes; p.halo_nreg = 0;
+                    for (int ph = 0; ph < 4; ph++)
+                        if (rmax[ph] >= rmin[ph]) {
+                            p.halo_reg_row[p.halo_nreg] = ph * g.plane + rmin[ph];
+                            p.halo_reg_nb[p.halo_nreg++] = (gtry * TC_BM + rmax[ph] - rmin[ph] + best_rb - 1) / best_rb;
+                        }
+                    p.grp = gtry; p.acc_bufs = std::max(2, std::min(4, p.tmem_cols / (p.grp * p.n_tile)));
+                    p.a_stage_bytes = bytes;
+                }
+                (void)used;
             }
             if (s2d && !p.halo) { plan_ok = false; return; }
             if (p.b_resident) {
@@ -1664,13 +1723,13 @@ bool tc_plan(const Op &o, const ArenaGeom &ag, uint8_t *scratch, size_t scratch_
     }
     if (!plan_ok) { delete t; return false; }
     if (t->tab) { /* widen the replication while the pipeline keeps its shape (resident weights, halo loads, >= 3 stages) */
-        const int res8 = p.b_resident, halo8 = p.halo, st8 = p.stages;
+        const int res8 = p.b_resident, halo8 = p.halo, st8 = p.stages, grp8 = p.grp;
         static const int rep_max = getenv("MARS_TC_TABREP") ? atoi(getenv("MARS_TC_TABREP")) : 32;
         for (int r2 = 32; r2 > 8; r2 >>= 1) {
             if (r2 > rep_max) continue;
             plan_smem(r2 * 1024 + cm64_bytes + stg_bytes);
             static const int min_st = getenv("MARS_TC_MINST") ? atoi(getenv("MARS_TC_MINST")) : 3;
-            if (plan_ok && !over && p.b_resident == res8 && p.halo == halo8 && p.stages >= std::min(st8, min_st)) { rep = r2; break; }
+            if (plan_ok && !over && p.b_resident == res8 && p.halo == halo8 && p.grp == grp8 && p.stages >= std::min(st8, min_st)) { rep = r2; break; }
         }
         if (rep == 8) plan_smem(8 * 1024 + cm64_bytes + stg_bytes);
         p.tab_rep = (uint32_t)rep;
@@ -1703,6 +1762,16 @@ bool tc_plan(const Op &o, const ArenaGeom &ag, uint8_t *scratch, size_t scratch_
             else if (g.prepass == 1) p.a_shift[tap] = (kh - o.pt) * g.Wp + kw;
             else p.a_shift[tap] = ((kh & 1) * 2 + (kw & 1)) * g.plane + (kh / 2) * g.Wp + kw / 2;
         }
+    if (p.halo == 2) { /* the tap's offset inside the stage, in 16-byte units: its phase's region + its shift inside the region */
+        for (int kh = 0; kh < o.kh; kh++)
+            for (int kw = 0; kw < o.kw; kw++) {
+                const int ph = (kh & 1) * 2 + (kw & 1), loc = (kh / 2) * g.Wp + kw / 2;
+                int boxes = 0, r = 0;
+                for (; r < p.halo_nreg; r++) { if (p.halo_reg_row[r] / g.plane == ph && p.halo_reg_row[r] - ph * g.plane <= loc) break; boxes += p.halo_reg_nb[r]; }
+                if (r == p.halo_nreg) { delete t; return false; }
+                p.a_shift[kh * o.kw + kw] = ((boxes * p.halo_rb + loc - (p.halo_reg_row[r] - ph * g.plane)) * p.a_row_bytes) >> 4;
+            }
+    }
     p.bias = o.bias >= 0 ? reinterpret_cast<const int32_t *>(ag.d_weights + o.bias) : nullptr;
     if (o.bias >= 0 && (o.bias % 4 || o.bias + 4 * (int64_t)o.oc > (int64_t)ag.W)) { delete t; return false; }
     p.cs = o.f0;
@@ -1799,8 +1868,10 @@ bool tc_plan(const Op &o, const ArenaGeom &ag, uint8_t *scratch, size_t scratch_
         ok = make_map3(&t->mapA, t->private_in ? (void *)scratch : (void *)t->src_slot0, (uint64_t)o.ih * o.iw, (uint64_t)o.ic, (uint64_t)ag.capacity,
                        (uint64_t)o.ih * o.iw, t->private_in ? scratch_stride : ag.slot_stride, TC_BM, (uint32_t)p.bk, CU_TENSOR_MAP_SWIZZLE_128B);
     else if (ok && s2d) /* 16-byte pixels, linear rows (no swizzle): the MMA reads them as overlapping 32-byte K rows */
-        ok = make_map3(&t->mapA, scratch, 16, (uint64_t)g.npix, (uint64_t)ag.capacity, 16, scratch_stride, 16, (uint32_t)p.halo_rb,
-                       CU_TENSOR_MAP_SWIZZLE_NONE);
+        ok = p.halo_wide ? make_map3(&t->mapA, scratch, 256, (uint64_t)g.npix / 16, (uint64_t)ag.capacity, 256, scratch_stride, 256, (uint32_t)p.halo_rb,
+                                     CU_TENSOR_MAP_SWIZZLE_NONE)
+                         : make_map3(&t->mapA, scratch, 16, (uint64_t)g.npix, (uint64_t)ag.capacity, 16, scratch_stride, 16, (uint32_t)p.halo_rb,
+                                     CU_TENSOR_MAP_SWIZZLE_NONE);
     else if (ok && g.prepass == 5) /* the arena tensor's pixels are the K rows: dims (C, pixels, images), K-major box {bk, 128} */
         ok = make_map3(&t->mapA, t->gather_direct ? (void *)t->src_slot0 : (void *)scratch, (uint64_t)o.ic, (uint64_t)o.ih * o.iw, (uint64_t)ag.capacity,
                        (uint64_t)o.ic, t->gather_direct ? ag.slot_stride : scratch_stride, (uint32_t)p.bk, TC_BM, ksw);

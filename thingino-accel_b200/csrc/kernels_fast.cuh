@@ -415,7 +415,13 @@ __global__ void __launch_bounds__(256) k_maxpool_sep(ArenaView v, KOp o, int TH)
 /* 5x5 stride-1 maxpool (the SPPF pools): one thread per output column word walks down the rows with the horizontal maxima
  * of the current and the next four rows in registers -- no shared memory, no barriers, long-lived threads whose loads for
  * the following rows are in flight while the current row is reduced.  Same clipping as k_maxpool_sep (right / bottom edge,
- * pads ignored; -128 is the identity).  grid = (column blocks, row chunks, images). */
+ * pads ignored; -128 is the identity).  grid = (column blocks, row chunks, images).
+ * The maxima are taken on sign-extended 16-bit pairs: __vmaxs4 is emulated on sm_100a (the first version of this kernel was
+ * ALU bound at 113 instructions per output word, ncu: alu 75 %), VIMNMX3.S16 is one instruction for three operands. */
+struct S16x4 { uint32_t lo, hi; }; /* bytes 0,1 and 2,3 of a word as two s16x2 words */
+__device__ __forceinline__ S16x4 s16x4_from_s8x4(uint32_t w) { return {__byte_perm(w, 0u, 0x9180u), __byte_perm(w, 0u, 0xB3A2u)}; }
+__device__ __forceinline__ S16x4 s16x4_max3(S16x4 a, S16x4 b, S16x4 c) { return {__vimax3_s16x2(a.lo, b.lo, c.lo), __vimax3_s16x2(a.hi, b.hi, c.hi)}; }
+__device__ __forceinline__ uint32_t s8x4_from_s16x4(S16x4 a) { return __byte_perm(a.lo, a.hi, 0x6420u); }
 __global__ void __launch_bounds__(128) k_maxpool5_col(ArenaView v, KOp o, int rows_per_block) {
     pdl_begin(); /* dependents may be scheduled; wait for the previous kernel of the step before touching the arena */
     const Img im = make_img(v, blockIdx.z);
@@ -425,23 +431,31 @@ __global__ void __launch_bounds__(128) k_maxpool5_col(ArenaView v, KOp o, int ro
     const int x = xw / c4, kx = min(5, o.iw - x);
     const int y0 = blockIdx.y * rows_per_block, y1 = min(y0 + rows_per_block, o.oh);
     const uint32_t *in = reinterpret_cast<const uint32_t *>(im.s_minus_W + o.in0) + (x * c4 + (xw - x * c4));
-    uint32_t *out = reinterpret_cast<uint32_t *>(im.s_minus_W + o.out) + xw;
+    uint32_t *out = reinterpret_cast<uint32_t *>(im.s_minus_W + o.out) + xw + (int64_t)y0 * OW;
     const uint32_t NEG = 0x80808080u;
-    auto hmax = [&](int r) -> uint32_t { /* horizontal window maximum of input row r; rows past the bottom edge do not exist */
-        if (r >= o.ih) return NEG;
-        const uint32_t *p = in + (int64_t)r * RW;
-        uint32_t m = p[0];
-        if (kx > 1) m = __vmaxs4(m, p[c4]);
-        if (kx > 2) m = __vmaxs4(m, p[2 * c4]);
-        if (kx > 3) m = __vmaxs4(m, p[3 * c4]);
-        if (kx > 4) m = __vmaxs4(m, p[4 * c4]);
+    /* word offsets of the window's columns; columns past the right edge re-read column 0 (max is idempotent) */
+    const int o1 = kx > 1 ? c4 : 0, o2 = kx > 2 ? 2 * c4 : 0, o3 = kx > 3 ? 3 * c4 : 0, o4 = kx > 4 ? 4 * c4 : 0;
+    const uint32_t *p = in + (int64_t)y0 * RW;
+    int r = y0;
+    const uint32_t *const p_last = in + (int64_t)(o.ih - 1) * RW;
+    auto hmax = [&]() -> S16x4 { /* horizontal window maximum of input row r (then advances); rows past the bottom edge do not exist */
+        /* no branch: a row past the edge re-reads the last row and is replaced by the identity afterwards, so the loads of the
+         * unrolled rows are independent and all in flight together (the branchy version was latency bound: one row per round trip) */
+        const bool ok = r < o.ih;
+        const uint32_t *q = ok ? p : p_last;
+        const uint32_t w0 = q[0], w1 = q[o1], w2 = q[o2], w3 = q[o3], w4 = q[o4];
+        const S16x4 a = s16x4_from_s8x4(ok ? w0 : NEG), b = s16x4_from_s8x4(w1), c = s16x4_from_s8x4(w2), d = s16x4_from_s8x4(w3), e = s16x4_from_s8x4(w4);
+        S16x4 m = s16x4_max3(s16x4_max3(a, b, c), d, e);
+        if (!ok) m = s16x4_from_s8x4(NEG);
+        r++; p += RW;
         return m;
     };
-    uint32_t h0 = hmax(y0), h1 = hmax(y0 + 1), h2 = hmax(y0 + 2), h3 = hmax(y0 + 3);
+    S16x4 h0 = hmax(), h1 = hmax(), h2 = hmax(), h3 = hmax();
 #pragma unroll 4
     for (int y = y0; y < y1; y++) {
-        const uint32_t h4 = hmax(y + 4);
-        out[(int64_t)y * OW] = __vmaxs4(__vmaxs4(__vmaxs4(h0, h1), __vmaxs4(h2, h3)), h4);
+        const S16x4 h4 = hmax();
+        *out = s8x4_from_s16x4(s16x4_max3(s16x4_max3(h0, h1, h2), h3, h4));
+        out += OW;
         h0 = h1; h1 = h2; h2 = h3; h3 = h4;
     }
 }
@@ -496,6 +510,28 @@ static inline bool fast_spatial_ok(const ArenaView &v, const KOp &o) {
                o.ih > 0 && o.iw > 0 && o.sh > 0 && o.sw > 0;
     return false;
 }
+/* the one-load-many-stores kernel needs input and output ranges that do not touch (the planner only sends hazard-free ops here,
+ * but the check is cheap) */
+static inline bool upsample_ranges_overlap(const KOp &o) {
+    const int64_t ib = (int64_t)o.ih * o.iw * o.ic, ob = (int64_t)o.oh * o.ow * o.ic;
+    return o.in0 < o.out + ob && o.out < o.in0 + ib;
+}
+/* nearest upsample with exact integer ratios (oh == ih * sh, ow == iw * sw, 1 <= sw <= 4): a thread owns one INPUT word and
+ * stores it to its sh x sw output positions -- one load, sh * sw stores and one index split per input word instead of two
+ * divisions per output word (ncu on k_upsample_rep: alu 64 %, xu 28 %, 47 instructions per output warp-word). */
+__global__ void __launch_bounds__(256) k_upsample_exact(ArenaView v, KOp o) {
+    pdl_begin();
+    const Img im = make_img(v, blockIdx.z);
+    const int c4 = o.ic >> 2, irw = o.iw * c4, orw = o.ow * c4;
+    const int w = blockIdx.x * 256 + threadIdx.x, yi = blockIdx.y;
+    if (w >= irw) return;
+    const int xi = w / c4, c = w - xi * c4;
+    const uint32_t val = (reinterpret_cast<const uint32_t *>(im.s_minus_W + o.in0))[(int64_t)yi * irw + w];
+    uint32_t *out = reinterpret_cast<uint32_t *>(im.s_minus_W + o.out) + (int64_t)yi * o.sh * orw + xi * o.sw * c4 + c;
+    for (int dy = 0; dy < o.sh; dy++, out += orw)
+        for (int dx = 0; dx < o.sw; dx++) out[dx * c4] = val;
+}
+
 static inline void launch_fast_spatial(const ArenaView &v, const KOp &o, int n_img, cudaStream_t s) {
     if (o.kind == OP_MAXPOOL && o.sh == 1 && o.sw == 1 && o.kh == 5 && o.kw == 5 && o.oh <= o.ih && o.ow <= o.iw && n_img <= 65535) {
         const int OW = o.ow * (o.ic >> 2), rows = 64;
@@ -513,6 +549,11 @@ static inline void launch_fast_spatial(const ArenaView &v, const KOp &o, int n_i
             launch_pdl(k_maxpool_sep, dim3(g), dim3(256), (size_t)((size_t)2 * (TH + o.kh - 1) * RW * 4), s, v, o, TH);
             return;
         }
+    }
+    if (o.kind == OP_UPSAMPLE && o.sh >= 1 && o.sw >= 1 && o.sw <= 4 && o.sh <= 4 && o.oh == o.ih * o.sh && o.ow == o.iw * o.sw && o.ih <= 65535 && n_img <= 65535 &&
+        !upsample_ranges_overlap(o)) {
+        launch_pdl(k_upsample_exact, dim3(dim3((o.iw * (o.ic >> 2) + 255) / 256, o.ih, n_img)), dim3(256), (size_t)(0), s, v, o);
+        return;
     }
     if (o.kind == OP_UPSAMPLE && o.oh <= 65535 && (long long)o.ow * (o.ic >> 2) < 65536) {
         launch_pdl(k_upsample_rep, dim3(dim3((o.oh + UPS_ROWS - 1) / UPS_ROWS, n_img)), dim3(256), (size_t)(0), s, v, o);

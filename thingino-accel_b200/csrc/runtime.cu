@@ -38,6 +38,7 @@
 #include "mars_internal.h"
 #include "postproc.cuh"
 #include "preproc.cuh"
+#include "nna_layout.cuh"
 
 namespace marsb200 {
 
