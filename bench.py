@@ -394,9 +394,11 @@ def run_cuda_arm(args):
         for later tensors), so the seeded images are put back first -- outside the timed region, which is bracketed by CUDA
         events on the launching stream and ends AFTER the detection gather."""
         gm.upload_inputs(0, B, host_in, in_bytes)
+        if world > 1:  # the untimed restore takes a different time on every rank: start the timed region together, or rank 0's
+            barrier()  # gather would wait for the slowest rank's H2D copy inside its own timed region
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record(lib_stream)
-        gm.step_resident(0, B, NMS_THRESH, DETECT)
+        gm.enqueue_step_resident(0, B, NMS_THRESH, DETECT)  # no host round trip between the kernels and the collective
         gather()
         e1.record(lib_stream)
         e1.synchronize()

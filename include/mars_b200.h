@@ -104,6 +104,9 @@ mars_error_t mars_b200_run_batch(mars_model_t *m, int n, const void *inputs, siz
                                  void *outputs, size_t out_stride);
 /* run all layers, then (with_detect) decode + NMS, as ONE device-timed region */
 mars_error_t mars_b200_step_resident(mars_model_t *m, int first, int n, float nms_thresh, int with_detect);
+/* the same step without the host synchronisation: returns once the work is enqueued on the model's compute stream
+ * (mars_b200_compute_stream); the caller orders its own work behind it there -- e.g. the NCCL gather of the records -- and waits itself */
+mars_error_t mars_b200_enqueue_step_resident(mars_model_t *m, int first, int n, float nms_thresh, int with_detect);
 /* device addresses of the resident detection records, for a device-side gather (NCCL):
  * dets = mars_det_t[capacity][*stride_dets], counts = int32[capacity] */
 void mars_b200_detections_device(mars_model_t *m, void **dets, void **counts, int *stride_dets);

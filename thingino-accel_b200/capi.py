@@ -158,6 +158,7 @@ SIGNATURES = {
     "mars_b200_run_resident": (C.c_int, [PM, C.c_int, C.c_int]),
     "mars_b200_detect_resident": (C.c_int, [PM, C.c_int, C.c_int, C.c_float]),
     "mars_b200_step_resident": (C.c_int, [PM, C.c_int, C.c_int, C.c_float, C.c_int]),
+    "mars_b200_enqueue_step_resident": (C.c_int, [PM, C.c_int, C.c_int, C.c_float, C.c_int]),
     "mars_b200_download_detections": (C.c_int, [PM, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int]),
     "mars_b200_detect_batch": (C.c_int, [PM, C.c_int, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_int, C.c_float]),
     "mars_b200_submit_batch": (C.c_int, [PM, C.c_int, C.c_int, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_int, C.c_float]),
@@ -370,6 +371,10 @@ class MarsModel:
     def step_resident(self, first, n, thresh=0.45, with_detect=True):
         self._check(lib().mars_b200_step_resident(self.m, first, n, thresh, 1 if with_detect else 0), "step_resident")
         return float(lib().mars_b200_last_gpu_ms(self.m))
+
+    def enqueue_step_resident(self, first, n, thresh=0.45, with_detect=True):
+        """step_resident without the host synchronisation: the work is on compute_stream() when this returns"""
+        self._check(lib().mars_b200_enqueue_step_resident(self.m, first, n, thresh, 1 if with_detect else 0), "enqueue_step_resident")
 
     def compute_stream(self):
         """cudaStream_t handle (int) of the stream the model's kernels run on"""

@@ -1328,6 +1328,18 @@ mars_error_t mars_b200_step_resident(mars_model_t *model, int first, int n, floa
     return e;
 }
 
+/* the same step, enqueued only: the call returns as soon as the launches (one CUDA-graph replay from the second time on) are on the
+ * model's compute stream; the caller orders its own work behind them there (mars_b200_compute_stream) and synchronises itself */
+mars_error_t mars_b200_enqueue_step_resident(mars_model_t *model, int first, int n, float nms_thresh, int with_detect) {
+    Model *m = as_model(model);
+    if (!m) return MARS_ERR_INVALID_FILE;
+    CU_OK(cudaSetDevice(m->device), MARS_ERR_NNA_INIT_FAILED);
+    if (!range_ok(m, first, n)) return MARS_ERR_INVALID_TENSOR;
+    mars_error_t e = compile_model(m);
+    if (e != MARS_OK) return e;
+    return enqueue_step_graphed(m, first, n, nms_thresh, with_detect);
+}
+
 static mars_error_t copy_dets(Model *m, int first, int n, mars_det_t *dets, int32_t *counts, int maxd, cudaStream_t s) {
     if (maxd > 1000) maxd = 1000;
     if (maxd < 0) maxd = 0;
