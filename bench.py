@@ -552,11 +552,11 @@ def run_cuda_arm(args):
                 roof["frac_of_layer_mix_ceiling"] = roof["achieved"] / sc
             roof["peak_i8_source"] = "profiles/r02a_tc_peak_i8.txt: tools/tc_peak.cu, back-to-back tcgen05.mma.kind::i8 M=128 K=32 from resident shared memory, best issue configuration per N"
             # DRAM bytes per launch of the dominant kernel group from the committed ncu capture of THIS build (profiles/), per image x batch
-            tpath = os.path.join(ROOT, "profiles", "r02_traffic_conv_tc.json")
+            tpath = os.path.join(ROOT, "profiles", "r03_traffic_conv_tc.json")
             if CFG is CONFIGS["int8"] and os.path.exists(tpath):
                 tr = json.load(open(tpath))
                 roof["traffic"] = tr["dram_bytes_per_image"] * B / tr["launches_per_step"]
-                roof["traffic_source"] = ("profiles/r02_traffic_conv_tc.json: ncu dram__bytes_read.sum + dram__bytes_write.sum of the %d tensor-core conv launches of one "
+                roof["traffic_source"] = ("profiles/r03_traffic_conv_tc.json: ncu dram__bytes_read.sum + dram__bytes_write.sum of the %d tensor-core conv launches of one "
                                           "step at %d images/GPU, per launch; %s" % (tr["launches_per_step"], tr["batch_per_gpu"],
                                           "measured at this batch" if tr["batch_per_gpu"] == B else "static per-image figure scaled to %d images/GPU" % B))
                 roof["hbm_gbs_achieved"] = roof["traffic"] / (roof["avg_launch_ms"] * 1e-3) / 1e9

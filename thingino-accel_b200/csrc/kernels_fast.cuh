@@ -516,20 +516,22 @@ static inline bool upsample_ranges_overlap(const KOp &o) {
     const int64_t ib = (int64_t)o.ih * o.iw * o.ic, ob = (int64_t)o.oh * o.ow * o.ic;
     return o.in0 < o.out + ob && o.out < o.in0 + ib;
 }
-/* nearest upsample with exact integer ratios (oh == ih * sh, ow == iw * sw, 1 <= sw <= 4): a thread owns one INPUT word and
- * stores it to its sh x sw output positions -- one load, sh * sw stores and one index split per input word instead of two
- * divisions per output word (ncu on k_upsample_rep: alu 64 %, xu 28 %, 47 instructions per output warp-word). */
+/* nearest upsample whose output is covered by whole input pixels (oh <= ih * sh, ow <= iw * sw, so that y / sh and x / sw never
+ * clamp): a thread owns one INPUT word and stores it to its (up to) sh x sw output positions -- one load, sh * sw stores and one
+ * index split per input word instead of two divisions per output word (ncu on k_upsample_rep: alu 64 %, xu 28 %, 47
+ * instructions per output warp-word).  Only the input rows / columns the output reads are visited. */
 __global__ void __launch_bounds__(256) k_upsample_exact(ArenaView v, KOp o) {
     pdl_begin();
     const Img im = make_img(v, blockIdx.z);
     const int c4 = o.ic >> 2, irw = o.iw * c4, orw = o.ow * c4;
     const int w = blockIdx.x * 256 + threadIdx.x, yi = blockIdx.y;
-    if (w >= irw) return;
     const int xi = w / c4, c = w - xi * c4;
+    if (xi * o.sw >= o.ow) return; /* (also: w beyond the input row) */
     const uint32_t val = (reinterpret_cast<const uint32_t *>(im.s_minus_W + o.in0))[(int64_t)yi * irw + w];
     uint32_t *out = reinterpret_cast<uint32_t *>(im.s_minus_W + o.out) + (int64_t)yi * o.sh * orw + xi * o.sw * c4 + c;
-    for (int dy = 0; dy < o.sh; dy++, out += orw)
-        for (int dx = 0; dx < o.sw; dx++) out[dx * c4] = val;
+    const int ny = min(o.sh, o.oh - yi * o.sh), nx = min(o.sw, o.ow - xi * o.sw);
+    for (int dy = 0; dy < ny; dy++, out += orw)
+        for (int dx = 0; dx < nx; dx++) out[dx * c4] = val;
 }
 
 static inline void launch_fast_spatial(const ArenaView &v, const KOp &o, int n_img, cudaStream_t s) {
@@ -550,9 +552,10 @@ static inline void launch_fast_spatial(const ArenaView &v, const KOp &o, int n_i
             return;
         }
     }
-    if (o.kind == OP_UPSAMPLE && o.sh >= 1 && o.sw >= 1 && o.sw <= 4 && o.sh <= 4 && o.oh == o.ih * o.sh && o.ow == o.iw * o.sw && o.ih <= 65535 && n_img <= 65535 &&
-        !upsample_ranges_overlap(o)) {
-        launch_pdl(k_upsample_exact, dim3(dim3((o.iw * (o.ic >> 2) + 255) / 256, o.ih, n_img)), dim3(256), (size_t)(0), s, v, o);
+    if (o.kind == OP_UPSAMPLE && o.sh >= 1 && o.sw >= 1 && o.sw <= 4 && o.sh <= 4 && o.oh <= o.ih * o.sh && o.ow <= o.iw * o.sw && o.oh <= 65535 * o.sh &&
+        n_img <= 65535 && !upsample_ranges_overlap(o)) {
+        const int rows_in = (o.oh + o.sh - 1) / o.sh, cols_in = (o.ow + o.sw - 1) / o.sw; /* the input rows / pixels the output reads */
+        launch_pdl(k_upsample_exact, dim3(dim3((cols_in * (o.ic >> 2) + 255) / 256, rows_in, n_img)), dim3(256), (size_t)(0), s, v, o);
         return;
     }
     if (o.kind == OP_UPSAMPLE && o.oh <= 65535 && (long long)o.ow * (o.ic >> 2) < 65536) {

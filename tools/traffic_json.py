@@ -1,6 +1,6 @@
 """tools/traffic_json.py -- ncu CSV (dram__bytes_read.sum, dram__bytes_write.sum, gpu__time_duration.sum of the tensor-core conv launches of one
-step) -> profiles/r02_traffic_conv_tc.json, which bench.py reads for roofline.traffic.
-usage: python tools/traffic_json.py gpurun_out/traffic.csv 1024 > profiles/r02_traffic_conv_tc.json"""
+step) -> profiles/r03_traffic_conv_tc.json, which bench.py reads for roofline.traffic.
+usage: python tools/traffic_json.py gpurun_out/traffic.csv 1024 > profiles/r03_traffic_conv_tc.json"""
 import csv
 import json
 import sys
