@@ -93,6 +93,7 @@ struct TcParams {
      * the stage.  Stride 1 / s2d: one region.  halo == 2 (stride 2 over the phase-split copy): one region per 2x2 phase that has
      * taps, and a_shift[tap] already is the tap's offset inside the stage in 16-byte units */
     int halo_nreg, halo_reg_row[4], halo_reg_nb[4];
+    int tps;                 /* taps per pipeline step (copy-based kxk layers with one k block per tap, no halo): a stage holds the A tiles -- and, when the weights are not resident, the B tiles -- of tps consecutive taps */
     int halo_wide;           /* s2d: the halo region travels as 256-byte rows (16 pixels): halo_rb counts those rows, halo_min is a multiple of 16 */
     int acc_bufs;            /* TMEM accumulator ring depth */
     int grp, m_groups;       /* M tiles (128 rows each) per pipeline step and accumulator hand-over; groups per image */
@@ -789,13 +790,15 @@ k_conv_tc(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUte
                         if (++s == stages) { s = 0; ph ^= 1; }
                     }
                 } else {
-                    for (int i = 0; i < nsteps; i++) {
+                    const int T = p.tps; /* taps per step (1 unless the plan merged taps: then one k block per tap) */
+                    for (int i = 0; i < nsteps; i += T) {
                         mbar_wait(sa_full + 8u * s, ph);
                         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                        const uint32_t a_st = a_lo0 + s * a_st16, b_lo = b_lo0 + (b_res ? i : s) * b_st16;
+                        uint32_t a_st = a_lo0 + s * a_st16 + lane * a_tile16, b_lo = b_lo0 + (b_res ? i : s * T) * b_st16;
                         if (TC_DBG(p) != 4 && TC_DBG(p) != 9)
-                            for (int j = 0; j < nj; j++)
-                                    umma_i8_parts(acc + (uint32_t)(lane * n_tile), a_st + lane * a_tile16 + a_j16 * j, hi_a, b_lo + 2u * j, hi_k, idesc, (uint32_t)((i | j) != 0));
+                            for (int t = 0; t < T; t++, a_st += G * a_tile16, b_lo += b_st16)
+                                for (int j = 0; j < nj; j++)
+                                    umma_i8_parts(acc + (uint32_t)(lane * n_tile), a_st + a_j16 * j, hi_a, b_lo + 2u * j, hi_k, idesc, (uint32_t)((i | t | j) != 0));
                         umma_commit(sa_empty + 8u * s); /* frees the stage when these MMAs retire */
                         if (++s == stages) { s = 0; ph ^= 1; }
                     }
@@ -838,11 +841,27 @@ k_conv_tc(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUte
                     }
                 }
             } else {
-                const uint32_t tx = p.a_tx_bytes + (b_res ? 0u : (uint32_t)(p.n_tile * bk));
+                const int T = p.tps;
+                const uint32_t tx = p.a_tx_bytes + (b_res ? 0u : (uint32_t)(T * p.n_tile * bk));
                 const bool rect = p.rect != 0;
                 for (TileIter ti(blockIdx.x, gridDim.x, tiles_per_img); ti.img < n_img; ti.next()) {
                     const int mg = n_tiles == 1 ? ti.rem : ti.rem / n_tiles, n0 = (ti.rem - mg * n_tiles) * p.n_tile;
                     const int q0 = mg * G * TC_BM, zc = p.img0 + ti.img;
+                    if (T > 1) { /* several taps per step (K-major copy, one k block per tap): the step's loads share one barrier */
+                        for (int tap = 0; tap < ntaps; tap += T) {
+                            mbar_wait(sa_empty + 8u * s, ph);
+                            const uint32_t full = sa_full + 8u * s;
+                            if (TC_DBG(p) == 3 || TC_DBG(p) == 9) { mbar_arrive(full); if (++s == stages) { s = 0; ph ^= 1; } continue; }
+                            mbar_expect_tx(full, tx);
+                            for (int t = 0; t < T; t++) {
+                                const int qa = q0 + s_shift[tap + t];
+                                for (int g = 0; g < G; g++) tma_load_3d(a_base + s * a_stb + (t * G + g) * a_tb, &mapA, full, 0, qa + g * TC_BM, zc);
+                                if (!b_res) tma_load_3d(b_base + (s * T + t) * b_stb, &mapB, full, 0, n0, tap + t);
+                            }
+                            if (++s == stages) { s = 0; ph ^= 1; }
+                        }
+                        continue;
+                    }
                     for (int tap = 0; tap < ntaps; tap++) {
                         const int sh = s_shift[tap], qa = q0 + sh; /* rect mode: sh = kh << 16 | kw */
                         for (int kb = 0; kb < ksteps; kb++) {
@@ -1627,7 +1646,7 @@ bool tc_plan(const Op &o, const ArenaGeom &ag, uint8_t *scratch, size_t scratch_
     /* dynamic shared memory of a CTA: stages + weights + table (+ 1 KiB alignment slack); 227 KiB per SM, ~7 KiB static */
     auto plan_smem = [&](int tab_bytes) {
         const int budget = (t->ctas_per_sm == 1 ? 200 * 1024 : 104 * 1024) - tab_bytes;
-        p.grp = grp0; p.acc_bufs = acc0; p.a_stage_bytes = a_stage0; p.halo = 0; p.halo_wide = 0; p.halo_nreg = 0; p.b_resident = 0; plan_ok = true;
+        p.grp = grp0; p.acc_bufs = acc0; p.a_stage_bytes = a_stage0; p.halo = 0; p.halo_wide = 0; p.halo_nreg = 0; p.b_resident = 0; p.tps = 1; plan_ok = true;
         if (gather) { /* + 3 x 4 KiB patch ring + 8 KiB patch-word tables */
             if (p.grp > 2) { p.grp = 2; p.a_stage_bytes = p.grp * p.a_tile_bytes; p.acc_bufs = std::max(2, std::min(4, p.tmem_cols / (p.grp * p.n_tile))); }
             p.stages = std::max(2, std::min(8, (budget - (int)p.b_stage_bytes - 20480 - 1024) / (int)p.a_stage_bytes));
@@ -1704,11 +1723,23 @@ bool tc_plan(const Op &o, const ArenaGeom &ag, uint8_t *scratch, size_t scratch_
                 (void)used;
             }
             if (s2d && !p.halo) { plan_ok = false; return; }
+            /* several taps per pipeline step: a step costs the single MMA / producer lanes 0.2-0.5 us of barrier hand-overs whatever it
+             * holds (profiles/r03a), and a tap of a Ci = 32 / 64 layer is only 4-16 KiB */
+            static const int tps_max = getenv("MARS_TC_TPS") ? atoi(getenv("MARS_TC_TPS")) : 1; /* opt-in: measured no gain (32->64 3x3 s2 with three taps per step: 2.26 ms against 2.18 ms) -- under load the SM's issue slots, not the hand-overs, are what the layer waits for */
+            static const int tps_minst = getenv("MARS_TC_TPS_MINST") ? atoi(getenv("MARS_TC_TPS_MINST")) : 2;
+            if (!p.halo && !rect && (g.prepass == 1 || g.prepass == 2) && g.ntaps > 1 && p.ksteps_per_tap == 1) {
+                for (int T = std::min(tps_max, g.ntaps); T > 1; T--) {
+                    if (g.ntaps % T) continue;
+                    const long long stage = (long long)T * (p.a_stage_bytes + (p.b_resident ? 0 : p.b_stage_bytes));
+                    const long long room = (long long)budget - (p.b_resident ? (long long)b_all : 0);
+                    if (stage * tps_minst <= room) { p.tps = T; p.a_stage_bytes *= T; break; }
+                }
+            }
             if (p.b_resident) {
                 p.stages = std::max(2, std::min(8, (budget - (int)b_all) / (int)p.a_stage_bytes));
                 t->smem = 1024 + (size_t)p.stages * p.a_stage_bytes + b_all;
             } else {
-                const int stage_bytes = (int)(p.a_stage_bytes + p.b_stage_bytes);
+                const int stage_bytes = (int)(p.a_stage_bytes + p.tps * p.b_stage_bytes);
                 p.stages = std::max(2, std::min(8, budget / stage_bytes));
                 t->smem = 1024 + (size_t)p.stages * stage_bytes;
             }
@@ -1723,13 +1754,13 @@ bool tc_plan(const Op &o, const ArenaGeom &ag, uint8_t *scratch, size_t scratch_
     }
     if (!plan_ok) { delete t; return false; }
     if (t->tab) { /* widen the replication while the pipeline keeps its shape (resident weights, halo loads, >= 3 stages) */
-        const int res8 = p.b_resident, halo8 = p.halo, st8 = p.stages, grp8 = p.grp;
+        const int res8 = p.b_resident, halo8 = p.halo, st8 = p.stages, grp8 = p.grp, tps8 = p.tps;
         static const int rep_max = getenv("MARS_TC_TABREP") ? atoi(getenv("MARS_TC_TABREP")) : 32;
         for (int r2 = 32; r2 > 8; r2 >>= 1) {
             if (r2 > rep_max) continue;
             plan_smem(r2 * 1024 + cm64_bytes + stg_bytes);
             static const int min_st = getenv("MARS_TC_MINST") ? atoi(getenv("MARS_TC_MINST")) : 3;
-            if (plan_ok && !over && p.b_resident == res8 && p.halo == halo8 && p.grp == grp8 && p.stages >= std::min(st8, min_st)) { rep = r2; break; }
+            if (plan_ok && !over && p.b_resident == res8 && p.halo == halo8 && p.grp == grp8 && p.tps == tps8 && p.stages >= std::min(st8, min_st)) { rep = r2; break; }
         }
         if (rep == 8) plan_smem(8 * 1024 + cm64_bytes + stg_bytes);
         p.tab_rep = (uint32_t)rep;
