@@ -476,3 +476,39 @@ def test_submit_wait_batches_match_the_synchronous_path(pkg, ob):
     with pytest.raises(pkg.capi.MarsError):
         gm.submit_batch(0, half + 1, xs, xs.shape[1], dets[0], counts[0])
     gm.close()
+
+
+def test_enqueue_only_step_equals_the_synchronous_step(pkg):
+    """mars_b200_enqueue_step_resident (no host synchronisation; the caller waits on the compute stream) leaves the same outputs and
+    detection records as mars_b200_step_resident -- first plain launches, then the captured graph"""
+    blob = pkg.marsfile.build_yolov5(width=0.125, size=160, seed=9).to_bytes()
+    gm = pkg.MarsModel(blob, arena_bytes=8 << 20, batch=3)
+    xs = np.random.default_rng(33).integers(-128, 128, size=(3, 3 * 160 * 160), dtype=np.int8)
+    gm.upload_inputs(0, 3, xs, xs.shape[1])
+    gm.step_resident(0, 3, 0.45, True)
+    want_out = gm.download_outputs(0, 3).copy()
+    wd, wc = gm.download_detections(0, 3)
+    wd, wc = wd.copy(), wc.copy()
+    for _ in range(3):  # 1st: plain, 2nd: capture, 3rd: replay
+        gm.upload_inputs(0, 3, xs, xs.shape[1])
+        gm.enqueue_step_resident(0, 3, 0.45, True)
+        got_out = gm.download_outputs(0, 3)  # synchronous copies on the same stream order behind the enqueued step
+        gd, gc = gm.download_detections(0, 3)
+        assert np.array_equal(got_out, want_out)
+        assert np.array_equal(gc, wc)
+        for i in range(3):
+            assert gd[i, :gc[i]].tobytes() == wd[i, :wc[i]].tobytes()
+    gm.close()
+
+
+def test_opt_in_pipeline_variants_stay_bit_exact():
+    """MARS_TC_HALO2 (one pipeline step per tile on stride-2 layers) and MARS_TC_TPS (several taps per step) are read once per process:
+    the conv micro shapes and the yolov5-shaped batch run again in a child process with both switched on"""
+    import subprocess
+    import sys
+    env = dict(os.environ, MARS_TC_HALO2="1", MARS_TC_TPS="3")
+    r = subprocess.run([sys.executable, "-m", "pytest", os.path.abspath(__file__), "-q", "-x", "-m", "gpu", "-p", "no:cacheprovider",
+                        "-k", "(test_micro_models and conv) or (test_generated_yolov5_batch and 320)"], env=env, capture_output=True, text=True,
+                       cwd=os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert " passed" in r.stdout
