@@ -85,6 +85,35 @@ __global__ void __launch_bounds__(256) k_nchw_to_ndhwc32(const uint8_t *__restri
     }
 }
 
+/* NCHW -> NDHWC32 without shared memory (planes of a multiple of 4 pixels, 4-byte aligned): a lane owns four adjacent pixels.  It reads
+ * their word from each of the 32 channel planes of the group (a warp reads 128 contiguous bytes of one plane per instruction),
+ * transposes 4 channels x 4 pixels at a time in registers (8 PRMT) and ends up with the complete 32-byte rows of its four pixels:
+ * 128 contiguous output bytes per lane, 4 KiB per warp.  0.8 instructions per byte against 2.2 for the byte gather out of the tile.
+ * grid = (chunks of 8 warps x 128 pixels, D_C32, N); block = 256. */
+__global__ void __launch_bounds__(256) k_nchw_to_ndhwc32_reg(const uint8_t *__restrict__ src, uint8_t *__restrict__ dst, int C, long long HW) {
+    const int d = blockIdx.y, n = blockIdx.z, D = gridDim.y;
+    const long long q = (long long)blockIdx.x * 256 + threadIdx.x; /* pixel quad */
+    if (4 * q >= HW) return;
+    const int c_lo = d * 32, nc = min(32, C - c_lo);
+    const uint32_t *pl = reinterpret_cast<const uint32_t *>(src + ((long long)n * C + c_lo) * HW) + q;
+    const long long pw = HW >> 2; /* words per plane */
+    uint32_t o[4][8]; /* [pixel][4-channel word] */
+#pragma unroll
+    for (int g = 0; g < 8; g++) {
+        const uint32_t a = 4 * g + 0 < nc ? __ldg(pl + (4 * g + 0) * pw) : 0u, b = 4 * g + 1 < nc ? __ldg(pl + (4 * g + 1) * pw) : 0u;
+        const uint32_t c = 4 * g + 2 < nc ? __ldg(pl + (4 * g + 2) * pw) : 0u, e = 4 * g + 3 < nc ? __ldg(pl + (4 * g + 3) * pw) : 0u;
+        const uint32_t t0 = __byte_perm(a, b, 0x5140u), t1 = __byte_perm(a, b, 0x7362u), u0 = __byte_perm(c, e, 0x5140u), u1 = __byte_perm(c, e, 0x7362u);
+        o[0][g] = __byte_perm(t0, u0, 0x5410u); o[1][g] = __byte_perm(t0, u0, 0x7632u);
+        o[2][g] = __byte_perm(t1, u1, 0x5410u); o[3][g] = __byte_perm(t1, u1, 0x7632u);
+    }
+    uint4 *out = reinterpret_cast<uint4 *>(dst + (((long long)n * D + d) * HW + 4 * q) * 32);
+#pragma unroll
+    for (int p = 0; p < 4; p++) {
+        out[2 * p] = make_uint4(o[p][0], o[p][1], o[p][2], o[p][3]);
+        out[2 * p + 1] = make_uint4(o[p][4], o[p][5], o[p][6], o[p][7]);
+    }
+}
+
 /* NDHWC32 -> NCHW: the same tile the other way round */
 __global__ void __launch_bounds__(256) k_ndhwc32_to_nchw(const uint8_t *__restrict__ src, uint8_t *__restrict__ dst, int C, long long HW) {
     __shared__ __align__(16) uint8_t tile[32][NNA_TILE_PX + 4];
